@@ -1,0 +1,146 @@
+/*
+ * swn_b200.h -- C ABI of the B200-native shallow-wavenet generation path.
+ *
+ * The reference (patrickltobing/shallow-wavenet) has no FFI layer: its boundary for this
+ * path is the Python class API of src/nets.  This header is the boundary a
+ * non-Python host binds instead; the Python mirror of the reference API
+ * (shallow-wavenet_b200/nets/{cswnv_shift1,dswnv}.py) is a thin ctypes caller of exactly
+ * these entry points.  Each entry point cites the reference interface it replaces
+ * (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; swn_last_error() gives the
+ *     message of the last failing call on the calling thread;
+ *   - a handle is bound to one CUDA device, is not thread-safe, and owns every device
+ *     allocation it makes;
+ *   - "dev" pointers are device pointers owned by the caller (e.g. torch tensors), "host"
+ *     pointers are host memory; `stream` is a cudaStream_t passed as void* (NULL = default);
+ *   - there is NO CPU fallback: on a device that is not sm_100 (B200) swn_create fails.
+ */
+#ifndef SWN_B200_H
+#define SWN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWN_ABI_VERSION 1
+
+typedef struct swn_model* swn_handle;
+
+enum { SWN_KIND_CSWNV = 0,      /* Laplace / LPC vocoder, src/nets/cswnv_shift1.py:130 */
+       SWN_KIND_DSWNV = 1 };    /* mu-law softmax vocoder, src/nets/dswnv.py:190       */
+
+/* Constructor arguments: CSWNV.__init__ (src/nets/cswnv_shift1.py:131-133) and
+ * DSWNV.__init__ (src/nets/dswnv.py:191-193).  Unused fields (seg/lpc/aux_conv2d_flag for
+ * DSWNV; n_quantize/audio_in_flag for CSWNV) are ignored. */
+typedef struct swn_config {
+    int32_t kind;
+    int32_t n_quantize;
+    int32_t n_aux;
+    int32_t hid_chn;
+    int32_t skip_chn;
+    int32_t aux_kernel_size;
+    int32_t aux_dilation_size;
+    int32_t dilation_depth;
+    int32_t dilation_repeat;
+    int32_t kernel_size;
+    int32_t upsampling_factor;
+    int32_t seg;
+    int32_t lpc;
+    int32_t aux_conv2d_flag;
+    int32_t wav_conv_flag;
+    int32_t audio_in_flag;
+} swn_config;
+
+/* What swn_generate does.  One call = conditioning already done (swn_condition), then the
+ * warm-up over the padded seed and the whole sampling loop of
+ * CSWNV.batch_fast_generate (src/nets/cswnv_shift1.py:314-402) /
+ * DSWNV.batch_fast_generate (src/nets/dswnv.py:312-374) as ONE persistent kernel. */
+typedef struct swn_gen_args {
+    int64_t n_samples;        /* max(n_samples_list); generated = (n_samples/seg)*seg per utterance */
+    uint64_t seed;            /* Philox4x32-10 key when noise_dev == NULL */
+    const float* noise_dev;   /* optional injected noise (parity tests):
+                                 CSWNV eps [B][n_gen] in (-0.4999,0.5)   (cswnv_shift1.py:373)
+                                 DSWNV q   [B][n_gen][Q] ~ Exp(1)        (multinomial fast path, dswnv.py:365) */
+    const void* forced_dev;   /* optional teacher forcing: samples fed back instead of the sampled
+                                 ones; float [B][n_gen] (CSWNV) / int64 [B][n_gen] (DSWNV) */
+    void* out_dev;            /* generated samples, float [B][n_gen] / int64 [B][n_gen] */
+    float* head_dev;          /* optional raw out_2 rows per step, [B][n_gen/seg][head_dim]
+                                 (head_dim = 2*seg+lpc or n_quantize) */
+    const void* seed_dev;     /* optional seed waveform (the `audio` argument of batch_fast_generate):
+                                 float [B][seg] (CSWNV) / int64 [B][1] (DSWNV); NULL = the decode
+                                 scripts' seed (zeros / n_quantize/2, decode_cswnv_laplace-shift1.py:93,
+                                 decode_dswnv_softmax.py:94-99) */
+    int32_t batch_tile;       /* utterances processed together per pipeline slot; 0 = auto */
+    int32_t reserved;
+} swn_gen_args;
+
+typedef struct swn_info {
+    int32_t abi_version;
+    int32_t receptive_field;  /* cswnv_shift1.py:182 */
+    int32_t eff_seg;          /* samples per loop step */
+    int32_t head_dim;
+    int32_t n_sm;             /* SMs used by the persistent kernel */
+    int32_t ctas_per_layer;
+    int32_t head_ctas;
+    int32_t smem_bytes;       /* dynamic shared memory per CTA of the last launch */
+    int32_t batch_tile;       /* of the last launch */
+    int32_t n_slots;          /* pipeline slots (ceil(B / batch_tile)) of the last launch */
+    int64_t weight_bytes;     /* packed in-loop weights resident on the device */
+    int64_t cond_bytes;       /* conditioning table bytes of the last swn_condition */
+    float last_cond_ms;       /* device time of the last swn_condition (CUDA events) */
+    float last_gen_ms;        /* device time of the last swn_generate persistent kernel */
+    int64_t kernel_launches;  /* kernels launched by this handle so far */
+} swn_info;
+
+/* CSWNV(...) / DSWNV(...) followed by model.cuda() (decode_cswnv_laplace-shift1.py:208-223,
+ * decode_dswnv_softmax.py:216-230). */
+int swn_create(const swn_config* cfg, int device, swn_handle* out);
+
+/* model.load_state_dict(...) (decode_cswnv_laplace-shift1.py:224): one call per state_dict
+ * entry, `key` is the reference parameter name, `host` is contiguous
+ * fp32 in the reference's own shape.  Shapes are checked against the constructor arguments. */
+int swn_set_tensor(swn_handle h, const char* key, const float* host, const int64_t* shape, int32_t ndim);
+
+/* Checks that every parameter was supplied, folds/packs the weights into the kernel layout
+ * and uploads them.  Must be called after the last swn_set_tensor and before swn_condition. */
+int swn_finalize(swn_handle h);
+
+/* x = upsampling(conv_aux(scale_in(aux))) + replicate pad + seg window + in_x[l] for all
+ * layers (cswnv_shift1.py:297-311,282; dswnv.py:302-309,291), evaluated once per batch at
+ * frame rate.  aux_dev: fp32 [B][n_aux][T_f] (zero padded to the longest utterance exactly
+ * as decode_cswnv_laplace-shift1.py:30-48 does). */
+int swn_condition(swn_handle h, const float* aux_dev, int32_t B, int32_t T_f, void* stream);
+
+/* The hot loop.  Requires a preceding swn_condition with the same B. Asynchronous on
+ * `stream` except for argument validation. */
+int swn_generate(swn_handle h, const swn_gen_args* args, void* stream);
+
+/* Blocks until the stream is idle and reports a device-side failure of the last
+ * swn_generate (e.g. the in-kernel watchdog fired) as a non-zero status. */
+int swn_sync(swn_handle h, void* stream);
+
+/* End-to-end convenience for hosts without a device allocator: host aux in, host samples
+ * out (H2D copy, swn_condition, swn_generate, D2H copy, synchronise).
+ * out_host: float [B][n_gen] (CSWNV) or int64 [B][n_gen] (DSWNV). */
+int swn_generate_host(swn_handle h, const float* aux_host, int32_t B, int32_t T_f, int64_t n_samples,
+                      uint64_t seed, void* out_host);
+
+int swn_get_info(swn_handle h, swn_info* info);
+
+/* Philox4x32-10 stream used by the sampler, for host-side reproduction in tests:
+ * fills out[n] with the uniforms the kernel draws for utterance b, samples n0..n0+n-1
+ * (CSWNV: one per sample; DSWNV: Q per sample, row-major). */
+int swn_philox_uniform(uint64_t seed, int32_t kind, int32_t n_quantize, int64_t b, int64_t n0, int64_t n, float* out_host);
+
+int swn_destroy(swn_handle h);
+
+const char* swn_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWN_B200_H */

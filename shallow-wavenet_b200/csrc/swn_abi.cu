@@ -1,0 +1,685 @@
+// C ABI (include/swn_b200.h) of the B200-native shallow-wavenet generation path:
+// model handle, state_dict ingestion + weight folding/packing, CTA work plan, conditioning
+// and the launch of the persistent generation kernel.  No CPU compute path exists here:
+// every entry point that produces samples launches the sm_100a kernels.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/swn_b200.h"
+#include "swn_gen.cuh"
+#include "swn_launch.h"
+
+namespace {
+
+thread_local char g_err[1024] = "";
+
+int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+#define CUDA_OK(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) return fail("%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+struct HostTensor {
+    std::vector<int64_t> shape;
+    std::vector<float> data;
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int ensure(size_t count) {
+        if (count <= n && p) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+        n = count;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct swn_model {
+    swn_config cfg;
+    int device = 0;
+    int n_sm = 0;
+    bool finalized = false;
+    std::map<std::string, HostTensor> t;
+
+    // derived
+    int H = 0, Hp = 0, S = 0, Sp = 0, K = 0, L = 0, seg = 1, lpc = 0, n1 = 0, n1p = 0, n2 = 0, Q = 0, U = 0, R = 0;
+    int Ca = 0, Cap = 0, NP = 0, NCH = 0;
+    std::vector<int> dil;
+    int NH = 4, G = 0, Geff = 0;
+
+    // packed host weights + per-CTA plan pieces that do not depend on the batch
+    std::vector<float> wbuf_h;
+    struct LayerCta { int pair0, npairs, skip0, nskip; int64_t w_off, b_off, ws_off; };
+    struct HeadCta { int a0, na, b0, nb, c0, nc, i0, ni; int64_t wa_off, ca_off, wb_off, bb_off, wc_off, bc_off; };
+    std::vector<std::vector<LayerCta>> lcta;   // [L][Geff]
+    std::vector<HeadCta> hcta;                 // [NH]
+
+    // device: weights and tables
+    DevBuf<float> wbuf, pconst, gain, in_tab, in_bias, xa_tab;
+    // conditioning weights
+    struct ConvW { DevBuf<float> w_t, b; int Ci, Co, ks, dil, pad; };
+    std::vector<ConvW> aux_convs;              // scale_in followed by the conv_aux layers
+    DevBuf<float> wp;                          // [Cap][NP]
+    // conditioning state
+    DevBuf<float> act0, act1, ptab;
+    int condB = 0, condTf = 0;
+    long long plan_key = -1;
+    // generation scratch
+    DevBuf<CtaDesc> desc;
+    DevBuf<unsigned long long> ll;
+    DevBuf<float> ring_scratch;
+    DevBuf<int32_t> status;
+    DevBuf<float> e2e_aux;
+    DevBuf<char> e2e_out;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool cond_timed = false, gen_timed = false;
+    swn_info info;
+
+    const HostTensor* get(const std::string& k) const {
+        auto it = t.find(k);
+        return it == t.end() ? nullptr : &it->second;
+    }
+};
+
+namespace {
+
+bool shape_is(const HostTensor* x, std::initializer_list<int64_t> s) {
+    return x && x->shape == std::vector<int64_t>(s);
+}
+
+int need(const swn_model* m, const std::string& key, std::initializer_list<int64_t> s, const HostTensor** out) {
+    const HostTensor* x = m->get(key);
+    if (!x) return fail("state_dict entry '%s' was not supplied", key.c_str());
+    if (!shape_is(x, s)) {
+        std::string got, want;
+        for (auto v : x->shape) got += std::to_string(v) + ",";
+        for (auto v : s) want += std::to_string(v) + ",";
+        return fail("state_dict entry '%s' has shape (%s) but the constructor arguments imply (%s)", key.c_str(),
+                    got.c_str(), want.c_str());
+    }
+    *out = x;
+    return 0;
+}
+
+int ipow(int b, int e) { int r = 1; while (e-- > 0) r *= b; return r; }
+
+template <typename T>
+int upload(DevBuf<T>& d, const std::vector<T>& h) {
+    if (d.ensure(h.size())) return 1;
+    if (!h.empty()) CUDA_OK(cudaMemcpy(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+void split_range(int n, int parts, int i, int* lo, int* cnt) {
+    const int a = (int)((long long)n * i / parts), b = (int)((long long)n * (i + 1) / parts);
+    *lo = a; *cnt = b - a;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* swn_last_error(void) { return g_err; }
+
+int swn_create(const swn_config* cfg, int device, swn_handle* out) {
+    if (!cfg || !out) return fail("swn_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail("swn_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail("swn_create: device %d out of range (have %d)", device, ndev);
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail("swn_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+                    prop.minor);
+    if (cfg->kind != SWN_KIND_CSWNV && cfg->kind != SWN_KIND_DSWNV) return fail("swn_create: unknown kind %d", cfg->kind);
+    swn_model* m = new swn_model();
+    m->cfg = *cfg;
+    m->device = device;
+    m->n_sm = prop.multiProcessorCount;
+    const bool is_c = cfg->kind == SWN_KIND_CSWNV;
+    m->H = cfg->hid_chn; m->S = cfg->skip_chn; m->K = cfg->kernel_size;
+    m->L = cfg->dilation_depth * cfg->dilation_repeat;
+    m->seg = is_c ? cfg->seg : 1;
+    m->lpc = is_c ? cfg->lpc : 0;
+    m->Q = cfg->n_quantize; m->U = cfg->upsampling_factor;
+    m->n1 = is_c ? m->S : m->Q;
+    m->n2 = is_c ? 2 * m->seg + m->lpc : m->Q;
+    m->Hp = round_up(m->H, 64); m->Sp = round_up(m->S, 64); m->n1p = round_up(m->n1, 64);
+    m->NCH = m->Hp / 64;
+    m->Ca = cfg->n_aux * ipow(cfg->aux_kernel_size, cfg->aux_dilation_size);
+    m->Cap = round_up(m->Ca, 16);
+    m->NP = m->L * m->seg * 2 * m->H;
+    int R = m->K - 1;
+    for (int r = 0; r < cfg->dilation_repeat; ++r)
+        for (int d = 0; d < cfg->dilation_depth; ++d) {
+            m->dil.push_back(ipow(m->K, d));
+            R += ipow(m->K, d + 1) - ipow(m->K, d);
+        }
+    m->R = R;
+    const char* bad = nullptr;
+    if (m->H < 4 || m->S < 4 || m->K < 2 || m->L < 1 || m->U < 1 || cfg->n_aux < 1) bad = "non-positive dimension";
+    else if (m->NCH > 4) bad = "hid_chn > 256 is not instantiated";
+    else if (m->seg < 1 || m->K + m->seg > 32) bad = "kernel_size + seg > 32";
+    else if (m->lpc < 0 || m->lpc > 8) bad = "lpc > 8";
+    else if (!is_c && m->Q != 256) bad = "n_quantize must be 256 (the reference's OneHot is fixed at depth 256, dswnv.py:68)";
+    else if (is_c && cfg->audio_in_flag) bad = "audio_in_flag is a DSWNV option";
+    else if (swn::batch_tiles_for_seg(m->seg)[0] == 0) bad = "seg not in {1,2,3,4,5,10}";
+    else if (cfg->aux_kernel_size % 2 == 0) bad = "aux_kernel_size must be odd";
+    if (bad) { int rc = fail("swn_create: unsupported configuration: %s", bad); delete m; return rc; }
+    m->NH = 4;
+    m->G = (m->n_sm - m->NH) / m->L;
+    if (m->G < 1) { int rc = fail("swn_create: %d SMs cannot host %d layers", m->n_sm, m->L); delete m; return rc; }
+    m->Geff = std::min(m->G, m->H);
+    if ((m->H + m->Geff - 1) / m->Geff > 2 * SWN_NWARPS) {
+        int rc = fail("swn_create: %d gate pairs per CTA exceed %d", (m->H + m->Geff - 1) / m->Geff, 2 * SWN_NWARPS);
+        delete m; return rc;
+    }
+    memset(&m->info, 0, sizeof(m->info));
+    m->info.abi_version = SWN_ABI_VERSION;
+    m->info.receptive_field = m->R;
+    m->info.eff_seg = m->seg;
+    m->info.head_dim = m->n2;
+    m->info.n_sm = m->n_sm;
+    m->info.ctas_per_layer = m->Geff;
+    m->info.head_ctas = m->NH;
+    *out = m;
+    return 0;
+}
+
+int swn_set_tensor(swn_handle h, const char* key, const float* host, const int64_t* shape, int32_t ndim) {
+    if (!h || !key || !host || (!shape && ndim > 0)) return fail("swn_set_tensor: null argument");
+    HostTensor x;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) { x.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+    x.data.assign(host, host + n);
+    h->t[key] = std::move(x);
+    h->finalized = false;
+    return 0;
+}
+
+int swn_finalize(swn_handle m) {
+    if (!m) return fail("swn_finalize: null handle");
+    CUDA_OK(cudaSetDevice(m->device));
+    const swn_config& c = m->cfg;
+    const bool is_c = c.kind == SWN_KIND_CSWNV;
+    const int H = m->H, Hp = m->Hp, S = m->S, Sp = m->Sp, K = m->K, L = m->L, seg = m->seg, Q = m->Q, U = m->U;
+    const int Ca = m->Ca, n1 = m->n1, n1p = m->n1p, n2 = m->n2, twoH = 2 * H;
+    const HostTensor *x, *y;
+
+    // ---------------- conditioning weights: scale_in + conv_aux chain (cswnv_shift1.py:152-154)
+    for (auto& cw : m->aux_convs) { cw.w_t.release(); cw.b.release(); }
+    m->aux_convs.clear();
+    m->aux_convs.resize(1 + c.aux_dilation_size);
+    {
+        if (need(m, "scale_in.weight", {c.n_aux, c.n_aux, 1}, &x) || need(m, "scale_in.bias", {c.n_aux}, &y)) return 1;
+        auto& cw = m->aux_convs[0];
+        cw.Ci = c.n_aux; cw.Co = c.n_aux; cw.ks = 1; cw.dil = 1; cw.pad = 0;
+        std::vector<float> wt((size_t)c.n_aux * c.n_aux);
+        for (int co = 0; co < c.n_aux; ++co)
+            for (int ci = 0; ci < c.n_aux; ++ci) wt[(size_t)ci * c.n_aux + co] = x->data[(size_t)co * c.n_aux + ci];
+        if (upload(cw.w_t, wt) || upload(cw.b, y->data)) return 1;
+    }
+    for (int i = 0; i < c.aux_dilation_size; ++i) {
+        const int ks = c.aux_kernel_size;
+        const int Ci = c.n_aux * ipow(ks, i), Co = c.n_aux * ipow(ks, i + 1);
+        const std::string base = "conv_aux.conv." + std::to_string(i);
+        if (need(m, base + ".weight", {Co, Ci, ks}, &x) || need(m, base + ".bias", {Co}, &y)) return 1;
+        auto& cw = m->aux_convs[i + 1];
+        cw.Ci = Ci; cw.Co = Co; cw.ks = ks; cw.dil = ipow(ks, i); cw.pad = (ipow(ks, i + 1) - ipow(ks, i)) / 2;
+        std::vector<float> wt((size_t)Ci * ks * Co);
+        for (int co = 0; co < Co; ++co)
+            for (int ci = 0; ci < Ci; ++ci)
+                for (int kk = 0; kk < ks; ++kk)
+                    wt[((size_t)ci * ks + kk) * Co + co] = x->data[((size_t)co * Ci + ci) * ks + kk];
+        if (upload(cw.w_t, wt) || upload(cw.b, y->data)) return 1;
+    }
+    // upsampling: per-phase gain + bias (cswnv_shift1.py:48-51)
+    const HostTensor *up_w, *up_b;
+    if (need(m, "upsampling.conv.weight", {1, 1, 1, U}, &up_w) || need(m, "upsampling.conv.bias", {1}, &up_b)) return 1;
+    if (upload(m->gain, up_w->data)) return 1;
+    const double b_u = up_b->data[0];
+
+    // in_x of every layer -> projection matrix Wp[Cap][NP] and constants (DESIGN.md "conditioning hoist")
+    const bool conv2d = is_c && c.aux_conv2d_flag && seg > 1;
+    const int A_in = conv2d ? Ca : Ca * seg;                    // in_x in-channels from the aux path
+    const int A_tot = A_in + ((!is_c && c.audio_in_flag) ? Q : 0);
+    const HostTensor *w2d = nullptr, *b2d = nullptr;
+    if (conv2d && (need(m, "aux_conv2d.weight", {Ca, Ca, seg, 1}, &w2d) || need(m, "aux_conv2d.bias", {Ca}, &b2d))) return 1;
+    std::vector<float> wp((size_t)m->Cap * m->NP, 0.f), pconst((size_t)L * twoH), xa;
+    if (!is_c && c.audio_in_flag) xa.assign((size_t)L * Q * twoH, 0.f);
+    std::vector<double> weff((size_t)Ca * seg);
+    for (int l = 0; l < L; ++l) {
+        const std::string base = "in_x." + std::to_string(l);
+        if (need(m, base + ".weight", {twoH, A_tot, 1}, &x) || need(m, base + ".bias", {twoH}, &y)) return 1;
+        for (int row = 0; row < twoH; ++row) {
+            const float* wr = x->data.data() + (size_t)row * A_tot;
+            double beff = y->data[row];
+            if (conv2d) {
+                // in_x(aux_conv2d(unfold(x)))  (cswnv_shift1.py:306-308): compose the two affine maps
+                std::fill(weff.begin(), weff.end(), 0.0);
+                for (int c2 = 0; c2 < Ca; ++c2) {
+                    const double w = wr[c2];
+                    beff += w * b2d->data[c2];
+                    const float* src = w2d->data.data() + (size_t)c2 * Ca * seg;   // [c][s]
+                    for (int i = 0; i < Ca * seg; ++i) weff[i] += w * src[i];
+                }
+            } else {
+                for (int i = 0; i < Ca * seg; ++i) weff[i] = wr[i];                // channel index c*seg+s (cswnv:310-311)
+            }
+            double wsum = 0.0;
+            for (int cc = 0; cc < Ca; ++cc)
+                for (int s = 0; s < seg; ++s) {
+                    const double w = weff[(size_t)cc * seg + s];
+                    wsum += w;
+                    wp[(size_t)cc * m->NP + ((size_t)l * seg + s) * twoH + row] = (float)w;
+                }
+            pconst[(size_t)l * twoH + row] = (float)(beff + b_u * wsum);
+            if (!xa.empty())
+                for (int q = 0; q < Q; ++q) xa[((size_t)l * Q + q) * twoH + row] = wr[A_in + q];
+        }
+    }
+    if (upload(m->wp, wp) || upload(m->pconst, pconst)) return 1;
+    if (!xa.empty() && upload(m->xa_tab, xa)) return 1;
+
+    // ---------------- input stage tables (causal conv over the audio, cswnv_shift1.py:164-167,352; dswnv.py:222-226,345)
+    {
+        const HostTensor *wc, *bc, *ww = nullptr, *bw = nullptr;
+        const int cin = c.wav_conv_flag ? H : (is_c ? 1 : Q);
+        if (need(m, "causal.conv.weight", {H, cin, K}, &wc) || need(m, "causal.conv.bias", {H}, &bc)) return 1;
+        if (c.wav_conv_flag && (need(m, "wav_conv.weight", {H, is_c ? 1 : Q, 1}, &ww) || need(m, "wav_conv.bias", {H}, &bw)))
+            return 1;
+        std::vector<float> tab;
+        if (is_c) {
+            tab.assign((size_t)K * 2 * H, 0.f);
+            for (int j = 0; j < K; ++j)
+                for (int r = 0; r < H; ++r) {
+                    double cb = 0.0, v = 0.0;
+                    if (c.wav_conv_flag) {
+                        for (int k = 0; k < H; ++k) {
+                            const double w = wc->data[((size_t)r * H + k) * K + j];
+                            v += w * ww->data[k]; cb += w * bw->data[k];
+                        }
+                    } else {
+                        v = wc->data[(size_t)r * K + j];
+                    }
+                    tab[((size_t)j * 2) * H + r] = (float)cb;
+                    tab[((size_t)j * 2 + 1) * H + r] = (float)v;
+                }
+        } else {
+            tab.assign((size_t)K * Q * H, 0.f);
+            for (int j = 0; j < K; ++j)
+                for (int r = 0; r < H; ++r) {
+                    if (c.wav_conv_flag) {
+                        double cb = 0.0;
+                        for (int k = 0; k < H; ++k) cb += (double)wc->data[((size_t)r * H + k) * K + j] * bw->data[k];
+                        for (int q = 0; q < Q; ++q) {
+                            double v = cb;
+                            for (int k = 0; k < H; ++k)
+                                v += (double)wc->data[((size_t)r * H + k) * K + j] * ww->data[(size_t)k * Q + q];
+                            tab[((size_t)j * Q + q) * H + r] = (float)v;
+                        }
+                    } else {
+                        for (int q = 0; q < Q; ++q) tab[((size_t)j * Q + q) * H + r] = wc->data[((size_t)r * Q + q) * K + j];
+                    }
+                }
+        }
+        if (upload(m->in_tab, tab) || upload(m->in_bias, bc->data)) return 1;
+    }
+
+    // ---------------- in-loop weights, packed per CTA
+    std::vector<float>& W = m->wbuf_h;
+    W.clear();
+    auto alloc = [&](size_t n) { size_t off = (W.size() + 3) & ~size_t(3); W.resize(off + n, 0.f); return (int64_t)off; };
+    m->lcta.assign(L, {});
+    std::vector<const HostTensor*> skw(L), skb(L);
+    for (int l = 0; l < L; ++l) {
+        if (need(m, "out_skip." + std::to_string(l) + ".weight", {S, H, 1}, &skw[l]) ||
+            need(m, "out_skip." + std::to_string(l) + ".bias", {S}, &skb[l])) return 1;
+    }
+    for (int l = 0; l < L; ++l) {
+        const std::string base = "dil_h." + std::to_string(l) + ".conv";
+        if (need(m, base + ".weight", {twoH, H, K}, &x) || need(m, base + ".bias", {twoH}, &y)) return 1;
+        for (int g = 0; g < m->Geff; ++g) {
+            swn_model::LayerCta lc;
+            split_range(H, m->Geff, g, &lc.pair0, &lc.npairs);
+            split_range(S, m->Geff, g, &lc.skip0, &lc.nskip);
+            if (l == 0) lc.nskip = 0;
+            const int np = lc.npairs;
+            lc.w_off = alloc((size_t)K * np * 2 * Hp);
+            for (int j = 0; j < K; ++j)
+                for (int pi = 0; pi < np; ++pi)
+                    for (int zc = 0; zc < 2; ++zc) {
+                        const int row = zc * H + lc.pair0 + pi;
+                        float* dst = W.data() + lc.w_off + ((size_t)(j * np + pi) * 2 + zc) * Hp;
+                        for (int k = 0; k < H; ++k) dst[k] = x->data[((size_t)row * H + k) * K + j];
+                    }
+            lc.b_off = alloc((size_t)np * 2);
+            for (int pi = 0; pi < np; ++pi) {
+                W[lc.b_off + pi * 2] = y->data[lc.pair0 + pi];
+                W[lc.b_off + pi * 2 + 1] = y->data[H + lc.pair0 + pi];
+            }
+            lc.ws_off = alloc((size_t)std::max(lc.nskip, 1) * Hp);
+            for (int r = 0; r < lc.nskip; ++r)
+                for (int k = 0; k < H; ++k)
+                    W[lc.ws_off + (size_t)r * Hp + k] = skw[l - 1]->data[(size_t)(lc.skip0 + r) * H + k];
+            m->lcta[l].push_back(lc);
+        }
+    }
+    {
+        const HostTensor *w1, *b1, *w2, *b2;
+        if (need(m, "out_1.weight", {n1, S, 1}, &w1) || need(m, "out_1.bias", {n1}, &b1) ||
+            need(m, "out_2.weight", {n2, n1, 1}, &w2) || need(m, "out_2.bias", {n2}, &b2)) return 1;
+        m->hcta.clear();
+        for (int hc = 0; hc < m->NH; ++hc) {
+            swn_model::HeadCta q;
+            split_range(S, m->NH, hc, &q.a0, &q.na);
+            split_range(n1, m->NH, hc, &q.b0, &q.nb);
+            if (is_c) { q.c0 = 0; q.nc = n2; } else split_range(n2, m->NH, hc, &q.c0, &q.nc);
+            split_range(H, m->NH, hc, &q.i0, &q.ni);
+            q.wa_off = alloc((size_t)std::max(q.na, 1) * Hp);
+            q.ca_off = alloc((size_t)std::max(q.na, 1));
+            for (int r = 0; r < q.na; ++r) {
+                for (int k = 0; k < H; ++k) W[q.wa_off + (size_t)r * Hp + k] = skw[L - 1]->data[(size_t)(q.a0 + r) * H + k];
+                double cs = 0.0;
+                for (int l = 0; l < L; ++l) cs += skb[l]->data[q.a0 + r];
+                W[q.ca_off + r] = (float)cs;
+            }
+            q.wb_off = alloc((size_t)std::max(q.nb, 1) * Sp);
+            q.bb_off = alloc((size_t)std::max(q.nb, 1));
+            for (int r = 0; r < q.nb; ++r) {
+                for (int k = 0; k < S; ++k) W[q.wb_off + (size_t)r * Sp + k] = w1->data[(size_t)(q.b0 + r) * S + k];
+                W[q.bb_off + r] = b1->data[q.b0 + r];
+            }
+            q.wc_off = alloc((size_t)std::max(q.nc, 1) * n1p);
+            q.bc_off = alloc((size_t)std::max(q.nc, 1));
+            for (int r = 0; r < q.nc; ++r) {
+                for (int k = 0; k < n1; ++k) W[q.wc_off + (size_t)r * n1p + k] = w2->data[(size_t)(q.c0 + r) * n1 + k];
+                W[q.bc_off + r] = b2->data[q.c0 + r];
+            }
+            m->hcta.push_back(q);
+        }
+    }
+    if (upload(m->wbuf, W)) return 1;
+    if (m->status.ensure(8)) return 1;
+    for (int i = 0; i < 4; ++i)
+        if (!m->ev[i]) CUDA_OK(cudaEventCreate(&m->ev[i]));
+    m->info.weight_bytes = (int64_t)W.size() * 4;
+    m->finalized = true;
+    m->condB = 0;
+    m->plan_key = -1;
+    return 0;
+}
+
+int swn_condition(swn_handle m, const float* aux_dev, int32_t B, int32_t T_f, void* stream) {
+    if (!m || !aux_dev) return fail("swn_condition: null argument");
+    if (!m->finalized) return fail("swn_condition: call swn_finalize first");
+    if (B < 1 || T_f < 1) return fail("swn_condition: B=%d T_f=%d", B, T_f);
+    CUDA_OK(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t amax = 0;
+    for (auto& cw : m->aux_convs) amax = std::max(amax, (size_t)std::max(cw.Co, m->Cap));
+    if (m->act0.ensure((size_t)B * amax * T_f) || m->act1.ensure((size_t)B * amax * T_f)) return 1;
+    if (m->ptab.ensure((size_t)B * T_f * m->NP)) return 1;
+    CUDA_OK(cudaEventRecord(m->ev[0], st));
+    const float* cur = aux_dev;
+    float* bufs[2] = {m->act0.p, m->act1.p};
+    int which = 0;
+    for (size_t i = 0; i < m->aux_convs.size(); ++i) {
+        auto& cw = m->aux_convs[i];
+        const int last = (i + 1 == m->aux_convs.size());
+        CUDA_OK(swn::launch_aux_conv(cur, cw.w_t.p, cw.b.p, bufs[which], B, cw.Ci, cw.Co, T_f, cw.ks, cw.dil, cw.pad, last, st));
+        cur = bufs[which];
+        which ^= 1;
+        m->info.kernel_launches++;
+    }
+    // cur is now frame-major y^T [B*T_f][Cap]
+    CUDA_OK(swn::launch_proj_gemm(cur, m->wp.p, m->ptab.p, (long long)B * T_f, m->NP, m->Cap, st));
+    m->info.kernel_launches++;
+    CUDA_OK(cudaEventRecord(m->ev[1], st));
+    m->cond_timed = true;
+    m->condB = B; m->condTf = T_f;
+    m->info.cond_bytes = (int64_t)B * T_f * m->NP * 4;
+    return 0;
+}
+
+int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
+    if (!m || !a) return fail("swn_generate: null argument");
+    if (!m->finalized || m->condB < 1) return fail("swn_generate: call swn_finalize and swn_condition first");
+    if (!a->out_dev) return fail("swn_generate: out_dev is null");
+    CUDA_OK(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = m->condB, Tf = m->condTf, seg = m->seg, H = m->H, Hp = m->Hp, K = m->K, L = m->L, S = m->S;
+    const int64_t n_iter = a->n_samples / seg;
+    if (n_iter < 1) return fail("swn_generate: n_samples=%lld yields no loop step (seg=%d)", (long long)a->n_samples, seg);
+    if (n_iter * seg > (int64_t)Tf * m->U)
+        return fail("swn_generate: n_samples=%lld exceeds T_f*upsampling_factor=%lld", (long long)a->n_samples,
+                    (long long)Tf * m->U);
+    if (n_iter + m->R + 2 > 0x7fffffffLL) return fail("swn_generate: too many steps");
+
+    // ---- batch tile
+    int BS = 0;
+    const int* tiles = swn::batch_tiles_for_seg(seg);
+    if (a->batch_tile > 0) {
+        for (const int* t = tiles; *t; ++t) if (*t == a->batch_tile) BS = *t;
+        if (!BS) return fail("swn_generate: batch_tile=%d is not instantiated for seg=%d", a->batch_tile, seg);
+    } else {
+        BS = tiles[0];
+        for (const int* t = tiles; *t; ++t) if (*t >= B) BS = *t;      // smallest tile covering B, else the largest
+    }
+    const int M = (B + BS - 1) / BS;
+    const int NC = BS * seg;
+    swn::launch_fn fn = nullptr;
+    switch (m->NCH) {
+        case 1: fn = swn::find_kernel_nch1(seg, BS); break;
+        case 2: fn = swn::find_kernel_nch2(seg, BS); break;
+        case 3: fn = swn::find_kernel_nch3(seg, BS); break;
+        case 4: fn = swn::find_kernel_nch4(seg, BS); break;
+    }
+    if (!fn) return fail("swn_generate: no kernel for hid_chn=%d seg=%d batch_tile=%d", H, seg, BS);
+
+    // ---- per-CTA plan: shared memory placement
+    const int smem_floats = SWN_MAX_SMEM / 4;
+    std::vector<CtaDesc> desc(m->n_sm);
+    for (auto& d : desc) { memset(&d, 0, sizeof(d)); d.role = ROLE_IDLE; }
+    size_t ring_total = 0;
+    int smem_used_max = 0;
+    int cta = 0;
+    for (int l = 0; l < L; ++l)
+        for (int g = 0; g < m->Geff; ++g, ++cta) {
+            const auto& lc = m->lcta[l][g];
+            CtaDesc& d = desc[cta];
+            d.role = ROLE_LAYER; d.layer = l; d.dil = m->dil[l];
+            d.pair0 = lc.pair0; d.npairs = lc.npairs; d.skip0 = lc.skip0; d.nskip = lc.nskip;
+            d.w_off = lc.w_off; d.b_off = lc.b_off; d.ws_off = lc.ws_off;
+            d.ring_len = (K - 1) * d.dil + seg;
+            int used = 0;
+            d.sm_h = used; used += 2 * NC * Hp;
+            const int tap_f = lc.npairs * 2 * Hp;
+            d.sm_w = used;
+            d.smem_taps = std::max(0, std::min(K, tap_f ? (smem_floats - used) / tap_f : K));
+            used += d.smem_taps * tap_f;
+            d.sm_ws = used;
+            d.skip_in_smem = (d.smem_taps == K && used + lc.nskip * Hp <= smem_floats);
+            if (d.skip_in_smem) used += lc.nskip * Hp;
+            const size_t ring_f = (size_t)M * d.ring_len * lc.npairs * 2 * BS;
+            d.sm_ring = used;
+            d.ring_in_smem = (d.skip_in_smem && used + ring_f <= (size_t)smem_floats);
+            if (d.ring_in_smem) used += (int)ring_f;
+            else { d.ring_off = (int64_t)ring_total; ring_total += (ring_f + 3) & ~size_t(3); }
+            smem_used_max = std::max(smem_used_max, used);
+        }
+    const size_t hist_f = (size_t)M * BS * (32 + 8);
+    for (int hc = 0; hc < m->NH; ++hc, ++cta) {
+        const auto& q = m->hcta[hc];
+        CtaDesc& d = desc[cta];
+        d.role = ROLE_HEAD; d.layer = hc;
+        d.a0 = q.a0; d.na = q.na; d.b0 = q.b0; d.nb = q.nb; d.c0 = q.c0; d.nc = q.nc; d.i0 = q.i0; d.ni = q.ni;
+        d.wa_off = q.wa_off; d.ca_off = q.ca_off; d.wb_off = q.wb_off; d.bb_off = q.bb_off; d.wc_off = q.wc_off; d.bc_off = q.bc_off;
+        int used = 0;
+        d.sm_x0 = used; used += BS * Hp;
+        d.sm_x1 = used; used += BS * m->Sp;
+        d.sm_x2 = used; used += BS * m->n1p;
+        d.sm_misc = used;
+        used += BS * ((q.na + 3) & ~3) + BS * ((q.nc + 3) & ~3) + (int)hist_f + BS * seg + BS + 8;
+        used = (used + 3) & ~3;
+        if (used > smem_floats)
+            return fail("swn_generate: batch of %d utterances needs %d KB of head-CTA state; split the batch", B, used / 256);
+        d.sm_wa = used; d.wa_in_smem = used + q.na * Hp <= smem_floats; if (d.wa_in_smem) used += q.na * Hp;
+        d.sm_wb = used; d.wb_in_smem = used + q.nb * m->Sp <= smem_floats; if (d.wb_in_smem) used += q.nb * m->Sp;
+        d.sm_wc = used; d.wc_in_smem = used + q.nc * m->n1p <= smem_floats; if (d.wc_in_smem) used += q.nc * m->n1p;
+        smem_used_max = std::max(smem_used_max, used);
+    }
+    const int grid = cta;
+    const size_t smem_bytes = (size_t)smem_used_max * 4;
+
+    // the plan only changes with (B, batch tile); re-upload it only then, after the stream drained
+    const long long plan_key = ((long long)B << 32) | ((long long)BS << 16) | (long long)seg;
+    if (plan_key != m->plan_key) {
+        CUDA_OK(cudaStreamSynchronize(st));
+        if (upload(m->desc, desc)) return 1;
+        m->plan_key = plan_key;
+    }
+    // ---- exchange buffers
+    const size_t n_ring = (size_t)(L + 1) * M * NC * H;
+    const size_t n_skip = (size_t)std::max(L - 1, 1) * M * BS * S;
+    const size_t n_hx1 = (size_t)M * BS * S, n_hx2 = (size_t)M * BS * m->n1, n_hx3 = (size_t)M * m->NH * BS * 2;
+    const size_t n_idx = (size_t)M * BS;
+    const size_t n_ll = n_ring + n_skip + n_hx1 + n_hx2 + n_hx3 + n_idx;
+    if (m->ll.ensure(n_ll) || m->ring_scratch.ensure(std::max<size_t>(ring_total, 4))) return 1;
+    CUDA_OK(cudaMemsetAsync(m->ll.p, 0, n_ll * sizeof(unsigned long long), st));
+    if (ring_total) CUDA_OK(cudaMemsetAsync(m->ring_scratch.p, 0, ring_total * sizeof(float), st));
+    CUDA_OK(cudaMemsetAsync(m->status.p, 0, 8 * sizeof(int32_t), st));
+
+    GenParams P;
+    memset(&P, 0, sizeof(P));
+    P.kind = m->cfg.kind; P.H = H; P.Hp = Hp; P.S = S; P.Sp = m->Sp; P.K = K; P.L = L; P.lpc = m->lpc;
+    P.n1 = m->n1; P.n1p = m->n1p; P.n2 = m->n2; P.Q = m->Q; P.U = m->U; P.R = m->R; P.B = B; P.M = M; P.Tf = Tf;
+    const int rem = (m->R + 1) % seg;
+    P.t_first = rem == 0 ? 0 : rem - seg;
+    P.it0 = (m->R + 1 - P.t_first) / seg - 1;
+    P.n_iter = (int)n_iter;
+    P.n_it = P.it0 + P.n_iter;
+    P.NH = m->NH;
+    P.audio_in = (m->cfg.kind == SWN_KIND_DSWNV && m->cfg.audio_in_flag) ? 1 : 0;
+    P.n_out = n_iter * seg;
+    P.desc = m->desc.p;
+    P.wbuf = m->wbuf.p;
+    P.P = m->ptab.p; P.pconst = m->pconst.p; P.gain = m->gain.p;
+    P.in_tab = m->in_tab.p; P.in_bias = m->in_bias.p; P.xa_tab = m->xa_tab.p;
+    P.ring_ll = m->ll.p;
+    P.skip_ll = P.ring_ll + n_ring;
+    P.hx1 = P.skip_ll + n_skip;
+    P.hx2 = P.hx1 + n_hx1;
+    P.hx3 = P.hx2 + n_hx2;
+    P.idx_ll = P.hx3 + n_hx3;
+    P.ring_scratch = m->ring_scratch.p;
+    P.noise = a->noise_dev; P.seed = a->seed; P.forced = a->forced_dev; P.seedw = a->seed_dev; P.out = a->out_dev; P.head_out = a->head_dev;
+    P.status = m->status.p;
+    P.timeout_cycles = 4000000000ULL;
+
+    CUDA_OK(cudaEventRecord(m->ev[2], st));
+    cudaError_t e = fn(P, grid, smem_bytes, st);
+    if (e != cudaSuccess) return fail("persistent kernel launch failed: %s (grid %d, %zu B smem)", cudaGetErrorString(e), grid, smem_bytes);
+    CUDA_OK(cudaEventRecord(m->ev[3], st));
+    m->gen_timed = true;
+    m->info.kernel_launches++;
+    m->info.smem_bytes = (int32_t)smem_bytes;
+    m->info.batch_tile = BS;
+    m->info.n_slots = M;
+    return 0;
+}
+
+int swn_sync(swn_handle m, void* stream) {
+    if (!m) return fail("swn_sync: null handle");
+    CUDA_OK(cudaSetDevice(m->device));
+    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (m->cond_timed) { cudaEventElapsedTime(&m->info.last_cond_ms, m->ev[0], m->ev[1]); m->cond_timed = false; }
+    if (m->gen_timed) {
+        cudaEventElapsedTime(&m->info.last_gen_ms, m->ev[2], m->ev[3]);
+        m->gen_timed = false;
+        int32_t stv[8];
+        CUDA_OK(cudaMemcpy(stv, m->status.p, sizeof(stv), cudaMemcpyDeviceToHost));
+        if (stv[0] != 0)
+            return fail("persistent kernel aborted: watchdog fired at wait site %d (tag %d, CTA %d)", stv[1], stv[2], stv[3]);
+    }
+    return 0;
+}
+
+int swn_generate_host(swn_handle m, const float* aux_host, int32_t B, int32_t T_f, int64_t n_samples, uint64_t seed,
+                      void* out_host) {
+    if (!m || !aux_host || !out_host) return fail("swn_generate_host: null argument");
+    if (!m->finalized) return fail("swn_generate_host: call swn_finalize first");
+    CUDA_OK(cudaSetDevice(m->device));
+    const size_t n_aux = (size_t)B * m->cfg.n_aux * T_f;
+    const int64_t n_gen = (n_samples / m->seg) * m->seg;
+    const size_t esz = m->cfg.kind == SWN_KIND_CSWNV ? sizeof(float) : sizeof(long long);
+    if (m->e2e_aux.ensure(n_aux) || m->e2e_out.ensure((size_t)B * n_gen * esz)) return 1;
+    CUDA_OK(cudaMemcpyAsync(m->e2e_aux.p, aux_host, n_aux * sizeof(float), cudaMemcpyHostToDevice, 0));
+    if (swn_condition(m, m->e2e_aux.p, B, T_f, nullptr)) return 1;
+    swn_gen_args a;
+    memset(&a, 0, sizeof(a));
+    a.n_samples = n_samples; a.seed = seed; a.out_dev = m->e2e_out.p;
+    if (swn_generate(m, &a, nullptr)) return 1;
+    CUDA_OK(cudaMemcpyAsync(out_host, m->e2e_out.p, (size_t)B * n_gen * esz, cudaMemcpyDeviceToHost, 0));
+    return swn_sync(m, nullptr);
+}
+
+int swn_get_info(swn_handle m, swn_info* info) {
+    if (!m || !info) return fail("swn_get_info: null argument");
+    *info = m->info;
+    return 0;
+}
+
+int swn_philox_uniform(uint64_t seed, int32_t kind, int32_t n_quantize, int64_t b, int64_t n0, int64_t n, float* out_host) {
+    if (!out_host) return fail("swn_philox_uniform: null argument");
+    if (kind == SWN_KIND_CSWNV) {
+        for (int64_t i = 0; i < n; ++i) out_host[i] = swn::philox_uniform(seed, b, n0 + i, 0);
+    } else {
+        for (int64_t i = 0; i < n; ++i)
+            for (int r = 0; r < n_quantize; ++r) out_host[i * n_quantize + r] = swn::philox_uniform(seed, b, n0 + i, r);
+    }
+    return 0;
+}
+
+int swn_destroy(swn_handle m) {
+    if (!m) return 0;
+    cudaSetDevice(m->device);
+    m->wbuf.release(); m->pconst.release(); m->gain.release(); m->in_tab.release(); m->in_bias.release();
+    m->xa_tab.release(); m->wp.release(); m->act0.release(); m->act1.release(); m->ptab.release();
+    m->desc.release(); m->ll.release(); m->ring_scratch.release(); m->status.release();
+    m->e2e_aux.release(); m->e2e_out.release();
+    for (auto& cw : m->aux_convs) { cw.w_t.release(); cw.b.release(); }
+    for (int i = 0; i < 4; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+    delete m;
+    return 0;
+}
+
+}  // extern "C"

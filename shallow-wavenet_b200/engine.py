@@ -1,0 +1,123 @@
+# -*- coding: utf-8 -*-
+"""Host-side owner of one ``swn_handle``: pushes a ``state_dict`` through the C ABI and
+drives conditioning + the persistent generation kernel.  torch is used for device memory and
+the current stream only."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _abi
+
+
+class Engine(object):
+    def __init__(self, kind, cfg_kwargs, state_dict, device):
+        lib = _abi.load()
+        self.lib = lib
+        self.kind = kind
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _abi.SwnError("the B200 generation path needs a CUDA device (call model.cuda()); "
+                                "there is no CPU fallback")
+        cfg = _abi.SwnConfig()
+        cfg.kind = _abi.KIND_CSWNV if kind == "cswnv" else _abi.KIND_DSWNV
+        for k, v in cfg_kwargs.items():
+            setattr(cfg, k, int(v))
+        h = ctypes.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _abi.check(lib.swn_create(ctypes.byref(cfg), dev_index, ctypes.byref(h)))
+        self.h = h
+        self.dev_index = dev_index
+        for key, val in state_dict.items():
+            a = np.ascontiguousarray(val.detach().to("cpu", torch.float32).numpy())
+            shape = (ctypes.c_int64 * a.ndim)(*a.shape)
+            _abi.check(lib.swn_set_tensor(h, key.encode(), a.ctypes.data_as(ctypes.c_void_p), shape, a.ndim))
+        _abi.check(lib.swn_finalize(h))
+        self.info = self.get_info()
+
+    def get_info(self):
+        info = _abi.SwnInfo()
+        _abi.check(self.lib.swn_get_info(self.h, ctypes.byref(info)))
+        return info.as_dict()
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def condition(self, aux):
+        """aux: float32 CUDA tensor [B, n_aux, T_f]."""
+        assert aux.is_cuda and aux.dtype == torch.float32 and aux.is_contiguous()
+        B, _, Tf = aux.shape
+        _abi.check(self.lib.swn_condition(self.h, ctypes.c_void_p(aux.data_ptr()), B, Tf, self._stream()))
+        self._B = B
+
+    def generate(self, n_samples, seed=0, noise=None, forced=None, seed_audio=None, return_heads=False,
+                 batch_tile=0, sync=True):
+        info = self.info
+        seg, hd = info["eff_seg"], info["head_dim"]
+        B = self._B
+        n_gen = (int(n_samples) // seg) * seg
+        is_c = self.kind == "cswnv"
+        out = torch.empty((B, n_gen), dtype=torch.float32 if is_c else torch.int64, device=self.device)
+        heads = torch.empty((B, n_gen // seg, hd), dtype=torch.float32, device=self.device) if return_heads else None
+        a = _abi.SwnGenArgs()
+        a.n_samples = int(n_samples)
+        a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        keep = []
+
+        def dev(t, dtype, shape):
+            if t is None:
+                return None
+            t = torch.as_tensor(t).to(self.device, dtype).contiguous()
+            assert tuple(t.shape) == tuple(shape), (tuple(t.shape), tuple(shape))
+            keep.append(t)
+            return t.data_ptr()
+        a.noise_dev = dev(noise, torch.float32, (B, n_gen) if is_c else (B, n_gen, 256))
+        a.forced_dev = dev(forced, torch.float32 if is_c else torch.int64, (B, n_gen))
+        a.seed_dev = dev(seed_audio, torch.float32 if is_c else torch.int64, (B, seg))
+        a.out_dev = out.data_ptr()
+        a.head_dev = heads.data_ptr() if heads is not None else None
+        a.batch_tile = int(batch_tile)
+        _abi.check(self.lib.swn_generate(self.h, ctypes.byref(a), self._stream()))
+        self._keep = keep
+        if sync:
+            self.sync()
+        return out, heads
+
+    def sync(self):
+        _abi.check(self.lib.swn_sync(self.h, self._stream()))
+        self.info = self.get_info()
+        self._keep = None
+
+    def generate_host(self, aux_host, n_samples, seed=0):
+        """Host buffers in, host buffers out (the ABI's end-to-end entry point)."""
+        aux_host = np.ascontiguousarray(aux_host, np.float32)
+        B, _, Tf = aux_host.shape
+        seg = self.info["eff_seg"]
+        n_gen = (int(n_samples) // seg) * seg
+        out = np.empty((B, n_gen), np.float32 if self.kind == "cswnv" else np.int64)
+        _abi.check(self.lib.swn_generate_host(self.h, aux_host.ctypes.data_as(ctypes.c_void_p), B, Tf,
+                                              int(n_samples), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                              out.ctypes.data_as(ctypes.c_void_p)))
+        self.info = self.get_info()
+        return out
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.swn_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def philox_uniform(seed, kind, b, n0, n, n_quantize=256):
+    """Host replica of the uniforms the in-kernel sampler draws (tests)."""
+    lib = _abi.load()
+    k = _abi.KIND_CSWNV if kind == "cswnv" else _abi.KIND_DSWNV
+    out = np.empty((n,) if kind == "cswnv" else (n, n_quantize), np.float32)
+    _abi.check(lib.swn_philox_uniform(int(seed), k, n_quantize, int(b), int(n0), int(n),
+                                      out.ctypes.data_as(ctypes.c_void_p)))
+    return out
