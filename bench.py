@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+# -*- coding: utf-8 -*-
+"""Benchmark of the B200-native shallow-wavenet generation path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg1|cfg3|...]
+
+One "step" = one pass of the hot path over one batch of synthetic utterances: conditioning +
+warm-up + the whole autoregressive loop (``batch_fast_generate``).  The default workload is
+BASELINE.json configs[1] (DSWNV mu-law softmax, 16 kHz, batch 1, 5 s); with ``--gpus N`` every
+rank generates its own copy of that workload (utterances shard with no collective: weak
+scaling).  Rank 0 prints ONE JSON line.
+
+``--impl reference`` times the CPU port of the reference's algorithm (``oracle/``; the Python
+reference itself cannot travel to the GPU box) on the host cores, on a bounded sample of the
+same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kind, fs, ctor overrides, B per GPU, frames, description)
+    "cfg1": ("cswnv", 22050, dict(seg=5, lpc=4), 1, 200,
+             "cfg1: CSWNV Laplace seg=5 lpc=4 H=192 S=256 k=7 L=6, 22.05 kHz, batch 1, 1 s (22000 samples)"),
+    "cfg2": ("dswnv", 16000, dict(), 1, 1000,
+             "cfg2: DSWNV mu-law softmax H=256 S=256 Q=256 k=7 L=6, 16 kHz, batch 1, 5 s (80000 samples)"),
+    "cfg3": ("cswnv", 22050, dict(seg=5, lpc=4), 64, 1000,
+             "cfg3: CSWNV Laplace seg=5 lpc=4 H=192, 22.05 kHz, batch 64 x 5 s (110000 samples each)"),
+    "cfg4": ("cswnv", 22050, dict(seg=5, lpc=4), 64, 2000,
+             "cfg4: CSWNV Laplace seg=5 lpc=4 H=192, 22.05 kHz, batch 64 per GPU x 10 s"),
+    "cfg5": ("dswnv", 24000, dict(), 128, 12000,
+             "cfg5: DSWNV mu-law softmax H=256, 24 kHz, batch 128 per GPU x 60 s"),
+    "cfg2s": ("dswnv", 16000, dict(), 1, 100,
+              "cfg2 short: DSWNV H=256, 16 kHz, batch 1, 0.5 s (8000 samples)"),
+}
+
+
+def model_kwargs(kind, fs, over):
+    from shallow_wavenet_b200 import synth
+    kw = synth.cswnv_kwargs(fs) if kind == "cswnv" else synth.dswnv_kwargs(fs)
+    kw.update(over)
+    return kw
+
+
+def in_loop_macs(kind, kw):
+    """Algorithmic in-loop MACs per generated sample and in-loop weight count."""
+    H, S, k = kw["hid_chn"], kw["skip_chn"], kw["kernel_size"]
+    L = kw["dilation_depth"] * kw["dilation_repeat"]
+    if kind == "cswnv":
+        seg, lpc = kw["seg"], kw["lpc"]
+        macs = H + H * H * k + L * (2 * H * H * k + H * S) + (S * S + S * (2 * seg + lpc)) / float(seg)
+        weights = H * H * k + L * (2 * H * H * k + H * S) + S * S + S * (2 * seg + lpc)
+    else:
+        Q = kw["n_quantize"]
+        macs = k * H + L * (2 * H * H * k + H * S) + S * Q + Q * Q
+        weights = H * Q * k + L * (2 * H * H * k + H * S) + S * Q + Q * Q
+    return macs, weights
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super(ClockSampler, self).__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_run(kind, kw, frames, sample_frames, threads):
+    """Time the CPU port of the reference algorithm (oracle) on a bounded sample of the workload."""
+    import torch
+    from oracle import swn_oracle as O
+    from shallow_wavenet_b200 import synth
+    torch.set_num_threads(threads)
+    model = synth.make_model(kind, **kw)
+    sd = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+    okw = dict(kw)
+    cfg = O.SWNConfig(kind=kind, **okw)
+    aux = synth.synth_aux(kw["n_aux"], frames, 1)[:, :, :sample_frames]
+    n = sample_frames * kw["upsampling_factor"]
+    rng = np.random.default_rng(0)
+    if kind == "cswnv":
+        noise = rng.uniform(-0.4999, 0.5, (1, n)).astype(np.float32)
+    else:
+        noise = rng.exponential(1.0, (1, n, 256)).astype(np.float32)
+    t0 = time.perf_counter()
+    O.generate(cfg, sd, aux, n, noise)
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-frames", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    kind, fs, over, B, frames, desc = WORKLOADS[args.workload]
+    kw = model_kwargs(kind, fs, over)
+    U = kw["upsampling_factor"]
+    n_samples = frames * U
+    macs, n_weights = in_loop_macs(kind, kw)
+    metric = "generated samples/sec"
+    common = {"metric": metric, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+              "data": "synthetic (random-init weights, synthetic WORLD-style aux, Philox noise)"}
+    config = {"workload": desc, "utterances_per_gpu": B, "samples_per_utterance": n_samples, "fs": fs,
+              "l2": "flushed between timed steps (256 MiB write)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU port)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import torch
+        threads = os.cpu_count() or 1
+        sf = args.cpu_sample_frames or (40 if kind == "dswnv" else 20)
+        vals = []
+        n = 0
+        for i in range(args.warmup + args.steps):
+            v, n, dt = cpu_port_run(kind, kw, frames, sf, threads)
+            if i >= args.warmup:
+                vals.append((v, dt))
+        v = float(np.mean([x[0] for x in vals]))
+        ms = float(np.mean([x[1] for x in vals]) * 1e3)
+        sample = ("oracle port of %s.batch_fast_generate, B=1, %d samples (%d frames of the workload) incl. its %d-step "
+                  "warm-up, per step" % ("CSWNV" if kind == "cswnv" else "DSWNV", n, sf, 691))
+        line = dict(common)
+        line.update({"impl": "reference", "value": v, "ms_per_step": ms, "rtf": v / fs, "config": config,
+                     "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
+                                      "torch_threads": torch.get_num_threads()},
+                     "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "gpu_launches": 0})
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import shallow_wavenet_b200 as S
+    from shallow_wavenet_b200 import synth, engine as E
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a B200; there is no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
+    torch.cuda.set_device(dev)
+
+    model = synth.make_model(kind, **kw).to(dev)
+    aux_host = torch.from_numpy(synth.synth_aux(kw["n_aux"], frames, B, seed=1234 + rank)).pin_memory()
+    aux_dev = aux_host.to(dev)
+    seg = kw.get("seg", 1) if kind == "cswnv" else 1
+    seed_audio = torch.zeros(B, seg) if kind == "cswnv" else torch.full((B, 1), 128, dtype=torch.long)
+    eng = model.engine()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    n_gen = (n_samples // seg) * seg
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def resident_step(i):
+        eng.condition(aux_dev)
+        out, _ = eng.generate(n_samples, seed=1000 + i, sync=False)
+        return out
+
+    for i in range(args.warmup):
+        resident_step(i)
+        eng.sync()
+
+    # ---- timed: inputs resident in HBM, CUDA events on the launching stream, L2 flushed between steps
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    barrier()
+    launches0 = eng.get_info()["kernel_launches"]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    gen_ms, cond_ms = [], []
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        ev[i][0].record()
+        resident_step(args.warmup + i)
+        ev[i][1].record()
+        eng.sync()
+        gen_ms.append(eng.info["last_gen_ms"]); cond_ms.append(eng.info["last_cond_ms"])
+    barrier()
+    launches = eng.get_info()["kernel_launches"] - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    clocks = sampler.finish()
+
+    # ---- end to end through the public API: pinned host aux in, host samples out, every step
+    e2e_t = []
+    for i in range(max(1, min(args.steps, 3))):
+        barrier()
+        t0 = time.perf_counter()
+        outs = model.batch_fast_generate(seed_audio, aux_host, [n_samples] * B, seed=2000 + i)
+        torch.cuda.synchronize(dev)
+        e2e_t.append(time.perf_counter() - t0)
+        assert len(outs) == B and len(outs[0]) == n_gen
+    e2e_s = float(np.mean(e2e_t))
+
+    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    samples_per_step_all = world * B * n_gen
+    value = samples_per_step_all * args.steps / (total_ms * 1e-3)
+    e2e_value = samples_per_step_all / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        info = eng.get_info()
+        # dominant kernel: the persistent generation kernel; per launch it runs n_it sequential steps,
+        # each of which must read every in-loop weight once from on-chip memory
+        kern_ms = float(np.mean(gen_ms))
+        seg_steps = n_gen // seg + info["receptive_field"] // seg + 1
+        weight_bytes = n_weights * 4.0
+        n_slots = info["n_slots"]
+        alg_bytes = weight_bytes * seg_steps * n_slots
+        smem_peak = E.measure_smem_bandwidth(dev.index or 0)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        flops = 2.0 * macs * B * n_gen / (kern_ms * 1e-3)
+        roofline = {"bound": "smem", "kernel": "swn_generate_kernel (persistent, 1 launch per step)",
+                    "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
+                    "peak_source": "measured live: aggregate LDS.128 bandwidth, 1 CTA/SM (swn_measure_smem_bandwidth)",
+                    "algorithmic_bytes_per_time_step": weight_bytes, "time_steps_per_launch": seg_steps * n_slots,
+                    "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms * args.steps / total_ms,
+                    "achieved_tflops_fp32": flops / 1e12,
+                    "vs_hbm": {"peak": peaks.get("hbm_gbs"), "frac": (achieved / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
+                               "note": "weights are SMEM-resident; HBM is not the bound (frac>1 = residency pays)"},
+                    "traffic": None}
+        line = dict(common)
+        line.update({"value": value, "ms_per_step": total_ms / args.steps, "rtf": value / fs, "config": config,
+                     "rtf_per_utterance": value / fs / (world * B),
+                     "conditioning_ms": float(np.mean(cond_ms)), "kernel_ms": kern_ms,
+                     "clocks": clocks, "roofline": roofline,
+                     "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(aux_host.numel() * 4),
+                             "d2h_bytes_per_step": int(B * n_gen * (4 if kind == "cswnv" else 8)),
+                             "api": "%s.batch_fast_generate(pinned host aux) -> list of numpy arrays" % ("CSWNV" if kind == "cswnv" else "DSWNV")},
+                     "gpu_launches": int(launches),
+                     "plan": {k: info[k] for k in ("n_sm", "ctas_per_layer", "head_ctas", "smem_bytes", "batch_tile", "n_slots")}})
+        if not args.no_cpu_baseline and world >= 1:
+            threads = os.cpu_count() or 1
+            sf = args.cpu_sample_frames or (40 if kind == "dswnv" else 20)
+            v, n, dt = cpu_port_run(kind, kw, frames, sf, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+                                    "sample": "oracle port of batch_fast_generate, B=1, %d samples (+ the %d-step warm-up), "
+                                              "%.1f s wall" % (n, info["receptive_field"] + 1, dt)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -75,7 +75,10 @@ typedef struct swn_gen_args {
                                  scripts' seed (zeros / n_quantize/2, decode_cswnv_laplace-shift1.py:93,
                                  decode_dswnv_softmax.py:94-99) */
     int32_t batch_tile;       /* utterances processed together per pipeline slot; 0 = auto */
-    int32_t reserved;
+    int32_t poll_mode;        /* tuning: 0 = default, 1 = pure per-word polling, 2 = sentinel + per-word */
+    uint64_t* prof_dev;       /* optional instrumentation: [prof_count][grid][4] %globaltimer stamps */
+    int32_t prof_start;       /* first loop iteration stamped */
+    int32_t prof_count;
 } swn_gen_args;
 
 typedef struct swn_info {
@@ -94,6 +97,8 @@ typedef struct swn_info {
     float last_cond_ms;       /* device time of the last swn_condition (CUDA events) */
     float last_gen_ms;        /* device time of the last swn_generate persistent kernel */
     int64_t kernel_launches;  /* kernels launched by this handle so far */
+    int32_t grid;             /* CTAs of the last persistent launch */
+    int32_t reserved;
 } swn_info;
 
 /* CSWNV(...) / DSWNV(...) followed by model.cuda() (decode_cswnv_laplace-shift1.py:208-223,
@@ -135,6 +140,10 @@ int swn_get_info(swn_handle h, swn_info* info);
  * fills out[n] with the uniforms the kernel draws for utterance b, samples n0..n0+n-1
  * (CSWNV: one per sample; DSWNV: Q per sample, row-major). */
 int swn_philox_uniform(uint64_t seed, int32_t kind, int32_t n_quantize, int64_t b, int64_t n0, int64_t n, float* out_host);
+
+/* Measurement aid (no reference counterpart): aggregate shared-memory read bandwidth of the
+ * device in GB/s, the denominator of the batch-1 step roofline. */
+int swn_measure_smem_bandwidth(int device, double* gb_per_s);
 
 int swn_destroy(swn_handle h);
 

@@ -264,6 +264,47 @@ def teacher_forced(cfg: SWNConfig, sd: Dict, aux, gen) -> np.ndarray:
     return out.transpose(1, 2).contiguous().numpy()
 
 
+def teacher_forced_tail(cfg: SWNConfig, sd: Dict, aux, gen, n_tail: int) -> np.ndarray:
+    """Head outputs of the LAST ``n_tail`` loop steps only.  The receptive field is finite
+    (R columns, cswnv_shift1.py:182), so evaluating the layers over the last R + n_tail*seg
+    columns with zero history gives exactly the values of the full-length evaluation there;
+    this is what lets the full-size (BASELINE.json) runs be checked in seconds.
+    Returns [B, n_tail, head_dim]."""
+    W = _weights(sd)
+    aux = _t(aux)
+    B = aux.shape[0]
+    seg = cfg.eff_seg
+    gen_np = np.asarray(gen)
+    n_iter = gen_np.shape[1] // seg
+    R = cfg.receptive_field
+    n_tail = min(n_tail, n_iter)
+    with torch.no_grad():
+        x = cond_features(cfg, W, aux)
+        a_full = _audio_full(cfg, gen_np, B, n_iter * seg)
+        T = R + (n_iter - 1) * seg + 1
+        # columns needed: [t_lo, T) with R extra columns of context for the layers and k-1 for the causal conv
+        t_lo = max(0, T - ((n_tail - 1) * seg + 1) - R - cfg.kernel_size)
+        h, extra = _input_hidden(cfg, W, a_full[:, t_lo: T + seg - 1] if cfg.kind == "cswnv" else a_full[:, t_lo:T])
+        if t_lo > 0:
+            # the first k-1 columns saw zero padding instead of real audio: drop them
+            drop = cfg.kernel_size - 1
+            h = h[:, :, drop:]
+            t_lo += drop
+            if extra is not None:
+                extra = extra[:, :, drop:]
+        xw = x[:, :, t_lo:T]
+        if extra is not None:
+            xw = torch.cat((xw, extra), 1)
+        s = None
+        for l in range(len(cfg.dil_facts)):
+            skip, h = _cell(cfg, W, l, xw, h)
+            s = skip if s is None else s + skip
+        out = _head(W, s)                                # columns t_lo .. T-1
+        first = R + (n_iter - n_tail) * seg - t_lo
+        out = out[:, :, first::seg]
+    return out.transpose(1, 2).contiguous().numpy()
+
+
 # --------------------------------------------------------------------------
 # sampling
 # --------------------------------------------------------------------------

@@ -17,7 +17,8 @@ KIND_DSWNV = 1
 
 # every symbol include/swn_b200.h declares (checked by tests/test_abi_symbols.py)
 SYMBOLS = ("swn_create", "swn_set_tensor", "swn_finalize", "swn_condition", "swn_generate", "swn_sync",
-           "swn_generate_host", "swn_get_info", "swn_philox_uniform", "swn_destroy", "swn_last_error")
+           "swn_generate_host", "swn_get_info", "swn_philox_uniform", "swn_measure_smem_bandwidth", "swn_destroy",
+           "swn_last_error")
 
 
 class SwnConfig(ctypes.Structure):
@@ -30,7 +31,8 @@ class SwnConfig(ctypes.Structure):
 class SwnGenArgs(ctypes.Structure):
     _fields_ = [("n_samples", ctypes.c_int64), ("seed", ctypes.c_uint64), ("noise_dev", ctypes.c_void_p),
                 ("forced_dev", ctypes.c_void_p), ("out_dev", ctypes.c_void_p), ("head_dev", ctypes.c_void_p),
-                ("seed_dev", ctypes.c_void_p), ("batch_tile", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("seed_dev", ctypes.c_void_p), ("batch_tile", ctypes.c_int32), ("poll_mode", ctypes.c_int32),
+                ("prof_dev", ctypes.c_void_p), ("prof_start", ctypes.c_int32), ("prof_count", ctypes.c_int32)]
 
 
 class SwnInfo(ctypes.Structure):
@@ -38,7 +40,8 @@ class SwnInfo(ctypes.Structure):
                 ("head_dim", ctypes.c_int32), ("n_sm", ctypes.c_int32), ("ctas_per_layer", ctypes.c_int32),
                 ("head_ctas", ctypes.c_int32), ("smem_bytes", ctypes.c_int32), ("batch_tile", ctypes.c_int32),
                 ("n_slots", ctypes.c_int32), ("weight_bytes", ctypes.c_int64), ("cond_bytes", ctypes.c_int64),
-                ("last_cond_ms", ctypes.c_float), ("last_gen_ms", ctypes.c_float), ("kernel_launches", ctypes.c_int64)]
+                ("last_cond_ms", ctypes.c_float), ("last_gen_ms", ctypes.c_float), ("kernel_launches", ctypes.c_int64),
+                ("grid", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -70,6 +73,7 @@ def load():
     lib.swn_generate_host.argtypes = [vp, vp, i32, i32, i64, u64, vp]
     lib.swn_get_info.argtypes = [vp, ctypes.POINTER(SwnInfo)]
     lib.swn_philox_uniform.argtypes = [u64, i32, i32, i64, i64, i64, vp]
+    lib.swn_measure_smem_bandwidth.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     lib.swn_destroy.argtypes = [vp]
     lib.swn_last_error.argtypes = []
     lib.swn_last_error.restype = ctypes.c_char_p

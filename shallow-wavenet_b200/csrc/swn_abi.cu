@@ -604,6 +604,10 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
     P.noise = a->noise_dev; P.seed = a->seed; P.forced = a->forced_dev; P.seedw = a->seed_dev; P.out = a->out_dev; P.head_out = a->head_dev;
     P.status = m->status.p;
     P.timeout_cycles = 4000000000ULL;
+    P.prof = (unsigned long long*)a->prof_dev; P.prof_start = a->prof_start; P.prof_count = a->prof_dev ? a->prof_count : 0;
+    P.poll_mode = a->poll_mode == 2 ? 1 : 0;      // measured: pure per-word polling is not slower (profiles/)
+    P.poll_sleep_ns = 40;
+    m->info.grid = grid;
 
     CUDA_OK(cudaEventRecord(m->ev[2], st));
     cudaError_t e = fn(P, grid, smem_bytes, st);
@@ -666,6 +670,16 @@ int swn_philox_uniform(uint64_t seed, int32_t kind, int32_t n_quantize, int64_t 
         for (int64_t i = 0; i < n; ++i)
             for (int r = 0; r < n_quantize; ++r) out_host[i * n_quantize + r] = swn::philox_uniform(seed, b, n0 + i, r);
     }
+    return 0;
+}
+
+int swn_measure_smem_bandwidth(int device, double* gb_per_s) {
+    if (!gb_per_s) return fail("swn_measure_smem_bandwidth: null argument");
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("swn_measure_smem_bandwidth: device is not sm_100");
+    CUDA_OK(swn::measure_smem_bandwidth(prop.multiProcessorCount, gb_per_s, nullptr));
     return 0;
 }
 

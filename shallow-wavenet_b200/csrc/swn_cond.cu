@@ -8,6 +8,7 @@
 //     in_x[l](x')[t] = const_l + sum_s gain[phase(t+s)] * Pt[frame(t+s)][l][s][:]
 // with Pt = y^T . Wp computed here once per frame (DESIGN.md "conditioning hoist").
 #include <cuda_runtime.h>
+#include <algorithm>
 #include "swn_launch.h"
 
 namespace swn {
@@ -147,6 +148,60 @@ cudaError_t launch_proj_gemm(const float* A, const float* Bm, float* C, long lon
     dim3 grid((N + GB_N - 1) / GB_N, (unsigned)((M + GB_M - 1) / GB_M));
     proj_gemm_kernel<<<grid, GB_THREADS, 0, st>>>(A, Bm, C, M, N, K);
     return cudaGetLastError();
+}
+
+
+// ---------------------------------------------------------------- shared-memory bandwidth probe
+// Measures the aggregate LDS bandwidth of the chip (one CTA per SM streaming a 192 KB buffer with
+// 128-bit loads).  bench.py uses it as the denominator of the batch-1 step roofline: at batch 1
+// every time step has to read all SMEM-resident weights once.
+__global__ void __launch_bounds__(1024, 1) smem_bw_kernel(float* __restrict__ out, int iters, int n4) {
+    extern __shared__ float4 sbuf[];
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) sbuf[i] = make_float4(i, 1.f, 2.f, 3.f);
+    __syncthreads();
+    float4 a0 = make_float4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0;
+    for (int it = 0; it < iters; ++it) {
+        for (int i = threadIdx.x; i + 3 * 1024 < n4; i += 4 * 1024) {
+            const float4 v0 = sbuf[i], v1 = sbuf[i + 1024], v2 = sbuf[i + 2048], v3 = sbuf[i + 3072];
+            a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+            a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+            a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+            a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0.x + a0.y + a0.z + a0.w + a1.x + a1.y + a1.z + a1.w +
+                                                 a2.x + a2.y + a2.z + a2.w + a3.x + a3.y + a3.z + a3.w;
+}
+
+cudaError_t measure_smem_bandwidth(int n_sm, double* gb_per_s, double* sm_mhz) {
+    const int n4 = 12 * 1024;                       // 192 KB
+    const size_t smem = (size_t)n4 * 16;
+    cudaError_t e = cudaFuncSetAttribute(smem_bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    float* out = nullptr;
+    e = cudaMalloc((void**)&out, (size_t)n_sm * 1024 * sizeof(float));
+    if (e != cudaSuccess) return e;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    const int iters = 4000;
+    smem_bw_kernel<<<n_sm, 1024, smem>>>(out, 200, n4);      // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(a);
+        smem_bw_kernel<<<n_sm, 1024, smem>>>(out, iters, n4);
+        cudaEventRecord(b);
+        e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        const double bytes = (double)n_sm * iters * (double)(n4 / 4096 * 4096) * 16.0;
+        best = std::max(best, bytes / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(out);
+    *gb_per_s = best;
+    if (sm_mhz) *sm_mhz = best * 1e9 / ((double)n_sm * 128.0) / 1e6;   // implied clock at 128 B/clk/SM
+    return e;
 }
 
 }  // namespace swn

@@ -65,6 +65,32 @@ __device__ __forceinline__ bool ll_wait(const unsigned long long* p, uint32_t ta
     }
 }
 
+// Cheap first phase of a wait: lane 0 of the warp watches ONE word of the vector with a sleep
+// between polls, so that the ~140 CTAs that are idle at any time do not flood L2 with polls;
+// the per-word LL polls start only when the vector is about to be complete.
+__device__ __forceinline__ void sentinel_wait(const unsigned long long* p, uint32_t tag, const GenParams& P) {
+    if (P.poll_mode == 0) return;
+    if ((threadIdx.x & 31) == 0) {
+        uint32_t spins = 0;
+        while ((uint32_t)(ld_ll(p) >> 32) != tag) {
+            __nanosleep(P.poll_sleep_ns);
+            if (((++spins) & 1023u) == 0 && ((volatile int32_t*)P.status)[0] != 0) break;   // ll_wait reports the abort
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define SWN_PROF(ev)                                                                              \
+    do {                                                                                          \
+        if (P.prof && threadIdx.x == 0 && it >= P.prof_start && it < P.prof_start + P.prof_count) \
+            P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 4 + (ev)] = gtime();  \
+    } while (0)
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -232,6 +258,7 @@ __device__ void layer_cta(const GenParams& P, const CtaDesc& D, float* smem) {
             // ---- wait for the input vectors of this block (H x NC words)
             {
                 const unsigned long long* src = in_ll + (size_t)m * NC * H;
+                sentinel_wait(src, tag, P);
                 for (int i = tid; i < NC * H; i += SWN_NTHREADS) {
                     uint32_t bits;
                     ok = ll_wait(src + i, tag, bits, P, 100 + l) && ok;
@@ -240,6 +267,7 @@ __device__ void layer_cta(const GenParams& P, const CtaDesc& D, float* smem) {
                 }
             }
             if (__syncthreads_or(!ok)) return;
+            SWN_PROF(0);
 
             // ---- register-resident slice of the inputs: lane owns k = c*64 + 2*lane, +1
             float2 h[NC][NCH];
@@ -292,6 +320,7 @@ __device__ void layer_cta(const GenParams& P, const CtaDesc& D, float* smem) {
                 }
             }
 
+            SWN_PROF(1);
             // ---- pass B (off the critical path): contributions to future blocks
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) {
@@ -334,6 +363,7 @@ __device__ void layer_cta(const GenParams& P, const CtaDesc& D, float* smem) {
                     }
                 }
             }
+            SWN_PROF(2);
         }
     }
 }
@@ -344,20 +374,40 @@ template <int SEG>
 __device__ __forceinline__ void laplace_step(const GenParams& P, const float* o, float* lp, const float* eps,
                                              const float* forced, float* smp) {
     const int lpc = P.lpc;
+    float l[8];
+#pragma unroll
+    for (int mm = 0; mm < 8; ++mm) l[mm] = (mm < lpc) ? lp[mm] : 0.f;
 #pragma unroll
     for (int j = 0; j < SEG; ++j) {
         float lpv = 0.f;
         // ass = a.flip(-1) times the buffer ordered oldest -> newest: a[0] multiplies the newest
-        for (int mm = 0; mm < lpc; ++mm) lpv += o[2 * SEG + lpc - 1 - mm] * lp[mm];
+#pragma unroll
+        for (int mm = 0; mm < 8; ++mm)
+            if (mm < lpc) lpv += o[2 * SEG + lpc - 1 - mm] * l[mm];
         const float e = eps[j];
         const float sgn = (e > 0.f) ? 1.f : ((e < 0.f) ? -1.f : 0.f);
         const float b = sigmoidf_(o[SEG + j]);               // exp(logsigmoid(.))
         float v = lpv + o[j] - b * sgn * log1pf(-2.f * fabsf(e));
         v = fminf(fmaxf(v, -1.f), 1.f);
         smp[j] = v;
-        const float fed = forced ? forced[j] : v;
-        for (int mm = 0; mm + 1 < lpc; ++mm) lp[mm] = lp[mm + 1];
-        if (lpc > 0) lp[lpc - 1] = fed;
+#pragma unroll
+        for (int mm = 0; mm < 7; ++mm)
+            if (mm + 1 < lpc) l[mm] = l[mm + 1];
+#pragma unroll
+        for (int mm = 0; mm < 8; ++mm)
+            if (mm == lpc - 1) l[mm] = v;
+    }
+    if (forced) {
+        // teacher forcing: inside the segment the recursion ran on its own samples (as the reference's
+        // sampler would); the history handed to the next step is the forced waveform
+        for (int j = 0; j < SEG; ++j) {
+            for (int mm = 0; mm + 1 < lpc; ++mm) lp[mm] = lp[mm + 1];
+            if (lpc > 0) lp[lpc - 1] = forced[j];
+        }
+    } else {
+#pragma unroll
+        for (int mm = 0; mm < 8; ++mm)
+            if (mm < lpc) lp[mm] = l[mm];
     }
 }
 
@@ -475,6 +525,7 @@ __device__ void head_cta(const GenParams& P, const CtaDesc& D, float* smem) {
             // ---- wait for layer L-1 (flow control in warm-up, data when active)
             {
                 const unsigned long long* src = lastl + (size_t)m * NC * H;
+                sentinel_wait(src, tag, P);
                 for (int i = tid; i < NC * H; i += SWN_NTHREADS) {
                     uint32_t bits;
                     ok = ll_wait(src + i, tag, bits, P, 200) && ok;
@@ -497,6 +548,7 @@ __device__ void head_cta(const GenParams& P, const CtaDesc& D, float* smem) {
                 }
             }
             if (__syncthreads_or(!ok)) return;
+            SWN_PROF(0);
             if (active) {
                 // ---- stage A: relu(sum_l skip_l)   (cswnv_shift1.py:367 inner sum)
                 for (int r = warp; r < D.na; r += SWN_NWARPS) {
@@ -515,6 +567,7 @@ __device__ void head_cta(const GenParams& P, const CtaDesc& D, float* smem) {
                     x1[b * Sp + k] = __uint_as_float(bits);
                 }
                 if (__syncthreads_or(!ok)) return;
+                SWN_PROF(1);
                 // ---- stage B: relu(out_1(.))
                 for (int r = warp; r < D.nb; r += SWN_NWARPS) {
                     for (int b = 0; b < BS; ++b) {
@@ -529,6 +582,7 @@ __device__ void head_cta(const GenParams& P, const CtaDesc& D, float* smem) {
                     x2[b * n1p + k] = __uint_as_float(bits);
                 }
                 if (__syncthreads_or(!ok)) return;
+                SWN_PROF(2);
                 // ---- stage C: out_2 rows
                 const int ncp = (D.nc + 3) & ~3;
                 for (int r = warp; r < D.nc; r += SWN_NWARPS) {
@@ -622,6 +676,7 @@ __device__ void head_cta(const GenParams& P, const CtaDesc& D, float* smem) {
             }
             // ---- inputs of the next block
             if (it + 1 < P.n_it) input_stage(it + 1, m);
+            SWN_PROF(3);
         }
     }
 }

@@ -33,4 +33,6 @@ cudaError_t launch_aux_conv(const float* in, const float* w_t, const float* bias
                             int T, int ks, int dil, int pad, int transpose_out, cudaStream_t st);
 cudaError_t launch_proj_gemm(const float* A, const float* Bm, float* C, long long M, int N, int K, cudaStream_t st);
 
+cudaError_t measure_smem_bandwidth(int n_sm, double* gb_per_s, double* sm_mhz);
+
 }  // namespace swn

@@ -51,7 +51,7 @@ class Engine(object):
         self._B = B
 
     def generate(self, n_samples, seed=0, noise=None, forced=None, seed_audio=None, return_heads=False,
-                 batch_tile=0, sync=True):
+                 batch_tile=0, sync=True, poll_mode=0, prof=None, prof_start=0):
         info = self.info
         seg, hd = info["eff_seg"], info["head_dim"]
         B = self._B
@@ -77,6 +77,12 @@ class Engine(object):
         a.out_dev = out.data_ptr()
         a.head_dev = heads.data_ptr() if heads is not None else None
         a.batch_tile = int(batch_tile)
+        a.poll_mode = int(poll_mode)
+        if prof is not None:       # int64 CUDA tensor [count, grid, 4]
+            keep.append(prof)
+            a.prof_dev = prof.data_ptr()
+            a.prof_start = int(prof_start)
+            a.prof_count = int(prof.shape[0])
         _abi.check(self.lib.swn_generate(self.h, ctypes.byref(a), self._stream()))
         self._keep = keep
         if sync:
@@ -121,3 +127,11 @@ def philox_uniform(seed, kind, b, n0, n, n_quantize=256):
     _abi.check(lib.swn_philox_uniform(int(seed), k, n_quantize, int(b), int(n0), int(n),
                                       out.ctypes.data_as(ctypes.c_void_p)))
     return out
+
+
+def measure_smem_bandwidth(device=0):
+    """Aggregate shared-memory read bandwidth in GB/s (roofline denominator of the batch-1 step)."""
+    lib = _abi.load()
+    v = ctypes.c_double()
+    _abi.check(lib.swn_measure_smem_bandwidth(int(device), ctypes.byref(v)))
+    return v.value

@@ -58,9 +58,8 @@ class _SWNBase(nn.Module):
     _kind = None
 
     # ------------------------------------------------------------------ construction
-    def _build_common(self, in_audio_ch):
-        """Parameter tree shared by both vocoders (cswnv_shift1.py:151-189, dswnv.py:210-248)."""
-        k, H, S = self.kernel_size, self.n_hidch, self.n_skipch
+    def _build_aux(self):
+        """Conditioning parameters (cswnv_shift1.py:151-157, dswnv.py:210-217)."""
         ak = self.aux_kernel_size
         self.scale_in = _ParamConv((self.n_aux, self.n_aux, 1))
         layers = nn.ModuleList()
@@ -73,6 +72,10 @@ class _SWNBase(nn.Module):
                                    upsampling_factor=self.upsampling_factor)
         if self.do_prob > 0:
             self.aux_drop = nn.Dropout(p=self.do_prob)
+
+    def _build_audio_in(self, in_audio_ch):
+        """wav_conv / causal input conv (cswnv_shift1.py:163-167, dswnv.py:222-226)."""
+        k, H = self.kernel_size, self.n_hidch
         if self.wav_conv_flag:
             self.wav_conv = _ParamConv((H, in_audio_ch, 1))
             self.causal = _Wrapped(_ParamConv((H, H, k)), dil_fact=0, dilation=1, padding=k - 1)

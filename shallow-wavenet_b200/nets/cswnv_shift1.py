@@ -34,12 +34,13 @@ class CSWNV(_SWNBase):
         self.aux_conv2d_flag = aux_conv2d_flag
         self.wav_conv_flag = wav_conv_flag
 
-        self._build_common(in_audio_ch=1)
+        self._build_aux()
         self.in_aux_dim = n_aux * self.conv_aux.rec_field
         if aux_conv2d_flag and seg > 1:
             self.aux_conv2d = _ParamConv((self.in_aux_dim, self.in_aux_dim, seg, 1))
         elif seg > 1:
             self.in_aux_dim *= seg
+        self._build_audio_in(in_audio_ch=1)
         self._build_cells(self.in_aux_dim)
         self.out_1 = _ParamConv((skip_chn, skip_chn, 1))
         self.out_2 = _ParamConv((2 * seg + lpc, skip_chn, 1))

@@ -48,9 +48,10 @@ class DSWNV(_SWNBase):
         self.audio_in_flag = audio_in_flag
         self.wav_conv_flag = wav_conv_flag
 
-        self._build_common(in_audio_ch=n_quantize)
+        self._build_aux()
         self.in_aux_dim = n_aux * self.conv_aux.rec_field
         self.in_tot_dim = self.in_aux_dim + (self.in_audio_dim if audio_in_flag else 0)
+        self._build_audio_in(in_audio_ch=n_quantize)
         self._build_cells(self.in_tot_dim)
         self.out_1 = _ParamConv((n_quantize, skip_chn, 1))
         self.out_2 = _ParamConv((n_quantize, n_quantize, 1))
