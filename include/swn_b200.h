@@ -76,9 +76,11 @@ typedef struct swn_gen_args {
                                  decode_dswnv_softmax.py:94-99) */
     int32_t batch_tile;       /* utterances processed together per pipeline slot; 0 = auto */
     int32_t poll_mode;        /* tuning: 0 = default, 1 = pure per-word polling, 2 = sentinel + per-word */
-    uint64_t* prof_dev;       /* optional instrumentation: [prof_count][grid][4] %globaltimer stamps */
+    uint64_t* prof_dev;       /* optional instrumentation: [prof_count][grid][8] %globaltimer stamps */
     int32_t prof_start;       /* first loop iteration stamped */
     int32_t prof_count;
+    int32_t kernel_sel;       /* 0 = auto, 1 = force the layer-group kernel, 2 = force the cluster kernel */
+    int32_t reserved;
 } swn_gen_args;
 
 typedef struct swn_info {
@@ -98,7 +100,7 @@ typedef struct swn_info {
     float last_gen_ms;        /* device time of the last swn_generate persistent kernel */
     int64_t kernel_launches;  /* kernels launched by this handle so far */
     int32_t grid;             /* CTAs of the last persistent launch */
-    int32_t reserved;
+    int32_t kernel_variant;   /* 1 = layer groups over the chip, 2 = core cluster + helpers */
 } swn_info;
 
 /* CSWNV(...) / DSWNV(...) followed by model.cuda() (decode_cswnv_laplace-shift1.py:208-223,

@@ -32,7 +32,8 @@ class SwnGenArgs(ctypes.Structure):
     _fields_ = [("n_samples", ctypes.c_int64), ("seed", ctypes.c_uint64), ("noise_dev", ctypes.c_void_p),
                 ("forced_dev", ctypes.c_void_p), ("out_dev", ctypes.c_void_p), ("head_dev", ctypes.c_void_p),
                 ("seed_dev", ctypes.c_void_p), ("batch_tile", ctypes.c_int32), ("poll_mode", ctypes.c_int32),
-                ("prof_dev", ctypes.c_void_p), ("prof_start", ctypes.c_int32), ("prof_count", ctypes.c_int32)]
+                ("prof_dev", ctypes.c_void_p), ("prof_start", ctypes.c_int32), ("prof_count", ctypes.c_int32),
+                ("kernel_sel", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class SwnInfo(ctypes.Structure):
@@ -41,7 +42,7 @@ class SwnInfo(ctypes.Structure):
                 ("head_ctas", ctypes.c_int32), ("smem_bytes", ctypes.c_int32), ("batch_tile", ctypes.c_int32),
                 ("n_slots", ctypes.c_int32), ("weight_bytes", ctypes.c_int64), ("cond_bytes", ctypes.c_int64),
                 ("last_cond_ms", ctypes.c_float), ("last_gen_ms", ctypes.c_float), ("kernel_launches", ctypes.c_int64),
-                ("grid", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("grid", ctypes.c_int32), ("kernel_variant", ctypes.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

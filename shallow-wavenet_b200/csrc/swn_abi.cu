@@ -14,6 +14,7 @@
 
 #include "../../include/swn_b200.h"
 #include "swn_gen.cuh"
+#include "swn_core.cuh"
 #include "swn_launch.h"
 
 namespace {
@@ -96,6 +97,25 @@ struct swn_model {
     DevBuf<int32_t> status;
     DevBuf<float> e2e_aux;
     DevBuf<char> e2e_out;
+    // ---- v2: core cluster + helpers (swn_core.cuh)
+    bool core_ok = false;
+    int n_core_taps = 0;
+    std::vector<int> tap_base;
+    struct HelpLayer { int ntaps = 0, dmin = 0; std::vector<int> delay, tapj; };
+    std::vector<HelpLayer> hl;
+    std::vector<float> in_tab_h;
+    std::vector<float> wbuf2_h;                 // core section, then (per plan) the helper section
+    size_t wbuf2_core_floats = 0;
+    std::vector<swn::CoreCta> ccta;
+    DevBuf<float> wbuf2, ring2;
+    DevBuf<swn::CoreCta> cdesc;
+    DevBuf<swn::HelpCta> hdesc;
+    DevBuf<unsigned long long> ll2;
+    long long core_plan_key = -1;
+    int core_grid = 0, core_n_help = 0;
+    size_t core_smem = 0, core_ring_total = 0;
+    swn::CoreParams core_tmpl;
+    size_t core_n_hin = 0, core_n_hacc = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool cond_timed = false, gen_timed = false;
     swn_info info;
@@ -141,6 +161,184 @@ void split_range(int n, int parts, int i, int* lo, int* cnt) {
 }
 
 }  // namespace
+
+
+static cudaError_t m_core_launch_dispatch(swn_model* m, int BS, const swn::CoreParams& P, cudaStream_t st) {
+    swn::core_fns fn = {nullptr, nullptr};
+    switch (m->NCH) {
+        case 1: fn = swn::find_core_kernel_nch1(BS); break;
+        case 2: fn = swn::find_core_kernel_nch2(BS); break;
+        case 3: fn = swn::find_core_kernel_nch3(BS); break;
+        case 4: fn = swn::find_core_kernel_nch4(BS); break;
+    }
+    if (!fn.launch) return cudaErrorInvalidValue;
+    int dummy = 0;
+    cudaError_t e = fn.prepare(m->core_smem, &dummy);
+    if (e != cudaSuccess) return e;
+    return fn.launch(P, m->core_grid, m->core_smem, st);
+}
+
+// ---- v2 launch: returns 0 = launched, 2 = not applicable (caller falls back to v1), 1 = error
+static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, int B, int Tf, int64_t n_iter) {
+    const int H = m->H, Hp = m->Hp, K = m->K, L = m->L, S = m->S, Q = m->Q;
+    const bool is_c = m->cfg.kind == SWN_KIND_CSWNV;
+    int BS = 0;
+    for (int t : {1, 2, 4}) if (!BS && t >= B) BS = t;
+    if (a->batch_tile > 0) BS = a->batch_tile;
+    if (BS != 1 && BS != 2 && BS != 4) return 2;
+    if (B > BS) return 2;
+    if ((K - 1) * BS > 32) return 2;
+    const int NC = BS;
+    swn::core_fns fn = {nullptr, nullptr};
+    switch (m->NCH) {
+        case 1: fn = swn::find_core_kernel_nch1(BS); break;
+        case 2: fn = swn::find_core_kernel_nch2(BS); break;
+        case 3: fn = swn::find_core_kernel_nch3(BS); break;
+        case 4: fn = swn::find_core_kernel_nch4(BS); break;
+    }
+    if (!fn.launch) return 2;
+    const long long key = BS;
+    if (key != m->core_plan_key) {
+        CUDA_OK(cudaStreamSynchronize(st));
+        const int smem_floats = SWN_MAX_SMEM / 4;
+        // ---- core CTA shared-memory layout: IDENTICAL in all 16 CTAs (peers address each other's buffers
+        // with mapa on their own offsets), so it is sized for the largest row counts
+        size_t core_used = 0;
+        {
+            int mx_skip = 0, mx_nb = 0, mx_nc = 0, mx_ni = 0;
+            for (auto& q : m->ccta) {
+                mx_skip = std::max(mx_skip, q.nskip); mx_nb = std::max(mx_nb, q.nb);
+                mx_nc = std::max(mx_nc, q.nc); mx_ni = std::max(mx_ni, q.ni);
+            }
+            size_t u = 0;
+            auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
+            swn::CoreCta lay;
+            lay.sm_skip = take((size_t)L * mx_skip * Hp);
+            lay.sm_w1 = take((size_t)mx_nb * m->Sp);
+            lay.sm_w2 = take((size_t)mx_nc * m->n1p);
+            lay.sm_tin = take(is_c ? 0 : (size_t)Q * ((mx_ni + 3) & ~3));
+            lay.sm_ring = take((size_t)L * 2 * 16 * 2 * BS);
+            lay.sm_hx = take((size_t)(L + 1) * NC * Hp * 2);        // hx, x1, x2, gx stay contiguous (zeroed as one block)
+            lay.sm_x1 = take((size_t)NC * m->Sp * 2);
+            lay.sm_x2 = take((size_t)NC * m->n1p * 2);
+            lay.sm_gx = take((size_t)NC * 256 * 2);
+            lay.sm_pre = take((size_t)2 * L * 16 * NC * (sizeof(swn::PreSlot) / 4));
+            lay.sm_misc = take((size_t)NC * (16 + 8 + 16));
+            lay.sm_tmem_slot = take(4);
+            core_used = u;
+            for (auto& q : m->ccta) {
+                q.sm_skip = lay.sm_skip; q.sm_w1 = lay.sm_w1; q.sm_w2 = lay.sm_w2; q.sm_tin = lay.sm_tin;
+                q.sm_ring = lay.sm_ring; q.sm_hx = lay.sm_hx; q.sm_x1 = lay.sm_x1; q.sm_x2 = lay.sm_x2;
+                q.sm_gx = lay.sm_gx; q.sm_pre = lay.sm_pre; q.sm_misc = lay.sm_misc; q.sm_tmem_slot = lay.sm_tmem_slot;
+            }
+        }
+        if (core_used > (size_t)smem_floats) return 2;
+        // ---- how many clusters can be co-resident with the largest footprint we may need
+        int max_cl = 0;
+        CUDA_OK(fn.prepare(SWN_MAX_SMEM, &max_cl));
+        int n_help_layers = 0;
+        for (int l = 0; l < L; ++l) n_help_layers += m->hl[l].ntaps > 0;
+        if (max_cl < 1 || (n_help_layers > 0 && max_cl < 2)) return 2;
+        const int n_help = n_help_layers ? (max_cl - 1) * swn::CORE_CL : 0;
+        const int GH = n_help_layers ? n_help / n_help_layers : 0;
+        if (n_help_layers && GH < 1) return 2;
+        // ---- helper CTAs: pack their taps, place their rings
+        std::vector<float>& V = m->wbuf2_h;
+        V.resize(m->wbuf2_core_floats);
+        auto alloc2 = [&](size_t n) { size_t off = (V.size() + 3) & ~size_t(3); V.resize(off + n, 0.f); return (int64_t)off; };
+        std::vector<swn::HelpCta> hd;
+        size_t ring_total = 0, help_used = 0;
+        const int twoH = 2 * H;
+        for (int l = 0; l < L; ++l) {
+            const auto& hl = m->hl[l];
+            if (!hl.ntaps) continue;
+            const HostTensor* x = m->get("dil_h." + std::to_string(l) + ".conv.weight");
+            const int GHe = std::min(GH, H);
+            for (int g = 0; g < GHe; ++g) {
+                swn::HelpCta d;
+                memset(&d, 0, sizeof(d));
+                d.layer = l; d.dil = m->dil[l]; d.ntaps = hl.ntaps; d.dmin = hl.dmin;
+                split_range(H, GHe, g, &d.pair0, &d.npairs);
+                d.ring_len = hl.delay.back() + 2;
+                for (int j = 0; j < hl.ntaps; ++j) d.delay[j] = hl.delay[j];
+                const int np = d.npairs;
+                d.w_off = alloc2((size_t)hl.ntaps * np * 2 * Hp);
+                for (int j = 0; j < hl.ntaps; ++j)
+                    for (int pi = 0; pi < np; ++pi)
+                        for (int zc = 0; zc < 2; ++zc) {
+                            const int row = zc * H + d.pair0 + pi;
+                            float* dst = V.data() + d.w_off + ((size_t)(j * np + pi) * 2 + zc) * Hp;
+                            for (int k = 0; k < H; ++k) dst[k] = x->data[((size_t)row * H + k) * K + hl.tapj[j]];
+                        }
+                size_t u = 0;
+                auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
+                d.sm_w = take((size_t)hl.ntaps * np * 2 * Hp);
+                d.sm_h = take((size_t)2 * NC * Hp);
+                const size_t ring_f = (size_t)d.ring_len * np * 2 * BS;
+                d.sm_ring = (int32_t)u;
+                d.ring_in_smem = (u + ring_f <= (size_t)smem_floats);
+                if (d.ring_in_smem) u += (ring_f + 3) & ~size_t(3);
+                else { d.ring_off = (int64_t)ring_total; ring_total += (ring_f + 3) & ~size_t(3); }
+                if (u > (size_t)smem_floats) return 2;
+                help_used = std::max(help_used, u);
+                hd.push_back(d);
+            }
+        }
+        (void)twoH;
+        const int n_help_used = (int)hd.size();
+        const int grid = swn::CORE_CL * (1 + (n_help_used + swn::CORE_CL - 1) / swn::CORE_CL);
+        if (grid / swn::CORE_CL > max_cl) return 2;
+        m->core_smem = std::max(core_used, help_used) * 4;
+        m->core_grid = grid; m->core_n_help = n_help_used; m->core_ring_total = ring_total;
+        if (upload(m->wbuf2, V)) return 1;
+        if (upload(m->cdesc, m->ccta)) return 1;
+        if (hd.empty()) hd.push_back(swn::HelpCta());
+        if (upload(m->hdesc, hd)) return 1;
+        // ---- exchange rings
+        swn::CoreParams& P = m->core_tmpl;
+        memset(&P, 0, sizeof(P));
+        size_t n_hin = 0, n_hacc = 0;
+        for (int l = 0; l < L; ++l) {
+            const auto& hl = m->hl[l];
+            P.dil[l] = m->dil[l]; P.tap_base[l] = m->tap_base[l];
+            P.has_help[l] = hl.ntaps > 0; P.hdmin[l] = hl.dmin;
+            P.hslots[l] = hl.dmin + 2; P.hacc_nt[l] = hl.dmin + 2;
+            P.hin_off[l] = (int64_t)n_hin; P.hacc_off[l] = (int64_t)n_hacc;
+            if (hl.ntaps) { n_hin += (size_t)P.hslots[l] * NC * H; n_hacc += (size_t)P.hacc_nt[l] * 2 * H * NC; }
+        }
+        m->core_n_hin = n_hin; m->core_n_hacc = n_hacc;
+        if (m->ll2.ensure(n_hin + n_hacc + 8) || m->ring2.ensure(std::max<size_t>(ring_total, 4))) return 1;
+        m->core_plan_key = key;
+    }
+    swn::CoreParams P = m->core_tmpl;
+    P.kind = m->cfg.kind; P.H = H; P.Hp = Hp; P.S = S; P.Sp = m->Sp; P.K = K; P.L = L; P.lpc = m->lpc;
+    P.n1 = m->n1; P.n1p = m->n1p; P.n2 = m->n2; P.Q = Q; P.U = m->U; P.R = m->R; P.B = B; P.Tf = Tf;
+    P.it0 = m->R; P.n_iter = (int)n_iter; P.n_it = m->R + (int)n_iter;
+    P.n_core_taps = m->n_core_taps; P.n_help = m->core_n_help; P.audio_in = 0;
+    P.n_out = n_iter;
+    P.cdesc = m->cdesc.p; P.hdesc = m->hdesc.p; P.wbuf = m->wbuf2.p;
+    P.P = m->ptab.p; P.pconst = m->pconst.p; P.gain = m->gain.p;
+    P.in_tab = m->in_tab.p; P.in_bias = m->in_bias.p; P.xa_tab = nullptr;
+    P.hin_ll = m->ll2.p; P.hacc_ll = m->ll2.p + m->core_n_hin; P.ring_scratch = m->ring2.p;
+    P.noise = a->noise_dev; P.seed = a->seed; P.forced = a->forced_dev; P.seedw = a->seed_dev; P.out = a->out_dev;
+    P.head_out = a->head_dev; P.status = m->status.p; P.timeout_cycles = 4000000000ULL;
+    P.prof = (unsigned long long*)a->prof_dev; P.prof_start = a->prof_start; P.prof_count = a->prof_dev ? a->prof_count : 0;
+    CUDA_OK(cudaMemsetAsync(m->ll2.p, 0, (m->core_n_hin + m->core_n_hacc) * sizeof(unsigned long long), st));
+    if (m->core_ring_total) CUDA_OK(cudaMemsetAsync(m->ring2.p, 0, m->core_ring_total * sizeof(float), st));
+    CUDA_OK(cudaMemsetAsync(m->status.p, 0, 8 * sizeof(int32_t), st));
+    CUDA_OK(cudaEventRecord(m->ev[2], st));
+    cudaError_t e = m_core_launch_dispatch(m, BS, P, st);
+    if (e != cudaSuccess) return fail("cluster kernel launch failed: %s (grid %d, %zu B smem)", cudaGetErrorString(e), m->core_grid, m->core_smem);
+    CUDA_OK(cudaEventRecord(m->ev[3], st));
+    m->gen_timed = true;
+    m->info.kernel_launches++;
+    m->info.smem_bytes = (int32_t)m->core_smem;
+    m->info.batch_tile = BS;
+    m->info.n_slots = 1;
+    m->info.grid = m->core_grid;
+    m->info.kernel_variant = 2;
+    return 0;
+}
 
 extern "C" {
 
@@ -352,6 +550,7 @@ int swn_finalize(swn_handle m) {
                 }
         }
         if (upload(m->in_tab, tab) || upload(m->in_bias, bc->data)) return 1;
+        m->in_tab_h = tab;
     }
 
     // ---------------- in-loop weights, packed per CTA
@@ -427,6 +626,106 @@ int swn_finalize(swn_handle m) {
             m->hcta.push_back(q);
         }
     }
+
+    // ---------------- v2 packing: the 16 CTAs of the core cluster (swn_core.cuh)
+    m->core_ok = false;
+    m->core_plan_key = -1;
+    {
+        const bool audio_in = (!is_c && c.audio_in_flag);
+        int nct = 0;
+        m->tap_base.assign(L, 0);
+        m->hl.assign(L, swn_model::HelpLayer());
+        for (int l = 0; l < L; ++l) {
+            m->tap_base[l] = nct;
+            const int d = m->dil[l];
+            const int ncore = (d == 1 && K >= 2) ? 2 : 1;
+            nct += ncore;
+            auto& hl = m->hl[l];
+            for (int j = K - 1 - ncore; j >= 0; --j) {          // increasing delay
+                hl.tapj.push_back(j);
+                hl.delay.push_back((K - 1 - j) * d);
+            }
+            hl.ntaps = (int)hl.tapj.size();
+            hl.dmin = hl.ntaps ? hl.delay[0] : 0;
+        }
+        m->n_core_taps = nct;
+        const int tcols = 2 * 2 * m->NCH;
+        const bool fits = seg == 1 && !audio_in && H <= 256 && S <= 256 && n1 <= 256 && K <= swn::CORE_KMAX && L <= 16 &&
+                          nct * tcols <= 128 && (is_c ? n2 <= 16 : n2 <= 256);
+        if (fits) {
+            std::vector<float>& V = m->wbuf2_h;
+            V.clear();
+            auto alloc2 = [&](size_t n) { size_t off = (V.size() + 3) & ~size_t(3); V.resize(off + n, 0.f); return (int64_t)off; };
+            m->ccta.assign(swn::CORE_CL, swn::CoreCta());
+            std::vector<const HostTensor*> dw(L), db(L);
+            for (int l = 0; l < L; ++l)
+                if (need(m, "dil_h." + std::to_string(l) + ".conv.weight", {twoH, H, K}, &dw[l]) ||
+                    need(m, "dil_h." + std::to_string(l) + ".conv.bias", {twoH}, &db[l])) return 1;
+            const HostTensor *w1, *b1, *w2, *b2;
+            if (need(m, "out_1.weight", {n1, S, 1}, &w1) || need(m, "out_1.bias", {n1}, &b1) ||
+                need(m, "out_2.weight", {n2, n1, 1}, &w2) || need(m, "out_2.bias", {n2}, &b2)) return 1;
+            for (int r = 0; r < swn::CORE_CL; ++r) {
+                swn::CoreCta& q = m->ccta[r];
+                memset(&q, 0, sizeof(q));
+                split_range(H, swn::CORE_CL, r, &q.pair0, &q.npairs);
+                split_range(S, swn::CORE_CL, r, &q.skip0, &q.nskip);
+                split_range(n1, swn::CORE_CL, r, &q.b0, &q.nb);
+                if (is_c) { q.c0 = 0; q.nc = n2; } else split_range(n2, swn::CORE_CL, r, &q.c0, &q.nc);
+                q.i0 = q.pair0; q.ni = q.npairs;
+                const int np = q.npairs;
+                q.tap_off = alloc2((size_t)std::max(nct * np, 1) * 2 * Hp);
+                q.bias_off = alloc2((size_t)std::max(L * np, 1) * 2);
+                for (int l = 0; l < L; ++l) {
+                    const int ncore = (l + 1 < L ? m->tap_base[l + 1] : nct) - m->tap_base[l];
+                    for (int e = 0; e < ncore; ++e) {
+                        const int j = K - 1 - e, ct = m->tap_base[l] + e;
+                        for (int pi = 0; pi < np; ++pi)
+                            for (int zc = 0; zc < 2; ++zc) {
+                                const int row = zc * H + q.pair0 + pi;
+                                float* dst = V.data() + q.tap_off + ((size_t)(ct * np + pi) * 2 + zc) * Hp;
+                                for (int k = 0; k < H; ++k) dst[k] = dw[l]->data[((size_t)row * H + k) * K + j];
+                            }
+                    }
+                    for (int pi = 0; pi < np; ++pi) {
+                        V[q.bias_off + (size_t)(l * np + pi) * 2] = db[l]->data[q.pair0 + pi];
+                        V[q.bias_off + (size_t)(l * np + pi) * 2 + 1] = db[l]->data[H + q.pair0 + pi];
+                    }
+                }
+                q.skip_off = alloc2((size_t)std::max(L * q.nskip, 1) * Hp);
+                q.skipc_off = alloc2((size_t)std::max(q.nskip, 1));
+                for (int l = 0; l < L; ++l)
+                    for (int rr = 0; rr < q.nskip; ++rr)
+                        for (int k = 0; k < H; ++k)
+                            V[q.skip_off + ((size_t)l * q.nskip + rr) * Hp + k] = skw[l]->data[(size_t)(q.skip0 + rr) * H + k];
+                for (int rr = 0; rr < q.nskip; ++rr) {
+                    double cs = 0.0;
+                    for (int l = 0; l < L; ++l) cs += skb[l]->data[q.skip0 + rr];
+                    V[q.skipc_off + rr] = (float)cs;
+                }
+                q.w1_off = alloc2((size_t)std::max(q.nb, 1) * Sp);
+                q.b1_off = alloc2((size_t)std::max(q.nb, 1));
+                for (int rr = 0; rr < q.nb; ++rr) {
+                    for (int k = 0; k < S; ++k) V[q.w1_off + (size_t)rr * Sp + k] = w1->data[(size_t)(q.b0 + rr) * S + k];
+                    V[q.b1_off + rr] = b1->data[q.b0 + rr];
+                }
+                q.w2_off = alloc2((size_t)std::max(q.nc, 1) * n1p);
+                q.b2_off = alloc2((size_t)std::max(q.nc, 1));
+                for (int rr = 0; rr < q.nc; ++rr) {
+                    for (int k = 0; k < n1; ++k) V[q.w2_off + (size_t)rr * n1p + k] = w2->data[(size_t)(q.c0 + rr) * n1 + k];
+                    V[q.b2_off + rr] = b2->data[q.c0 + rr];
+                }
+                const int nip = (q.ni + 3) & ~3;
+                q.tin_off = alloc2((size_t)std::max(Q, 1) * std::max(nip, 4));
+                if (!is_c)
+                    for (int qq = 0; qq < Q; ++qq)
+                        for (int rr = 0; rr < q.ni; ++rr)
+                            V[q.tin_off + (size_t)qq * nip + rr] = m->in_tab_h[((size_t)(K - 1) * Q + qq) * H + q.i0 + rr];
+            }
+            m->wbuf2_core_floats = (V.size() + 3) & ~size_t(3);
+            V.resize(m->wbuf2_core_floats, 0.f);
+            m->core_ok = true;
+        }
+    }
     if (upload(m->wbuf, W)) return 1;
     if (m->status.ensure(8)) return 1;
     for (int i = 0; i < 4; ++i)
@@ -484,6 +783,15 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
                     (long long)Tf * m->U);
     if (n_iter + m->R + 2 > 0x7fffffffLL) return fail("swn_generate: too many steps");
 
+    // ---- small batches, one sample per step: the cluster kernel (v2); everything else: layer groups (v1)
+    if (m->core_ok && a->kernel_sel != 1) {
+        const int rc = generate_core(m, a, st, B, Tf, n_iter);
+        if (rc == 0) return 0;
+        if (rc == 1) return 1;
+        if (a->kernel_sel == 2) return fail("swn_generate: the cluster kernel is not applicable to this configuration/batch");
+    } else if (a->kernel_sel == 2) {
+        return fail("swn_generate: the cluster kernel is not applicable to this configuration");
+    }
     // ---- batch tile
     int BS = 0;
     const int* tiles = swn::batch_tiles_for_seg(seg);
@@ -618,6 +926,7 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
     m->info.smem_bytes = (int32_t)smem_bytes;
     m->info.batch_tile = BS;
     m->info.n_slots = M;
+    m->info.kernel_variant = 1;
     return 0;
 }
 

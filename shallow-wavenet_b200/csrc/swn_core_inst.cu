@@ -1,0 +1,64 @@
+// Instantiations of the cluster ("core + helpers") latency kernel for one hidden-size class.
+#include "swn_core.cuh"
+#include "swn_launch.h"
+
+#ifndef SWN_NCH
+#error "compile with -DSWN_NCH=<1..4>"
+#endif
+
+namespace swn {
+
+template <int NCH, int BS>
+static cudaError_t core_prepare(size_t smem, int* max_clusters) {
+    auto k = swn_core_kernel<NCH, BS>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CORE_CL * 8);
+    cfg.blockDim = dim3(SWN_NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CORE_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaOccupancyMaxActiveClusters(max_clusters, (const void*)k, &cfg);
+}
+
+template <int NCH, int BS>
+static cudaError_t core_launch(const CoreParams& p, int grid, size_t smem, cudaStream_t st) {
+    auto k = swn_core_kernel<NCH, BS>;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(SWN_NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;          // all clusters co-resident: they spin on each other
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k, p);
+    if (e == cudaSuccess) return e;
+    // some drivers reject cooperative + compile-time cluster dims: the grid never exceeds the
+    // co-resident cluster count (checked by the caller), so a plain launch is equivalent
+    (void)cudaGetLastError();
+    cfg.numAttrs = 0;
+    return cudaLaunchKernelEx(&cfg, k, p);
+}
+
+#define SWN_CAT2(a, b) a##b
+#define SWN_CAT(a, b) SWN_CAT2(a, b)
+
+core_fns SWN_CAT(find_core_kernel_nch, SWN_NCH)(int bs) {
+    core_fns f = {nullptr, nullptr};
+    switch (bs) {
+        case 1: f.prepare = &core_prepare<SWN_NCH, 1>; f.launch = &core_launch<SWN_NCH, 1>; break;
+        case 2: f.prepare = &core_prepare<SWN_NCH, 2>; f.launch = &core_launch<SWN_NCH, 2>; break;
+        case 4: f.prepare = &core_prepare<SWN_NCH, 4>; f.launch = &core_launch<SWN_NCH, 4>; break;
+        default: break;
+    }
+    return f;
+}
+
+}  // namespace swn

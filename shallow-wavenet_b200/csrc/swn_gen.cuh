@@ -88,7 +88,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define SWN_PROF(ev)                                                                              \
     do {                                                                                          \
         if (P.prof && threadIdx.x == 0 && it >= P.prof_start && it < P.prof_start + P.prof_count) \
-            P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 4 + (ev)] = gtime();  \
+            P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 8 + (ev)] = gtime();  \
     } while (0)
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -371,9 +371,8 @@ __device__ void layer_cta(const GenParams& P, const CtaDesc& D, float* smem) {
 // ------------------------------------------------------------------ head CTA
 // Laplace / LPC sampler of one utterance for one loop step (cswnv_shift1.py:368-391).
 template <int SEG>
-__device__ __forceinline__ void laplace_step(const GenParams& P, const float* o, float* lp, const float* eps,
+__device__ __forceinline__ void laplace_step(const int lpc, const float* o, float* lp, const float* eps,
                                              const float* forced, float* smp) {
-    const int lpc = P.lpc;
     float l[8];
 #pragma unroll
     for (int mm = 0; mm < 8; ++mm) l[mm] = (mm < lpc) ? lp[mm] : 0.f;
@@ -607,7 +606,7 @@ __device__ void head_cta(const GenParams& P, const CtaDesc& D, float* smem) {
                             eps[j] = P.noise ? P.noise[(size_t)bglob * P.n_out + nbase + j]
                                              : laplace_eps(P.seed, bglob, nbase + j);
                         const float* forced = P.forced ? (const float*)P.forced + (size_t)bglob * P.n_out + nbase : nullptr;
-                        laplace_step<SEG>(P, oc + b * ncp, lpb + ((size_t)m * BS + b) * 8, eps, forced, smp);
+                        laplace_step<SEG>(P.lpc, oc + b * ncp, lpb + ((size_t)m * BS + b) * 8, eps, forced, smp);
 #pragma unroll
                         for (int j = 0; j < SEG; ++j) {
                             const float fed = forced ? forced[j] : smp[j];

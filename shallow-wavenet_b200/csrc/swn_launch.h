@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include "swn_common.h"
 
+namespace swn { struct CoreParams; }
+
 namespace swn {
 
 typedef cudaError_t (*launch_fn)(const GenParams& p, int grid, size_t smem, cudaStream_t st);
@@ -11,6 +13,15 @@ launch_fn find_kernel_nch1(int seg, int bs);
 launch_fn find_kernel_nch2(int seg, int bs);
 launch_fn find_kernel_nch3(int seg, int bs);
 launch_fn find_kernel_nch4(int seg, int bs);
+
+struct core_fns {
+    cudaError_t (*prepare)(size_t smem, int* max_clusters);
+    cudaError_t (*launch)(const CoreParams& p, int grid, size_t smem, cudaStream_t st);
+};
+core_fns find_core_kernel_nch1(int bs);
+core_fns find_core_kernel_nch2(int bs);
+core_fns find_core_kernel_nch3(int bs);
+core_fns find_core_kernel_nch4(int bs);
 
 // batch tiles instantiated for a given seg (descending), terminated by 0
 inline const int* batch_tiles_for_seg(int seg) {

@@ -3,6 +3,7 @@
 drives conditioning + the persistent generation kernel.  torch is used for device memory and
 the current stream only."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -51,7 +52,7 @@ class Engine(object):
         self._B = B
 
     def generate(self, n_samples, seed=0, noise=None, forced=None, seed_audio=None, return_heads=False,
-                 batch_tile=0, sync=True, poll_mode=0, prof=None, prof_start=0):
+                 batch_tile=0, sync=True, poll_mode=0, prof=None, prof_start=0, kernel_sel=0):
         info = self.info
         seg, hd = info["eff_seg"], info["head_dim"]
         B = self._B
@@ -78,7 +79,8 @@ class Engine(object):
         a.head_dev = heads.data_ptr() if heads is not None else None
         a.batch_tile = int(batch_tile)
         a.poll_mode = int(poll_mode)
-        if prof is not None:       # int64 CUDA tensor [count, grid, 4]
+        a.kernel_sel = int(kernel_sel) or int(os.environ.get("SWN_KERNEL_SEL", "0"))   # debugging aid
+        if prof is not None:       # int64 CUDA tensor [count, grid, 8]
             keep.append(prof)
             a.prof_dev = prof.data_ptr()
             a.prof_start = int(prof_start)

@@ -33,7 +33,7 @@ for name in golden_names():
         serr = float(np.abs(smp - g["samples"]).max())
     print("%-26s forced: head max abs %.3e rel %.3e  first-step err %.3e  sample err %s  (%.2fs) info=%s" % (
         name, herr.max(), rel, herr[:, 0].max(), serr, time.time() - t,
-        {k: m.engine().info[k] for k in ("batch_tile", "n_slots", "smem_bytes", "last_gen_ms")}))
+        {k: m.engine().info[k] for k in ("kernel_variant", "grid", "batch_tile", "n_slots", "smem_bytes", "last_gen_ms")}))
     try:
         outs2 = m.batch_fast_generate(seed_audio, torch.from_numpy(g["aux"]), [N] * B, noise=g["noise"])
         smp2 = np.stack(outs2)
