@@ -76,7 +76,7 @@ typedef struct swn_gen_args {
                                  decode_dswnv_softmax.py:94-99) */
     int32_t batch_tile;       /* utterances processed together per pipeline slot; 0 = auto */
     int32_t poll_mode;        /* tuning: 0 = default, 1 = pure per-word polling, 2 = sentinel + per-word */
-    uint64_t* prof_dev;       /* optional instrumentation: [prof_count][grid][8] %globaltimer stamps */
+    uint64_t* prof_dev;       /* optional instrumentation: [prof_count][grid][32] %globaltimer stamps */
     int32_t prof_start;       /* first loop iteration stamped */
     int32_t prof_count;
     int32_t kernel_sel;       /* 0 = auto, 1 = force the layer-group kernel, 2 = force the cluster kernel */

@@ -218,13 +218,13 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
             lay.sm_w2 = take((size_t)mx_nc * m->n1p);
             lay.sm_tin = take(is_c ? 0 : (size_t)Q * ((mx_ni + 3) & ~3));
             lay.sm_ring = take((size_t)L * 2 * 16 * 2 * BS);
-            lay.sm_hx = take((size_t)(L + 1) * NC * Hp * 2);        // hx, x1, x2, gx stay contiguous (zeroed as one block)
-            lay.sm_x1 = take((size_t)NC * m->Sp * 2);
-            lay.sm_x2 = take((size_t)NC * m->n1p * 2);
-            lay.sm_gx = take((size_t)NC * 256 * 2);
+            lay.sm_hx = take((size_t)(L + 1) * NC * Hp);            // hx, x1, x2, gx stay contiguous (zeroed as one block)
+            lay.sm_x1 = take((size_t)NC * m->Sp);
+            lay.sm_x2 = take((size_t)NC * m->n1p);
+            lay.sm_gx = take((size_t)NC * 256);
             lay.sm_pre = take((size_t)2 * L * 16 * NC * (sizeof(swn::PreSlot) / 4));
-            lay.sm_misc = take((size_t)NC * (16 + 8 + 16));
-            lay.sm_tmem_slot = take(4);
+            lay.sm_misc = take((size_t)NC * (16 + 8 + 16) + (size_t)L * 16 * 4 + (size_t)(8 * 16 + 2 * 8 * 16) * NC + 8 * 2 * 16);
+            lay.sm_tmem_slot = take(4 + 2 * (size_t)(L + 4));      // TMEM base slot, then L+4 mbarriers
             core_used = u;
             for (auto& q : m->ccta) {
                 q.sm_skip = lay.sm_skip; q.sm_w1 = lay.sm_w1; q.sm_w2 = lay.sm_w2; q.sm_tin = lay.sm_tin;
@@ -259,7 +259,7 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
                 memset(&d, 0, sizeof(d));
                 d.layer = l; d.dil = m->dil[l]; d.ntaps = hl.ntaps; d.dmin = hl.dmin;
                 split_range(H, GHe, g, &d.pair0, &d.npairs);
-                d.ring_len = hl.delay.back() + 2;
+                d.ring_len = 4; while (d.ring_len < hl.delay.back() + 2) d.ring_len *= 2;      // power of two
                 for (int j = 0; j < hl.ntaps; ++j) d.delay[j] = hl.delay[j];
                 const int np = d.npairs;
                 d.w_off = alloc2((size_t)hl.ntaps * np * 2 * Hp);
@@ -302,7 +302,8 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
             const auto& hl = m->hl[l];
             P.dil[l] = m->dil[l]; P.tap_base[l] = m->tap_base[l];
             P.has_help[l] = hl.ntaps > 0; P.hdmin[l] = hl.dmin;
-            P.hslots[l] = hl.dmin + 2; P.hacc_nt[l] = hl.dmin + 2;
+            int p2 = 4; while (p2 < hl.dmin + 2) p2 *= 2;                    // ring depths are powers of two (index masks)
+            P.hslots[l] = p2; P.hacc_nt[l] = p2;
             P.hin_off[l] = (int64_t)n_hin; P.hacc_off[l] = (int64_t)n_hacc;
             if (hl.ntaps) { n_hin += (size_t)P.hslots[l] * NC * H; n_hacc += (size_t)P.hacc_nt[l] * 2 * H * NC; }
         }

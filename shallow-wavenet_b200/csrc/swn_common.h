@@ -70,7 +70,7 @@ struct GenParams {
     float* head_out;
     int32_t* status;                // [0] abort flag, [1] where, [2] iteration
     unsigned long long timeout_cycles;
-    unsigned long long* prof;       // optional [prof_count][grid][8] globaltimer stamps
+    unsigned long long* prof;       // optional [prof_count][grid][32] globaltimer stamps
     int32_t prof_start, prof_count;
     int32_t poll_mode, poll_sleep_ns;
 };

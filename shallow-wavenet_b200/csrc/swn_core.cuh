@@ -105,6 +105,29 @@ __device__ __forceinline__ unsigned long long ld_smem_ll(const unsigned long lon
     return v;
 }
 
+// ---- mbarrier + st.async: the exchange inside the cluster.  A producer lane stores one fp32 into a
+// peer's shared memory and, in the same instruction, credits 4 bytes to that peer's mbarrier; a
+// consumer warp sleeps in mbarrier.try_wait (no issue slots, no shared-memory polling) and is woken
+// when the whole vector has landed.  Measured one-way latency 339 cycles vs 428 for a polled
+// {value,tag} word (tools/microbench/hop_latency.cu).
+__device__ __forceinline__ void mbar_init(unsigned long long* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arm(unsigned long long* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(unsigned long long* b, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_mbar) : "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc_all(uint32_t* slot) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -138,65 +161,73 @@ __device__ __forceinline__ void tmem_st(uint32_t a, const float (&r)[N]) {
     for (int i = 0; i < N; i += 4) tmem_st4(a + i, &r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t a, float* r) {
+    uint32_t x[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]), "=r"(x[8]),
+                   "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15])
+                 : "r"(a));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(x[i]);
+}
+// N floats (multiple of 16) per thread, asynchronous: tmem_wait_ld() before use
+template <int N>
+__device__ __forceinline__ void tmem_ldw(uint32_t a, float (&r)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; i += 16) tmem_ld16(a + i, &r[i]);
+}
+
+// Sum 8 per-lane partials over the 32 lanes: afterwards lane L holds the total of value (L >> 2)
+// (9 shuffles instead of 40).
+__device__ __forceinline__ float reduce8(const float (&v)[8], int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    float u[4], t2[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b4 ? v[i] : v[i + 4], keep = b4 ? v[i + 4] : v[i];
+        u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b3 ? u[i] : u[i + 2], keep = b3 ? u[i + 2] : u[i];
+        t2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float send = b2 ? t2[0] : t2[1], keep = b2 ? t2[1] : t2[0];
+    float sres = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    sres += __shfl_xor_sync(0xffffffffu, sres, 2);
+    sres += __shfl_xor_sync(0xffffffffu, sres, 1);
+    return sres;
+}
+
+#define SWN_CCLK(ev)                                                                               \
+    do {                                                                                           \
+        if (P.prof && threadIdx.x == 0 && l == 3 && it >= P.prof_start && it < P.prof_start + P.prof_count) \
+            P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + (ev)] = (unsigned long long)clock64(); \
+    } while (0)
 #define SWN_CPROF(ev)                                                                              \
     do {                                                                                           \
         if (P.prof && threadIdx.x == 0 && it >= P.prof_start && it < P.prof_start + P.prof_count) \
-            P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 8 + (ev)] = gtime();   \
+            P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + (ev)] = gtime();  \
     } while (0)
 
-// Wait until the lane's slice of an LL vector in LOCAL shared memory carries `tag`, return it in
-// registers (lane owns k = c*64 + 2*lane, +1).  Polling local SMEM costs no off-SM traffic.
-template <int NCH>
-__device__ __forceinline__ bool wait_vec(const unsigned long long* vec, uint32_t tag, float2 (&h)[NCH], int lane,
-                                         const CoreParams& P, int where) {
+// Sleep on a local mbarrier until the phase with `parity` has completed (with the watchdog).
+static __device__ __noinline__ bool mbar_wait_slow(unsigned long long* b, uint32_t parity, const CoreParams& P, int where) {
     uint32_t spins = 0;
-    long long t_start = 0;
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        const unsigned long long* p = vec + c * 64 + 2 * lane;
-        const int k0 = c * 64 + 2 * lane;
-        const bool pad0 = k0 >= P.H, pad1 = k0 + 1 >= P.H;      // padded words are never written (value 0)
-        for (;;) {
-            const ulonglong2 v = ld_smem_ll2(p);
-            if ((pad0 || (uint32_t)(v.x >> 32) == tag) && (pad1 || (uint32_t)(v.y >> 32) == tag)) {
-                h[c].x = __uint_as_float((uint32_t)v.x); h[c].y = __uint_as_float((uint32_t)v.y);
-                break;
-            }
-            if (((++spins) & 1023u) == 0) {
-                volatile int32_t* st = P.status;
-                if (t_start == 0) t_start = clock64();
-                if (st[0] != 0) return false;
-                if ((unsigned long long)(clock64() - t_start) > (P.timeout_cycles >> 1)) {
-                    if (atomicCAS((int*)P.status, 0, 1) == 0) { st[1] = where; st[2] = (int)tag; st[3] = blockIdx.x; }
-                    return false;
-                }
-            }
-        }
-    }
-    return true;
-}
-
-// Two adjacent LL words in local shared memory (with the watchdog); padded words are not tag-checked.
-__device__ __forceinline__ bool wait_pair(const unsigned long long* p, uint32_t tag, bool pad0, bool pad1, ulonglong2& v,
-                                          const CoreParams& P, int where) {
-    uint32_t spins = 0;
-    long long t_start = 0;
+    long long t_start = clock64();
     for (;;) {
-        v = ld_smem_ll2(p);
-        if ((pad0 || (uint32_t)(v.x >> 32) == tag) && (pad1 || (uint32_t)(v.y >> 32) == tag)) return true;
-        if (((++spins) & 1023u) == 0) {
+        if (mbar_try(b, parity)) return true;
+        if (((++spins) & 15u) == 0) {
             volatile int32_t* st = P.status;
-            if (t_start == 0) t_start = clock64();
             if (st[0] != 0) return false;
             if ((unsigned long long)(clock64() - t_start) > (P.timeout_cycles >> 1)) {
-                if (atomicCAS((int*)P.status, 0, 1) == 0) { st[1] = where; st[2] = (int)tag; st[3] = blockIdx.x; }
+                if (atomicCAS((int*)P.status, 0, 1) == 0) { st[1] = where; st[2] = (int)parity; st[3] = blockIdx.x; }
                 return false;
             }
         }
     }
 }
 
-__device__ __forceinline__ bool wait_gword(const unsigned long long* p, uint32_t tag, uint32_t& payload, const CoreParams& P,
+static __device__ __noinline__ bool wait_gword(const unsigned long long* p, uint32_t tag, uint32_t& payload, const CoreParams& P,
                                            int where) {
     uint32_t spins = 0;
     long long t_start = 0;
@@ -213,6 +244,11 @@ __device__ __forceinline__ bool wait_gword(const unsigned long long* p, uint32_t
             }
         }
     }
+}
+
+__device__ __forceinline__ bool mbar_wait(unsigned long long* b, uint32_t parity, const CoreParams& P, int where) {
+    if (mbar_try(b, parity)) return true;
+    return mbar_wait_slow(b, parity, P, where);
 }
 
 // ------------------------------------------------------------------ helper CTA
@@ -242,7 +278,7 @@ __device__ void helper_cta(const CoreParams& P, const HelpCta& D, float* smem) {
     __syncthreads();
     const unsigned long long* in_ll = P.hin_ll + P.hin_off[l];
     unsigned long long* acc_ll = P.hacc_ll + P.hacc_off[l];
-    const int nslot = P.hslots[l], NT = P.hacc_nt[l];
+    const int slot_mask = P.hslots[l] - 1, nt_mask = P.hacc_nt[l] - 1, rl_mask = RL - 1;   // all powers of two
     // lane <-> (tap j, column c) for the ring update
     const int my_j = lane / NC, my_c = lane - my_j * NC;
     const bool my_live = my_j < nt;
@@ -254,13 +290,15 @@ __device__ void helper_cta(const CoreParams& P, const HelpCta& D, float* smem) {
         hsel ^= 1;
         bool ok = true;
         {
-            const unsigned long long* src = in_ll + (size_t)(it % nslot) * NC * H;
-            for (int i = tid; i < NC * H; i += SWN_NTHREADS) {
-                uint32_t bits;
-                ok = wait_gword(src + i, tag, bits, P, 300 + l) && ok;
-                const int c = i / H, k = i - c * H;
-                hbuf[c * HP + k] = __uint_as_float(bits);
-            }
+            const unsigned long long* src = in_ll + (size_t)(it & slot_mask) * NC * H;
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                for (int k = tid; k < H; k += SWN_NTHREADS) {
+                    unsigned long long v = ld_ll(src + c * H + k);
+                    uint32_t bits = (uint32_t)v;
+                    if ((uint32_t)(v >> 32) != tag) ok = wait_gword(src + c * H + k, tag, bits, P, 300 + l) && ok;
+                    hbuf[c * HP + k] = __uint_as_float(bits);
+                }
         }
         if (__syncthreads_or(!ok)) return;
         float2 h[NC][NCH];
@@ -285,12 +323,12 @@ __device__ void helper_cta(const CoreParams& P, const HelpCta& D, float* smem) {
             }
             if (my_live) {
                 const int T = it + my_delay;
-                float* r0 = ring + ((size_t)((T % RL) * np + pi) * 2) * BS + my_c;
+                float* r0 = ring + (((T & rl_mask) * np + pi) * 2) * BS + my_c;
                 const float a = r0[0] + mz, b = r0[BS] + mc;
                 if (my_j == 0) {
                     // smallest delay: the sum for target time T is complete -> hand it to the core, clear the slot
                     r0[0] = 0.f; r0[BS] = 0.f;
-                    unsigned long long* dst = acc_ll + ((size_t)(T % NT) * 2 * H) * NC;
+                    unsigned long long* dst = acc_ll + (size_t)((T & nt_mask) * 2 * H) * NC;
                     st_ll(dst + (size_t)(D.pair0 + pi) * NC + my_c, a, (uint32_t)T + 1u);
                     st_ll(dst + (size_t)(H + D.pair0 + pi) * NC + my_c, b, (uint32_t)T + 1u);
                 } else {
@@ -319,32 +357,41 @@ struct PreSlot {            // what a gate lane needs besides the mat-vec, prefe
 
 template <int NCH, int BS>
 __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
-    constexpr int NC = BS, HP = NCH * 64, FPT = 2 * NCH, TCOLS = 2 * FPT;     // TMEM columns per tap per thread
+    // TMEM columns per tap per thread: a quarter-warp-group thread keeps 8 rows (4 gate pairs) x FPT weights
+    constexpr int NC = BS, HP = NCH * 64, FPT = 2 * NCH, TCOLS = 8 * FPT;
     constexpr int HIST = 16;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = P.H, S = P.S, Sp = P.Sp, K = P.K, L = P.L, n1 = P.n1, n1p = P.n1p, n2 = P.n2, Q = P.Q;
     const uint32_t rank = cluster_ctarank();
     const bool is_c = P.kind == 0;
     const int np = D.npairs;
-    const bool has_pair = warp < np;
+    const int quarter = warp & 3;                               // TMEM lane quarter == the 4 gate pairs 4*quarter..+3
     const int nip = (D.ni + 3) & ~3;
 
-    // ---- shared memory carve-up
+    // ---- shared memory carve-up (identical offsets in all 16 CTAs)
     float* sSkip = smem + D.sm_skip;                       // [L][nskip][HP]
     float* sW1 = smem + D.sm_w1;                           // [nb][Sp]
     float* sW2 = smem + D.sm_w2;                           // [nc][n1p]
     float* sTin = smem + D.sm_tin;                         // DSWNV [Q][nip]
     float* ring = smem + D.sm_ring;                        // [L][2][16][2][BS]  delay-1 partial sums
-    unsigned long long* hx = reinterpret_cast<unsigned long long*>(smem + D.sm_hx);   // [L+1][NC][HP] LL vectors
-    unsigned long long* x1 = reinterpret_cast<unsigned long long*>(smem + D.sm_x1);   // [NC][Sp]
-    unsigned long long* x2 = reinterpret_cast<unsigned long long*>(smem + D.sm_x2);   // [NC][n1p]
-    unsigned long long* gx = reinterpret_cast<unsigned long long*>(smem + D.sm_gx);   // [NC][256] Gumbel scores
+    float* hx = smem + D.sm_hx;                            // [L+1][NC][HP] exchanged layer inputs
+    float* x1 = smem + D.sm_x1;                            // [NC][Sp]  relu(sum of skips)
+    float* x2 = smem + D.sm_x2;                            // [NC][n1p] relu(out_1)
+    float* gx = smem + D.sm_gx;                            // [NC][256] Gumbel scores
     PreSlot* pre = reinterpret_cast<PreSlot*>(smem + D.sm_pre);                        // [2][L][16][NC]
     float* misc = smem + D.sm_misc;
     float* hist = misc;                                    // [NC][HIST] fed-back samples / indices
     float* lpb = hist + NC * HIST;                         // [NC][8]
     float* o2 = lpb + NC * 8;                              // [NC][16] out_2 rows (CSWNV)
+    float4* lc = reinterpret_cast<float4*>(o2 + NC * 16);  // [L][16] per (layer, warp): conditioning const z/c, bias z/c
+    float* cacc = reinterpret_cast<float*>(lc + L * 16);   // [8][16][NC]  input-stage partial sums by time slot
+    float* cstage = cacc + 8 * 16 * NC;                    // [2][8][16][NC] gathered table entries in flight (cp.async)
+    float* sfir = cstage + 2 * 8 * 16 * NC;                // CSWNV [8][2][16] FIR taps (cb, v) of this CTA's rows
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + D.sm_tmem_slot);
+    unsigned long long* mb = reinterpret_cast<unsigned long long*>(tmem_slot + 2);     // [L+1] h vectors, then x1, x2, gx
+    unsigned long long* mb_x1 = mb + (L + 1), *mb_x2 = mb + (L + 2), *mb_gx = mb + (L + 3);
+    const uint32_t bytes_h = (uint32_t)(H * NC * 4), bytes_x1 = (uint32_t)(S * NC * 4), bytes_x2 = (uint32_t)(n1 * NC * 4),
+                   bytes_gx = (uint32_t)(Q * NC * 4);
 
     auto stage = [&](float* dst, const float* src, int n) {
         const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -357,33 +404,58 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
     if (!is_c) stage(sTin, P.wbuf + D.tin_off, Q * nip);
     for (int i = tid; i < L * 2 * 16 * 2 * BS; i += SWN_NTHREADS) ring[i] = 0.f;
     {
-        // zero all LL buffers (tags start at 1; padded words stay {0,0} and are never tag-checked)
+        // exchanged vectors: padded elements stay 0 forever
         const int nw = (L + 1) * NC * HP + NC * Sp + NC * n1p + NC * 256;
-        for (int i = tid; i < nw; i += SWN_NTHREADS) hx[i] = 0ull;
+        for (int i = tid; i < nw; i += SWN_NTHREADS) hx[i] = 0.f;
         unsigned long long* pz = reinterpret_cast<unsigned long long*>(pre);
         for (int i = tid; i < (int)(2 * L * 16 * NC * sizeof(PreSlot) / 8); i += SWN_NTHREADS) pz[i] = 0ull;
     }
     for (int i = tid; i < NC * (HIST + 8 + 16); i += SWN_NTHREADS) misc[i] = 0.f;
     __syncthreads();
     for (int i = tid; i < NC * HIST; i += SWN_NTHREADS) hist[i] = is_c ? 0.f : __int_as_float(Q / 2);
+    for (int i = tid; i < L * 16; i += SWN_NTHREADS) {
+        const int l = i >> 4, wv = i & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (wv < D.npairs) {
+            v.x = P.pconst[l * 2 * H + D.pair0 + wv]; v.y = P.pconst[l * 2 * H + H + D.pair0 + wv];
+            v.z = P.wbuf[D.bias_off + (l * D.npairs + wv) * 2]; v.w = P.wbuf[D.bias_off + (l * D.npairs + wv) * 2 + 1];
+        }
+        lc[i] = v;
+    }
+    for (int i = tid; i < 8 * 16 * NC + 2 * 8 * 16 * NC; i += SWN_NTHREADS) cacc[i] = 0.f;
+    for (int i = tid; i < 8 * 2 * 16; i += SWN_NTHREADS) {
+        const int j = i >> 5, w2 = (i >> 4) & 1, r = i & 15;
+        sfir[i] = (is_c && j < K && r < D.ni) ? P.in_tab[(j * 2 + w2) * H + D.i0 + r] : 0.f;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < L + 4; ++i) mbar_init(mb + i, 1);
+        mbar_fence_init();
+        for (int i = 0; i <= L; ++i) mbar_arm(mb + i, bytes_h);          // phase 0 of every vector
+        mbar_arm(mb_x1, bytes_x1); mbar_arm(mb_x2, bytes_x2); mbar_arm(mb_gx, bytes_gx);
+    }
     if (warp == 0) tmem_alloc_all(tmem_slot);
     tmem_fence_before();
     __syncthreads();
     tmem_fence_after();
     const uint32_t tbase = *tmem_slot;
-    const uint32_t taddr0 = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 128);
-    // ---- tensor memory <- the core taps of this warp's gate pair (thread-private columns)
-    if (has_pair) {
+    const uint32_t taddr0 = tbase + ((uint32_t)(32 * quarter) << 16);
+    // ---- tensor memory <- the core taps: warp q < 4 fills its lane quarter with the taps of gate pairs 4q..4q+3
+    // (thread-private columns: tap c occupies columns [c*TCOLS, (c+1)*TCOLS), row rr = 2*pair + {z,c} at rr*FPT)
+    if (warp < 4) {
         for (int c = 0; c < P.n_core_taps; ++c) {
-            const float* wr = P.wbuf + D.tap_off + ((size_t)(c * np + warp) * 2) * HP;
-            float w[TCOLS];
 #pragma unroll
-            for (int cc = 0; cc < NCH; ++cc) {
-                const float2 a = reinterpret_cast<const float2*>(wr)[cc * 32 + lane];
-                const float2 b = reinterpret_cast<const float2*>(wr + HP)[cc * 32 + lane];
-                w[2 * cc] = a.x; w[2 * cc + 1] = a.y; w[FPT + 2 * cc] = b.x; w[FPT + 2 * cc + 1] = b.y;
+            for (int rr = 0; rr < 8; ++rr) {
+                const int pl = 4 * quarter + (rr >> 1);
+                float wv[FPT];
+#pragma unroll
+                for (int cc = 0; cc < NCH; ++cc) {
+                    float2 a = make_float2(0.f, 0.f);
+                    if (pl < np)
+                        a = reinterpret_cast<const float2*>(P.wbuf + D.tap_off + ((size_t)(c * np + pl) * 2 + (rr & 1)) * HP)[cc * 32 + lane];
+                    wv[2 * cc] = a.x; wv[2 * cc + 1] = a.y;
+                }
+                tmem_st<FPT>(taddr0 + c * TCOLS + rr * FPT, wv);
             }
-            tmem_st<TCOLS>(taddr0 + c * TCOLS, w);
         }
         tmem_wait_st();
     }
@@ -397,260 +469,337 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
         }
     }
     __syncthreads();
-    cluster_sync_all();                                            // every CTA's buffers are initialised
+    cluster_sync_all();                                            // every CTA's buffers and barriers are ready
 
     const uint32_t peer = (uint32_t)(lane & (CORE_CL - 1));
     const uint32_t hx_peer = mapa(smem_u32(hx), peer), x1_peer = mapa(smem_u32(x1), peer),
-                   x2_peer = mapa(smem_u32(x2), peer), gx_peer = mapa(smem_u32(gx), peer);
-    const float* bias = P.wbuf + D.bias_off;
+                   x2_peer = mapa(smem_u32(x2), peer), gx_peer = mapa(smem_u32(gx), peer), mb_peer = mapa(smem_u32(mb), peer);
     const int twoH = 2 * H;
-    const int col = lane;                                          // gate lane <-> column
-    const int my_i = D.pair0 + warp;
+    // ---- roles inside the CTA (one warp group = 4 warps = one warp per SM sub-partition):
+    //   warps 0-3   "chain" warps: each evaluates the delay-0 tap of 4 gate pairs (8 rows), gates, publishes
+    //   warps 4-7   delay-1 taps of the dilation-1 layers + prefetch of next step's gate operands
+    //   warps 8-15  two rows each of every out_skip
+    // A lane of a chain / delay-1 warp belongs to pair-slot (lane >> 3) of its quarter; column = (lane & 7) for
+    // per-column duties (NC <= 8).
+    const int pslot = lane >> 3;                                   // 0..3
+    const int plocal = 4 * quarter + pslot;                        // gate pair inside this CTA
+    const bool pvalid = plocal < np;
+    const int my_i = D.pair0 + plocal;                             // row index in H
+    const int sub = lane & 7;                                      // lane inside the pair group
+    const int skr0 = 2 * (warp - 8), skr1 = skr0 + 1;              // skip rows of warps 8..15
+    const uint32_t hxp0 = mapa(smem_u32(hx), (uint32_t)sub), hxp1 = mapa(smem_u32(hx), (uint32_t)sub + 8);
+    const uint32_t mbp0 = mapa(smem_u32(mb), (uint32_t)sub), mbp1 = mapa(smem_u32(mb), (uint32_t)sub + 8);
+    const float b1w = (warp < D.nb) ? __ldg(P.wbuf + D.b1_off + warp) : 0.f;
+    const float b2w = (warp < D.nc) ? __ldg(P.wbuf + D.b2_off + warp) : 0.f;
+    float cst0 = 0.f, cst1 = 0.f;
+    if (warp >= 8) {
+        if (skr0 < D.nskip) cst0 = __ldg(P.wbuf + D.skipc_off + skr0);
+        if (skr1 < D.nskip) cst1 = __ldg(P.wbuf + D.skipc_off + skr1);
+    }
 
-    // ---- prefetch (cp.async) of the gate operands of (layer l, time tt) into pre[tt&1][l][warp][col]
-    auto prefetch_gate = [&](int l, int tt) {
-        if (has_pair && col < NC && tt < P.n_it) {
-            PreSlot* ps = pre + (((size_t)(tt & 1) * L + l) * 16 + warp) * NC + col;
-            const int bglob = min(col, P.B - 1);
-            int f = 0;
-            if (tt >= P.R) f = (tt - P.R) / P.U;
-            const float* pr = P.P + (((size_t)bglob * P.Tf + f) * L + l) * twoH;
-            cp_async4(&ps->pz, pr + my_i);
-            cp_async4(&ps->pc, pr + H + my_i);
+    // ---- prefetch (cp.async) of the gate operands of (layer l, time tt) into pre[tt&1][l][pair][col], done by the
+    // delay-1 warps (4-7): lane sub < NC of every pair group handles column sub
+    const bool pf_lane = warp >= 4 && warp < 8 && pvalid && sub < NC;
+    const int bg_col = min(sub, P.B - 1);
+    const float* ptab_b = P.P + (size_t)bg_col * P.Tf * L * twoH + my_i;
+    auto prefetch_gate = [&](int l, int tt, const float* prow) {
+        if (pf_lane && tt < P.n_it) {
+            PreSlot* ps = pre + (((tt & 1) * L + l) * 16 + plocal) * NC + sub;
+            cp_async4(&ps->pz, prow + l * twoH);
+            cp_async4(&ps->pc, prow + l * twoH + H);
             if (P.has_help[l] && tt >= P.hdmin[l]) {
-                const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + ((size_t)(tt % P.hacc_nt[l]) * twoH) * NC;
-                cp_async8(&ps->hz, src + (size_t)my_i * NC + col);
-                cp_async8(&ps->hc, src + (size_t)(H + my_i) * NC + col);
+                const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + ((tt & (P.hacc_nt[l] - 1)) * twoH + my_i) * NC + sub;
+                cp_async8(&ps->hz, src);
+                cp_async8(&ps->hc, src + H * NC);
             }
         }
-        cp_async_commit();
     };
 
-    // ---- input stage: h0 rows of this CTA for time itn, published into every peer's hx[0]
-    // cpn[c] = bias + all taps but the newest (known one step ahead); the newest tap is added here.
-    float cpn[NC];
-    float vnew = 0.f;
+    // ---- input stage: h0 rows of this CTA (row = i0 + warp), published into every peer's hx[0].
+    // Scatter form again: the sample fed at time tau adds tap (K-1-d) into the partial sum of time tau+d
+    // (cacc ring).  Lane d-1 handles delay d >= 1; delay 0 (the newest tap) is added at publish time from
+    // shared memory.  DSWNV: the older taps are gathered from the L2-resident table with cp.async and
+    // folded in one step later (they are needed one step later at the earliest).
     const int in_row = D.i0 + warp;
     const bool has_in = warp < D.ni;
-    if (has_in && is_c) vnew = __ldg(P.in_tab + ((K - 1) * 2 + 1) * H + in_row);
-    auto input_partial = [&](int itn) {                             // for time itn, taps j < K-1
-        if (!has_in) return;
+    const float in_b = has_in ? __ldg(P.in_bias + in_row) : 0.f;
+    auto fold_stage = [&](int tau) {                                // fold the gathers issued for the sample of time tau
+        if (!has_in || is_c || lane >= K - 1 || tau < 0) return;
+        const int d = lane + 1;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            float acc = __ldg(P.in_bias + in_row);
-            if (is_c) acc += __ldg(P.in_tab + ((K - 1) * 2) * H + in_row);       // cb of the newest tap (always valid)
-            for (int j = 0; j + 1 < K; ++j) {
-                const int tau = itn - (K - 1) + j;
-                if (tau < 0) continue;                               // conv zero padding
-                const int n = tau - P.R - 1;
-                if (is_c) {
-                    const float a = (n >= -1) ? hist[c * HIST + ((n + HIST) % HIST)] : 0.f;
-                    acc += __ldg(P.in_tab + (j * 2) * H + in_row) + __ldg(P.in_tab + (j * 2 + 1) * H + in_row) * a;
-                } else {
-                    const int q = (n >= -1) ? __float_as_int(hist[c * HIST + ((n + HIST) % HIST)]) : Q / 2;
-                    acc += __ldg(P.in_tab + ((size_t)j * Q + q) * H + in_row);
-                }
-            }
-            cpn[c] = acc;
+            float* dst = cacc + (((tau + d) & 7) * 16 + warp) * NC + c;
+            *dst += cstage[(((tau & 1) * 8 + lane) * 16 + warp) * NC + c];
         }
     };
-    auto input_publish = [&](int itn) {
+    auto feed = [&](int tau) {                                      // the sample of time tau is known (hist)
+        if (!has_in || lane >= K - 1) return;
+        const int d = lane + 1, j = K - 1 - d;
+        const int n = tau - P.R - 1;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (is_c) {
+                const float a = (n >= -1) ? hist[c * HIST + ((n + HIST) & (HIST - 1))] : 0.f;
+                cacc[(((tau + d) & 7) * 16 + warp) * NC + c] += sfir[(j * 2) * 16 + warp] + sfir[(j * 2 + 1) * 16 + warp] * a;
+            } else {
+                const int q = (n >= -1) ? __float_as_int(hist[c * HIST + ((n + HIST) & (HIST - 1))]) : Q / 2;
+                cp_async4(&cstage[(((tau & 1) * 8 + lane) * 16 + warp) * NC + c], P.in_tab + ((size_t)j * Q + q) * H + in_row);
+            }
+        }
+    };
+    auto input_publish = [&](int itn) {                             // h0 of time itn (its own sample is in hist)
         if (!has_in) return;
         const uint32_t tagn = (uint32_t)itn + 1u;
         const int n = itn - P.R - 1;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            float acc = cpn[c];
+            float* slot = cacc + ((itn & 7) * 16 + warp) * NC + c;
+            float acc = in_b + *slot;
             if (is_c) {
-                const float a = (n >= -1) ? hist[c * HIST + ((n + HIST) % HIST)] : 0.f;
-                acc = fmaf(vnew, a, acc);
+                const float a = (n >= -1) ? hist[c * HIST + ((n + HIST) & (HIST - 1))] : 0.f;
+                acc += sfir[((K - 1) * 2) * 16 + warp] + sfir[((K - 1) * 2 + 1) * 16 + warp] * a;
             } else {
-                const int q = (n >= -1) ? __float_as_int(hist[c * HIST + ((n + HIST) % HIST)]) : Q / 2;
+                const int q = (n >= -1) ? __float_as_int(hist[c * HIST + ((n + HIST) & (HIST - 1))]) : Q / 2;
                 acc += sTin[q * nip + warp];
             }
+            __syncwarp();
+            if (lane == 0) *slot = 0.f;                              // the slot is reused 8 steps later
             const float v = softsignf_(acc);
-            if (lane < CORE_CL) st_cluster_ll(hx_peer + (uint32_t)((c * HP + in_row) * 8), v, tagn);
+            if (lane < CORE_CL) st_async_f32(hx_peer + (uint32_t)((c * HP + in_row) * 4), v, mb_peer);
             if (lane == 16 && P.has_help[0])
-                st_ll(P.hin_ll + P.hin_off[0] + ((size_t)(itn % P.hslots[0]) * NC + c) * H + in_row, v, tagn);
+                st_ll(P.hin_ll + P.hin_off[0] + ((itn & (P.hslots[0] - 1)) * NC + c) * H + in_row, v, tagn);
         }
     };
-    for (int l = 0; l < L; ++l) prefetch_gate(l, 0);
-    input_partial(0);
-    input_publish(0);
-    input_partial(1);
+    for (int l = 0; l < L; ++l) prefetch_gate(l, 0, ptab_b);
+    cp_async_commit();
+    int fc = 0, jc = 0;                                            // frame / phase of the current time step
+    input_publish(0);                                              // time 0 sees only its own (padding) sample
+    feed(0);
+    cp_async_commit();
 
     bool ok = true;
     for (int it = 0; it < P.n_it; ++it) {
         const bool active = it >= P.it0;
         const uint32_t tag = (uint32_t)it + 1u;
+        const uint32_t par = (uint32_t)it & 1u;
         const int istep = it - P.it0;
+        const uint32_t hpar = (uint32_t)istep & 1u;                // phase of the head vectors (advance only when active)
         const int t = it;
-        float sk[NC];                                              // running sum of this warp's skip row
+        float sk0[NC], sk1[NC];                                    // running sums of this warp's two skip rows (warps 8-15)
 #pragma unroll
-        for (int c = 0; c < NC; ++c) sk[c] = 0.f;
+        for (int c = 0; c < NC; ++c) { sk0[c] = 0.f; sk1[c] = 0.f; }
         float w[TCOLS];
-        if (has_pair) tmem_ld<TCOLS>(taddr0 + P.tap_base[0] * TCOLS, w);
-        float gq = 1.f;
-        if (t >= P.R) gq = __ldg(P.gain + (t - P.R) % P.U); else gq = __ldg(P.gain);
-        cp_async_wait_all();                                       // gate operands of this step (issued one step ago)
+        if (warp < 4) tmem_ldw<TCOLS>(taddr0 + P.tap_base[0] * TCOLS, w);
+        long long hwait = 0;
+        const float gq = __ldg(P.gain + jc);
+        int fn = fc, jn = jc;                                      // frame / phase of time t+1
+        if (t + 1 > P.R && ++jn == P.U) { jn = 0; ++fn; }
+        const float* prow_next = ptab_b + (size_t)fn * L * twoH;
+        // Gumbel noise of this warp's logit row: independent of the data, so it is drawn before the chain starts
+        float gn[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) gn[c] = 0.f;
+        if (active && !is_c && warp < D.nc) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int bglob = min(c, P.B - 1);
+                const float q = P.noise ? __ldg(P.noise + ((size_t)bglob * P.n_out + istep) * Q + D.c0 + warp)
+                                        : softmax_q(P.seed, bglob, istep, D.c0 + warp);
+                gn[c] = -logf(q);
+            }
+        }
+        cp_async_wait_all();                                       // gate operands / table entries issued one step ago
         __syncwarp();
+        fold_stage(it);                                            // table entries gathered for the sample of time `it`
+        __syncthreads();                                           // pre[] (written by warps 4-7) is read by warps 0-3
         SWN_CPROF(0);
         for (int l = 0; l < L; ++l) {
-            // ---- gate operands that do not depend on the layer input
+            const bool ld1 = P.dil[l] == 1;
+            // ---- chain warps: gate operands that do not depend on the layer input (one pair group = 8 lanes)
             float pz = 0.f, pc = 0.f, hz = 0.f, hcv = 0.f, rz = 0.f, rc = 0.f, bz = 0.f, bc = 0.f;
-            if (has_pair && col < NC) {
-                const PreSlot ps = pre[(((size_t)(t & 1) * L + l) * 16 + warp) * NC + col];
-                pz = fmaf(gq, ps.pz, __ldg(P.pconst + l * twoH + my_i));
-                pc = fmaf(gq, ps.pc, __ldg(P.pconst + l * twoH + H + my_i));
-                bz = __ldg(bias + (l * np + warp) * 2); bc = __ldg(bias + (l * np + warp) * 2 + 1);
+            if (warp < 4 && pvalid && sub < NC) {
+                const PreSlot ps = pre[((par * L + l) * 16 + plocal) * NC + sub];
+                const float4 c4 = lc[l * 16 + plocal];
+                pz = fmaf(gq, ps.pz, c4.x); pc = fmaf(gq, ps.pc, c4.y); bz = c4.z; bc = c4.w;
                 if (P.has_help[l] && t >= P.hdmin[l]) {
                     uint32_t a = (uint32_t)ps.hz, b = (uint32_t)ps.hc;
-                    if ((uint32_t)(ps.hz >> 32) != (uint32_t)t + 1u || (uint32_t)(ps.hc >> 32) != (uint32_t)t + 1u) {
+                    if ((uint32_t)(ps.hz >> 32) != tag || (uint32_t)(ps.hc >> 32) != tag) {
                         // the helper was late when the prefetch was issued: wait for it here
-                        const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + ((size_t)(t % P.hacc_nt[l]) * twoH) * NC;
-                        ok = wait_gword(src + (size_t)my_i * NC + col, (uint32_t)t + 1u, a, P, 400 + l) && ok;
-                        ok = wait_gword(src + (size_t)(H + my_i) * NC + col, (uint32_t)t + 1u, b, P, 400 + l) && ok;
+                        const long long tw0 = clock64();
+                        const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + ((t & (P.hacc_nt[l] - 1)) * twoH + my_i) * NC + sub;
+                        ok = wait_gword(src, tag, a, P, 400 + l) && ok;
+                        ok = wait_gword(src + H * NC, tag, b, P, 400 + l) && ok;
+                        hwait += clock64() - tw0;
                     }
                     hz = __uint_as_float(a); hcv = __uint_as_float(b);
                 }
-                if (P.dil[l] == 1) {
-                    const float* r0 = ring + (((size_t)(l * 2 + (t & 1)) * 16 + warp) * 2) * BS + col;
+                if (ld1) {
+                    const float* r0 = ring + (((l * 2 + (int)par) * 16 + plocal) * 2) * BS + sub;
                     rz = r0[0]; rc = r0[BS];
                 }
             }
-            // ---- wait for the layer input in local shared memory
+            // ---- sleep until the layer input has landed in local shared memory
+            ok = mbar_wait(mb + l, par, P, 500 + l) && ok;
+            if (!__all_sync(0xffffffffu, ok)) { ok = false; break; }
+            if (tid == 0) mbar_arm(mb + l, bytes_h);               // next phase (next time step)
+            if (l < 6) SWN_CPROF(1 + l);
             float2 h[NC][NCH];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) ok = wait_vec<NCH>(hx + ((size_t)l * NC + c) * HP, tag, h[c], lane, P, 500 + l) && ok;
-            if (!__all_sync(0xffffffffu, ok)) { ok = false; break; }
-            if (has_pair) {
+            for (int c = 0; c < NC; ++c) load_frag<NCH>(h[c], hx + (l * NC + c) * HP, lane);
+            if (warp < 4) {
+                // ================= chain warp: delay-0 tap of 4 gate pairs, gate, publish =================
                 tmem_wait_ld();
-                float myz = 0.f, myc = 0.f;
+                float hn = 0.f;                                    // lane (pair group, sub = column) ends up with its value
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    float az = 0.f, ac = 0.f, bz2 = 0.f, bc2 = 0.f;
+                    float v8[8];
 #pragma unroll
-                    for (int cc = 0; cc < NCH; ++cc) {
-                        az = fmaf(w[2 * cc], h[c][cc].x, az); bz2 = fmaf(w[2 * cc + 1], h[c][cc].y, bz2);
-                        ac = fmaf(w[FPT + 2 * cc], h[c][cc].x, ac); bc2 = fmaf(w[FPT + 2 * cc + 1], h[c][cc].y, bc2);
+                    for (int rr = 0; rr < 8; ++rr) {
+                        float a = 0.f, b = 0.f;
+#pragma unroll
+                        for (int cc = 0; cc < NCH; ++cc) {
+                            a = fmaf(w[rr * FPT + 2 * cc], h[c][cc].x, a);
+                            b = fmaf(w[rr * FPT + 2 * cc + 1], h[c][cc].y, b);
+                        }
+                        v8[rr] = a + b;
                     }
-                    const float vz = warp_sum(az + bz2), vc = warp_sum(ac + bc2);
-                    if (lane == c) { myz = vz; myc = vc; }
+                    const float mine = reduce8(v8, lane);          // lane holds row (lane >> 2): even = z, odd = candidate
+                    const float other = __shfl_xor_sync(0xffffffffu, mine, 4);
+                    const float qz = (lane & 4) ? other : mine, qc = (lane & 4) ? mine : other;
+                    if (sub == c) {
+                        // ---- gate (cswnv_shift1.py:281-285)
+                        const float gz = (qz + bz + rz + hz) * pz;
+                        const float gc = (qc + bc + rc + hcv) * pc;
+                        const float z = sigmoidf_(gz);
+                        const float carry = hx[(l * NC + c) * HP + (pvalid ? my_i : 0)];
+                        hn = (1.f - z) * tanhf(gc) + z * carry;
+                    }
                 }
-                // ---- gate (cswnv_shift1.py:281-285); lane c holds column c
-                float hn = 0.f;
-                if (col < NC) {
-                    const float gz = (myz + bz + rz + hz) * pz;
-                    const float gc = (myc + bc + rc + hcv) * pc;
-                    const float z = sigmoidf_(gz);
-                    const float carry = __uint_as_float((uint32_t)ld_smem_ll(hx + ((size_t)l * NC + col) * HP + my_i));
-                    hn = (1.f - z) * tanhf(gc) + z * carry;
-                }
-                // ---- fan out: lanes 0..15 write the value into the 16 CTAs, lane 16 feeds the helpers
+                // ---- fan out: in every pair group, lane sub writes CTAs sub and sub+8; lane sub==0 feeds the helpers
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    const float v = __shfl_sync(0xffffffffu, hn, c);
-                    if (lane < CORE_CL) st_cluster_ll(hx_peer + (uint32_t)((((l + 1) * NC + c) * HP + my_i) * 8), v, tag);
-                    if (lane == 16 && l + 1 < L && P.has_help[l + 1])
-                        st_ll(P.hin_ll + P.hin_off[l + 1] + ((size_t)(it % P.hslots[l + 1]) * NC + c) * H + my_i, v, tag);
+                    const float v = __shfl_sync(0xffffffffu, hn, (lane & 24) + c);
+                    if (pvalid) {
+                        const uint32_t off = (uint32_t)((((l + 1) * NC + c) * HP + my_i) * 4);
+                        const uint32_t mbo = (uint32_t)((l + 1) * 8);
+                        st_async_f32(hxp0 + off, v, mbp0 + mbo);
+                        st_async_f32(hxp1 + off, v, mbp1 + mbo);
+                        if (sub == 0 && l + 1 < L && P.has_help[l + 1])
+                            st_ll(P.hin_ll + P.hin_off[l + 1] + ((it & (P.hslots[l + 1] - 1)) * NC + c) * H + my_i, v, tag);
+                    }
                 }
-                // ---- off the critical path: prefetch next step's gate operands, the delay-1 tap, next layer's tap
-                prefetch_gate(l, t + 1);
-                if (P.dil[l] == 1 && K >= 2) {
-                    float w1[TCOLS];
-                    tmem_ld<TCOLS>(taddr0 + (P.tap_base[l] + 1) * TCOLS, w1);
+                if (l + 1 < L) tmem_ldw<TCOLS>(taddr0 + P.tap_base[l + 1] * TCOLS, w);
+            } else if (warp < 8) {
+                // ================= delay-1 tap of dilation-1 layers (for the next step) + operand prefetch =================
+                prefetch_gate(l, t + 1, prow_next);
+                if (ld1 && K >= 2) {
+                    tmem_ldw<TCOLS>(taddr0 + (P.tap_base[l] + 1) * TCOLS, w);
                     tmem_wait_ld();
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
-                        float az = 0.f, ac = 0.f;
+                        float v8[8];
 #pragma unroll
-                        for (int cc = 0; cc < NCH; ++cc) {
-                            az = fmaf(w1[2 * cc], h[c][cc].x, az); az = fmaf(w1[2 * cc + 1], h[c][cc].y, az);
-                            ac = fmaf(w1[FPT + 2 * cc], h[c][cc].x, ac); ac = fmaf(w1[FPT + 2 * cc + 1], h[c][cc].y, ac);
+                        for (int rr = 0; rr < 8; ++rr) {
+                            float a = 0.f, b = 0.f;
+#pragma unroll
+                            for (int cc = 0; cc < NCH; ++cc) {
+                                a = fmaf(w[rr * FPT + 2 * cc], h[c][cc].x, a);
+                                b = fmaf(w[rr * FPT + 2 * cc + 1], h[c][cc].y, b);
+                            }
+                            v8[rr] = a + b;
                         }
-                        const float vz = warp_sum(az), vc = warp_sum(ac);
-                        if (lane == c) {
-                            float* r0 = ring + (((size_t)(l * 2 + ((t + 1) & 1)) * 16 + warp) * 2) * BS + c;
-                            r0[0] = vz; r0[BS] = vc;
-                        }
+                        const float mine = reduce8(v8, lane);
+                        if ((lane & 3) == 0 && pvalid)             // row (lane >> 2) = 2 * pair slot + {z, c}
+                            ring[(((l * 2 + (int)(par ^ 1u)) * 16 + plocal) * 2 + ((lane >> 2) & 1)) * BS + c] = mine;
                     }
                 }
-                if (l + 1 < L) tmem_ld<TCOLS>(taddr0 + P.tap_base[l + 1] * TCOLS, w);
-            } else {
-                cp_async_commit();                                 // keep the group count uniform
-            }
-            // ---- skip row of this warp: out_skip[l-1] applied to the input of layer l
-            if (active && l >= 1 && warp < D.nskip) {
-                float2 ws[NCH];
-                load_frag<NCH>(ws, sSkip + ((size_t)(l - 1) * D.nskip + warp) * HP, lane);
+            } else if (active && l >= 1) {
+                // ================= two rows of out_skip[l-1] applied to the input of layer l =================
+                if (skr0 < D.nskip) {
+                    float2 ws[NCH];
+                    load_frag<NCH>(ws, sSkip + ((l - 1) * D.nskip + skr0) * HP, lane);
 #pragma unroll
-                for (int c = 0; c < NC; ++c) sk[c] += dot_frag<NCH>(ws, h[c]);
+                    for (int c = 0; c < NC; ++c) sk0[c] += dot_frag<NCH>(ws, h[c]);
+                }
+                if (skr1 < D.nskip) {
+                    float2 ws[NCH];
+                    load_frag<NCH>(ws, sSkip + ((l - 1) * D.nskip + skr1) * HP, lane);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) sk1[c] += dot_frag<NCH>(ws, h[c]);
+                }
             }
             __syncwarp();
         }
+        cp_async_commit();
         if (__syncthreads_or(!ok)) { ok = false; break; }
-        SWN_CPROF(1);
+        SWN_CPROF(7);
+        if (P.prof && threadIdx.x == 0 && it >= P.prof_start && it < P.prof_start + P.prof_count)
+            P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + 13] = (unsigned long long)hwait;
+        // the output of the last layer (always consumed, so that its barrier advances every step)
+        ok = mbar_wait(mb + L, par, P, 510) && ok;
+        if (tid == 0) mbar_arm(mb + L, bytes_h);
         if (active) {
             // ---- out_skip[L-1] on the output of the last layer; relu(sum of skips) -> x1 on every CTA
-            {
+            if (warp >= 8) {
                 float2 hl[NC][NCH];
 #pragma unroll
-                for (int c = 0; c < NC; ++c) ok = wait_vec<NCH>(hx + ((size_t)L * NC + c) * HP, tag, hl[c], lane, P, 510) && ok;
-                if (warp < D.nskip) {
-                    float2 ws[NCH];
-                    load_frag<NCH>(ws, sSkip + ((size_t)(L - 1) * D.nskip + warp) * HP, lane);
-                    const float cst = __ldg(P.wbuf + D.skipc_off + warp);
+                for (int c = 0; c < NC; ++c) load_frag<NCH>(hl[c], hx + (L * NC + c) * HP, lane);
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        const float v = warp_sum(sk[c] + dot_frag<NCH>(ws, hl[c])) + cst;
-                        if (lane < CORE_CL) st_cluster_ll(x1_peer + (uint32_t)((c * Sp + D.skip0 + warp) * 8), fmaxf(v, 0.f), tag);
+                for (int half = 0; half < 2; ++half) {
+                    const int row = half ? skr1 : skr0;
+                    if (row < D.nskip) {
+                        float2 ws[NCH];
+                        load_frag<NCH>(ws, sSkip + ((L - 1) * D.nskip + row) * HP, lane);
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            const float v = warp_sum((half ? sk1[c] : sk0[c]) + dot_frag<NCH>(ws, hl[c])) + (half ? cst1 : cst0);
+                            if (lane < CORE_CL)
+                                st_async_f32(x1_peer + (uint32_t)((c * Sp + D.skip0 + row) * 4), fmaxf(v, 0.f), mb_peer + (uint32_t)((L + 1) * 8));
+                        }
                     }
                 }
             }
-            SWN_CPROF(2);
+            SWN_CPROF(8);
             // ---- out_1 row of this warp (relu) -> x2 on every CTA
             if (warp < D.nb) {
+                ok = mbar_wait(mb_x1, hpar, P, 520) && ok;
                 float acc1[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) acc1[c] = 0.f;
                 for (int cc = 0; cc < (Sp >> 6); ++cc) {
                     const float2 wv = reinterpret_cast<const float2*>(sW1 + (size_t)warp * Sp)[cc * 32 + lane];
-                    const bool pad = (cc * 64 + 2 * lane) >= S, pad1 = (cc * 64 + 2 * lane + 1) >= S;   // never written
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
-                        const unsigned long long* p = x1 + (size_t)c * Sp + cc * 64 + 2 * lane;
-                        ulonglong2 v;
-                        ok = wait_pair(p, tag, pad, pad1, v, P, 520) && ok;
-                        acc1[c] = fmaf(wv.x, __uint_as_float((uint32_t)v.x), acc1[c]);
-                        acc1[c] = fmaf(wv.y, __uint_as_float((uint32_t)v.y), acc1[c]);
+                        const float2 v = reinterpret_cast<const float2*>(x1 + (size_t)c * Sp)[cc * 32 + lane];
+                        acc1[c] = fmaf(wv.x, v.x, acc1[c]);
+                        acc1[c] = fmaf(wv.y, v.y, acc1[c]);
                     }
                 }
-                const float b1 = __ldg(P.wbuf + D.b1_off + warp);
+                const float b1 = b1w;
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     const float v = warp_sum(acc1[c]) + b1;
-                    if (lane < CORE_CL) st_cluster_ll(x2_peer + (uint32_t)((c * n1p + D.b0 + warp) * 8), fmaxf(v, 0.f), tag);
+                    if (lane < CORE_CL)
+                        st_async_f32(x2_peer + (uint32_t)((c * n1p + D.b0 + warp) * 4), fmaxf(v, 0.f), mb_peer + (uint32_t)((L + 2) * 8));
                 }
             }
-            SWN_CPROF(3);
+            SWN_CPROF(9);
             // ---- out_2 rows
+            if (warp < D.nc) ok = mbar_wait(mb_x2, hpar, P, 530) && ok;
             for (int r = warp; r < D.nc; r += SWN_NWARPS) {
                 float acc2[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) acc2[c] = 0.f;
                 for (int cc = 0; cc < (n1p >> 6); ++cc) {
                     const float2 wv = reinterpret_cast<const float2*>(sW2 + (size_t)r * n1p)[cc * 32 + lane];
-                    const bool pad = (cc * 64 + 2 * lane) >= n1, pad1 = (cc * 64 + 2 * lane + 1) >= n1;
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
-                        const unsigned long long* p = x2 + (size_t)c * n1p + cc * 64 + 2 * lane;
-                        ulonglong2 v;
-                        ok = wait_pair(p, tag, pad, pad1, v, P, 530) && ok;
-                        acc2[c] = fmaf(wv.x, __uint_as_float((uint32_t)v.x), acc2[c]);
-                        acc2[c] = fmaf(wv.y, __uint_as_float((uint32_t)v.y), acc2[c]);
+                        const float2 v = reinterpret_cast<const float2*>(x2 + (size_t)c * n1p)[cc * 32 + lane];
+                        acc2[c] = fmaf(wv.x, v.x, acc2[c]);
+                        acc2[c] = fmaf(wv.y, v.y, acc2[c]);
                     }
                 }
-                const float b2 = __ldg(P.wbuf + D.b2_off + r);
+                const float b2 = (r == warp) ? b2w : __ldg(P.wbuf + D.b2_off + r);
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     const float o = warp_sum(acc2[c]) + b2;
@@ -660,10 +809,15 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                     } else {
                         const int row = D.c0 + r;
                         if (lane == 0 && P.head_out && c < P.B) P.head_out[((size_t)c * P.n_iter + istep) * n2 + row] = o;
-                        const float q = P.noise ? P.noise[((size_t)bglob * P.n_out + istep) * Q + row]
-                                                : softmax_q(P.seed, bglob, istep, row);
-                        const float g = o - logf(q);
-                        if (lane < CORE_CL) st_cluster_ll(gx_peer + (uint32_t)((c * 256 + row) * 8), g, tag);
+                        float g;
+                        if (r == warp) {
+                            g = o + gn[c];
+                        } else {
+                            const float q = P.noise ? P.noise[((size_t)bglob * P.n_out + istep) * Q + row]
+                                                    : softmax_q(P.seed, bglob, istep, row);
+                            g = o - logf(q);
+                        }
+                        if (lane < CORE_CL) st_async_f32(gx_peer + (uint32_t)((c * 256 + row) * 4), g, mb_peer + (uint32_t)((L + 3) * 8));
                     }
                 }
             }
@@ -684,17 +838,15 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                 }
             } else if (warp == 0) {
                 // ---- argmax over the 256 published Gumbel scores (first maximum wins), one warp per CTA
+                ok = mbar_wait(mb_gx, hpar, P, 540) && ok;
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     float best = -CUDART_INF_F; int bi = 0x7fffffff;
                     for (int r0 = 0; r0 < Q; r0 += 64) {
-                        const unsigned long long* p = gx + (size_t)c * 256 + r0 + 2 * lane;
-                        ulonglong2 v;
-                        ok = wait_pair(p, tag, false, false, v, P, 540) && ok;
-                        const float g0 = __uint_as_float((uint32_t)v.x), g1 = __uint_as_float((uint32_t)v.y);
+                        const float2 v = reinterpret_cast<const float2*>(gx + (size_t)c * 256 + r0)[lane];
                         const int i0 = r0 + 2 * lane;
-                        if (g0 > best) { best = g0; bi = i0; }
-                        if (g1 > best) { best = g1; bi = i0 + 1; }
+                        if (v.x > best) { best = v.x; bi = i0; }
+                        if (v.y > best) { best = v.y; bi = i0 + 1; }
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
@@ -713,13 +865,18 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                 }
             }
             if (__syncthreads_or(!ok)) { ok = false; break; }
+            // every consumer of this step's head vectors is past them: arm their next phase
+            if (tid == 0) { mbar_arm(mb_x1, bytes_x1); mbar_arm(mb_x2, bytes_x2); if (!is_c) mbar_arm(mb_gx, bytes_gx); }
         }
-        SWN_CPROF(4);
+        SWN_CPROF(10);
         if (it + 1 < P.n_it) {
             input_publish(it + 1);
-            input_partial(it + 2);
+            SWN_CPROF(11);
+            feed(it + 1);
+            cp_async_commit();
         }
-        SWN_CPROF(5);
+        SWN_CPROF(12);
+        fc = fn; jc = jn;
     }
     // ---- teardown
     cp_async_wait_all();

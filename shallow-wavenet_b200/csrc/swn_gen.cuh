@@ -44,15 +44,14 @@ __device__ __forceinline__ void st_ll_u32(unsigned long long* p, uint32_t val, u
 }
 
 // Spin until the word carries `tag`; returns false when the watchdog fired or another CTA
-// aborted (every caller funnels the result through __syncthreads_or and leaves).
-__device__ __forceinline__ bool ll_wait(const unsigned long long* p, uint32_t tag, uint32_t& payload,
-                                        const GenParams& P, int where) {
-    unsigned long long v = ld_ll(p);
-    if ((uint32_t)(v >> 32) == tag) { payload = (uint32_t)v; return true; }
+// aborted (every caller funnels the result through __syncthreads_or and leaves).  The slow path is
+// kept out of line: the persistent loops are latency-bound and must stay instruction-cache resident.
+static __device__ __noinline__ bool ll_wait_slow(const unsigned long long* p, uint32_t tag, uint32_t& payload,
+                                          const GenParams& P, int where) {
     long long t_start = clock64();
     uint32_t spins = 0;
     for (;;) {
-        v = ld_ll(p);
+        const unsigned long long v = ld_ll(p);
         if ((uint32_t)(v >> 32) == tag) { payload = (uint32_t)v; return true; }
         if (((++spins) & 255u) == 0) {
             volatile int32_t* st = P.status;
@@ -63,6 +62,12 @@ __device__ __forceinline__ bool ll_wait(const unsigned long long* p, uint32_t ta
             }
         }
     }
+}
+__device__ __forceinline__ bool ll_wait(const unsigned long long* p, uint32_t tag, uint32_t& payload,
+                                        const GenParams& P, int where) {
+    const unsigned long long v = ld_ll(p);
+    if ((uint32_t)(v >> 32) == tag) { payload = (uint32_t)v; return true; }
+    return ll_wait_slow(p, tag, payload, P, where);
 }
 
 // Cheap first phase of a wait: lane 0 of the warp watches ONE word of the vector with a sleep
@@ -88,7 +93,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define SWN_PROF(ev)                                                                              \
     do {                                                                                          \
         if (P.prof && threadIdx.x == 0 && it >= P.prof_start && it < P.prof_start + P.prof_count) \
-            P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 8 + (ev)] = gtime();  \
+            P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + (ev)] = gtime();  \
     } while (0)
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -147,7 +152,7 @@ __device__ __host__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
 // uniform in [0,1) with 24 bits
 __device__ __host__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 // the uniform number the sampler draws for (utterance b, generated sample n, lane r)
-__device__ __host__ __forceinline__ float philox_uniform(unsigned long long seed, long long b, long long n, int r) {
+static __device__ __host__ __noinline__ float philox_uniform(unsigned long long seed, long long b, long long n, int r) {
     uint32_t o[4];
     philox4x32_10((uint32_t)n, (uint32_t)((unsigned long long)n >> 32), (uint32_t)b, (uint32_t)(r >> 2),
                   (uint32_t)seed, (uint32_t)(seed >> 32), o);
@@ -371,7 +376,7 @@ __device__ void layer_cta(const GenParams& P, const CtaDesc& D, float* smem) {
 // ------------------------------------------------------------------ head CTA
 // Laplace / LPC sampler of one utterance for one loop step (cswnv_shift1.py:368-391).
 template <int SEG>
-__device__ __forceinline__ void laplace_step(const int lpc, const float* o, float* lp, const float* eps,
+static __device__ __noinline__ void laplace_step(const int lpc, const float* o, float* lp, const float* eps,
                                              const float* forced, float* smp) {
     float l[8];
 #pragma unroll

@@ -80,7 +80,7 @@ class Engine(object):
         a.batch_tile = int(batch_tile)
         a.poll_mode = int(poll_mode)
         a.kernel_sel = int(kernel_sel) or int(os.environ.get("SWN_KERNEL_SEL", "0"))   # debugging aid
-        if prof is not None:       # int64 CUDA tensor [count, grid, 8]
+        if prof is not None:       # int64 CUDA tensor [count, grid, 32]
             keep.append(prof)
             a.prof_dev = prof.data_ptr()
             a.prof_start = int(prof_start)

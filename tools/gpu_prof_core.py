@@ -1,0 +1,44 @@
+"""Timeline of the v2 cluster kernel (core CTAs) from %globaltimer stamps; also prints throughput."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+import bench
+from shallow_wavenet_b200 import synth
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2s"
+kind, fs, over, B, frames, desc = bench.WORKLOADS[wl]
+kw = bench.model_kwargs(kind, fs, over)
+model = synth.make_model(kind, **kw).cuda()
+aux = torch.from_numpy(synth.synth_aux(kw["n_aux"], frames, B)).cuda()
+eng = model.engine()
+n = frames * kw["upsampling_factor"]
+for sel in (2, 1):
+    eng.condition(aux)
+    try:
+        eng.generate(n, seed=1, kernel_sel=sel)
+    except Exception as e:
+        print("kernel_sel", sel, "failed:", e); continue
+    grid = eng.info["grid"]
+    cnt = 64
+    prof = torch.zeros((cnt, grid, 32), dtype=torch.int64, device="cuda")
+    eng.condition(aux)
+    eng.generate(n, seed=1, kernel_sel=sel, prof=prof, prof_start=3000)
+    info = eng.info
+    steps = n + info["receptive_field"] + 1
+    print("== %s kernel_variant=%d kernel %.2f ms, %.3f us/step, %.0f samples/s (RTF %.1f), grid %d smem %d" % (
+        wl, info["kernel_variant"], info["last_gen_ms"], info["last_gen_ms"] * 1e3 / steps, B * n / info["last_gen_ms"] * 1e3,
+        B * n / info["last_gen_ms"] * 1e3 / fs, grid, info["smem_bytes"]))
+    if info["kernel_variant"] != 2:
+        continue
+    pall = prof.cpu().numpy().astype(np.float64)[8:-1, :16]
+    p = pall[:, :, :14]      # core CTAs
+    base = p[:, :, 0].min(axis=1, keepdims=True)[:, :, None]
+    rel = p - base
+    names = ["iter start", "L0 input ready", "L1 input ready", "L2 input ready", "L3 input ready", "L4 input ready", "L5 input ready",
+             "layers done", "x1 published", "x2 published", "sampled", "next h0 published", "next partial done"]
+    print("   helper-wait cycles in layer loop (thread 0 of each core CTA): mean %.0f" % p[:, :, 13].mean())
+    per = np.diff(p[:, 0, 0]).mean()
+    print("   step period %.0f ns" % per)
+    for e, nme in enumerate(names):
+        print("   %-20s mean %.0f ns  (min CTA %.0f, max CTA %.0f)" % (nme, rel[:, :, e].mean(), rel[:, :, e].mean(0).min(), rel[:, :, e].mean(0).max()))

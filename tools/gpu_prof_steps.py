@@ -20,7 +20,7 @@ for mode in modes:
     eng.generate(n, seed=1, poll_mode=mode)           # warm
     grid = eng.info["grid"]
     cnt = 64
-    prof = torch.zeros((cnt, grid, 4), dtype=torch.int64, device="cuda")
+    prof = torch.zeros((cnt, grid, 32), dtype=torch.int64, device="cuda")
     eng.condition(aux)
     out, _ = eng.generate(n, seed=1, poll_mode=mode, prof=prof, prof_start=3000)
     info = eng.info
