@@ -282,7 +282,9 @@ def main():
             pass
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
         flops = 2.0 * macs * B * n_gen / (kern_ms * 1e-3)
-        roofline = {"bound": "smem", "kernel": "swn_generate_kernel (persistent, 1 launch per step)",
+        kname = {1: "swn_generate_kernel (layer groups over the chip, persistent)",
+                 2: "swn_core_kernel (16-CTA core cluster + helper CTAs, persistent)"}.get(info.get("kernel_variant"), "?")
+        roofline = {"bound": "smem", "kernel": kname + ", 1 launch per step",
                     "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
                     "peak_source": "measured live: aggregate LDS.128 bandwidth, 1 CTA/SM (swn_measure_smem_bandwidth)",
                     "algorithmic_bytes_per_time_step": weight_bytes, "time_steps_per_launch": seg_steps * n_slots,
@@ -300,7 +302,8 @@ def main():
                              "d2h_bytes_per_step": int(B * n_gen * (4 if kind == "cswnv" else 8)),
                              "api": "%s.batch_fast_generate(pinned host aux) -> list of numpy arrays" % ("CSWNV" if kind == "cswnv" else "DSWNV")},
                      "gpu_launches": int(launches),
-                     "plan": {k: info[k] for k in ("n_sm", "ctas_per_layer", "head_ctas", "smem_bytes", "batch_tile", "n_slots")}})
+                     "plan": {k: info[k] for k in ("kernel_variant", "grid", "n_sm", "ctas_per_layer", "head_ctas", "smem_bytes",
+                                                   "batch_tile", "n_slots")}})
         if not args.no_cpu_baseline and world >= 1:
             threads = os.cpu_count() or 1
             sf = args.cpu_sample_frames or (40 if kind == "dswnv" else 20)

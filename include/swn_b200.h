@@ -89,8 +89,8 @@ typedef struct swn_info {
     int32_t eff_seg;          /* samples per loop step */
     int32_t head_dim;
     int32_t n_sm;             /* SMs used by the persistent kernel */
-    int32_t ctas_per_layer;
-    int32_t head_ctas;
+    int32_t ctas_per_layer;   /* variant 1: CTAs per layer group; variant 2: CTAs of the core cluster (16) */
+    int32_t head_ctas;        /* variant 1: head CTAs; variant 2: helper CTAs */
     int32_t smem_bytes;       /* dynamic shared memory per CTA of the last launch */
     int32_t batch_tile;       /* of the last launch */
     int32_t n_slots;          /* pipeline slots (ceil(B / batch_tile)) of the last launch */

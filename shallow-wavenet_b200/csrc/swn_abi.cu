@@ -338,6 +338,8 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
     m->info.n_slots = 1;
     m->info.grid = m->core_grid;
     m->info.kernel_variant = 2;
+    m->info.ctas_per_layer = swn::CORE_CL;          // the core cluster; the other CTAs are helpers
+    m->info.head_ctas = m->core_n_help;
     return 0;
 }
 
@@ -928,6 +930,8 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
     m->info.batch_tile = BS;
     m->info.n_slots = M;
     m->info.kernel_variant = 1;
+    m->info.ctas_per_layer = m->Geff;
+    m->info.head_ctas = m->NH;
     return 0;
 }
 
