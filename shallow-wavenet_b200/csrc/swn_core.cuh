@@ -649,7 +649,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
             if (warp < 4) {
                 // ================= chain warp: delay-0 tap of 4 gate pairs, gate, publish =================
                 tmem_wait_ld();
-                float hn = 0.f;                                    // lane (pair group, sub = column) ends up with its value
+                float myqz = 0.f, myqc = 0.f;                      // lane (pair group, sub = column) keeps its column's sums
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     float v8[8];
@@ -666,14 +666,20 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                     const float mine = reduce8(v8, lane);          // lane holds row (lane >> 2): even = z, odd = candidate
                     const float other = __shfl_xor_sync(0xffffffffu, mine, 4);
                     const float qz = (lane & 4) ? other : mine, qc = (lane & 4) ? mine : other;
-                    if (sub == c) {
-                        // ---- gate (cswnv_shift1.py:281-285)
-                        const float gz = (qz + bz + rz + hz) * pz;
-                        const float gc = (qc + bc + rc + hcv) * pc;
-                        const float z = sigmoidf_(gz);
-                        const float carry = hx[(l * NC + c) * HP + (pvalid ? my_i : 0)];
-                        hn = (1.f - z) * tanhf(gc) + z * carry;
-                    }
+                    if (sub == c) { myqz = qz; myqc = qc; }
+                }
+                // ---- gate (cswnv_shift1.py:281-285), all columns at once (lane sub = column sub)
+                float hn = 0.f;
+                if (sub < NC) {
+                    const float gz = (myqz + bz + rz + hz) * pz;
+                    const float gc = (myqc + bc + rc + hcv) * pc;
+                    // sigmoid / tanh through ex2.approx + rcp (abs. error ~1e-7, inside the 1e-4 head tolerance);
+                    // both exponentials are independent, so their latencies overlap
+                    const float ez = __expf(-gz), ec = __expf(-2.f * fabsf(gc));
+                    const float z = __frcp_rn(1.f + ez);
+                    const float th = copysignf((1.f - ec) * __frcp_rn(1.f + ec), gc);
+                    const float carry = hx[(l * NC + sub) * HP + (pvalid ? my_i : 0)];
+                    hn = (1.f - z) * th + z * carry;
                 }
                 // ---- fan out: in every pair group, lane sub writes CTAs sub and sub+8; lane sub==0 feeds the helpers
 #pragma unroll
@@ -786,38 +792,29 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
             SWN_CPROF(9);
             // ---- out_2 rows
             if (warp < D.nc) ok = mbar_wait(mb_x2, hpar, P, 530) && ok;
-            for (int r = warp; r < D.nc; r += SWN_NWARPS) {
+            if (warp < D.nc) {
+                const int r = warp;
                 float acc2[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) acc2[c] = 0.f;
                 for (int cc = 0; cc < (n1p >> 6); ++cc) {
-                    const float2 wv = reinterpret_cast<const float2*>(sW2 + (size_t)r * n1p)[cc * 32 + lane];
+                    const float2 wv = reinterpret_cast<const float2*>(sW2 + r * n1p)[cc * 32 + lane];
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
-                        const float2 v = reinterpret_cast<const float2*>(x2 + (size_t)c * n1p)[cc * 32 + lane];
+                        const float2 v = reinterpret_cast<const float2*>(x2 + c * n1p)[cc * 32 + lane];
                         acc2[c] = fmaf(wv.x, v.x, acc2[c]);
                         acc2[c] = fmaf(wv.y, v.y, acc2[c]);
                     }
                 }
-                const float b2 = (r == warp) ? b2w : __ldg(P.wbuf + D.b2_off + r);
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    const float o = warp_sum(acc2[c]) + b2;
-                    const int bglob = min(c, P.B - 1);
+                    const float o = warp_sum(acc2[c]) + b2w;
                     if (is_c) {
                         if (lane == 0) o2[c * 16 + r] = o;
                     } else {
                         const int row = D.c0 + r;
-                        if (lane == 0 && P.head_out && c < P.B) P.head_out[((size_t)c * P.n_iter + istep) * n2 + row] = o;
-                        float g;
-                        if (r == warp) {
-                            g = o + gn[c];
-                        } else {
-                            const float q = P.noise ? P.noise[((size_t)bglob * P.n_out + istep) * Q + row]
-                                                    : softmax_q(P.seed, bglob, istep, row);
-                            g = o - logf(q);
-                        }
-                        if (lane < CORE_CL) st_async_f32(gx_peer + (uint32_t)((c * 256 + row) * 4), g, mb_peer + (uint32_t)((L + 3) * 8));
+                        if (lane < CORE_CL) st_async_f32(gx_peer + (uint32_t)((c * 256 + row) * 4), o + gn[c], mb_peer + (uint32_t)((L + 3) * 8));
+                        if (lane == 16 && P.head_out && c < P.B) P.head_out[((size_t)c * P.n_iter + istep) * n2 + row] = o;
                     }
                 }
             }
@@ -843,17 +840,17 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                 for (int c = 0; c < NC; ++c) {
                     float best = -CUDART_INF_F; int bi = 0x7fffffff;
                     for (int r0 = 0; r0 < Q; r0 += 64) {
-                        const float2 v = reinterpret_cast<const float2*>(gx + (size_t)c * 256 + r0)[lane];
+                        const float2 v = reinterpret_cast<const float2*>(gx + c * 256 + r0)[lane];
                         const int i0 = r0 + 2 * lane;
                         if (v.x > best) { best = v.x; bi = i0; }
                         if (v.y > best) { best = v.y; bi = i0 + 1; }
                     }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-                    }
+                    // warp arg-max with the integer reduction unit: order-preserving key, redux.max, then the
+                    // smallest index among the lanes that hold the maximum (first maximum wins, as torch.argmax)
+                    uint32_t key = __float_as_uint(best);
+                    key = (key & 0x80000000u) ? ~key : (key | 0x80000000u);
+                    const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+                    bi = (int)__reduce_min_sync(0xffffffffu, key == kmax ? (uint32_t)bi : 0xffffffffu);
                     if (lane == 0) {
                         int fed = bi;
                         if (c < P.B) {
