@@ -163,6 +163,94 @@ void split_range(int n, int parts, int i, int* lo, int* cnt) {
 }  // namespace
 
 
+// ---- v1 packing: L layer groups of `geff` CTAs + NH head CTAs (weights of a head group are shared by all head groups)
+static int pack_v1(swn_model* m, int geff) {
+    const swn_config& c = m->cfg;
+    const bool is_c = c.kind == SWN_KIND_CSWNV;
+    const int H = m->H, Hp = m->Hp, S = m->S, Sp = m->Sp, K = m->K, L = m->L;
+    const int n1 = m->n1, n1p = m->n1p, n2 = m->n2, twoH = 2 * H;
+    const HostTensor *x, *y;
+    m->Geff = geff;
+    // ---------------- in-loop weights, packed per CTA
+    std::vector<float>& W = m->wbuf_h;
+    W.clear();
+    auto alloc = [&](size_t n) { size_t off = (W.size() + 3) & ~size_t(3); W.resize(off + n, 0.f); return (int64_t)off; };
+    m->lcta.assign(L, {});
+    std::vector<const HostTensor*> skw(L), skb(L);
+    for (int l = 0; l < L; ++l) {
+        if (need(m, "out_skip." + std::to_string(l) + ".weight", {S, H, 1}, &skw[l]) ||
+            need(m, "out_skip." + std::to_string(l) + ".bias", {S}, &skb[l])) return 1;
+    }
+    for (int l = 0; l < L; ++l) {
+        const std::string base = "dil_h." + std::to_string(l) + ".conv";
+        if (need(m, base + ".weight", {twoH, H, K}, &x) || need(m, base + ".bias", {twoH}, &y)) return 1;
+        for (int g = 0; g < geff; ++g) {
+            swn_model::LayerCta lc;
+            split_range(H, geff, g, &lc.pair0, &lc.npairs);
+            split_range(S, geff, g, &lc.skip0, &lc.nskip);
+            if (l == 0) lc.nskip = 0;
+            const int np = lc.npairs;
+            lc.w_off = alloc((size_t)K * np * 2 * Hp);
+            for (int j = 0; j < K; ++j)
+                for (int pi = 0; pi < np; ++pi)
+                    for (int zc = 0; zc < 2; ++zc) {
+                        const int row = zc * H + lc.pair0 + pi;
+                        float* dst = W.data() + lc.w_off + ((size_t)(j * np + pi) * 2 + zc) * Hp;
+                        for (int k = 0; k < H; ++k) dst[k] = x->data[((size_t)row * H + k) * K + j];
+                    }
+            lc.b_off = alloc((size_t)np * 2);
+            for (int pi = 0; pi < np; ++pi) {
+                W[lc.b_off + pi * 2] = y->data[lc.pair0 + pi];
+                W[lc.b_off + pi * 2 + 1] = y->data[H + lc.pair0 + pi];
+            }
+            lc.ws_off = alloc((size_t)std::max(lc.nskip, 1) * Hp);
+            for (int r = 0; r < lc.nskip; ++r)
+                for (int k = 0; k < H; ++k)
+                    W[lc.ws_off + (size_t)r * Hp + k] = skw[l - 1]->data[(size_t)(lc.skip0 + r) * H + k];
+            m->lcta[l].push_back(lc);
+        }
+    }
+    {
+        const HostTensor *w1, *b1, *w2, *b2;
+        if (need(m, "out_1.weight", {n1, S, 1}, &w1) || need(m, "out_1.bias", {n1}, &b1) ||
+            need(m, "out_2.weight", {n2, n1, 1}, &w2) || need(m, "out_2.bias", {n2}, &b2)) return 1;
+        m->hcta.clear();
+        for (int hc = 0; hc < m->NH; ++hc) {
+            swn_model::HeadCta q;
+            split_range(S, m->NH, hc, &q.a0, &q.na);
+            split_range(n1, m->NH, hc, &q.b0, &q.nb);
+            if (is_c) { q.c0 = 0; q.nc = n2; } else split_range(n2, m->NH, hc, &q.c0, &q.nc);
+            split_range(H, m->NH, hc, &q.i0, &q.ni);
+            q.wa_off = alloc((size_t)std::max(q.na, 1) * Hp);
+            q.ca_off = alloc((size_t)std::max(q.na, 1));
+            for (int r = 0; r < q.na; ++r) {
+                for (int k = 0; k < H; ++k) W[q.wa_off + (size_t)r * Hp + k] = skw[L - 1]->data[(size_t)(q.a0 + r) * H + k];
+                double cs = 0.0;
+                for (int l = 0; l < L; ++l) cs += skb[l]->data[q.a0 + r];
+                W[q.ca_off + r] = (float)cs;
+            }
+            q.wb_off = alloc((size_t)std::max(q.nb, 1) * Sp);
+            q.bb_off = alloc((size_t)std::max(q.nb, 1));
+            for (int r = 0; r < q.nb; ++r) {
+                for (int k = 0; k < S; ++k) W[q.wb_off + (size_t)r * Sp + k] = w1->data[(size_t)(q.b0 + r) * S + k];
+                W[q.bb_off + r] = b1->data[q.b0 + r];
+            }
+            q.wc_off = alloc((size_t)std::max(q.nc, 1) * n1p);
+            q.bc_off = alloc((size_t)std::max(q.nc, 1));
+            for (int r = 0; r < q.nc; ++r) {
+                for (int k = 0; k < n1; ++k) W[q.wc_off + (size_t)r * n1p + k] = w2->data[(size_t)(q.c0 + r) * n1 + k];
+                W[q.bc_off + r] = b2->data[q.c0 + r];
+            }
+            m->hcta.push_back(q);
+        }
+    }
+
+    if (upload(m->wbuf, m->wbuf_h)) return 1;
+    m->info.weight_bytes = (int64_t)m->wbuf_h.size() * 4;
+    m->plan_key = -1;
+    return 0;
+}
+
 static cudaError_t m_core_launch_dispatch(swn_model* m, int BS, const swn::CoreParams& P, cudaStream_t st) {
     swn::core_fns fn = {nullptr, nullptr};
     switch (m->NCH) {
@@ -556,80 +644,13 @@ int swn_finalize(swn_handle m) {
         m->in_tab_h = tab;
     }
 
-    // ---------------- in-loop weights, packed per CTA
-    std::vector<float>& W = m->wbuf_h;
-    W.clear();
-    auto alloc = [&](size_t n) { size_t off = (W.size() + 3) & ~size_t(3); W.resize(off + n, 0.f); return (int64_t)off; };
-    m->lcta.assign(L, {});
+    // ---------------- in-loop weights of the layer-group kernel (v1), packed per CTA
+    if (pack_v1(m, std::min(m->G, m->H))) return 1;
     std::vector<const HostTensor*> skw(L), skb(L);
     for (int l = 0; l < L; ++l) {
         if (need(m, "out_skip." + std::to_string(l) + ".weight", {S, H, 1}, &skw[l]) ||
             need(m, "out_skip." + std::to_string(l) + ".bias", {S}, &skb[l])) return 1;
     }
-    for (int l = 0; l < L; ++l) {
-        const std::string base = "dil_h." + std::to_string(l) + ".conv";
-        if (need(m, base + ".weight", {twoH, H, K}, &x) || need(m, base + ".bias", {twoH}, &y)) return 1;
-        for (int g = 0; g < m->Geff; ++g) {
-            swn_model::LayerCta lc;
-            split_range(H, m->Geff, g, &lc.pair0, &lc.npairs);
-            split_range(S, m->Geff, g, &lc.skip0, &lc.nskip);
-            if (l == 0) lc.nskip = 0;
-            const int np = lc.npairs;
-            lc.w_off = alloc((size_t)K * np * 2 * Hp);
-            for (int j = 0; j < K; ++j)
-                for (int pi = 0; pi < np; ++pi)
-                    for (int zc = 0; zc < 2; ++zc) {
-                        const int row = zc * H + lc.pair0 + pi;
-                        float* dst = W.data() + lc.w_off + ((size_t)(j * np + pi) * 2 + zc) * Hp;
-                        for (int k = 0; k < H; ++k) dst[k] = x->data[((size_t)row * H + k) * K + j];
-                    }
-            lc.b_off = alloc((size_t)np * 2);
-            for (int pi = 0; pi < np; ++pi) {
-                W[lc.b_off + pi * 2] = y->data[lc.pair0 + pi];
-                W[lc.b_off + pi * 2 + 1] = y->data[H + lc.pair0 + pi];
-            }
-            lc.ws_off = alloc((size_t)std::max(lc.nskip, 1) * Hp);
-            for (int r = 0; r < lc.nskip; ++r)
-                for (int k = 0; k < H; ++k)
-                    W[lc.ws_off + (size_t)r * Hp + k] = skw[l - 1]->data[(size_t)(lc.skip0 + r) * H + k];
-            m->lcta[l].push_back(lc);
-        }
-    }
-    {
-        const HostTensor *w1, *b1, *w2, *b2;
-        if (need(m, "out_1.weight", {n1, S, 1}, &w1) || need(m, "out_1.bias", {n1}, &b1) ||
-            need(m, "out_2.weight", {n2, n1, 1}, &w2) || need(m, "out_2.bias", {n2}, &b2)) return 1;
-        m->hcta.clear();
-        for (int hc = 0; hc < m->NH; ++hc) {
-            swn_model::HeadCta q;
-            split_range(S, m->NH, hc, &q.a0, &q.na);
-            split_range(n1, m->NH, hc, &q.b0, &q.nb);
-            if (is_c) { q.c0 = 0; q.nc = n2; } else split_range(n2, m->NH, hc, &q.c0, &q.nc);
-            split_range(H, m->NH, hc, &q.i0, &q.ni);
-            q.wa_off = alloc((size_t)std::max(q.na, 1) * Hp);
-            q.ca_off = alloc((size_t)std::max(q.na, 1));
-            for (int r = 0; r < q.na; ++r) {
-                for (int k = 0; k < H; ++k) W[q.wa_off + (size_t)r * Hp + k] = skw[L - 1]->data[(size_t)(q.a0 + r) * H + k];
-                double cs = 0.0;
-                for (int l = 0; l < L; ++l) cs += skb[l]->data[q.a0 + r];
-                W[q.ca_off + r] = (float)cs;
-            }
-            q.wb_off = alloc((size_t)std::max(q.nb, 1) * Sp);
-            q.bb_off = alloc((size_t)std::max(q.nb, 1));
-            for (int r = 0; r < q.nb; ++r) {
-                for (int k = 0; k < S; ++k) W[q.wb_off + (size_t)r * Sp + k] = w1->data[(size_t)(q.b0 + r) * S + k];
-                W[q.bb_off + r] = b1->data[q.b0 + r];
-            }
-            q.wc_off = alloc((size_t)std::max(q.nc, 1) * n1p);
-            q.bc_off = alloc((size_t)std::max(q.nc, 1));
-            for (int r = 0; r < q.nc; ++r) {
-                for (int k = 0; k < n1; ++k) W[q.wc_off + (size_t)r * n1p + k] = w2->data[(size_t)(q.c0 + r) * n1 + k];
-                W[q.bc_off + r] = b2->data[q.c0 + r];
-            }
-            m->hcta.push_back(q);
-        }
-    }
-
     // ---------------- v2 packing: the 16 CTAs of the core cluster (swn_core.cuh)
     m->core_ok = false;
     m->core_plan_key = -1;
@@ -729,11 +750,9 @@ int swn_finalize(swn_handle m) {
             m->core_ok = true;
         }
     }
-    if (upload(m->wbuf, W)) return 1;
     if (m->status.ensure(8)) return 1;
     for (int i = 0; i < 4; ++i)
         if (!m->ev[i]) CUDA_OK(cudaEventCreate(&m->ev[i]));
-    m->info.weight_bytes = (int64_t)W.size() * 4;
     m->finalized = true;
     m->condB = 0;
     m->plan_key = -1;
@@ -816,6 +835,20 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
     }
     if (!fn) return fail("swn_generate: no kernel for hid_chn=%d seg=%d batch_tile=%d", H, seg, BS);
 
+    // ---- head groups: the head is a serial chain of ~4 L2 hops per slot, so several independent head groups
+    // (each NH CTAs, each serving the slots m % NHG == g) keep the layer groups fed when the batch is pipelined
+    int NHG = std::max(1, std::min(7, M));
+    int geff = 0;
+    for (; NHG >= 1; --NHG) {
+        const int G = (m->n_sm - m->NH * NHG) / L;
+        geff = std::min(G, H);
+        if (G >= 1 && (H + geff - 1) / geff <= 2 * SWN_NWARPS) break;
+    }
+    if (NHG < 1) return fail("swn_generate: cannot place %d layers on %d SMs", L, m->n_sm);
+    if (geff != m->Geff) {
+        CUDA_OK(cudaStreamSynchronize(st));
+        if (pack_v1(m, geff)) return 1;
+    }
     // ---- per-CTA plan: shared memory placement
     const int smem_floats = SWN_MAX_SMEM / 4;
     std::vector<CtaDesc> desc(m->n_sm);
@@ -848,10 +881,11 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
             smem_used_max = std::max(smem_used_max, used);
         }
     const size_t hist_f = (size_t)M * BS * (32 + 8);
+    for (int hgi = 0; hgi < NHG; ++hgi)
     for (int hc = 0; hc < m->NH; ++hc, ++cta) {
         const auto& q = m->hcta[hc];
         CtaDesc& d = desc[cta];
-        d.role = ROLE_HEAD; d.layer = hc;
+        d.role = ROLE_HEAD; d.layer = hc; d.hgroup = hgi;
         d.a0 = q.a0; d.na = q.na; d.b0 = q.b0; d.nb = q.nb; d.c0 = q.c0; d.nc = q.nc; d.i0 = q.i0; d.ni = q.ni;
         d.wa_off = q.wa_off; d.ca_off = q.ca_off; d.wb_off = q.wb_off; d.bb_off = q.bb_off; d.wc_off = q.wc_off; d.bc_off = q.bc_off;
         int used = 0;
@@ -872,7 +906,7 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
     const size_t smem_bytes = (size_t)smem_used_max * 4;
 
     // the plan only changes with (B, batch tile); re-upload it only then, after the stream drained
-    const long long plan_key = ((long long)B << 32) | ((long long)BS << 16) | (long long)seg;
+    const long long plan_key = ((long long)B << 32) | ((long long)BS << 16) | ((long long)NHG << 8) | (long long)seg;
     if (plan_key != m->plan_key) {
         CUDA_OK(cudaStreamSynchronize(st));
         if (upload(m->desc, desc)) return 1;
@@ -898,7 +932,7 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
     P.it0 = (m->R + 1 - P.t_first) / seg - 1;
     P.n_iter = (int)n_iter;
     P.n_it = P.it0 + P.n_iter;
-    P.NH = m->NH;
+    P.NH = m->NH; P.NHG = NHG;
     P.audio_in = (m->cfg.kind == SWN_KIND_DSWNV && m->cfg.audio_in_flag) ? 1 : 0;
     P.n_out = n_iter * seg;
     P.desc = m->desc.p;

@@ -13,7 +13,8 @@ enum { ROLE_LAYER = 0, ROLE_HEAD = 1, ROLE_IDLE = 2 };
 // dynamic shared memory of the CTA.
 struct CtaDesc {
     int32_t role;
-    int32_t layer;        // layer index (ROLE_LAYER) or head CTA index (ROLE_HEAD)
+    int32_t layer;        // layer index (ROLE_LAYER) or head CTA index inside its head group (ROLE_HEAD)
+    int32_t hgroup;       // head group (ROLE_HEAD): owns the pipeline slots m with m % NHG == hgroup
     int32_t dil;          // dilation of dil_h[layer]
     int32_t pair0, npairs;      // gate pairs (z row i, candidate row H+i) owned: i in [pair0, pair0+npairs)
     int32_t skip0, nskip;       // rows of out_skip[layer-1] owned (layer >= 1)
@@ -41,7 +42,7 @@ struct CtaDesc {
 struct GenParams {
     int32_t kind, H, Hp, S, Sp, K, L, lpc, n1, n1p, n2, Q, U, R, B, M, Tf;
     int32_t t_first, it0, n_it, n_iter;
-    int32_t NH, audio_in;
+    int32_t NH, NHG, audio_in;
     int64_t n_out;                  // generated samples per utterance = n_iter * SEG
     const CtaDesc* desc;
     const float* wbuf;

@@ -256,8 +256,11 @@ __device__ void layer_cta(const GenParams& P, const CtaDesc& D, float* smem) {
                     pz[pp] = az; pc[pp] = ac;
                     const int slot = (t - P.t_first) % RL;
                     float* r0 = rg + ((size_t)(slot * np + pi) * 2) * BS + bl;
-                    rz[pp] = r0[0]; rc[pp] = r0[BS];
-                    r0[0] = 0.f; r0[BS] = 0.f;             // read-and-clear: the slot is reused RL steps later
+                    // read-and-clear: the slot is reused RL steps later.  A ring that lives in global memory is
+                    // updated with fire-and-forget reductions (below), so it is read at L2 (not through L1)
+                    if (D.ring_in_smem) { rz[pp] = r0[0]; rc[pp] = r0[BS]; }
+                    else { rz[pp] = __ldcg(r0); rc[pp] = __ldcg(r0 + BS); }
+                    r0[0] = 0.f; r0[BS] = 0.f;
                 }
             }
             // ---- wait for the input vectors of this block (H x NC words)
@@ -349,7 +352,8 @@ __device__ void layer_cta(const GenParams& P, const CtaDesc& D, float* smem) {
                                 if (lane == b) {
                                     const int slot = (t0 + ss + delta - P.t_first) % RL;
                                     float* r0 = rg + ((size_t)(slot * np + pi) * 2) * BS + b;
-                                    r0[0] += vz; r0[BS] += vc;
+                                    if (D.ring_in_smem) { r0[0] += vz; r0[BS] += vc; }
+                                    else { atomicAdd(r0, vz); atomicAdd(r0 + BS, vc); }   // RED: no round trip to wait for
                                 }
                             }
                         }
@@ -517,14 +521,15 @@ __device__ void head_cta(const GenParams& P, const CtaDesc& D, float* smem) {
         }
     };
 
-    // prologue: inputs of block 0 (all padding)
-    for (int m = 0; m < P.M; ++m) input_stage(0, m);
+    // prologue: inputs of block 0 (all padding); a head group only serves its own pipeline slots
+    const int hg = D.hgroup;
+    for (int m = hg; m < P.M; m += P.NHG) input_stage(0, m);
 
     for (int it = 0; it < P.n_it; ++it) {
         const bool active = it >= P.it0;
         const uint32_t tag = (uint32_t)it + 1u;
         const int istep = it - P.it0;                                    // generation step index
-        for (int m = 0; m < P.M; ++m) {
+        for (int m = hg; m < P.M; m += P.NHG) {
             bool ok = true;
             // ---- wait for layer L-1 (flow control in warm-up, data when active)
             {
