@@ -304,7 +304,7 @@ def main():
                      "gpu_launches": int(launches),
                      "plan": {k: info[k] for k in ("kernel_variant", "grid", "n_sm", "ctas_per_layer", "head_ctas", "smem_bytes",
                                                    "batch_tile", "n_slots")}})
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only (the other ranks would spin in the barrier)
             threads = os.cpu_count() or 1
             sf = args.cpu_sample_frames or (40 if kind == "dswnv" else 20)
             v, n, dt = cpu_port_run(kind, kw, frames, sf, threads)
