@@ -131,7 +131,8 @@ class _SWNBase(nn.Module):
             "use batch_fast_generate(..., forced=...) for teacher-forced head outputs")
 
     # ------------------------------------------------------------------ the generate call
-    def _generate(self, audio, aux, n_samples_list, intervals, noise, seed, forced, return_heads, batch_tile):
+    def _generate(self, audio, aux, n_samples_list, intervals, noise, seed, forced, return_heads, batch_tile,
+                  kernel_sel=0):
         eng = self.engine()
         dev = eng.device
         n_samples_list = [int(n) for n in n_samples_list]
@@ -150,7 +151,7 @@ class _SWNBase(nn.Module):
         start = time.time()
         eng.condition(aux)
         out, heads = eng.generate(max_samples, seed=seed, noise=noise, forced=forced, seed_audio=seed_audio,
-                                  return_heads=return_heads, batch_tile=batch_tile)
+                                  return_heads=return_heads, batch_tile=batch_tile, kernel_sel=kernel_sel)
         samples = out.cpu().numpy()                                  # the reference's single D2H (cswnv:426)
         dt = time.time() - start
         n_gen = samples.shape[1]

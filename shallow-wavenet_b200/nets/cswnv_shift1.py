@@ -54,7 +54,7 @@ class CSWNV(_SWNBase):
                     audio_in_flag=0)
 
     def batch_fast_generate(self, audio, aux, n_samples_list, intervals=4410, Laplace=True, *, noise=None,
-                            seed=None, forced=None, return_heads=False, batch_tile=0):
+                            seed=None, forced=None, return_heads=False, batch_tile=0, kernel_sel=0):
         """Same call as the reference (cswnv_shift1.py:287): ``audio`` [B, seg] seed waveform,
         ``aux`` [B, n_aux, T] zero-padded features, ``n_samples_list`` lengths; returns a list of
         float32 numpy arrays in [-1, 1].
@@ -62,9 +62,10 @@ class CSWNV(_SWNBase):
         Keyword-only extras (not in the reference): ``noise`` [B, N] injected uniforms in
         (-0.4999, 0.5) replacing the Philox stream, ``seed`` the Philox key, ``forced`` [B, N]
         samples fed back instead of the sampled ones (teacher forcing), ``return_heads`` to also
-        get the raw out_2 rows per step, ``batch_tile`` to pin the kernel's batch tile.
+        get the raw out_2 rows per step, ``batch_tile`` to pin the kernel's batch tile, ``kernel_sel`` (0 auto, 1 layer-group kernel,
+        2 cluster kernel).
         """
         if not Laplace:
             # the reference returns an unbound local in this case (cswnv_shift1.py:343,423)
             raise ValueError("only the Laplacian output distribution exists on this path")
-        return self._generate(audio, aux, n_samples_list, intervals, noise, seed, forced, return_heads, batch_tile)
+        return self._generate(audio, aux, n_samples_list, intervals, noise, seed, forced, return_heads, batch_tile, kernel_sel)

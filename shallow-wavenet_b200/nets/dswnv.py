@@ -64,13 +64,14 @@ class DSWNV(_SWNBase):
                     aux_conv2d_flag=0, wav_conv_flag=self.wav_conv_flag, audio_in_flag=self.audio_in_flag)
 
     def batch_fast_generate(self, audio, aux, n_samples_list, intervals=4410, *, noise=None, seed=None,
-                            forced=None, return_heads=False, batch_tile=0):
+                            forced=None, return_heads=False, batch_tile=0, kernel_sel=0):
         """Same call as the reference (dswnv.py:296): ``audio`` [B, 1] int64 seed (mu-law index),
         ``aux`` [B, n_aux, T], ``n_samples_list`` lengths; returns a list of int64 numpy arrays of
         mu-law indices.
 
         Keyword-only extras: ``noise`` [B, N, 256] Exp(1) variates (the ones torch.multinomial
         would draw), ``seed`` Philox key, ``forced`` [B, N] indices fed back instead of the sampled
-        ones, ``return_heads`` to also get the logits per step, ``batch_tile``.
+        ones, ``return_heads`` to also get the logits per step, ``batch_tile``, ``kernel_sel`` (0 auto,
+        1 layer-group kernel, 2 cluster kernel).
         """
-        return self._generate(audio, aux, n_samples_list, intervals, noise, seed, forced, return_heads, batch_tile)
+        return self._generate(audio, aux, n_samples_list, intervals, noise, seed, forced, return_heads, batch_tile, kernel_sel)

@@ -276,6 +276,36 @@ def test_host_buffer_entry_point():
     assert out.dtype == np.int64 and np.array_equal(out, ref)
 
 
+@pytest.mark.parametrize("name", ["dswnv_base", "dswnv_wavconv_k6", "cswnv_seg1_lpc0"])
+def test_both_kernel_variants_agree(name):
+    """Small batches with one sample per step run on the cluster kernel (variant 2) by default; the
+    layer-group kernel (variant 1) must give the same answer."""
+    g = load_golden(name)
+    m = _model_from_golden(g)
+    B, N = g["samples"].shape
+    seed_a = _seed_audio(g["kind"], B, 1)
+    res = {}
+    for sel in (1, 2):
+        outs, heads = m.batch_fast_generate(seed_a, torch.from_numpy(g["aux"]), [N] * B, noise=g["noise"],
+                                            forced=g["samples"], return_heads=True, kernel_sel=sel)
+        assert m.engine().info["kernel_variant"] == sel
+        _head_close(heads, g["heads"], "%s variant %d" % (name, sel))
+        res[sel] = (np.stack(outs), heads)
+    if g["kind"] == "dswnv":
+        assert np.array_equal(res[1][0], res[2][0])
+    else:
+        assert float(np.abs(res[1][0] - res[2][0]).max()) <= SAMPLE_ATOL
+    assert float(np.abs(res[1][1] - res[2][1]).max()) <= 2e-5
+
+
+def test_cluster_kernel_is_used_for_the_headline_workload():
+    model, cfg, sd, aux, kw = _recipe_case("dswnv", 16000, 1, 2, 3)
+    N = 2 * kw["upsampling_factor"]
+    model.batch_fast_generate(torch.full((1, 1), 128, dtype=torch.long), torch.from_numpy(aux), [N], seed=1)
+    info = model.engine().info
+    assert info["kernel_variant"] == 2 and info["grid"] % 16 == 0 and info["n_slots"] == 1
+
+
 # ----------------------------------------------------------------------------- full-size properties
 def test_full_size_cfg2_tail_and_sampler_properties():
     """BASELINE.json configs[1]: DSWNV, 16 kHz, batch 1, 5 s = 80000 samples, free running with Philox
