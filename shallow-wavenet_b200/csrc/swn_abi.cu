@@ -15,6 +15,7 @@
 #include "../../include/swn_b200.h"
 #include "swn_gen.cuh"
 #include "swn_core.cuh"
+#include "swn_batch.cuh"
 #include "swn_launch.h"
 
 namespace {
@@ -116,6 +117,17 @@ struct swn_model {
     size_t core_smem = 0, core_ring_total = 0;
     swn::CoreParams core_tmpl;
     size_t core_n_hin = 0, core_n_hacc = 0;
+    // ---- v3: pipelined batch kernel (swn_batch.cuh)
+    struct L3Cta { int pair0, npairs, skip0, nskip, rows, RP; int64_t w_off, b_off, wl_off; };
+    std::vector<std::vector<L3Cta>> l3;        // [L][g3]
+    int g3 = 0, Hp3 = 0;
+    int64_t w1_off3 = 0, b1_off3 = 0, w2_off3 = 0, b2_off3 = 0, cs_off3 = 0;
+    DevBuf<float> wbuf3, tiles3, skip3, lastskip3, ring3;
+    DevBuf<unsigned int> cnt3;
+    DevBuf<swn::BCta> desc3;
+    long long plan3_key = -1;
+    int grid3 = 0, nh3 = 0;
+    size_t smem3 = 0, ring3_total = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool cond_timed = false, gen_timed = false;
     swn_info info;
@@ -431,6 +443,234 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
     return 0;
 }
 
+
+// ---- v3 packing: per layer CTA the transposed GEMM operand Wt[k][row] (rows = all taps of the owned gate
+// pairs, then the owned out_skip[l-1] rows), head matrices row-major padded to 64
+static int pack_v3(swn_model* m, int geff) {
+    const int H = m->H, S = m->S, Sp = m->Sp, K = m->K, L = m->L, n1 = m->n1, n1p = m->n1p, n2 = m->n2, twoH = 2 * H;
+    const int Hp = round_up(H, 4);
+    std::vector<float> W;
+    auto alloc = [&](size_t n) { size_t off = (W.size() + 3) & ~size_t(3); W.resize(off + n, 0.f); return (int64_t)off; };
+    std::vector<const HostTensor*> skw(L), skb(L);
+    for (int l = 0; l < L; ++l) {
+        if (need(m, "out_skip." + std::to_string(l) + ".weight", {S, H, 1}, &skw[l]) ||
+            need(m, "out_skip." + std::to_string(l) + ".bias", {S}, &skb[l])) return 1;
+    }
+    m->l3.assign(L, {});
+    const HostTensor *x, *y;
+    for (int l = 0; l < L; ++l) {
+        const std::string base = "dil_h." + std::to_string(l) + ".conv";
+        if (need(m, base + ".weight", {twoH, H, K}, &x) || need(m, base + ".bias", {twoH}, &y)) return 1;
+        for (int g = 0; g < geff; ++g) {
+            swn_model::L3Cta c;
+            split_range(H, geff, g, &c.pair0, &c.npairs);
+            split_range(S, geff, g, &c.skip0, &c.nskip);
+            if (l == 0) c.nskip = 0;
+            const int np = c.npairs;
+            c.rows = 2 * K * np + c.nskip;
+            c.RP = round_up(c.rows, 8);
+            c.w_off = alloc((size_t)Hp * c.RP);
+            float* wt = W.data() + c.w_off;
+            for (int j = 0; j < K; ++j)
+                for (int pi = 0; pi < np; ++pi)
+                    for (int zc = 0; zc < 2; ++zc) {
+                        const int row = (j * np + pi) * 2 + zc, src = zc * H + c.pair0 + pi;
+                        for (int k = 0; k < H; ++k) wt[(size_t)k * c.RP + row] = x->data[((size_t)src * H + k) * K + j];
+                    }
+            for (int r = 0; r < c.nskip; ++r)
+                for (int k = 0; k < H; ++k)
+                    wt[(size_t)k * c.RP + 2 * K * np + r] = skw[l - 1]->data[(size_t)(c.skip0 + r) * H + k];
+            c.b_off = alloc((size_t)np * 2);
+            for (int pi = 0; pi < np; ++pi) {
+                W[c.b_off + pi * 2] = y->data[c.pair0 + pi];
+                W[c.b_off + pi * 2 + 1] = y->data[H + c.pair0 + pi];
+            }
+            c.wl_off = 0;
+            if (l == L - 1) {
+                c.wl_off = alloc((size_t)np * S);
+                for (int pi = 0; pi < np; ++pi)
+                    for (int r = 0; r < S; ++r) W[c.wl_off + (size_t)pi * S + r] = skw[L - 1]->data[(size_t)r * H + c.pair0 + pi];
+            }
+            m->l3[l].push_back(c);
+        }
+    }
+    const HostTensor *w1, *b1, *w2, *b2;
+    if (need(m, "out_1.weight", {n1, S, 1}, &w1) || need(m, "out_1.bias", {n1}, &b1) ||
+        need(m, "out_2.weight", {n2, n1, 1}, &w2) || need(m, "out_2.bias", {n2}, &b2)) return 1;
+    m->w1_off3 = alloc((size_t)n1 * Sp);
+    for (int r = 0; r < n1; ++r)
+        for (int k = 0; k < S; ++k) W[m->w1_off3 + (size_t)r * Sp + k] = w1->data[(size_t)r * S + k];
+    m->b1_off3 = alloc(n1);
+    for (int r = 0; r < n1; ++r) W[m->b1_off3 + r] = b1->data[r];
+    m->w2_off3 = alloc((size_t)n2 * n1p);
+    for (int r = 0; r < n2; ++r)
+        for (int k = 0; k < n1; ++k) W[m->w2_off3 + (size_t)r * n1p + k] = w2->data[(size_t)r * n1 + k];
+    m->b2_off3 = alloc(n2);
+    for (int r = 0; r < n2; ++r) W[m->b2_off3 + r] = b2->data[r];
+    m->cs_off3 = alloc(S);
+    for (int r = 0; r < S; ++r) {
+        double cs = 0.0;
+        for (int l = 0; l < L; ++l) cs += skb[l]->data[r];
+        W[m->cs_off3 + r] = (float)cs;
+    }
+    if (upload(m->wbuf3, W)) return 1;
+    m->g3 = geff; m->Hp3 = Hp;
+    m->plan3_key = -1;
+    return 0;
+}
+
+// ---- v3 launch: returns 0 = launched, 2 = not applicable (caller falls back to v1), 1 = error
+static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, int B, int Tf, int64_t n_iter) {
+    const int H = m->H, K = m->K, L = m->L, S = m->S, seg = m->seg;
+    const bool is_c = m->cfg.kind == SWN_KIND_CSWNV;
+    if (!is_c && m->cfg.audio_in_flag) return 2;
+    if (m->Sp > 256 || m->n1p > 256) return 2;
+    const int* tiles = swn::batch3_tiles_for_seg(seg);
+    if (!tiles[0]) return 2;
+    const int smem_floats = SWN_MAX_SMEM / 4;
+    // ---- CTAs per layer group and head CTAs
+    const int nh_min = 4;
+    int G = (m->n_sm - nh_min) / L;
+    if (G < 1) return 2;
+    const int geff = std::min(G, H);
+    if (geff != m->g3) {
+        CUDA_OK(cudaStreamSynchronize(st));
+        if (pack_v3(m, geff)) return 1;
+    }
+    const int Hp = m->Hp3;
+    const int n2p = round_up(m->n2, 4);
+    // ---- utterances per slot: explicit, or the largest tile that still leaves >= 12 slots in flight
+    std::vector<int> cand;
+    if (a->batch_tile > 0) {
+        for (const int* t = tiles; *t; ++t) if (*t == a->batch_tile) cand.push_back(*t);
+        if (cand.empty()) return a->kernel_sel == 3 ? fail("swn_generate: batch_tile=%d is not instantiated for the batch kernel at seg=%d", a->batch_tile, seg) : 2;
+    } else {
+        int first = -1;
+        for (const int* t = tiles; *t; ++t) if (first < 0 && (B + *t - 1) / *t >= 12) first = *t;
+        for (const int* t = tiles; *t; ++t) if (first < 0 ? true : *t <= first) cand.push_back(*t);
+        if (first < 0) std::reverse(cand.begin(), cand.end());     // small batches: smallest tile first
+    }
+    int BS = 0, M = 0, NH = 0, grid = 0;
+    size_t smem_max = 0, ring_total = 0;
+    std::vector<swn::BCta> desc;
+    for (int bs : cand) {
+        const int NC = bs * seg, OS = NC | 1;
+        if (((size_t)H * NC * 4) % 16 != 0) continue;
+        const int Mx = (B + bs - 1) / bs, Bp = Mx * bs;
+        const int nh = std::max(1, std::min(std::min(Mx, 16), m->n_sm - L * geff));
+        bool fits = true;
+        size_t used_max = 0, rt = 0;
+        desc.assign((size_t)L * geff + nh, swn::BCta());
+        int cta = 0;
+        for (int l = 0; l < L && fits; ++l)
+            for (int g = 0; g < geff; ++g, ++cta) {
+                const auto& c = m->l3[l][g];
+                swn::BCta& d = desc[cta];
+                memset(&d, 0, sizeof(d));
+                d.role = ROLE_LAYER; d.layer = l; d.hindex = g; d.dil = m->dil[l];
+                d.pair0 = c.pair0; d.npairs = c.npairs; d.skip0 = c.skip0; d.nskip = c.nskip; d.rows = c.rows; d.RP = c.RP;
+                d.ring_len = (K - 1) * d.dil + seg;
+                d.nprod_in = l == 0 ? 1 : geff;
+                d.is_last = l == L - 1;
+                d.w_off = c.w_off; d.b_off = c.b_off; d.wl_off = c.wl_off;
+                size_t u = 0;
+                auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
+                d.sm_w = take((size_t)Hp * c.RP);
+                d.sm_x = take((size_t)2 * Hp * NC);
+                d.sm_o = take((size_t)c.RP * OS);
+                d.sm_pre = take((size_t)c.npairs * NC * 4);
+                d.sm_hn = take((size_t)c.npairs * bs);
+                d.sm_wl = take(d.is_last ? (size_t)c.npairs * S : 0);
+                d.sm_bar = take(16);
+                const size_t ring_f = (size_t)d.ring_len * 2 * c.npairs * Bp;
+                d.sm_ring = (int32_t)u;
+                d.ring_in_smem = u + ring_f <= (size_t)smem_floats;
+                if (d.ring_in_smem) u += (ring_f + 3) & ~size_t(3);
+                else { d.ring_off = (int64_t)rt; rt += (ring_f + 3) & ~size_t(3); }
+                if (u > (size_t)smem_floats) { fits = false; break; }
+                used_max = std::max(used_max, u);
+            }
+        if (!fits) continue;
+        const int MO = (Mx + nh - 1) / nh;
+        const int kpmax = std::max(m->Sp, m->n1p);
+        for (int hc = 0; hc < nh; ++hc, ++cta) {
+            swn::BCta& d = desc[cta];
+            memset(&d, 0, sizeof(d));
+            d.role = ROLE_HEAD; d.hindex = hc;
+            size_t u = 0;
+            auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
+            d.sm_wring = take((size_t)swn::B3_NST * swn::B3_RCH * kpmax);
+            d.sm_x1 = take((size_t)bs * m->Sp);
+            d.sm_x2 = take((size_t)bs * m->n1p);
+            d.sm_oc = take((size_t)bs * n2p);
+            d.sm_tin = take((size_t)H * NC);
+            d.sm_hist = take((size_t)MO * bs * swn::B3_HIST);
+            d.sm_lpb = take((size_t)MO * bs * 8);
+            d.sm_misc = take(4 * swn::B3_NST + 8);
+            if (u > (size_t)smem_floats) { fits = false; break; }
+            used_max = std::max(used_max, u);
+        }
+        if (!fits) continue;
+        BS = bs; M = Mx; NH = nh; grid = cta; smem_max = used_max * 4; ring_total = rt;
+        break;
+    }
+    if (!BS) return 2;
+    const int NC = BS * seg;
+    swn::batch_launch_fn fn = swn::find_batch_kernel(seg, BS);
+    if (!fn) return 2;
+    const long long key = ((long long)B << 32) | ((long long)BS << 16) | ((long long)geff << 8) | (long long)NH;
+    if (key != m->plan3_key) {
+        CUDA_OK(cudaStreamSynchronize(st));
+        if (upload(m->desc3, desc)) return 1;
+        m->plan3_key = key;
+    }
+    const size_t n_tiles = (size_t)(L + 1) * M * H * NC;
+    const size_t n_cnt = (size_t)(L + 1) * M * swn::B3_CNT_STRIDE;
+    const size_t n_skip = (size_t)std::max(L - 1, 1) * M * S * BS;
+    const size_t n_last = (size_t)geff * M * S * BS;
+    if (m->tiles3.ensure(n_tiles) || m->cnt3.ensure(n_cnt) || m->skip3.ensure(n_skip) || m->lastskip3.ensure(n_last) ||
+        m->ring3.ensure(std::max<size_t>(ring_total, 4))) return 1;
+    CUDA_OK(cudaMemsetAsync(m->cnt3.p, 0, n_cnt * sizeof(unsigned int), st));
+    if (ring_total) CUDA_OK(cudaMemsetAsync(m->ring3.p, 0, ring_total * sizeof(float), st));
+    CUDA_OK(cudaMemsetAsync(m->status.p, 0, 8 * sizeof(int32_t), st));
+
+    swn::BatchParams P;
+    memset(&P, 0, sizeof(P));
+    P.kind = m->cfg.kind; P.H = H; P.Hp = Hp; P.S = S; P.Sp = m->Sp; P.K = K; P.L = L; P.lpc = m->lpc;
+    P.n1 = m->n1; P.n1p = m->n1p; P.n2 = m->n2; P.n2p = n2p; P.Q = m->Q; P.U = m->U; P.R = m->R; P.B = B; P.M = M; P.Tf = Tf;
+    const int rem = (m->R + 1) % seg;
+    P.t_first = rem == 0 ? 0 : rem - seg;
+    P.it0 = (m->R + 1 - P.t_first) / seg - 1;
+    P.n_iter = (int)n_iter;
+    P.n_it = P.it0 + P.n_iter;
+    P.NH = NH; P.G = geff;
+    P.n_out = n_iter * seg;
+    P.desc = m->desc3.p; P.wbuf = m->wbuf3.p;
+    P.P = m->ptab.p; P.pconst = m->pconst.p; P.gain = m->gain.p;
+    P.in_tab = m->in_tab.p; P.in_bias = m->in_bias.p;
+    P.w1_off = m->w1_off3; P.b1_off = m->b1_off3; P.w2_off = m->w2_off3; P.b2_off = m->b2_off3; P.cs_off = m->cs_off3;
+    P.tiles = m->tiles3.p; P.cnt = m->cnt3.p; P.skipbuf = m->skip3.p; P.lastskip = m->lastskip3.p; P.ring_scratch = m->ring3.p;
+    P.noise = a->noise_dev; P.seed = a->seed; P.forced = a->forced_dev; P.seedw = a->seed_dev; P.out = a->out_dev; P.head_out = a->head_dev;
+    P.status = m->status.p;
+    P.timeout_cycles = 4000000000ULL;
+    P.prof = (unsigned long long*)a->prof_dev; P.prof_start = a->prof_start; P.prof_count = a->prof_dev ? a->prof_count : 0;
+
+    CUDA_OK(cudaEventRecord(m->ev[2], st));
+    cudaError_t e = fn(P, grid, smem_max, st);
+    if (e != cudaSuccess) return fail("batch kernel launch failed: %s (grid %d, %zu B smem)", cudaGetErrorString(e), grid, smem_max);
+    CUDA_OK(cudaEventRecord(m->ev[3], st));
+    m->gen_timed = true;
+    m->info.kernel_launches++;
+    m->info.smem_bytes = (int32_t)smem_max;
+    m->info.batch_tile = BS;
+    m->info.n_slots = M;
+    m->info.grid = grid;
+    m->info.kernel_variant = 3;
+    m->info.ctas_per_layer = geff;
+    m->info.head_ctas = NH;
+    return 0;
+}
+
 extern "C" {
 
 const char* swn_last_error(void) { return g_err; }
@@ -654,6 +894,7 @@ int swn_finalize(swn_handle m) {
     // ---------------- v2 packing: the 16 CTAs of the core cluster (swn_core.cuh)
     m->core_ok = false;
     m->core_plan_key = -1;
+    m->g3 = 0; m->plan3_key = -1;
     {
         const bool audio_in = (!is_c && c.audio_in_flag);
         int nct = 0;
@@ -806,13 +1047,20 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
     if (n_iter + m->R + 2 > 0x7fffffffLL) return fail("swn_generate: too many steps");
 
     // ---- small batches, one sample per step: the cluster kernel (v2); everything else: layer groups (v1)
-    if (m->core_ok && a->kernel_sel != 1) {
+    if (m->core_ok && a->kernel_sel != 1 && a->kernel_sel != 3) {
         const int rc = generate_core(m, a, st, B, Tf, n_iter);
         if (rc == 0) return 0;
         if (rc == 1) return 1;
         if (a->kernel_sel == 2) return fail("swn_generate: the cluster kernel is not applicable to this configuration/batch");
     } else if (a->kernel_sel == 2) {
         return fail("swn_generate: the cluster kernel is not applicable to this configuration");
+    }
+    // ---- batches: the pipelined batch kernel (v3)
+    if (a->kernel_sel == 3 || (a->kernel_sel == 0 && B > 4)) {
+        const int rc = generate_batch(m, a, st, B, Tf, n_iter);
+        if (rc == 0) return 0;
+        if (rc == 1) return 1;
+        if (a->kernel_sel == 3) return fail("swn_generate: the batch kernel is not applicable to this configuration/batch");
     }
     // ---- batch tile
     int BS = 0;
@@ -1038,6 +1286,9 @@ int swn_destroy(swn_handle m) {
     m->xa_tab.release(); m->wp.release(); m->act0.release(); m->act1.release(); m->ptab.release();
     m->desc.release(); m->ll.release(); m->ring_scratch.release(); m->status.release();
     m->e2e_aux.release(); m->e2e_out.release();
+    m->wbuf3.release(); m->tiles3.release(); m->skip3.release(); m->lastskip3.release(); m->ring3.release();
+    m->cnt3.release(); m->desc3.release();
+    m->wbuf2.release(); m->ring2.release(); m->cdesc.release(); m->hdesc.release(); m->ll2.release();
     for (auto& cw : m->aux_convs) { cw.w_t.release(); cw.b.release(); }
     for (int i = 0; i < 4; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
     delete m;

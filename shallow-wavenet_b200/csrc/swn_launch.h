@@ -3,7 +3,7 @@
 #include <cuda_runtime.h>
 #include "swn_common.h"
 
-namespace swn { struct CoreParams; }
+namespace swn { struct CoreParams; struct BatchParams; }
 
 namespace swn {
 
@@ -22,6 +22,39 @@ core_fns find_core_kernel_nch1(int bs);
 core_fns find_core_kernel_nch2(int bs);
 core_fns find_core_kernel_nch3(int bs);
 core_fns find_core_kernel_nch4(int bs);
+
+// ---- variant 3: pipelined batch kernel (swn_batch.cuh), one object file per seg
+typedef cudaError_t (*batch_launch_fn)(const BatchParams& p, int grid, size_t smem, cudaStream_t st);
+batch_launch_fn find_batch_kernel_seg1(int bs);
+batch_launch_fn find_batch_kernel_seg2(int bs);
+batch_launch_fn find_batch_kernel_seg3(int bs);
+batch_launch_fn find_batch_kernel_seg4(int bs);
+batch_launch_fn find_batch_kernel_seg5(int bs);
+batch_launch_fn find_batch_kernel_seg10(int bs);
+inline batch_launch_fn find_batch_kernel(int seg, int bs) {
+    switch (seg) {
+        case 1: return find_batch_kernel_seg1(bs);
+        case 2: return find_batch_kernel_seg2(bs);
+        case 3: return find_batch_kernel_seg3(bs);
+        case 4: return find_batch_kernel_seg4(bs);
+        case 5: return find_batch_kernel_seg5(bs);
+        case 10: return find_batch_kernel_seg10(bs);
+        default: return nullptr;
+    }
+}
+// utterances per pipeline slot instantiated for a given seg (descending), terminated by 0
+inline const int* batch3_tiles_for_seg(int seg) {
+    static const int a[] = {16, 8, 4, 2, 1, 0};
+    static const int b[] = {8, 4, 2, 1, 0};
+    static const int c[] = {4, 2, 1, 0};
+    static const int none[] = {0};
+    switch (seg) {
+        case 1: return a;
+        case 2: case 5: return b;
+        case 3: case 4: case 10: return c;
+        default: return none;
+    }
+}
 
 // batch tiles instantiated for a given seg (descending), terminated by 0
 inline const int* batch_tiles_for_seg(int seg) {

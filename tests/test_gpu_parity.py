@@ -342,3 +342,98 @@ def test_full_size_cfg1_on_gpu_tail_property():
     n_tail = 8
     ref_tail = O.teacher_forced_tail(cfg, sd, aux, smp[None, :], n_tail)
     _head_close(heads[:, -n_tail:], ref_tail, "cfg1 tail")
+
+
+# ----------------------------------------------------------------------------- variant 3: pipelined batch kernel
+_V3_FIXTURES = [n for n in golden_names() if n != "dswnv_audio_in"]      # audio_in_flag stays on variant 1
+
+
+@pytest.mark.parametrize("tile", [1, 2])
+@pytest.mark.parametrize("name", _V3_FIXTURES)
+def test_batch_kernel_teacher_forced_matches_reference_fixture(name, tile):
+    g = load_golden(name)
+    m = _model_from_golden(g)
+    B, N = g["samples"].shape
+    outs, heads = m.batch_fast_generate(_seed_audio(g["kind"], B, g["cfg"].eff_seg), torch.from_numpy(g["aux"]),
+                                        [N] * B, noise=g["noise"], forced=g["samples"], return_heads=True,
+                                        kernel_sel=3, batch_tile=tile)
+    info = m.engine().info
+    assert info["kernel_variant"] == 3 and info["batch_tile"] == tile and info["n_slots"] == -(-B // tile)
+    _head_close(heads, g["heads"], "%s v3 tile %d" % (name, tile))
+    smp = np.stack(outs)
+    if g["kind"] == "dswnv":
+        assert np.array_equal(smp, g["samples"])
+    else:
+        assert float(np.abs(smp - g["samples"]).max()) <= SAMPLE_ATOL
+
+
+@pytest.mark.parametrize("name", _V3_FIXTURES)
+def test_batch_kernel_free_running_matches_reference_fixture(name):
+    g = load_golden(name)
+    m = _model_from_golden(g)
+    B, N = g["samples"].shape
+    outs = m.batch_fast_generate(_seed_audio(g["kind"], B, g["cfg"].eff_seg), torch.from_numpy(g["aux"]),
+                                 g["n_samples_list"], noise=g["noise"], kernel_sel=3)
+    assert m.engine().info["kernel_variant"] == 3
+    for b, o in enumerate(outs):
+        ref = g["samples"][b, :len(o)]
+        if g["kind"] == "dswnv":
+            assert np.array_equal(o, ref)
+        else:
+            assert float(np.abs(o - ref).max()) <= 5e-5
+
+
+@pytest.mark.parametrize("name,B,tile", [("dswnv_base", 11, 4), ("dswnv_base", 37, 8), ("dswnv_wavconv_k6", 19, 16),
+                                         ("cswnv_seg5_lpc4_wav", 13, 4), ("cswnv_seg5_lpc4_h64", 21, 8),
+                                         ("cswnv_seg2_lpc3", 9, 2), ("cswnv_seg1_lpc0", 33, 0)])
+def test_batch_kernel_many_slots_free_running_vs_oracle(name, B, tile):
+    """More utterances than one slot holds: the ring pipeline (slots in flight through the layer groups,
+    several head CTAs) against the oracle, free running on injected noise."""
+    g = load_golden(name)
+    m = _model_from_golden(g)
+    kw, cfg = g["kw"], g["cfg"]
+    rng = np.random.default_rng(B)
+    Tf, U = 4, kw["upsampling_factor"]
+    N = (Tf * U // cfg.eff_seg) * cfg.eff_seg
+    aux = rng.standard_normal((B, kw["n_aux"], Tf)).astype(np.float32)
+    if g["kind"] == "dswnv":
+        noise = rng.exponential(1.0, (B, N, 256)).astype(np.float32)
+    else:
+        noise = rng.uniform(-0.4999, 0.5, (B, N)).astype(np.float32)
+    outs, heads = m.batch_fast_generate(_seed_audio(g["kind"], B, cfg.eff_seg), torch.from_numpy(aux), [N] * B,
+                                        noise=noise, return_heads=True, batch_tile=tile)
+    info = m.engine().info
+    assert info["kernel_variant"] == 3 and info["n_slots"] == -(-B // info["batch_tile"])
+    ref_smp, ref_heads = O.generate(cfg, g["sd"], aux, N, noise, return_heads=True)
+    _head_close(heads, ref_heads, "%s B=%d" % (name, B))
+    if g["kind"] == "dswnv":
+        assert np.array_equal(np.stack(outs), ref_smp)
+    else:
+        assert float(np.abs(np.stack(outs) - ref_smp).max()) <= 5e-5
+
+
+@pytest.mark.parametrize("kind,fs,B,tile,over", [("cswnv", 22050, 9, 4, dict(seg=5, lpc=4)),
+                                                  ("cswnv", 22050, 17, 8, dict(seg=5, lpc=4)),
+                                                  ("cswnv", 22050, 6, 2, dict(seg=10, lpc=4)),
+                                                  ("dswnv", 24000, 20, 8, dict()),
+                                                  ("dswnv", 16000, 33, 16, dict())])
+def test_batch_kernel_recipe_size_teacher_forced_vs_oracle(kind, fs, B, tile, over):
+    model, cfg, sd, aux, kw = _recipe_case(kind, fs, B, 2, 21, **over)
+    seg = cfg.eff_seg
+    N = 2 * kw["upsampling_factor"]
+    rng = np.random.default_rng(8)
+    if kind == "cswnv":
+        forced = np.clip(0.3 * rng.standard_normal((B, N)), -1, 1).astype(np.float32)
+        noise = rng.uniform(-0.4999, 0.5, (B, N)).astype(np.float32)
+    else:
+        forced = rng.integers(0, 256, (B, N)).astype(np.int64)
+        noise = rng.exponential(1.0, (B, N, 256)).astype(np.float32)
+    outs, heads = model.batch_fast_generate(_seed_audio(kind, B, seg), torch.from_numpy(aux), [N] * B, noise=noise,
+                                            forced=forced, return_heads=True, batch_tile=tile)
+    info = model.engine().info
+    assert info["kernel_variant"] == 3 and info["batch_tile"] == tile
+    ref_heads = O.teacher_forced(cfg, sd, aux, forced)
+    _head_close(heads, ref_heads, "%s recipe B=%d" % (kind, B))
+    if kind == "dswnv":
+        mine = O.gumbel_argmax(heads.reshape(-1, 256), noise.reshape(-1, 256)).reshape(B, N)
+        assert np.array_equal(np.stack(outs), mine)
