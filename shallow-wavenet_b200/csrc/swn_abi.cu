@@ -118,11 +118,16 @@ struct swn_model {
     swn::CoreParams core_tmpl;
     size_t core_n_hin = 0, core_n_hacc = 0;
     // ---- v3: pipelined batch kernel (swn_batch.cuh)
-    struct L3Cta { int pair0, npairs, skip0, nskip, rows, RP; int64_t w_off, b_off, wl_off; };
+    struct L3Cta { int pair0, npairs, skip0, nskip, rows, RP; int64_t w_off, b_off; };
+    struct D3Cta { int64_t w_off, b_off; };
+    std::vector<D3Cta> dense3;
+    std::vector<float> wbuf3_h;
+    size_t wbuf3_base = 0;
+    long long dense3_key = -1;
     std::vector<std::vector<L3Cta>> l3;        // [L][g3]
     int g3 = 0, Hp3 = 0;
-    int64_t w1_off3 = 0, b1_off3 = 0, w2_off3 = 0, b2_off3 = 0, cs_off3 = 0;
-    DevBuf<float> wbuf3, tiles3, skip3, lastskip3, ring3;
+    int64_t w2_off3 = 0, b2_off3 = 0, cs_off3 = 0;
+    DevBuf<float> wbuf3, tiles3, skip3, ring3;
     DevBuf<unsigned int> cnt3;
     DevBuf<swn::BCta> desc3;
     long long plan3_key = -1;
@@ -444,12 +449,13 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
 }
 
 
-// ---- v3 packing: per layer CTA the transposed GEMM operand Wt[k][row] (rows = all taps of the owned gate
-// pairs, then the owned out_skip[l-1] rows), head matrices row-major padded to 64
+// ---- v3 packing (batch independent): per gated-cell CTA the transposed GEMM operand Wt[k][row] (rows = all
+// taps of the owned gate pairs, then the owned out_skip[l-1] rows); the head matrices are packed per plan
 static int pack_v3(swn_model* m, int geff) {
-    const int H = m->H, S = m->S, Sp = m->Sp, K = m->K, L = m->L, n1 = m->n1, n1p = m->n1p, n2 = m->n2, twoH = 2 * H;
+    const int H = m->H, S = m->S, K = m->K, L = m->L, twoH = 2 * H;
     const int Hp = round_up(H, 4);
-    std::vector<float> W;
+    std::vector<float>& W = m->wbuf3_h;
+    W.clear();
     auto alloc = [&](size_t n) { size_t off = (W.size() + 3) & ~size_t(3); W.resize(off + n, 0.f); return (int64_t)off; };
     std::vector<const HostTensor*> skw(L), skb(L);
     for (int l = 0; l < L; ++l) {
@@ -485,60 +491,43 @@ static int pack_v3(swn_model* m, int geff) {
                 W[c.b_off + pi * 2] = y->data[c.pair0 + pi];
                 W[c.b_off + pi * 2 + 1] = y->data[H + c.pair0 + pi];
             }
-            c.wl_off = 0;
-            if (l == L - 1) {
-                c.wl_off = alloc((size_t)np * S);
-                for (int pi = 0; pi < np; ++pi)
-                    for (int r = 0; r < S; ++r) W[c.wl_off + (size_t)pi * S + r] = skw[L - 1]->data[(size_t)r * H + c.pair0 + pi];
-            }
             m->l3[l].push_back(c);
         }
     }
-    const HostTensor *w1, *b1, *w2, *b2;
-    if (need(m, "out_1.weight", {n1, S, 1}, &w1) || need(m, "out_1.bias", {n1}, &b1) ||
-        need(m, "out_2.weight", {n2, n1, 1}, &w2) || need(m, "out_2.bias", {n2}, &b2)) return 1;
-    m->w1_off3 = alloc((size_t)n1 * Sp);
-    for (int r = 0; r < n1; ++r)
-        for (int k = 0; k < S; ++k) W[m->w1_off3 + (size_t)r * Sp + k] = w1->data[(size_t)r * S + k];
-    m->b1_off3 = alloc(n1);
-    for (int r = 0; r < n1; ++r) W[m->b1_off3 + r] = b1->data[r];
-    m->w2_off3 = alloc((size_t)n2 * n1p);
-    for (int r = 0; r < n2; ++r)
-        for (int k = 0; k < n1; ++k) W[m->w2_off3 + (size_t)r * n1p + k] = w2->data[(size_t)r * n1 + k];
-    m->b2_off3 = alloc(n2);
-    for (int r = 0; r < n2; ++r) W[m->b2_off3 + r] = b2->data[r];
+    const HostTensor *w2, *b2;
+    if (need(m, "out_2.weight", {m->n2, m->n1, 1}, &w2) || need(m, "out_2.bias", {m->n2}, &b2)) return 1;
+    m->w2_off3 = alloc((size_t)m->n2 * m->n1p);
+    for (int r = 0; r < m->n2; ++r)
+        for (int k = 0; k < m->n1; ++k) W[m->w2_off3 + (size_t)r * m->n1p + k] = w2->data[(size_t)r * m->n1 + k];
+    m->b2_off3 = alloc(m->n2);
+    for (int r = 0; r < m->n2; ++r) W[m->b2_off3 + r] = b2->data[r];
     m->cs_off3 = alloc(S);
     for (int r = 0; r < S; ++r) {
         double cs = 0.0;
         for (int l = 0; l < L; ++l) cs += skb[l]->data[r];
         W[m->cs_off3 + r] = (float)cs;
     }
-    if (upload(m->wbuf3, W)) return 1;
+    m->wbuf3_base = W.size();
     m->g3 = geff; m->Hp3 = Hp;
-    m->plan3_key = -1;
+    m->plan3_key = -1; m->dense3_key = -1;
     return 0;
 }
 
 // ---- v3 launch: returns 0 = launched, 2 = not applicable (caller falls back to v1), 1 = error
 static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, int B, int Tf, int64_t n_iter) {
-    const int H = m->H, K = m->K, L = m->L, S = m->S, seg = m->seg;
+    const int H = m->H, K = m->K, L = m->L, S = m->S, seg = m->seg, n1 = m->n1, n2 = m->n2;
     const bool is_c = m->cfg.kind == SWN_KIND_CSWNV;
     if (!is_c && m->cfg.audio_in_flag) return 2;
-    if (m->Sp > 256 || m->n1p > 256) return 2;
     const int* tiles = swn::batch3_tiles_for_seg(seg);
     if (!tiles[0]) return 2;
     const int smem_floats = SWN_MAX_SMEM / 4;
-    // ---- CTAs per layer group and head CTAs
-    const int nh_min = 4;
-    int G = (m->n_sm - nh_min) / L;
-    if (G < 1) return 2;
-    const int geff = std::min(G, H);
-    if (geff != m->g3) {
-        CUDA_OK(cudaStreamSynchronize(st));
-        if (pack_v3(m, geff)) return 1;
-    }
-    const int Hp = m->Hp3;
-    const int n2p = round_up(m->n2, 4);
+    const int n2p = round_up(n2, 4);
+    const bool tail_gemm = n2 <= 32;
+    // dense head stages: {input depth, output rows}
+    struct DenseSt { int kdim, rows; };
+    std::vector<DenseSt> dst = {{H, S}, {S, n1}};
+    if (!tail_gemm) dst.push_back({n1, n2});
+    const int ND = (int)dst.size();
     // ---- utterances per slot: explicit, or the largest tile that still leaves >= 12 slots in flight
     std::vector<int> cand;
     if (a->batch_tile > 0) {
@@ -550,38 +539,78 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
         for (const int* t = tiles; *t; ++t) if (first < 0 ? true : *t <= first) cand.push_back(*t);
         if (first < 0) std::reverse(cand.begin(), cand.end());     // small batches: smallest tile first
     }
-    int BS = 0, M = 0, NH = 0, grid = 0;
-    size_t smem_max = 0, ring_total = 0;
+    int BS = 0, M = 0, NT = 0, grid = 0, geff = 0;
+    size_t smem_max = 0, ring_total = 0, tiles_total = 0;
+    std::vector<int> nd(ND, 1);
     std::vector<swn::BCta> desc;
+    std::vector<int64_t> tile_off;           // per stage input tile offset (stages: L cells, ND dense, tail)
     for (int bs : cand) {
-        const int NC = bs * seg, OS = NC | 1;
-        if (((size_t)H * NC * 4) % 16 != 0) continue;
+        const int NC = bs * seg, OS = NC | 1, OSd = bs | 1;
+        if (((size_t)H * NC * 4) % 16 != 0 || ((size_t)H * bs * 4) % 16 != 0 || ((size_t)S * bs * 4) % 16 != 0 ||
+            ((size_t)n1 * bs * 4) % 16 != 0) continue;
         const int Mx = (B + bs - 1) / bs, Bp = Mx * bs;
-        const int nh = std::max(1, std::min(std::min(Mx, 16), m->n_sm - L * geff));
+        // CTAs a dense stage needs so that its rows fit in shared memory
+        bool ok = true;
+        int nd_min_total = 0;
+        for (int d = 0; d < ND && ok; ++d) {
+            const int kp = round_up(dst[d].kdim, 4);
+            int n = 1;
+            for (;; ++n) {
+                const int rows = (dst[d].rows + n - 1) / n, RP = round_up(rows, 8);
+                const size_t u = (size_t)kp * RP + 2 * (size_t)kp * bs + (size_t)RP * OSd + (size_t)rows * bs + 64;
+                if (u <= (size_t)smem_floats) break;
+                if (n >= dst[d].rows) { ok = false; break; }
+            }
+            nd[d] = n; nd_min_total += n;
+        }
+        if (!ok) continue;
+        const int G = (m->n_sm - nd_min_total - 1) / L;
+        if (G < 1) continue;
+        const int ge = std::min(G, H);
+        if (ge != m->g3) {
+            CUDA_OK(cudaStreamSynchronize(st));
+            if (pack_v3(m, ge)) return 1;
+        }
+        const int Hp = m->Hp3;
+        int left = m->n_sm - L * ge - nd_min_total;              // >= 1
+        int nt = std::max(1, std::min(std::min(Mx, 2), left));
+        left -= nt;
+        for (int d = 0; left > 0 && d < 8 * ND; ++d)              // spare SMs: more CTAs per dense stage (up to 8 each)
+            if (nd[d % ND] < 8 && nd[d % ND] < dst[d % ND].rows) { ++nd[d % ND]; --left; }
         bool fits = true;
         size_t used_max = 0, rt = 0;
-        desc.assign((size_t)L * geff + nh, swn::BCta());
+        int n_cta = L * ge + nt;
+        for (int d = 0; d < ND; ++d) n_cta += nd[d];
+        desc.assign((size_t)n_cta, swn::BCta());
+        // tiles: cell inputs [H][NC] x L, last-column tile [H][bs], dense outputs
+        tile_off.assign(L + ND + 1, 0);
+        size_t tt = 0;
+        for (int l = 0; l < L; ++l) { tile_off[l] = (int64_t)tt; tt += (size_t)Mx * H * NC; }
+        tile_off[L] = (int64_t)tt; tt += (size_t)Mx * H * bs;
+        for (int d = 0; d < ND; ++d) { tile_off[L + 1 + d] = (int64_t)tt; tt += (size_t)Mx * dst[d].rows * bs; }
         int cta = 0;
         for (int l = 0; l < L && fits; ++l)
-            for (int g = 0; g < geff; ++g, ++cta) {
+            for (int g = 0; g < ge; ++g, ++cta) {
                 const auto& c = m->l3[l][g];
                 swn::BCta& d = desc[cta];
                 memset(&d, 0, sizeof(d));
                 d.role = ROLE_LAYER; d.layer = l; d.hindex = g; d.dil = m->dil[l];
                 d.pair0 = c.pair0; d.npairs = c.npairs; d.skip0 = c.skip0; d.nskip = c.nskip; d.rows = c.rows; d.RP = c.RP;
+                d.kdim = H; d.kp = Hp;
                 d.ring_len = (K - 1) * d.dil + seg;
-                d.nprod_in = l == 0 ? 1 : geff;
+                d.cnt_in = l; d.cnt_out = l + 1;
+                d.nprod_in = l == 0 ? 1 : ge;
                 d.is_last = l == L - 1;
-                d.w_off = c.w_off; d.b_off = c.b_off; d.wl_off = c.wl_off;
+                d.in_off = tile_off[l]; d.in_slot_f = H * NC;
+                d.out_off = tile_off[l + 1]; d.out_slot_f = d.is_last ? H * bs : H * NC;
+                d.w_off = c.w_off; d.b_off = c.b_off;
                 size_t u = 0;
                 auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
                 d.sm_w = take((size_t)Hp * c.RP);
                 d.sm_x = take((size_t)2 * Hp * NC);
                 d.sm_o = take((size_t)c.RP * OS);
                 d.sm_pre = take((size_t)c.npairs * NC * 4);
-                d.sm_hn = take((size_t)c.npairs * bs);
-                d.sm_wl = take(d.is_last ? (size_t)c.npairs * S : 0);
-                d.sm_bar = take(16);
+                d.sm_bar = take(32);
                 const size_t ring_f = (size_t)d.ring_len * 2 * c.npairs * Bp;
                 d.sm_ring = (int32_t)u;
                 d.ring_in_smem = u + ring_f <= (size_t)smem_floats;
@@ -591,44 +620,104 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
                 used_max = std::max(used_max, u);
             }
         if (!fits) continue;
-        const int MO = (Mx + nh - 1) / nh;
-        const int kpmax = std::max(m->Sp, m->n1p);
-        for (int hc = 0; hc < nh; ++hc, ++cta) {
+        for (int sd = 0; sd < ND && fits; ++sd)
+            for (int i = 0; i < nd[sd]; ++i, ++cta) {
+                swn::BCta& d = desc[cta];
+                memset(&d, 0, sizeof(d));
+                d.role = swn::ROLE_DENSE; d.layer = sd; d.hindex = i;
+                split_range(dst[sd].rows, nd[sd], i, &d.row0, &d.nrows);
+                d.rows = d.nrows; d.RP = round_up(d.nrows, 8);
+                d.kdim = dst[sd].kdim; d.kp = round_up(d.kdim, 4);
+                d.cnt_in = L + sd; d.cnt_out = L + sd + 1;
+                d.nprod_in = sd == 0 ? ge : nd[sd - 1];
+                d.relu = sd < 2; d.add_skips = sd == 0;
+                d.in_off = tile_off[L + sd]; d.in_slot_f = d.kdim * bs;
+                d.out_off = tile_off[L + 1 + sd]; d.out_slot_f = dst[sd].rows * bs;
+                size_t u = 0;
+                auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
+                d.sm_w = take((size_t)d.kp * d.RP);
+                d.sm_x = take((size_t)2 * d.kp * bs);
+                d.sm_o = take((size_t)d.RP * OSd);
+                d.sm_pre = take((size_t)d.nrows * bs);
+                d.sm_bar = take(32);
+                if (u > (size_t)smem_floats) { fits = false; break; }
+                used_max = std::max(used_max, u);
+            }
+        if (!fits) continue;
+        const int MO = (Mx + nt - 1) / nt;
+        for (int hc = 0; hc < nt; ++hc, ++cta) {
             swn::BCta& d = desc[cta];
             memset(&d, 0, sizeof(d));
             d.role = ROLE_HEAD; d.hindex = hc;
             size_t u = 0;
             auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
-            d.sm_wring = take((size_t)swn::B3_NST * swn::B3_RCH * kpmax);
-            d.sm_x1 = take((size_t)bs * m->Sp);
             d.sm_x2 = take((size_t)bs * m->n1p);
             d.sm_oc = take((size_t)bs * n2p);
+            d.sm_w2 = take(tail_gemm ? (size_t)n2 * m->n1p : 0);
             d.sm_tin = take((size_t)H * NC);
+            d.sm_itab = take((is_c ? (size_t)K * 2 * H : 0) + H + n2);
+            d.sm_ain = take((size_t)NC * K * 2);
+            d.sm_noise = take(is_c ? (size_t)bs * seg : (size_t)bs * m->Q);
             d.sm_hist = take((size_t)MO * bs * swn::B3_HIST);
             d.sm_lpb = take((size_t)MO * bs * 8);
-            d.sm_misc = take(4 * swn::B3_NST + 8);
+            d.sm_misc = take(8);
             if (u > (size_t)smem_floats) { fits = false; break; }
             used_max = std::max(used_max, u);
         }
         if (!fits) continue;
-        BS = bs; M = Mx; NH = nh; grid = cta; smem_max = used_max * 4; ring_total = rt;
+        BS = bs; M = Mx; NT = nt; grid = cta; geff = ge; smem_max = used_max * 4; ring_total = rt; tiles_total = tt;
         break;
     }
     if (!BS) return 2;
-    const int NC = BS * seg;
     swn::batch_launch_fn fn = swn::find_batch_kernel(seg, BS);
     if (!fn) return 2;
-    const long long key = ((long long)B << 32) | ((long long)BS << 16) | ((long long)geff << 8) | (long long)NH;
+    // ---- dense stage weights depend on the CTA split: pack them behind the batch-independent part
+    long long dkey = ((long long)geff << 40);
+    for (int d = 0; d < ND; ++d) dkey = dkey * 16 + nd[d];
+    if (dkey != m->dense3_key) {
+        CUDA_OK(cudaStreamSynchronize(st));
+        std::vector<float>& W = m->wbuf3_h;
+        W.resize(m->wbuf3_base);
+        auto alloc = [&](size_t n) { size_t off = (W.size() + 3) & ~size_t(3); W.resize(off + n, 0.f); return (int64_t)off; };
+        const HostTensor *skw, *w1, *b1, *w2, *b2;
+        if (need(m, "out_skip." + std::to_string(L - 1) + ".weight", {S, H, 1}, &skw) ||
+            need(m, "out_1.weight", {n1, S, 1}, &w1) || need(m, "out_1.bias", {n1}, &b1) ||
+            need(m, "out_2.weight", {n2, n1, 1}, &w2) || need(m, "out_2.bias", {n2}, &b2)) return 1;
+        m->dense3.clear();
+        for (int sd = 0; sd < ND; ++sd)
+            for (int i = 0; i < nd[sd]; ++i) {
+                int row0, nrows;
+                split_range(dst[sd].rows, nd[sd], i, &row0, &nrows);
+                const int kdim = dst[sd].kdim, kp = round_up(kdim, 4), RP = round_up(nrows, 8);
+                const float* src = sd == 0 ? skw->data.data() : (sd == 1 ? w1->data.data() : w2->data.data());
+                swn_model::D3Cta dc;
+                dc.w_off = alloc((size_t)kp * RP);
+                for (int r = 0; r < nrows; ++r)
+                    for (int k = 0; k < kdim; ++k) W[dc.w_off + (size_t)k * RP + r] = src[(size_t)(row0 + r) * kdim + k];
+                dc.b_off = alloc(nrows);
+                for (int r = 0; r < nrows; ++r)
+                    W[dc.b_off + r] = sd == 0 ? W[m->cs_off3 + row0 + r] : (sd == 1 ? b1->data[row0 + r] : b2->data[row0 + r]);
+                m->dense3.push_back(dc);
+            }
+        if (upload(m->wbuf3, W)) return 1;
+        m->dense3_key = dkey;
+        m->plan3_key = -1;
+    }
+    {
+        int cta = L * geff, di = 0;
+        for (int sd = 0; sd < ND; ++sd)
+            for (int i = 0; i < nd[sd]; ++i, ++cta, ++di) { desc[cta].w_off = m->dense3[di].w_off; desc[cta].b_off = m->dense3[di].b_off; }
+    }
+    const int NC = BS * seg;
+    const long long key = ((long long)B << 32) | ((long long)BS << 16) | ((long long)geff << 8) | (long long)NT;
     if (key != m->plan3_key) {
         CUDA_OK(cudaStreamSynchronize(st));
         if (upload(m->desc3, desc)) return 1;
         m->plan3_key = key;
     }
-    const size_t n_tiles = (size_t)(L + 1) * M * H * NC;
-    const size_t n_cnt = (size_t)(L + 1) * M * swn::B3_CNT_STRIDE;
+    const size_t n_cnt = (size_t)(L + ND + 1) * M * swn::B3_CNT_STRIDE;
     const size_t n_skip = (size_t)std::max(L - 1, 1) * M * S * BS;
-    const size_t n_last = (size_t)geff * M * S * BS;
-    if (m->tiles3.ensure(n_tiles) || m->cnt3.ensure(n_cnt) || m->skip3.ensure(n_skip) || m->lastskip3.ensure(n_last) ||
+    if (m->tiles3.ensure(tiles_total) || m->cnt3.ensure(n_cnt) || m->skip3.ensure(n_skip) ||
         m->ring3.ensure(std::max<size_t>(ring_total, 4))) return 1;
     CUDA_OK(cudaMemsetAsync(m->cnt3.p, 0, n_cnt * sizeof(unsigned int), st));
     if (ring_total) CUDA_OK(cudaMemsetAsync(m->ring3.p, 0, ring_total * sizeof(float), st));
@@ -636,24 +725,27 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
 
     swn::BatchParams P;
     memset(&P, 0, sizeof(P));
-    P.kind = m->cfg.kind; P.H = H; P.Hp = Hp; P.S = S; P.Sp = m->Sp; P.K = K; P.L = L; P.lpc = m->lpc;
-    P.n1 = m->n1; P.n1p = m->n1p; P.n2 = m->n2; P.n2p = n2p; P.Q = m->Q; P.U = m->U; P.R = m->R; P.B = B; P.M = M; P.Tf = Tf;
+    P.kind = m->cfg.kind; P.H = H; P.S = S; P.K = K; P.L = L; P.lpc = m->lpc;
+    P.n1 = n1; P.n1p = m->n1p; P.n2 = n2; P.n2p = n2p; P.Q = m->Q; P.U = m->U; P.R = m->R; P.B = B; P.M = M; P.Tf = Tf;
     const int rem = (m->R + 1) % seg;
     P.t_first = rem == 0 ? 0 : rem - seg;
     P.it0 = (m->R + 1 - P.t_first) / seg - 1;
     P.n_iter = (int)n_iter;
     P.n_it = P.it0 + P.n_iter;
-    P.NH = NH; P.G = geff;
+    P.NT = NT; P.tail_gemm = tail_gemm ? 1 : 0;
+    P.tail_cnt = L + ND; P.tail_nprod = nd[ND - 1];
+    P.tail_in_off = tile_off[L + ND]; P.tail_slot_f = dst[ND - 1].rows * BS;
     P.n_out = n_iter * seg;
     P.desc = m->desc3.p; P.wbuf = m->wbuf3.p;
     P.P = m->ptab.p; P.pconst = m->pconst.p; P.gain = m->gain.p;
     P.in_tab = m->in_tab.p; P.in_bias = m->in_bias.p;
-    P.w1_off = m->w1_off3; P.b1_off = m->b1_off3; P.w2_off = m->w2_off3; P.b2_off = m->b2_off3; P.cs_off = m->cs_off3;
-    P.tiles = m->tiles3.p; P.cnt = m->cnt3.p; P.skipbuf = m->skip3.p; P.lastskip = m->lastskip3.p; P.ring_scratch = m->ring3.p;
+    P.w2_off = m->w2_off3; P.b2_off = m->b2_off3; P.cs_off = m->cs_off3;
+    P.tiles = m->tiles3.p; P.cnt = m->cnt3.p; P.skipbuf = m->skip3.p; P.ring_scratch = m->ring3.p;
     P.noise = a->noise_dev; P.seed = a->seed; P.forced = a->forced_dev; P.seedw = a->seed_dev; P.out = a->out_dev; P.head_out = a->head_dev;
     P.status = m->status.p;
     P.timeout_cycles = 4000000000ULL;
     P.prof = (unsigned long long*)a->prof_dev; P.prof_start = a->prof_start; P.prof_count = a->prof_dev ? a->prof_count : 0;
+    (void)NC;
 
     CUDA_OK(cudaEventRecord(m->ev[2], st));
     cudaError_t e = fn(P, grid, smem_max, st);
@@ -667,7 +759,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
     m->info.grid = grid;
     m->info.kernel_variant = 3;
     m->info.ctas_per_layer = geff;
-    m->info.head_ctas = NH;
+    m->info.head_ctas = grid - L * geff;
     return 0;
 }
 
@@ -1286,7 +1378,7 @@ int swn_destroy(swn_handle m) {
     m->xa_tab.release(); m->wp.release(); m->act0.release(); m->act1.release(); m->ptab.release();
     m->desc.release(); m->ll.release(); m->ring_scratch.release(); m->status.release();
     m->e2e_aux.release(); m->e2e_out.release();
-    m->wbuf3.release(); m->tiles3.release(); m->skip3.release(); m->lastskip3.release(); m->ring3.release();
+    m->wbuf3.release(); m->tiles3.release(); m->skip3.release(); m->ring3.release();
     m->cnt3.release(); m->desc3.release();
     m->wbuf2.release(); m->ring2.release(); m->cdesc.release(); m->hdesc.release(); m->ll2.release();
     for (auto& cw : m->aux_convs) { cw.w_t.release(); cw.b.release(); }

@@ -24,36 +24,45 @@
 
 namespace swn {
 
-constexpr int B3_NGW = 8;                 // GEMM warps 0..7
-constexpr int B3_LOADER = 8;              // warp 8: lane 0 is the loader
-constexpr int B3_EPI0 = 9;                // epilogue warps 9..15
+constexpr int B3_NGW = 4;                 // GEMM warps 0..3 (one per SM sub-partition)
+constexpr int B3_LOADER = 4;              // warp 4: lane 0 is the loader
+constexpr int B3_EPI0 = 5;                // epilogue warps 5..15
 constexpr int B3_NEPI = (SWN_NWARPS - B3_EPI0) * 32;
 constexpr int B3_CNT_STRIDE = 8;          // one counter per 32-byte sector
-constexpr int B3_RCH = 32;                // head: weight rows per streamed chunk
-constexpr int B3_NST = 4;                 // head: chunks in flight
 constexpr int B3_HIST = 32;
 
+enum { ROLE_DENSE = 3 };                  // besides ROLE_LAYER (gated cell), ROLE_HEAD (tail), ROLE_IDLE
+
+// One descriptor per CTA.  Pipeline stages: the L gated cells, then the dense stages of the output head
+// (A: relu(sum of skips) = out_skip[L-1] . h + the other layers' skips, B: relu(out_1), C: out_2 when it is
+// large), then the tail CTAs (small out_2, sampler, causal input stage of the next step).
 struct BCta {
-    int32_t role, layer, hindex;          // hindex: group index of a layer CTA / head CTA index
+    int32_t role, layer, hindex;          // layer: cell index / dense stage id; hindex: index inside the group / tail index
     int32_t dil;
-    int32_t pair0, npairs, skip0, nskip;
-    int32_t rows, RP;                     // GEMM rows (2*K*np + nskip) and their padding to 8
+    int32_t pair0, npairs, skip0, nskip;  // gated cell: owned gate pairs and rows of out_skip[layer-1]
+    int32_t row0, nrows;                  // dense stage: owned output rows
+    int32_t rows, RP;                     // GEMM rows and their padding to 8
+    int32_t kdim, kp;                     // GEMM depth (input channels) and its padding to 4
     int32_t ring_len, ring_in_smem;
-    int32_t nprod_in;                     // producers of the input tile (counter increments per iteration)
-    int32_t is_last;
-    int32_t sm_w, sm_x, sm_o, sm_pre, sm_hn, sm_wl, sm_ring, sm_bar;
-    int64_t w_off;                        // [Hp][RP]
-    int64_t b_off;                        // [np][2]
-    int64_t wl_off;                       // last layer: [np][S] columns of out_skip[L-1]
+    int32_t cnt_in, cnt_out, nprod_in;    // counter rows ([.][M]) of the input / output tile; producers of the input
+    int32_t is_last, relu, add_skips;
+    int32_t in_slot_f, out_slot_f;        // floats per slot of the input / output tile
+    int32_t sm_w, sm_x, sm_o, sm_pre, sm_ring, sm_bar;
+    int64_t in_off, out_off;              // float offsets of slot 0 inside BatchParams::tiles
+    int64_t w_off;                        // [kp][RP]
+    int64_t b_off;                        // gated cell: [np][2]; dense: [nrows]
     int64_t ring_off;                     // [RL][2*np][Bp] in ring_scratch
-    // head CTA shared-memory layout
-    int32_t sm_wring, sm_x1, sm_x2, sm_oc, sm_tin, sm_hist, sm_lpb, sm_misc;
+    // tail CTA shared-memory layout
+    int32_t sm_x2, sm_oc, sm_w2, sm_tin, sm_itab, sm_ain, sm_noise, sm_hist, sm_lpb, sm_misc;
 };
 
 struct BatchParams {
-    int32_t kind, H, Hp, S, Sp, K, L, lpc, n1, n1p, n2, n2p, Q, U, R, B, M, Tf;
+    int32_t kind, H, S, K, L, lpc, n1, n1p, n2, n2p, Q, U, R, B, M, Tf;
     int32_t t_first, it0, n_it, n_iter;
-    int32_t NH, G;                        // head CTAs, CTAs per layer group
+    int32_t NT;                           // tail CTAs
+    int32_t tail_gemm;                    // 1: the tail evaluates out_2 itself (few rows); 0: out_2 is dense stage C
+    int32_t tail_cnt, tail_nprod, tail_slot_f;   // counter row / producers / floats per slot of the tail's input
+    int64_t tail_in_off;
     int64_t n_out;
     const BCta* desc;
     const float* wbuf;
@@ -62,11 +71,11 @@ struct BatchParams {
     const float* gain;                    // [U]
     const float* in_tab;
     const float* in_bias;
-    int64_t w1_off, b1_off, w2_off, b2_off, cs_off;    // head weights inside wbuf
-    float* tiles;                         // [L+1][M][H][NC]
-    unsigned int* cnt;                    // [L+1][M] * B3_CNT_STRIDE
+    int64_t w2_off, b2_off;               // tail_gemm: out_2 row-major [n2][n1p] and its bias, inside wbuf
+    int64_t cs_off;                       // sum over layers of the out_skip biases [S]
+    float* tiles;                         // all exchange tiles (see the host plan)
+    unsigned int* cnt;                    // [stages+1][M] * B3_CNT_STRIDE
     float* skipbuf;                       // [L-1][M][S][BS]
-    float* lastskip;                      // [G][M][S][BS]
     float* ring_scratch;
     const float* noise;
     unsigned long long seed;
@@ -134,8 +143,9 @@ static __device__ __noinline__ bool b3_cnt_wait(const unsigned int* p, unsigned 
         }
     }
 }
+// Release increment: the stores of the whole team (ordered before this thread by its barrier) become visible
+// to whoever acquires the counter.
 __device__ __forceinline__ void b3_signal(unsigned int* p) {
-    __threadfence();
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
 
@@ -149,49 +159,60 @@ __host__ __device__ constexpr int b3_pick_tc(int nc) {
     return (nc % 5 == 0) ? 5 : (nc % 4 == 0) ? 4 : (nc % 3 == 0) ? 3 : (nc % 2 == 0) ? 2 : 1;
 }
 
-// ------------------------------------------------------------------ layer CTA
-template <int SEG, int BS>
-__device__ void b3_layer(const BatchParams& P, const BCta& D, float* smem) {
-    constexpr int NC = SEG * BS;
-    constexpr int TC = b3_pick_tc(NC);
-    constexpr int NCG = NC / TC;                    // column groups (NCG*TC == NC)
-    static_assert(NCG <= 32, "too many column groups");
-    constexpr int RGW = 32 / NCG;                   // row groups handled by one warp pass
-    constexpr int TR = (NC >= 40) ? 8 : 4;
-    constexpr int RPW = RGW * TR;                   // rows per warp pass
-    constexpr int OS = NC | 1;
+// ------------------------------------------------------------------ GEMM stage CTA (gated cell or dense stage)
+// Register tile of the fp32 GEMM for NCX columns: a thread owns TR rows x TC columns, a warp NCG column groups x
+// RGW row groups; KS warps split k for the same rows (their partial sums are added through the output tile).
+// Shared-memory loads, not FFMA issue, bound small tiles (every LDS.128 costs 4 LSU cycles even when it is a
+// broadcast), hence the large tiles where the column count allows them.
+template <int NCX>
+struct B3Tile {
+    static constexpr int TC = (NCX % 10 == 0 && NCX >= 40) ? 10 : (NCX <= 8) ? NCX : b3_pick_tc(NCX);
+    static constexpr int NCG = NCX / TC;            // column groups (NCG*TC == NCX)
+    static constexpr int RGW = 32 / NCG;            // row groups handled by one warp pass
+    static constexpr int TR = (NCX == 20 || NCX >= 40) ? 8 : 4;
+    static constexpr int RPW = RGW * TR;            // rows per warp pass
+    static constexpr int KS = (RPW >= 64) ? 2 : 1;  // k-splits
+    static constexpr int OS = NCX | 1;
+    static_assert(NCG >= 1 && NCG <= 32 && NCG * TC == NCX, "column groups");
+};
+
+// MODE 0: gated cell (cswnv_shift1.py:275-285) over NC = SEG*BS columns; MODE 1: dense head stage over BS columns.
+template <int SEG, int BS, int MODE>
+__device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
+    constexpr int NC = MODE == 0 ? SEG * BS : BS;
+    using T = B3Tile<NC>;
+    constexpr int TC = T::TC, NCG = T::NCG, RGW = T::RGW, TR = T::TR, RPW = T::RPW, OS = T::OS, KS = T::KS;
+    constexpr int SLOTS = B3_NGW / KS;              // row blocks in flight
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int l = D.layer, np = D.npairs, K = P.K, H = P.H, Hp = P.Hp, dil = D.dil, RL = D.ring_len, RP = D.RP;
+    const int l = D.layer, np = D.npairs, K = P.K, H = P.H, kp = D.kp, dil = D.dil, RL = D.ring_len, RP = D.RP;
     const int M = P.M, Bp = M * BS, np2 = 2 * np;
 
     float* Wt = smem + D.sm_w;
     float* Xs = smem + D.sm_x;
     float* Os = smem + D.sm_o;
     float4* pre = reinterpret_cast<float4*>(smem + D.sm_pre);
-    float* hn = smem + D.sm_hn;
-    float* Wl = smem + D.sm_wl;
+    float* pre1 = smem + D.sm_pre;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + D.sm_bar);
     unsigned long long* x_full = bars;              // [2]
     unsigned long long* x_empty = bars + 2;         // [2]
     unsigned long long* o_full = bars + 4;
     unsigned long long* o_empty = bars + 5;
     unsigned long long* ebar = bars + 6;            // barrier among the epilogue warps (abortable, unlike bar.sync)
+    unsigned long long* kbar = bars + 7;            // [SLOTS] first k-split stored its partial sums
+    unsigned long long* kback = bars + 7 + SLOTS;   // [SLOTS] second k-split added its own (only waited for between passes)
 
     const int nrb = (RP + RPW - 1) / RPW;
-    const int ngwa = nrb < B3_NGW ? nrb : B3_NGW;   // GEMM warps that own rows
+    const int nslot = nrb < SLOTS ? nrb : SLOTS;    // row-block slots in use
+    const int ngwa = nslot * KS;                    // GEMM warps that own work
 
     // ---- one-time staging
     {
         const float4* src = reinterpret_cast<const float4*>(P.wbuf + D.w_off);
         float4* dst = reinterpret_cast<float4*>(Wt);
-        const int n4 = Hp * RP / 4;
+        const int n4 = kp * RP / 4;
         for (int i = tid; i < n4; i += SWN_NTHREADS) dst[i] = src[i];
-        for (int i = tid; i < 2 * Hp * NC; i += SWN_NTHREADS) Xs[i] = 0.f;
-        if (D.is_last) {
-            const float* s2 = P.wbuf + D.wl_off;
-            for (int i = tid; i < np * P.S; i += SWN_NTHREADS) Wl[i] = s2[i];
-        }
-        if (D.ring_in_smem) {
+        for (int i = tid; i < 2 * kp * NC; i += SWN_NTHREADS) Xs[i] = 0.f;
+        if (MODE == 0 && D.ring_in_smem) {
             float* rg = smem + D.sm_ring;
             for (int i = tid; i < RL * np2 * Bp; i += SWN_NTHREADS) rg[i] = 0.f;
         }
@@ -200,6 +221,7 @@ __device__ void b3_layer(const BatchParams& P, const BCta& D, float* smem) {
             b3_mbar_init(&x_empty[0], ngwa + 1); b3_mbar_init(&x_empty[1], ngwa + 1);
             b3_mbar_init(o_full, ngwa); b3_mbar_init(o_empty, 1);
             b3_mbar_init(ebar, SWN_NWARPS - B3_EPI0);
+            for (int i = 0; i < SLOTS; ++i) { b3_mbar_init(&kbar[i], 1); b3_mbar_init(&kback[i], 1); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
@@ -207,65 +229,111 @@ __device__ void b3_layer(const BatchParams& P, const BCta& D, float* smem) {
     __syncthreads();
 
     const int nq = P.n_it * M;
-    const uint32_t tile_bytes = (uint32_t)(H * NC * sizeof(float));
-    const float* tile_in = P.tiles + (size_t)l * M * H * NC;
-    float* tile_out = P.tiles + (size_t)(l + 1) * M * H * NC;
+    const uint32_t tile_bytes = (uint32_t)(D.kdim * NC * sizeof(float));
+    const float* tile_in = P.tiles + D.in_off;
+    float* tile_out = P.tiles + D.out_off;
+    const unsigned int* cnt_in = P.cnt + (size_t)D.cnt_in * M * B3_CNT_STRIDE;
+    unsigned int* cnt_out = P.cnt + (size_t)D.cnt_out * M * B3_CNT_STRIDE;
 
     if (warp < B3_NGW) {
-        // =============================== GEMM warps
-        if (warp >= ngwa) return;
+        // =============================== GEMM warps: warp = (row-block slot, k-split)
+        const int slot = warp % SLOTS, ks = warp / SLOTS;
+        if (slot >= nslot) return;
         const int rg = lane / NCG, cg = lane - rg * NCG;
         const bool lane_ok = rg < RGW;
+        const int kchunk = (kp + KS - 1) / KS;
+        const int kb = ks * kchunk, ke = min(kp, kb + kchunk);
+        uint32_t kphase = 0;
         for (int q = 0; q < nq; ++q) {
             const int buf = q & 1;
             if (!b3_wait_warp(&x_full[buf], (q >> 1) & 1, P.status)) return;
-            const float* X = Xs + buf * Hp * NC;
+            const int it = q / M, m = q - it * M;
+            if (tid == 0) B3_PROF(1);
+            const float* X = Xs + buf * kp * NC;
             bool first = true;
-            for (int rb = warp; rb < nrb; rb += ngwa) {
+            for (int rb = slot; rb < nrb; rb += nslot) {
                 const int r0 = (rb * RGW + rg) * TR;
                 const bool act = lane_ok && r0 < RP;
-                float acc[TR][TC];
+                // packed fp32 FMA (FFMA2): one instruction updates the accumulators of two adjacent rows
+                unsigned long long acc2[TR / 2][TC];
 #pragma unroll
-                for (int i = 0; i < TR; ++i)
+                for (int i = 0; i < TR / 2; ++i)
 #pragma unroll
-                    for (int j = 0; j < TC; ++j) acc[i][j] = 0.f;
+                    for (int j = 0; j < TC; ++j) acc2[i][j] = 0ull;
                 if (act) {
                     const float* wp = Wt + r0;
                     const float* xp = X + cg * TC;
-#pragma unroll 4
-                    for (int k = 0; k < Hp; ++k) {
-                        float w[TR], x[TC];
+#pragma unroll 2
+                    for (int k = kb; k < ke; ++k) {
+                        unsigned long long w2[TR / 2];
+                        float x[TC];
 #pragma unroll
                         for (int i = 0; i < TR; i += 4) {
-                            const float4 v = *reinterpret_cast<const float4*>(wp + (size_t)k * RP + i);
-                            w[i] = v.x; w[i + 1] = v.y; w[i + 2] = v.z; w[i + 3] = v.w;
+                            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(wp + (size_t)k * RP + i);
+                            w2[i / 2] = v.x; w2[i / 2 + 1] = v.y;
                         }
-                        if constexpr (TC == 4) {
-                            const float4 v = *reinterpret_cast<const float4*>(xp + k * NC);
-                            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-                        } else if constexpr (TC == 2) {
-                            const float2 v = *reinterpret_cast<const float2*>(xp + k * NC);
-                            x[0] = v.x; x[1] = v.y;
+                        if constexpr (TC % 4 == 0) {
+#pragma unroll
+                            for (int j = 0; j < TC; j += 4) {
+                                const float4 v = *reinterpret_cast<const float4*>(xp + k * NC + j);
+                                x[j] = v.x; x[j + 1] = v.y; x[j + 2] = v.z; x[j + 3] = v.w;
+                            }
+                        } else if constexpr (TC % 2 == 0) {
+#pragma unroll
+                            for (int j = 0; j < TC; j += 2) {
+                                const float2 v = *reinterpret_cast<const float2*>(xp + k * NC + j);
+                                x[j] = v.x; x[j + 1] = v.y;
+                            }
                         } else {
 #pragma unroll
                             for (int j = 0; j < TC; ++j) x[j] = xp[k * NC + j];
                         }
 #pragma unroll
-                        for (int i = 0; i < TR; ++i)
+                        for (int j = 0; j < TC; ++j) {
+                            unsigned long long xx;
+                            asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x[j]));
 #pragma unroll
-                            for (int j = 0; j < TC; ++j) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
+                            for (int i = 0; i < TR / 2; ++i)
+                                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][j]) : "l"(xx), "l"(w2[i]));
+                        }
                     }
                 }
+                float acc[TR][TC];
+#pragma unroll
+                for (int i = 0; i < TR / 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < TC; ++j)
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * i][j]), "=f"(acc[2 * i + 1][j]) : "l"(acc2[i][j]));
                 if (first) {
                     first = false;
+                    if (tid == 0) B3_PROF(2);
                     if (q > 0 && !b3_wait_warp(o_empty, (q - 1) & 1, P.status)) return;
                 }
-                if (act) {
+                if (KS == 1 || ks == 0) {
+                    if (KS > 1 && rb != slot && !b3_wait_warp(&kback[slot], (kphase - 1) & 1, P.status)) return;
+                    if (act) {
 #pragma unroll
-                    for (int i = 0; i < TR; ++i)
+                        for (int i = 0; i < TR; ++i)
 #pragma unroll
-                        for (int j = 0; j < TC; ++j) Os[(r0 + i) * OS + cg * TC + j] = acc[i][j];
+                            for (int j = 0; j < TC; ++j) Os[(r0 + i) * OS + cg * TC + j] = acc[i][j];
+                    }
+                    if (KS > 1) {
+                        __syncwarp();
+                        if (lane == 0) b3_mbar_arrive(&kbar[slot]);
+                    }
+                } else {
+                    // second k-split: add to what the first one stored (fixed order: deterministic)
+                    if (!b3_wait_warp(&kbar[slot], kphase & 1, P.status)) return;
+                    if (act) {
+#pragma unroll
+                        for (int i = 0; i < TR; ++i)
+#pragma unroll
+                            for (int j = 0; j < TC; ++j) Os[(r0 + i) * OS + cg * TC + j] += acc[i][j];
+                    }
+                    __syncwarp();
+                    if (lane == 0) b3_mbar_arrive(&kback[slot]);
                 }
+                ++kphase;
             }
             __syncwarp();
             if (lane == 0) { b3_mbar_arrive(o_full); b3_mbar_arrive(&x_empty[buf]); }
@@ -279,11 +347,11 @@ __device__ void b3_layer(const BatchParams& P, const BCta& D, float* smem) {
         for (int q = 0; q < nq; ++q) {
             const int it = q / M, m = q - it * M, buf = q & 1;
             if (q >= 2 && !b3_mbar_wait(&x_empty[buf], ((q >> 1) - 1) & 1, P.status)) return;
-            if (!b3_cnt_wait(P.cnt + ((size_t)l * M + m) * B3_CNT_STRIDE, (unsigned)D.nprod_in * (unsigned)(it + 1), P, 100 + l)) return;
+            if (!b3_cnt_wait(cnt_in + (size_t)m * B3_CNT_STRIDE, (unsigned)D.nprod_in * (unsigned)(it + 1), P, 100 + MODE * 50 + l)) return;
             B3_PROF(0);
             b3_fence_proxy_async();
             b3_mbar_arm(&x_full[buf], tile_bytes);
-            b3_tma_load(Xs + buf * Hp * NC, tile_in + (size_t)m * H * NC, tile_bytes, &x_full[buf]);
+            b3_tma_load(Xs + buf * kp * NC, tile_in + (size_t)m * D.in_slot_f, tile_bytes, &x_full[buf]);
         }
         return;
     }
@@ -291,10 +359,6 @@ __device__ void b3_layer(const BatchParams& P, const BCta& D, float* smem) {
     // =================================== epilogue warps
     const int te = tid - B3_EPI0 * 32;
     const float* bias = P.wbuf + D.b_off;
-    float* ringS = smem + D.sm_ring;
-    float* ringG = P.ring_scratch + D.ring_off;
-    const int twoH = 2 * H;
-    const int nitems = np * NC;
     uint32_t ep = 0;
     auto epi_sync = [&]() -> bool {
         __syncwarp();
@@ -303,10 +367,45 @@ __device__ void b3_layer(const BatchParams& P, const BCta& D, float* smem) {
         ++ep;
         return ok;
     };
+
+    if constexpr (MODE == 1) {
+        // ---- dense head stage: out[row][b] = act(W.x + bias (+ the skips of layers 0..L-2))
+        const int nout = D.nrows * BS;
+        for (int q = 0; q < nq; ++q) {
+            const int it = q / M, m = q - it * M, buf = q & 1;
+            if (!b3_wait_warp(&x_full[buf], (q >> 1) & 1, P.status)) return;      // the skips are complete once the input is
+            for (int e = te; e < nout; e += B3_NEPI) {
+                const int r = e / BS;
+                float a = bias[r];
+                if (D.add_skips && P.L >= 2)      // running sum of the skips of layers 0..L-2 (chained through the cells)
+                    a += __ldcg(P.skipbuf + ((size_t)(P.L - 2) * M + m) * P.S * BS + (size_t)D.row0 * BS + e);
+                pre1[e] = a;
+            }
+            if (!b3_wait_warp(o_full, q & 1, P.status)) return;
+            if (te == 0) B3_PROF(4);
+            float* tout = tile_out + (size_t)m * D.out_slot_f + (size_t)D.row0 * BS;
+            for (int e = te; e < nout; e += B3_NEPI) {
+                const int r = e / BS, b = e - r * BS;
+                float v = pre1[e] + Os[r * OS + b];
+                if (D.relu) v = fmaxf(v, 0.f);
+                __stcg(tout + e, v);
+            }
+            if (!epi_sync()) return;
+            if (te == 0) {
+                b3_signal(cnt_out + (size_t)m * B3_CNT_STRIDE);
+                b3_mbar_arrive(o_empty); b3_mbar_arrive(&x_empty[buf]);
+                B3_PROF(5);
+            }
+        }
+        return;
+    } else {
+    float* ringS = smem + D.sm_ring;
+    float* ringG = P.ring_scratch + D.ring_off;
+    const int twoH = 2 * H;
+    const int nitems = np * NC;
     for (int q = 0; q < nq; ++q) {
         const int it = q / M, m = q - it * M, buf = q & 1;
         const int t0 = P.t_first + it * SEG;
-        const bool head_active = it >= P.it0;
         // ---- P1: everything the gate needs that does not depend on the GEMM
         for (int item = te; item < nitems; item += B3_NEPI) {
             const int pi = item / NC, col = item - pi * NC;
@@ -338,10 +437,15 @@ __device__ void b3_layer(const BatchParams& P, const BCta& D, float* smem) {
         }
         if (te == 0) B3_PROF(3);
         if (!b3_wait_warp(&x_full[buf], (q >> 1) & 1, P.status)) return;
+        // running sum of the skips of the layers below (complete once the input is): fetch it while the GEMM runs
+        const bool sk_pre = D.nskip * BS <= B3_NEPI;
+        float sk_prev = 0.f;
+        if (l >= 2 && sk_pre && te < D.nskip * BS)
+            sk_prev = __ldcg(P.skipbuf + ((size_t)(l - 2) * M + m) * P.S * BS + (size_t)D.skip0 * BS + te);
         if (!b3_wait_warp(o_full, q & 1, P.status)) return;
         if (te == 0) B3_PROF(4);
-        const float* X = Xs + buf * Hp * NC;
-        float* tout = tile_out + (size_t)m * H * NC;
+        const float* X = Xs + buf * kp * NC;
+        float* tout = tile_out + (size_t)m * D.out_slot_f;
         // ---- P2: gate (cswnv_shift1.py:281-285) and publish
         for (int item = te; item < nitems; item += B3_NEPI) {
             const int pi = item / NC, col = item - pi * NC;
@@ -360,174 +464,115 @@ __device__ void b3_layer(const BatchParams& P, const BCta& D, float* smem) {
                 const float z = sigmoidf_(qz * v.x);
                 hv = (1.f - z) * tanhf(qc * v.y) + z * X[(D.pair0 + pi) * NC + col];
             }
-            __stcg(tout + (size_t)(D.pair0 + pi) * NC + col, hv);
-            if (D.is_last && s == SEG - 1) hn[pi * BS + b] = hv;
+            if (!D.is_last) __stcg(tout + (size_t)(D.pair0 + pi) * NC + col, hv);
+            else if (s == SEG - 1) __stcg(tout + (size_t)(D.pair0 + pi) * BS + b, hv);     // the head only needs the last column
         }
-        // rows of out_skip[l-1] applied to the last time column of every utterance
-        if (l >= 1 && head_active) {
-            float* sk = P.skipbuf + ((size_t)(l - 1) * M + m) * P.S * BS;
+        // rows of out_skip[l-1] applied to the last time column of every utterance, added to the running sum
+        if (l >= 1) {
+            float* sk = P.skipbuf + ((size_t)(l - 1) * M + m) * P.S * BS + (size_t)D.skip0 * BS;
             for (int e = te; e < D.nskip * BS; e += B3_NEPI) {
                 const int r = e / BS, b = e - r * BS;
-                __stcg(sk + (size_t)(D.skip0 + r) * BS + b, Os[(K * np2 + r) * OS + (SEG - 1) * BS + b]);
-            }
-        }
-        if (D.is_last) {
-            if (!epi_sync()) return;
-            if (head_active) {
-                // out_skip[L-1] restricted to the rows of h this CTA owns (partial sums over k)
-                float* ls = P.lastskip + ((size_t)D.hindex * M + m) * P.S * BS;
-                for (int e = te; e < P.S * BS; e += B3_NEPI) {
-                    const int r = e / BS, b = e - r * BS;
-                    float a = 0.f;
-                    for (int pi = 0; pi < np; ++pi) a = fmaf(Wl[pi * P.S + r], hn[pi * BS + b], a);
-                    __stcg(ls + e, a);
-                }
+                float v = Os[(K * np2 + r) * OS + (SEG - 1) * BS + b];
+                if (l >= 2) v += sk_pre ? sk_prev : __ldcg(P.skipbuf + ((size_t)(l - 2) * M + m) * P.S * BS + (size_t)D.skip0 * BS + e);
+                __stcg(sk + e, v);
             }
         }
         if (!epi_sync()) return;
-        if (te == 0) { b3_signal(P.cnt + ((size_t)(l + 1) * M + m) * B3_CNT_STRIDE); B3_PROF(5); }
-        // ---- P3 (off the critical path): delayed taps into the ring of partial sums
-        if (dil >= SEG) {
-            // every (tap, column) has its own target slot
-            const int n3 = (K - 1) * SEG * np2 * BS;
+        if (te == 0) { b3_signal(cnt_out + (size_t)m * B3_CNT_STRIDE); B3_PROF(5); }
+        // ---- P3 (off the critical path): delayed taps into the ring of partial sums; the BS utterances of one
+        // (tap, row, time column) are contiguous in the GEMM output and in the ring
+        {
+            const bool uniq = dil >= SEG;               // every (tap, column) has its own target slot
+            const int nt = uniq ? (K - 1) * SEG : (K - 1) * dil;
+            const int n3 = nt * np2;
             for (int e = te; e < n3; e += B3_NEPI) {
-                const int b = e % BS;
-                int r = e / BS;
-                const int r2 = r % np2; r /= np2;
-                const int s = r % SEG;
-                const int j = r / SEG;                                   // tap 0..K-2
-                const int delta = (K - 1 - j) * dil;
-                const int slot = (t0 + s + delta - P.t_first) % RL;
-                const float val = Os[(j * np2 + r2) * OS + s * BS + b];
-                const size_t ro = ((size_t)slot * np2 + r2) * Bp + m * BS + b;
-                if (D.ring_in_smem) ringS[ro] += val;
-                else atomicAdd(ringG + ro, val);                         // RED: fire and forget, one writer per element
-            }
-        } else {
-            // several (tap, column) pairs share a target: one thread sums them in a fixed order
-            const int ntau = (K - 1) * dil;
-            const int n3 = ntau * np2 * BS;
-            for (int e = te; e < n3; e += B3_NEPI) {
-                const int b = e % BS;
-                int r = e / BS;
-                const int r2 = r % np2;
-                const int trel = SEG + r / np2;
-                float val = 0.f;
-                for (int j = K - 2; j >= 0; --j) {
-                    const int s = trel - (K - 1 - j) * dil;
-                    if (s < 0) break;
-                    if (s < SEG) val += Os[(j * np2 + r2) * OS + s * BS + b];
+                const int r2 = e % np2, tt = e / np2;
+                float val[BS];
+                int trel;
+                if (uniq) {
+                    const int s = tt % SEG, j = tt / SEG;                    // tap 0..K-2
+                    trel = s + (K - 1 - j) * dil;
+                    const float* o = Os + (j * np2 + r2) * OS + s * BS;
+#pragma unroll
+                    for (int b = 0; b < BS; ++b) val[b] = o[b];
+                } else {
+                    // several (tap, column) pairs share a target: summed by one thread in a fixed order
+                    trel = SEG + tt;
+#pragma unroll
+                    for (int b = 0; b < BS; ++b) val[b] = 0.f;
+                    for (int j = K - 2; j >= 0; --j) {
+                        const int s = trel - (K - 1 - j) * dil;
+                        if (s < 0) break;
+                        if (s < SEG) {
+                            const float* o = Os + (j * np2 + r2) * OS + s * BS;
+#pragma unroll
+                            for (int b = 0; b < BS; ++b) val[b] += o[b];
+                        }
+                    }
                 }
                 const int slot = (t0 + trel - P.t_first) % RL;
-                const size_t ro = ((size_t)slot * np2 + r2) * Bp + m * BS + b;
-                if (D.ring_in_smem) ringS[ro] += val;
-                else atomicAdd(ringG + ro, val);
+                const size_t ro = ((size_t)slot * np2 + r2) * Bp + m * BS;
+                if (D.ring_in_smem) {
+#pragma unroll
+                    for (int b = 0; b < BS; ++b) ringS[ro + b] += val[b];
+                } else if constexpr (BS % 4 == 0) {
+#pragma unroll
+                    for (int b = 0; b < BS; b += 4)                         // RED: fire and forget, one writer per element
+                        asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ringG + ro + b),
+                                     "f"(val[b]), "f"(val[b + 1]), "f"(val[b + 2]), "f"(val[b + 3]) : "memory");
+                } else {
+#pragma unroll
+                    for (int b = 0; b < BS; ++b) atomicAdd(ringG + ro + b, val[b]);
+                }
             }
         }
         if (!epi_sync()) return;
         if (te == 0) { b3_mbar_arrive(o_empty); b3_mbar_arrive(&x_empty[buf]); B3_PROF(6); }
     }
-}
-
-// ------------------------------------------------------------------ head CTA
-// sums of N accumulators over the 32 lanes with N-1 + log2(32/N) shuffles; returns the total of
-// accumulator `which` (a function of the lane), valid in every lane
-template <int N>
-__device__ __forceinline__ float b3_reduce_t(float (&v)[N], int lane, int& which) {
-    which = 0;
-    int off = 16;
-#pragma unroll
-    for (int n = N; n > 1; n >>= 1) {
-        const bool hi = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < n / 2; ++i) {
-            const float send = hi ? v[i] : v[i + n / 2];
-            const float keep = hi ? v[i + n / 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-        which += hi ? n / 2 : 0;
-        off >>= 1;
-    }
-    float r = v[0];
-    for (; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
-    return r;
-}
-
-// out[b][row] = act(W[row][:] . x[b][:] + bias[row]) for the rows of one streamed chunk.
-// Lane owns k = c*64 + 2*lane, +1; the CB columns of this warp's group are register resident.
-template <int CB, bool RELU>
-__device__ __forceinline__ void b3_head_rows(const float* __restrict__ wch, int nrows, int kp, const float2 (&xr)[4][CB],
-                                             const float* __restrict__ bias, int row0, float* __restrict__ out, int ostride,
-                                             int b0, int wr, int wstep, int lane) {
-    const int nchk = kp >> 6;
-    const int lowmask = (32 / CB) - 1;
-    for (int r = wr; r < nrows; r += wstep) {
-        const float2* w2 = reinterpret_cast<const float2*>(wch + (size_t)r * kp);
-        float acc[CB];
-#pragma unroll
-        for (int b = 0; b < CB; ++b) acc[b] = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if (c < nchk) {
-                const float2 w = w2[c * 32 + lane];
-#pragma unroll
-                for (int b = 0; b < CB; ++b) acc[b] = fmaf(w.x, xr[c][b].x, fmaf(w.y, xr[c][b].y, acc[b]));
-            }
-        }
-        int which;
-        float v = b3_reduce_t<CB>(acc, lane, which);
-        if ((lane & lowmask) == 0) {
-            v += __ldg(bias + row0 + r);
-            if (RELU) v = fmaxf(v, 0.f);
-            out[(size_t)(b0 + which) * ostride + row0 + r] = v;
-        }
     }
 }
 
+// ------------------------------------------------------------------ tail CTA
+// Serves whole slots (m = hindex, hindex + NT, ...): [out_2 when it is small] -> sampler -> causal input stage
+// of the next step.  The noise of the step is drawn before the wait for the head (off the critical path).
 template <int SEG, int BS>
-__device__ void b3_head(const BatchParams& P, const BCta& D, float* smem) {
+__device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
     constexpr int NC = SEG * BS;
-    constexpr int CB = BS > 8 ? 8 : BS;             // columns per warp group
-    constexpr int NGRP = BS / CB;
-    static_assert(BS % CB == 0 && (CB & (CB - 1)) == 0, "batch tile must be a power of two");
-    constexpr int WPG = SWN_NWARPS / NGRP;          // warps per column group
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int H = P.H, S = P.S, Sp = P.Sp, K = P.K, L = P.L, n1 = P.n1, n1p = P.n1p, n2 = P.n2, n2p = P.n2p, M = P.M;
+    const int H = P.H, K = P.K, n1 = P.n1, n1p = P.n1p, n2 = P.n2, n2p = P.n2p, M = P.M;
     const int hc = D.hindex;
     const bool is_c = P.kind == 0;
 
-    float* wring = smem + D.sm_wring;               // [NST][RCH * kpmax]
-    float* x1 = smem + D.sm_x1;                     // [BS][Sp]
-    float* x2 = smem + D.sm_x2;                     // [BS][n1p]
-    float* oc = smem + D.sm_oc;                     // [BS][n2p]
+    float* x2 = smem + D.sm_x2;                     // tail_gemm: [BS][n1p] relu(out_1), utterance-major
+    float* oc = smem + D.sm_oc;                     // [BS][n2p] out_2 rows
+    float* w2 = smem + D.sm_w2;                     // tail_gemm: [n2][n1p]
     float* tin = smem + D.sm_tin;                   // [H][NC]
+    float* itab = smem + D.sm_itab;                 // CSWNV: in_tab [K][2][H]; then (both kinds) in_bias [H], out_2 bias [n2]
+    float* ibias = itab + (is_c ? K * 2 * H : 0);
+    float* b2s = ibias + H;
+    float2* ain = reinterpret_cast<float2*>(smem + D.sm_ain);     // [NC][K]
+    float* nz = smem + D.sm_noise;                  // CSWNV: eps [BS][SEG]; DSWNV: -log q [BS][Q]
     float* hist = smem + D.sm_hist;                 // [MO][BS][HIST]
     float* lpb = smem + D.sm_lpb;                   // [MO][BS][8]
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + D.sm_misc);
-    unsigned long long* w_full = bars;              // [NST]
-    unsigned long long* w_empty = bars + B3_NST;    // [NST]
-    int* flag = reinterpret_cast<int*>(bars + 2 * B3_NST);
+    int* flag = reinterpret_cast<int*>(smem + D.sm_misc);
 
-    const int kpmax = Sp > n1p ? Sp : n1p;
-    const int chunk_floats = B3_RCH * kpmax;
-    const int nc1 = (n1 + B3_RCH - 1) / B3_RCH, nc2 = (n2 + B3_RCH - 1) / B3_RCH, nct = nc1 + nc2;
-    const int nown = hc < M ? (M - hc + P.NH - 1) / P.NH : 0;       // slots served: m = hc + i*NH
-    const long long total_chunks = (long long)nown * P.n_iter * nct;
+    const int nown = hc < M ? (M - hc + P.NT - 1) / P.NT : 0;       // slots served: m = hc + i*NT
 
-    for (int i = tid; i < BS * Sp; i += SWN_NTHREADS) x1[i] = 0.f;
     for (int i = tid; i < BS * n1p; i += SWN_NTHREADS) x2[i] = 0.f;
     for (int i = tid; i < nown * BS * B3_HIST; i += SWN_NTHREADS) hist[i] = is_c ? 0.f : __int_as_float(P.Q / 2);
     for (int i = tid; i < nown * BS * 8; i += SWN_NTHREADS) lpb[i] = 0.f;
-    if (tid == 0) {
-        for (int i = 0; i < B3_NST; ++i) { b3_mbar_init(&w_full[i], 1); b3_mbar_init(&w_empty[i], SWN_NWARPS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    if (is_c)
+        for (int i = tid; i < K * 2 * H; i += SWN_NTHREADS) itab[i] = P.in_tab[i];
+    for (int i = tid; i < H; i += SWN_NTHREADS) ibias[i] = P.in_bias[i];
+    for (int i = tid; i < n2; i += SWN_NTHREADS) b2s[i] = P.wbuf[P.b2_off + i];
+    if (P.tail_gemm)
+        for (int i = tid; i < n2 * n1p; i += SWN_NTHREADS) w2[i] = P.wbuf[P.w2_off + i];
     __syncthreads();
     if (P.seedw) {
         for (int e = tid; e < nown * BS * SEG; e += SWN_NTHREADS) {
             const int mb = e / SEG, j = e - mb * SEG;
             const int ml = mb / BS, b = mb - ml * BS;
-            int bglob = (hc + ml * P.NH) * BS + b; if (bglob >= P.B) bglob = P.B - 1;
+            int bglob = (hc + ml * P.NT) * BS + b; if (bglob >= P.B) bglob = P.B - 1;
             const float v = is_c ? ((const float*)P.seedw)[(size_t)bglob * SEG + j]
                                  : __int_as_float((int)(((const long long*)P.seedw)[bglob] % P.Q));
             hist[(size_t)mb * B3_HIST + ((j - SEG + B3_HIST) % B3_HIST)] = v;
@@ -537,122 +582,139 @@ __device__ void b3_head(const BatchParams& P, const BCta& D, float* smem) {
         __syncthreads();
     }
 
-    // ---- weight stream (out_1 rows, then out_2 rows, cyclically): chunk sequence numbers
-    long long pseq = 0, cseq = 0;
-    auto chunk_src = [&](int ci, const float*& src, uint32_t& bytes) {
-        if (ci < nc1) {
-            const int r0 = ci * B3_RCH, nr = min(B3_RCH, n1 - r0);
-            src = P.wbuf + P.w1_off + (size_t)r0 * Sp; bytes = (uint32_t)(nr * Sp * sizeof(float));
-        } else {
-            const int r0 = (ci - nc1) * B3_RCH, nr = min(B3_RCH, n2 - r0);
-            src = P.wbuf + P.w2_off + (size_t)r0 * n1p; bytes = (uint32_t)(nr * n1p * sizeof(float));
-        }
-    };
-    auto produce = [&]() -> bool {             // thread 0 only: keep up to NST chunks in flight
-        while (pseq < total_chunks && pseq < cseq + B3_NST) {
-            const int st = (int)(pseq % B3_NST);
-            if (pseq >= B3_NST && !b3_mbar_wait(&w_empty[st], (uint32_t)((pseq / B3_NST) - 1) & 1, P.status)) return false;
-            const float* src; uint32_t bytes;
-            chunk_src((int)(pseq % nct), src, bytes);
-            b3_mbar_arm(&w_full[st], bytes);
-            b3_tma_load(wring + (size_t)st * chunk_floats, src, bytes, &w_full[st]);
-            ++pseq;
-        }
-        return true;
-    };
-    if (tid == 0) produce();
-
-    // Input stage for iteration `itn` of slot m: h0 = softsign(causal(...)) (cswnv_shift1.py:352 / dswnv.py:345)
+    // Input stage for iteration `itn` of slot m: h0 = softsign(causal(...)) (cswnv_shift1.py:352 / dswnv.py:345).
+    // A thread owns one channel r of one utterance b: the SEG columns of that utterance share their taps.
     auto input_stage = [&](int itn, int m, int ml) {
         const int t0n = P.t_first + itn * SEG;
         const float* hs = hist + (size_t)ml * BS * B3_HIST;
-        for (int e = tid; e < H * NC; e += SWN_NTHREADS) {
-            const int c = e / H, r = e - c * H;
-            const int s = c / BS, b = c - s * BS;
-            const int t = t0n + s;
-            float v = 0.f;
-            if (t >= 0) {
-                float acc = __ldg(P.in_bias + r);
-                for (int j = 0; j < K; ++j) {
-                    const int tau = t - (K - 1) + j;
-                    if (tau < 0) continue;
-                    const int n = tau - P.R - 1;
-                    if (is_c) {
-                        const float a = (n >= -SEG) ? hs[b * B3_HIST + ((n + B3_HIST) % B3_HIST)] : 0.f;
-                        acc += __ldg(P.in_tab + (j * 2) * H + r) + __ldg(P.in_tab + (j * 2 + 1) * H + r) * a;
-                    } else {
-                        const int qq = (n >= -SEG) ? __float_as_int(hs[b * B3_HIST + ((n + B3_HIST) % B3_HIST)]) : P.Q / 2;
-                        acc += __ldg(P.in_tab + ((size_t)j * P.Q + qq) * H + r);
-                    }
+        float* dst = P.tiles + (size_t)m * H * NC;                   // layer 0 input (tile offset 0)
+        if (K <= 8) {
+            for (int e = tid; e < H * BS; e += SWN_NTHREADS) {
+                const int r = e / BS, b = e - r * BS;
+                // samples / indices seen by hidden times t0n-(K-1) .. t0n+SEG-1 (newest sample of hidden time tau: tau-R-1)
+                float a[SEG + 7];
+#pragma unroll
+                for (int i = 0; i < SEG + 7; ++i) {
+                    const int n = t0n - (K - 1) + i - P.R - 1;
+                    a[i] = (i < SEG + K - 1 && n >= -SEG) ? hs[b * B3_HIST + ((n + 64 * B3_HIST) % B3_HIST)]
+                                                           : (is_c ? 0.f : __int_as_float(P.Q / 2));
                 }
-                v = softsignf_(acc);
+                const float bias = ibias[r];
+                float acc[SEG];
+#pragma unroll
+                for (int s = 0; s < SEG; ++s) acc[s] = bias;
+                if (is_c) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < K) {
+                            const float cb = itab[(j * 2) * H + r], cv = itab[(j * 2 + 1) * H + r];
+#pragma unroll
+                            for (int s = 0; s < SEG; ++s) {
+                                const float vld = (t0n + s - (K - 1) + j >= 0) ? 1.f : 0.f;      // conv zero padding
+                                acc[s] = fmaf(vld, cb, fmaf(vld * a[s + j], cv, acc[s]));
+                            }
+                        }
+                    }
+                } else {
+                    float g[SEG][8];                         // all gathers in flight before the first add
+#pragma unroll
+                    for (int s = 0; s < SEG; ++s)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            g[s][j] = (j < K && t0n + s - (K - 1) + j >= 0)
+                                          ? __ldg(P.in_tab + ((size_t)j * P.Q + __float_as_int(a[s + j])) * H + r) : 0.f;
+#pragma unroll
+                    for (int s = 0; s < SEG; ++s)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[s] += g[s][j];
+                }
+#pragma unroll
+                for (int s = 0; s < SEG; ++s)
+                    __stcg(dst + (size_t)r * NC + s * BS + b, (t0n + s >= 0) ? softsignf_(acc[s]) : 0.f);
             }
-            tin[r * NC + c] = v;
+        } else {
+            for (int e = tid; e < H * NC; e += SWN_NTHREADS) {
+                const int r = e / NC, c = e - r * NC;
+                const int s = c / BS, b = c - s * BS;
+                const int t = t0n + s;
+                float v = 0.f;
+                if (t >= 0) {
+                    float acc = ibias[r];
+                    for (int j = 0; j < K; ++j) {
+                        const int tau = t - (K - 1) + j;
+                        if (tau < 0) continue;
+                        const int n = tau - P.R - 1;
+                        const float av = (n >= -SEG) ? hs[b * B3_HIST + ((n + 64 * B3_HIST) % B3_HIST)] : (is_c ? 0.f : __int_as_float(P.Q / 2));
+                        if (is_c) acc += itab[(j * 2) * H + r] + itab[(j * 2 + 1) * H + r] * av;
+                        else acc += __ldg(P.in_tab + ((size_t)j * P.Q + __float_as_int(av)) * H + r);
+                    }
+                    v = softsignf_(acc);
+                }
+                __stcg(dst + e, v);
+            }
         }
+        const int it = itn - 1;
+        if (tid == 0 && itn > 0) B3_PROF(5);
         __syncthreads();
-        float* dst = P.tiles + (size_t)m * H * NC;                   // layer 0 input
-        for (int e = tid; e < H * NC; e += SWN_NTHREADS) __stcg(dst + e, tin[e]);
-        __syncthreads();
+        if (tid == 0 && itn > 0) B3_PROF(6);
         if (tid == 0) b3_signal(P.cnt + (size_t)m * B3_CNT_STRIDE);
     };
 
-    for (int i = 0; i < nown; ++i) input_stage(0, hc + i * P.NH, i);
+    for (int i = 0; i < nown; ++i) input_stage(0, hc + i * P.NT, i);
 
-    const int wg = warp / WPG, wr = warp - wg * WPG;                  // column group and row phase of this warp
-    const int b0 = wg * CB;
+    const unsigned int* cnt_in = P.cnt + (size_t)P.tail_cnt * M * B3_CNT_STRIDE;
     for (int it = 0; it < P.n_it; ++it) {
         const bool active = it >= P.it0;
         const int istep = it - P.it0;
         for (int ml = 0; ml < nown; ++ml) {
-            const int m = hc + ml * P.NH;
-            // ---- wait for the last layer (flow control during warm-up, data when active)
+            const int m = hc + ml * P.NT;
+            // ---- the noise of this step does not depend on the network: draw it while the head is still busy
+            if (active) {
+                if (is_c) {
+                    for (int e = tid; e < BS * SEG; e += SWN_NTHREADS) {
+                        const int b = e / SEG, j = e - b * SEG;
+                        int bglob = m * BS + b; if (bglob >= P.B) bglob = P.B - 1;
+                        const long long n = (long long)istep * SEG + j;
+                        nz[e] = P.noise ? P.noise[(size_t)bglob * P.n_out + n] : laplace_eps(P.seed, bglob, n);
+                    }
+                } else {
+                    for (int e = tid; e < BS * n2; e += SWN_NTHREADS) {
+                        const int b = e / n2, rr = e - b * n2;
+                        int bglob = m * BS + b; if (bglob >= P.B) bglob = P.B - 1;
+                        const float qv = P.noise ? P.noise[((size_t)bglob * P.n_out + istep) * P.Q + rr] : softmax_q(P.seed, bglob, istep, rr);
+                        nz[e] = -logf(qv);
+                    }
+                }
+            }
+            // ---- wait for the head (flow control during warm-up, data when active)
             if (tid == 0)
-                *flag = b3_cnt_wait(P.cnt + ((size_t)L * M + m) * B3_CNT_STRIDE, (unsigned)P.G * (unsigned)(it + 1), P, 200) ? 1 : 0;
+                *flag = b3_cnt_wait(cnt_in + (size_t)m * B3_CNT_STRIDE, (unsigned)P.tail_nprod * (unsigned)(it + 1), P, 200) ? 1 : 0;
             __syncthreads();
             if (*flag == 0) return;
             if (tid == 0) B3_PROF(0);
             if (active) {
-                // ---- relu(sum_l skip_l) (cswnv_shift1.py:367 inner sum), fixed summation order
-                for (int e = tid; e < S * BS; e += SWN_NTHREADS) {
-                    const int r = e / BS, b = e - r * BS;
-                    float a = __ldg(P.wbuf + P.cs_off + r);
-                    for (int l2 = 0; l2 + 1 < L; ++l2) a += __ldcg(P.skipbuf + ((size_t)l2 * M + m) * S * BS + e);
-                    for (int g = 0; g < P.G; ++g) a += __ldcg(P.lastskip + ((size_t)g * M + m) * S * BS + e);
-                    x1[b * Sp + r] = fmaxf(a, 0.f);
+                const float* src = P.tiles + P.tail_in_off + (size_t)m * P.tail_slot_f;      // [rows][BS]
+                if (P.tail_gemm) {
+                    for (int e = tid; e < n1 * BS; e += SWN_NTHREADS) {
+                        const int k = e / BS, b = e - k * BS;
+                        x2[b * n1p + k] = __ldcg(src + e);
+                    }
+                    __syncthreads();
+                    if (tid == 0) B3_PROF(7);
+                    // out_2: few rows, one warp per (row, utterance), lanes split k
+                    for (int e = warp; e < n2 * BS; e += SWN_NWARPS) {
+                        const int rr = e / BS, b = e - rr * BS;
+                        const float v = warp_sum(dot_row(w2 + (size_t)rr * n1p, x2 + (size_t)b * n1p, n1p, lane));
+                        if (lane == 0) oc[b * n2p + rr] = v + b2s[rr];
+                    }
+                } else {
+                    for (int e = tid; e < n2 * BS; e += SWN_NTHREADS) {
+                        const int rr = e / BS, b = e - rr * BS;
+                        oc[b * n2p + rr] = __ldcg(src + e);
+                    }
                 }
                 __syncthreads();
                 if (tid == 0) B3_PROF(1);
-                bool ok = true;
-                // ---- stage B: relu(out_1(.)), stage C: out_2(.)
-                for (int stg = 0; stg < 2; ++stg) {
-                    const int kp = stg == 0 ? Sp : n1p;
-                    const float* xin = stg == 0 ? x1 : x2;
-                    float2 xr[4][CB];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-#pragma unroll
-                        for (int b = 0; b < CB; ++b)
-                            xr[c][b] = (c < (kp >> 6)) ? reinterpret_cast<const float2*>(xin + (size_t)(b0 + b) * kp)[c * 32 + lane]
-                                                       : make_float2(0.f, 0.f);
-                    const int ncs = stg == 0 ? nc1 : nc2;
-                    for (int ci = 0; ci < ncs; ++ci) {
-                        if (tid == 0) ok = produce();
-                        const int st = (int)(cseq % B3_NST);
-                        ok = b3_mbar_wait(&w_full[st], (uint32_t)(cseq / B3_NST) & 1, P.status) && ok;
-                        if (!ok) break;
-                        const float* wch = wring + (size_t)st * chunk_floats;
-                        const int r0 = ci * B3_RCH;
-                        if (stg == 0)
-                            b3_head_rows<CB, true>(wch, min(B3_RCH, n1 - r0), kp, xr, P.wbuf + P.b1_off, r0, x2, n1p, b0, wr, WPG, lane);
-                        else
-                            b3_head_rows<CB, false>(wch, min(B3_RCH, n2 - r0), kp, xr, P.wbuf + P.b2_off, r0, oc, n2p, b0, wr, WPG, lane);
-                        __syncwarp();
-                        if (lane == 0) b3_mbar_arrive(&w_empty[st]);
-                        ++cseq;
-                    }
-                    if (__syncthreads_or(!ok)) return;
-                }
-                if (tid == 0) B3_PROF(2);
                 float* hs = hist + (size_t)ml * BS * B3_HIST;
                 if (is_c) {
                     if (tid < BS) {
@@ -663,8 +725,7 @@ __device__ void b3_head(const BatchParams& P, const BCta& D, float* smem) {
                         const long long nbase = (long long)istep * SEG;
                         float eps[SEG], smp[SEG];
 #pragma unroll
-                        for (int j = 0; j < SEG; ++j)
-                            eps[j] = P.noise ? P.noise[(size_t)bglob * P.n_out + nbase + j] : laplace_eps(P.seed, bglob, nbase + j);
+                        for (int j = 0; j < SEG; ++j) eps[j] = nz[b * SEG + j];
                         const float* forced = P.forced ? (const float*)P.forced + (size_t)bglob * P.n_out + nbase : nullptr;
                         laplace_step<SEG>(P.lpc, oc + b * n2p, lpb + ((size_t)ml * BS + b) * 8, eps, forced, smp);
 #pragma unroll
@@ -676,9 +737,9 @@ __device__ void b3_head(const BatchParams& P, const BCta& D, float* smem) {
                     }
                     if (P.head_out) {
                         for (int e = tid; e < BS * n2; e += SWN_NTHREADS) {
-                            const int b = e / n2, r = e - b * n2;
+                            const int b = e / n2, rr = e - b * n2;
                             const int bglob = m * BS + b;
-                            if (bglob < P.B) P.head_out[((size_t)bglob * P.n_iter + istep) * n2 + r] = oc[b * n2p + r];
+                            if (bglob < P.B) P.head_out[((size_t)bglob * P.n_iter + istep) * n2 + rr] = oc[b * n2p + rr];
                         }
                     }
                 } else {
@@ -688,13 +749,11 @@ __device__ void b3_head(const BatchParams& P, const BCta& D, float* smem) {
                         const bool real = bglob < P.B;
                         if (!real) bglob = P.B - 1;
                         float best = -CUDART_INF_F; int bi = 0x7fffffff;
-                        for (int r = lane; r < n2; r += 32) {
-                            const float o = oc[b * n2p + r];
-                            if (P.head_out && real) P.head_out[((size_t)bglob * P.n_iter + istep) * n2 + r] = o;
-                            const float qv = P.noise ? P.noise[((size_t)bglob * P.n_out + istep) * P.Q + r]
-                                                     : softmax_q(P.seed, bglob, istep, r);
-                            const float g = o - logf(qv);
-                            if (g > best || (g == best && r < bi)) { best = g; bi = r; }
+                        for (int rr = lane; rr < n2; rr += 32) {
+                            const float o = oc[b * n2p + rr];
+                            if (P.head_out && real) P.head_out[((size_t)bglob * P.n_iter + istep) * n2 + rr] = o;
+                            const float g = o + nz[b * n2 + rr];
+                            if (g > best || (g == best && rr < bi)) { best = g; bi = rr; }
                         }
 #pragma unroll
                         for (int o2 = 16; o2 > 0; o2 >>= 1) {
@@ -726,8 +785,9 @@ template <int SEG, int BS>
 __global__ void __launch_bounds__(SWN_NTHREADS, 1) swn_batch_kernel(const __grid_constant__ BatchParams P) {
     extern __shared__ __align__(16) float smem[];
     const BCta& D = P.desc[blockIdx.x];
-    if (D.role == ROLE_LAYER) b3_layer<SEG, BS>(P, D, smem);
-    else if (D.role == ROLE_HEAD) b3_head<SEG, BS>(P, D, smem);
+    if (D.role == ROLE_LAYER) b3_stage<SEG, BS, 0>(P, D, smem);
+    else if (D.role == ROLE_DENSE) b3_stage<SEG, BS, 1>(P, D, smem);
+    else if (D.role == ROLE_HEAD) b3_tail<SEG, BS>(P, D, smem);
 }
 
 }  // namespace swn

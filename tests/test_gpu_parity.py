@@ -416,7 +416,7 @@ def test_batch_kernel_many_slots_free_running_vs_oracle(name, B, tile):
                                                   ("cswnv", 22050, 17, 8, dict(seg=5, lpc=4)),
                                                   ("cswnv", 22050, 6, 2, dict(seg=10, lpc=4)),
                                                   ("dswnv", 24000, 20, 8, dict()),
-                                                  ("dswnv", 16000, 33, 16, dict())])
+                                                  ("dswnv", 16000, 33, 8, dict())])
 def test_batch_kernel_recipe_size_teacher_forced_vs_oracle(kind, fs, B, tile, over):
     model, cfg, sd, aux, kw = _recipe_case(kind, fs, B, 2, 21, **over)
     seg = cfg.eff_seg

@@ -10,7 +10,7 @@ cases = []
 for B, tiles in ((64, (2, 4, 8)), (256, (4, 8))):
     for t in tiles:
         cases.append(("cswnv", 22050, dict(seg=5, lpc=4), B, t))
-for B, tiles in ((128, (4, 8, 16)),):
+for B, tiles in ((128, (4, 8)),):
     for t in tiles:
         cases.append(("dswnv", 24000, dict(), B, t))
 if len(sys.argv) > 1:
