@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -127,7 +128,7 @@ struct swn_model {
     std::vector<std::vector<L3Cta>> l3;        // [L][g3]
     int g3 = 0, Hp3 = 0;
     int64_t w2_off3 = 0, b2_off3 = 0, cs_off3 = 0;
-    DevBuf<float> wbuf3, tiles3, skip3, ring3;
+    DevBuf<float> wbuf3, tiles3, skip3, ring3, hist3;
     DevBuf<unsigned int> cnt3;
     DevBuf<swn::BCta> desc3;
     long long plan3_key = -1;
@@ -523,6 +524,9 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
     const int smem_floats = SWN_MAX_SMEM / 4;
     const int n2p = round_up(n2, 4);
     const bool tail_gemm = n2 <= 32;
+    // cell 0 can evaluate the causal input stage itself (CSWNV: the table is tiny).  Measured slower on B200: the
+    // builder warps compete with the GEMM warps for issue slots, so the tail builds the tile unless asked otherwise
+    const bool build_x = is_c && K <= 8 && getenv("SWN_BUILD_X") && atoi(getenv("SWN_BUILD_X")) == 1;
     // dense head stages: {input depth, output rows}
     struct DenseSt { int kdim, rows; };
     std::vector<DenseSt> dst = {{H, S}, {S, n1}};
@@ -611,6 +615,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
                 d.sm_o = take((size_t)c.RP * OS);
                 d.sm_pre = take((size_t)c.npairs * NC * 4);
                 d.sm_bar = take(32);
+                d.sm_build = take((build_x && l == 0) ? (size_t)K * 2 * H + 2 * H + 2 * (size_t)bs * (seg + 7) : 0);
                 const size_t ring_f = (size_t)d.ring_len * 2 * c.npairs * Bp;
                 d.sm_ring = (int32_t)u;
                 d.ring_in_smem = u + ring_f <= (size_t)smem_floats;
@@ -655,7 +660,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
             d.sm_oc = take((size_t)bs * n2p);
             d.sm_w2 = take(tail_gemm ? (size_t)n2 * m->n1p : 0);
             d.sm_tin = take((size_t)H * NC);
-            d.sm_itab = take((is_c ? (size_t)K * 2 * H : 0) + H + n2);
+            d.sm_itab = take((is_c ? (size_t)K * 2 * H : 0) + 2 * H + n2);
             d.sm_ain = take((size_t)NC * K * 2);
             d.sm_noise = take(is_c ? (size_t)bs * seg : (size_t)bs * m->Q);
             d.sm_hist = take((size_t)MO * bs * swn::B3_HIST);
@@ -718,6 +723,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
     const size_t n_cnt = (size_t)(L + ND + 1) * M * swn::B3_CNT_STRIDE;
     const size_t n_skip = (size_t)std::max(L - 1, 1) * M * S * BS;
     if (m->tiles3.ensure(tiles_total) || m->cnt3.ensure(n_cnt) || m->skip3.ensure(n_skip) ||
+        m->hist3.ensure((size_t)M * BS * swn::B3_HIST) ||
         m->ring3.ensure(std::max<size_t>(ring_total, 4))) return 1;
     CUDA_OK(cudaMemsetAsync(m->cnt3.p, 0, n_cnt * sizeof(unsigned int), st));
     if (ring_total) CUDA_OK(cudaMemsetAsync(m->ring3.p, 0, ring_total * sizeof(float), st));
@@ -740,6 +746,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
     P.P = m->ptab.p; P.pconst = m->pconst.p; P.gain = m->gain.p;
     P.in_tab = m->in_tab.p; P.in_bias = m->in_bias.p;
     P.w2_off = m->w2_off3; P.b2_off = m->b2_off3; P.cs_off = m->cs_off3;
+    P.hist_g = m->hist3.p; P.build_x = build_x ? 1 : 0;
     P.tiles = m->tiles3.p; P.cnt = m->cnt3.p; P.skipbuf = m->skip3.p; P.ring_scratch = m->ring3.p;
     P.noise = a->noise_dev; P.seed = a->seed; P.forced = a->forced_dev; P.seedw = a->seed_dev; P.out = a->out_dev; P.head_out = a->head_dev;
     P.status = m->status.p;
@@ -1378,7 +1385,7 @@ int swn_destroy(swn_handle m) {
     m->xa_tab.release(); m->wp.release(); m->act0.release(); m->act1.release(); m->ptab.release();
     m->desc.release(); m->ll.release(); m->ring_scratch.release(); m->status.release();
     m->e2e_aux.release(); m->e2e_out.release();
-    m->wbuf3.release(); m->tiles3.release(); m->skip3.release(); m->ring3.release();
+    m->wbuf3.release(); m->tiles3.release(); m->skip3.release(); m->ring3.release(); m->hist3.release();
     m->cnt3.release(); m->desc3.release();
     m->wbuf2.release(); m->ring2.release(); m->cdesc.release(); m->hdesc.release(); m->ll2.release();
     for (auto& cw : m->aux_convs) { cw.w_t.release(); cw.b.release(); }

@@ -27,9 +27,9 @@ namespace swn {
 constexpr int B3_NGW = 4;                 // GEMM warps 0..3 (one per SM sub-partition)
 constexpr int B3_LOADER = 4;              // warp 4: lane 0 is the loader
 constexpr int B3_EPI0 = 5;                // epilogue warps 5..15
-constexpr int B3_NEPI = (SWN_NWARPS - B3_EPI0) * 32;
 constexpr int B3_CNT_STRIDE = 8;          // one counter per 32-byte sector
 constexpr int B3_HIST = 32;
+constexpr int B3_NBW = 4;                 // cell 0 with build_x: warps 5..8 build the input tile, 9..15 are the epilogue
 
 enum { ROLE_DENSE = 3 };                  // besides ROLE_LAYER (gated cell), ROLE_HEAD (tail), ROLE_IDLE
 
@@ -47,7 +47,7 @@ struct BCta {
     int32_t cnt_in, cnt_out, nprod_in;    // counter rows ([.][M]) of the input / output tile; producers of the input
     int32_t is_last, relu, add_skips;
     int32_t in_slot_f, out_slot_f;        // floats per slot of the input / output tile
-    int32_t sm_w, sm_x, sm_o, sm_pre, sm_ring, sm_bar;
+    int32_t sm_w, sm_x, sm_o, sm_pre, sm_ring, sm_bar, sm_build;
     int64_t in_off, out_off;              // float offsets of slot 0 inside BatchParams::tiles
     int64_t w_off;                        // [kp][RP]
     int64_t b_off;                        // gated cell: [np][2]; dense: [nrows]
@@ -76,6 +76,8 @@ struct BatchParams {
     float* tiles;                         // all exchange tiles (see the host plan)
     unsigned int* cnt;                    // [stages+1][M] * B3_CNT_STRIDE
     float* skipbuf;                       // [L-1][M][S][BS]
+    float* hist_g;                        // build_x: [M][BS][HIST] fed-back samples (written by the tail, read by cell 0)
+    int32_t build_x;                      // 1: the CTAs of cell 0 evaluate the causal input stage themselves
     float* ring_scratch;
     const float* noise;
     unsigned long long seed;
@@ -201,6 +203,11 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
     unsigned long long* kbar = bars + 7;            // [SLOTS] first k-split stored its partial sums
     unsigned long long* kback = bars + 7 + SLOTS;   // [SLOTS] second k-split added its own (only waited for between passes)
 
+    const bool build = MODE == 0 && P.build_x && l == 0;      // this CTA evaluates the causal input stage itself
+    const int epi0 = build ? B3_EPI0 + B3_NBW : B3_EPI0;      // first epilogue warp
+    const int nepi = (SWN_NWARPS - epi0) * 32;
+    unsigned long long* bbar = bars + 15;           // barrier among the builder warps
+
     const int nrb = (RP + RPW - 1) / RPW;
     const int nslot = nrb < SLOTS ? nrb : SLOTS;    // row-block slots in use
     const int ngwa = nslot * KS;                    // GEMM warps that own work
@@ -212,15 +219,27 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
         const int n4 = kp * RP / 4;
         for (int i = tid; i < n4; i += SWN_NTHREADS) dst[i] = src[i];
         for (int i = tid; i < 2 * kp * NC; i += SWN_NTHREADS) Xs[i] = 0.f;
+        if (build) {
+            // in_tab [K][2][H], then cst[r] = in_bias[r] + sum_j cb_j[r] (all taps inside the sequence)
+            float* itab = smem + D.sm_build;
+            for (int i = tid; i < K * 2 * H; i += SWN_NTHREADS) itab[i] = P.in_tab[i];
+            for (int r = tid; r < H; r += SWN_NTHREADS) {
+                float c = P.in_bias[r];
+                for (int j = 0; j < K; ++j) c += P.in_tab[(j * 2) * H + r];
+                itab[K * 2 * H + r] = c;
+                itab[K * 2 * H + H + r] = P.in_bias[r];
+            }
+        }
         if (MODE == 0 && D.ring_in_smem) {
             float* rg = smem + D.sm_ring;
             for (int i = tid; i < RL * np2 * Bp; i += SWN_NTHREADS) rg[i] = 0.f;
         }
         if (tid == 0) {
-            b3_mbar_init(&x_full[0], 1); b3_mbar_init(&x_full[1], 1);
+            b3_mbar_init(&x_full[0], build ? B3_NBW : 1); b3_mbar_init(&x_full[1], build ? B3_NBW : 1);
+            b3_mbar_init(bbar, B3_NBW);
             b3_mbar_init(&x_empty[0], ngwa + 1); b3_mbar_init(&x_empty[1], ngwa + 1);
             b3_mbar_init(o_full, ngwa); b3_mbar_init(o_empty, 1);
-            b3_mbar_init(ebar, SWN_NWARPS - B3_EPI0);
+            b3_mbar_init(ebar, SWN_NWARPS - epi0);
             for (int i = 0; i < SLOTS; ++i) { b3_mbar_init(&kbar[i], 1); b3_mbar_init(&kback[i], 1); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -341,9 +360,76 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
         return;
     }
 
+    if (MODE == 0 && build && warp >= B3_EPI0 && warp < epi0) {
+        // =============================== builders (cell 0): softsign(causal(wav_conv(samples))) straight into the
+        // GEMM operand buffer (cswnv_shift1.py:352); a thread owns channel r of utterance b, whose SEG columns share taps
+        constexpr int NA = SEG + 7;
+        const int tb = tid - B3_EPI0 * 32;
+        const float* itab = smem + D.sm_build;
+        const float* cst = itab + K * 2 * H;
+        const float* ibias = cst + H;
+        float* av = smem + D.sm_build + K * 2 * H + 2 * H;          // [2][BS][NA]
+        uint32_t bp = 0;
+        for (int q = 0; q < nq; ++q) {
+            const int it = q / M, m = q - it * M, buf = q & 1;
+            const int t0 = P.t_first + it * SEG;
+            if (q >= 2 && !b3_wait_warp(&x_empty[buf], ((q >> 1) - 1) & 1, P.status)) return;
+            int ok = 1;
+            if (lane == 0) ok = b3_cnt_wait(cnt_in + (size_t)m * B3_CNT_STRIDE, (unsigned)(it + 1), P, 100) ? 1 : 0;
+            ok = __shfl_sync(0xffffffffu, ok, 0);
+            if (!ok) return;
+            if (tb == 0) B3_PROF(0);
+            float* a = av + buf * BS * NA;
+            for (int e = tb; e < BS * NA; e += B3_NBW * 32) {
+                const int b = e / NA, i = e - b * NA;
+                const int n = t0 - (K - 1) + i - P.R - 1;               // newest sample seen by hidden time t0-(K-1)+i
+                a[e] = (i < SEG + K - 1 && n >= -SEG) ? __ldcg(P.hist_g + ((size_t)m * BS + b) * B3_HIST + ((n + 64 * B3_HIST) % B3_HIST)) : 0.f;
+            }
+            __syncwarp();
+            if (lane == 0) b3_mbar_arrive(bbar);
+            if (!b3_wait_warp(bbar, bp & 1, P.status)) return;
+            ++bp;
+            float* X = Xs + buf * kp * NC;
+            const bool allv = t0 - (K - 1) >= 0;
+            for (int e = tb; e < H * BS; e += B3_NBW * 32) {
+                const int r = e / BS, b = e - r * BS;
+                float acc[SEG];
+                if (allv) {
+                    const float c = cst[r];
+#pragma unroll
+                    for (int s2 = 0; s2 < SEG; ++s2) acc[s2] = c;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < K) {
+                            const float cv = itab[(j * 2 + 1) * H + r];
+#pragma unroll
+                            for (int s2 = 0; s2 < SEG; ++s2) acc[s2] = fmaf(a[b * NA + s2 + j], cv, acc[s2]);
+                        }
+                    }
+#pragma unroll
+                    for (int s2 = 0; s2 < SEG; ++s2) X[r * NC + s2 * BS + b] = softsignf_(acc[s2]);
+                } else {
+                    for (int s2 = 0; s2 < SEG; ++s2) {
+                        float v = 0.f;
+                        if (t0 + s2 >= 0) {
+                            v = ibias[r];
+                            for (int j = 0; j < K; ++j)
+                                if (t0 + s2 - (K - 1) + j >= 0) v += itab[(j * 2) * H + r] + itab[(j * 2 + 1) * H + r] * a[b * NA + s2 + j];
+                            v = softsignf_(v);
+                        }
+                        X[r * NC + s2 * BS + b] = v;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) b3_mbar_arrive(&x_full[buf]);
+        }
+        return;
+    }
+
     if (warp == B3_LOADER) {
         // =============================== loader
-        if (lane != 0) return;
+        if (lane != 0 || build) return;
         for (int q = 0; q < nq; ++q) {
             const int it = q / M, m = q - it * M, buf = q & 1;
             if (q >= 2 && !b3_mbar_wait(&x_empty[buf], ((q >> 1) - 1) & 1, P.status)) return;
@@ -357,7 +443,7 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
     }
 
     // =================================== epilogue warps
-    const int te = tid - B3_EPI0 * 32;
+    const int te = tid - epi0 * 32;
     const float* bias = P.wbuf + D.b_off;
     uint32_t ep = 0;
     auto epi_sync = [&]() -> bool {
@@ -374,7 +460,7 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
         for (int q = 0; q < nq; ++q) {
             const int it = q / M, m = q - it * M, buf = q & 1;
             if (!b3_wait_warp(&x_full[buf], (q >> 1) & 1, P.status)) return;      // the skips are complete once the input is
-            for (int e = te; e < nout; e += B3_NEPI) {
+            for (int e = te; e < nout; e += nepi) {
                 const int r = e / BS;
                 float a = bias[r];
                 if (D.add_skips && P.L >= 2)      // running sum of the skips of layers 0..L-2 (chained through the cells)
@@ -384,7 +470,7 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
             if (!b3_wait_warp(o_full, q & 1, P.status)) return;
             if (te == 0) B3_PROF(4);
             float* tout = tile_out + (size_t)m * D.out_slot_f + (size_t)D.row0 * BS;
-            for (int e = te; e < nout; e += B3_NEPI) {
+            for (int e = te; e < nout; e += nepi) {
                 const int r = e / BS, b = e - r * BS;
                 float v = pre1[e] + Os[r * OS + b];
                 if (D.relu) v = fmaxf(v, 0.f);
@@ -407,7 +493,7 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
         const int it = q / M, m = q - it * M, buf = q & 1;
         const int t0 = P.t_first + it * SEG;
         // ---- P1: everything the gate needs that does not depend on the GEMM
-        for (int item = te; item < nitems; item += B3_NEPI) {
+        for (int item = te; item < nitems; item += nepi) {
             const int pi = item / NC, col = item - pi * NC;
             const int s = col / BS, b = col - s * BS;
             const int t = t0 + s;
@@ -416,15 +502,19 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
                 int bglob = m * BS + b; if (bglob >= P.B) bglob = P.B - 1;
                 const int i = D.pair0 + pi;
                 float az = __ldg(P.pconst + l * twoH + i), ac = __ldg(P.pconst + l * twoH + H + i);
+                // frame / phase of tau = t + sp (replicate pad before R): one division, then incremental
+                int d = t - P.R, f = 0, j = 0;
+                if (d > 0) { f = d / P.U; j = d - f * P.U; }
+                const float* pb = P.P + ((size_t)bglob * P.Tf * P.L + l) * SEG * twoH + i;
+                const size_t fstride = (size_t)P.L * SEG * twoH;
 #pragma unroll
                 for (int sp = 0; sp < SEG; ++sp) {
-                    const int tau = t + sp;
-                    int f = 0, j = 0;
-                    if (tau >= P.R) { f = (tau - P.R) / P.U; j = (tau - P.R) - f * P.U; }
                     const float g = __ldg(P.gain + j);
-                    const float* pr = P.P + ((((size_t)bglob * P.Tf + f) * P.L + l) * SEG + sp) * twoH;
-                    az = fmaf(g, __ldg(pr + i), az);
-                    ac = fmaf(g, __ldg(pr + H + i), ac);
+                    const float* pr = pb + (size_t)f * fstride + sp * twoH;
+                    az = fmaf(g, __ldg(pr), az);
+                    ac = fmaf(g, __ldg(pr + H), ac);
+                    ++d;
+                    if (d > 0 && ++j == P.U) { j = 0; ++f; }
                 }
                 const int slot = (t - P.t_first) % RL;
                 const size_t ro = ((size_t)slot * np2 + pi * 2) * Bp + m * BS + b;
@@ -438,7 +528,7 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
         if (te == 0) B3_PROF(3);
         if (!b3_wait_warp(&x_full[buf], (q >> 1) & 1, P.status)) return;
         // running sum of the skips of the layers below (complete once the input is): fetch it while the GEMM runs
-        const bool sk_pre = D.nskip * BS <= B3_NEPI;
+        const bool sk_pre = D.nskip * BS <= nepi;
         float sk_prev = 0.f;
         if (l >= 2 && sk_pre && te < D.nskip * BS)
             sk_prev = __ldcg(P.skipbuf + ((size_t)(l - 2) * M + m) * P.S * BS + (size_t)D.skip0 * BS + te);
@@ -447,7 +537,7 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
         const float* X = Xs + buf * kp * NC;
         float* tout = tile_out + (size_t)m * D.out_slot_f;
         // ---- P2: gate (cswnv_shift1.py:281-285) and publish
-        for (int item = te; item < nitems; item += B3_NEPI) {
+        for (int item = te; item < nitems; item += nepi) {
             const int pi = item / NC, col = item - pi * NC;
             const int s = col / BS, b = col - s * BS;
             const int t = t0 + s;
@@ -461,8 +551,12 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
                     const float* o = Os + ((j * np + pi) * 2) * OS + (s - delta) * BS + b;
                     qz += o[0]; qc += o[OS];
                 }
-                const float z = sigmoidf_(qz * v.x);
-                hv = (1.f - z) * tanhf(qc * v.y) + z * X[(D.pair0 + pi) * NC + col];
+                // sigmoid / tanh through ex2.approx + rcp (abs. error ~1e-7, inside the 1e-4 head tolerance)
+                const float gz = qz * v.x, gc = qc * v.y;
+                const float ez = __expf(-gz), ec = __expf(-2.f * fabsf(gc));
+                const float z = __frcp_rn(1.f + ez);
+                const float th = copysignf((1.f - ec) * __frcp_rn(1.f + ec), gc);
+                hv = (1.f - z) * th + z * X[(D.pair0 + pi) * NC + col];
             }
             if (!D.is_last) __stcg(tout + (size_t)(D.pair0 + pi) * NC + col, hv);
             else if (s == SEG - 1) __stcg(tout + (size_t)(D.pair0 + pi) * BS + b, hv);     // the head only needs the last column
@@ -470,7 +564,7 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
         // rows of out_skip[l-1] applied to the last time column of every utterance, added to the running sum
         if (l >= 1) {
             float* sk = P.skipbuf + ((size_t)(l - 1) * M + m) * P.S * BS + (size_t)D.skip0 * BS;
-            for (int e = te; e < D.nskip * BS; e += B3_NEPI) {
+            for (int e = te; e < D.nskip * BS; e += nepi) {
                 const int r = e / BS, b = e - r * BS;
                 float v = Os[(K * np2 + r) * OS + (SEG - 1) * BS + b];
                 if (l >= 2) v += sk_pre ? sk_prev : __ldcg(P.skipbuf + ((size_t)(l - 2) * M + m) * P.S * BS + (size_t)D.skip0 * BS + e);
@@ -485,7 +579,7 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
             const bool uniq = dil >= SEG;               // every (tap, column) has its own target slot
             const int nt = uniq ? (K - 1) * SEG : (K - 1) * dil;
             const int n3 = nt * np2;
-            for (int e = te; e < n3; e += B3_NEPI) {
+            for (int e = te; e < n3; e += nepi) {
                 const int r2 = e % np2, tt = e / np2;
                 float val[BS];
                 int trel;
@@ -550,6 +644,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
     float* itab = smem + D.sm_itab;                 // CSWNV: in_tab [K][2][H]; then (both kinds) in_bias [H], out_2 bias [n2]
     float* ibias = itab + (is_c ? K * 2 * H : 0);
     float* b2s = ibias + H;
+    float* cst = b2s + n2;                          // CSWNV: in_bias[r] + sum_j cb_j[r]
     float2* ain = reinterpret_cast<float2*>(smem + D.sm_ain);     // [NC][K]
     float* nz = smem + D.sm_noise;                  // CSWNV: eps [BS][SEG]; DSWNV: -log q [BS][Q]
     float* hist = smem + D.sm_hist;                 // [MO][BS][HIST]
@@ -565,6 +660,12 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
         for (int i = tid; i < K * 2 * H; i += SWN_NTHREADS) itab[i] = P.in_tab[i];
     for (int i = tid; i < H; i += SWN_NTHREADS) ibias[i] = P.in_bias[i];
     for (int i = tid; i < n2; i += SWN_NTHREADS) b2s[i] = P.wbuf[P.b2_off + i];
+    if (is_c)
+        for (int r = tid; r < H; r += SWN_NTHREADS) {
+            float c = P.in_bias[r];
+            for (int j = 0; j < K; ++j) c += P.in_tab[(j * 2) * H + r];
+            cst[r] = c;
+        }
     if (P.tail_gemm)
         for (int i = tid; i < n2 * n1p; i += SWN_NTHREADS) w2[i] = P.wbuf[P.w2_off + i];
     __syncthreads();
@@ -585,6 +686,13 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
     // Input stage for iteration `itn` of slot m: h0 = softsign(causal(...)) (cswnv_shift1.py:352 / dswnv.py:345).
     // A thread owns one channel r of one utterance b: the SEG columns of that utterance share their taps.
     auto input_stage = [&](int itn, int m, int ml) {
+        if (P.build_x) {                              // cell 0 builds its own input from the published samples
+            __syncthreads();
+            const int it = itn - 1;
+            if (tid == 0 && itn > 0) B3_PROF(6);
+            if (tid == 0) b3_signal(P.cnt + (size_t)m * B3_CNT_STRIDE);
+            return;
+        }
         const int t0n = P.t_first + itn * SEG;
         const float* hs = hist + (size_t)ml * BS * B3_HIST;
         float* dst = P.tiles + (size_t)m * H * NC;                   // layer 0 input (tile offset 0)
@@ -603,7 +711,19 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                 float acc[SEG];
 #pragma unroll
                 for (int s = 0; s < SEG; ++s) acc[s] = bias;
-                if (is_c) {
+                if (is_c && t0n - (K - 1) >= 0) {            // every tap lies inside the sequence (all but the first steps)
+                    const float c0 = cst[r];
+#pragma unroll
+                    for (int s = 0; s < SEG; ++s) acc[s] = c0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < K) {
+                            const float cv = itab[(j * 2 + 1) * H + r];
+#pragma unroll
+                            for (int s = 0; s < SEG; ++s) acc[s] = fmaf(a[s + j], cv, acc[s]);
+                        }
+                    }
+                } else if (is_c) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         if (j < K) {
@@ -660,6 +780,12 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
         if (tid == 0) b3_signal(P.cnt + (size_t)m * B3_CNT_STRIDE);
     };
 
+    if (P.build_x) {
+        for (int e = tid; e < nown * BS * B3_HIST; e += SWN_NTHREADS) {
+            const int ml = e / (BS * B3_HIST), rest = e - ml * (BS * B3_HIST);
+            __stcg(P.hist_g + (size_t)(hc + ml * P.NT) * BS * B3_HIST + rest, hist[e]);
+        }
+    }
     for (int i = 0; i < nown; ++i) input_stage(0, hc + i * P.NT, i);
 
     const unsigned int* cnt_in = P.cnt + (size_t)P.tail_cnt * M * B3_CNT_STRIDE;
@@ -701,11 +827,27 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                     }
                     __syncthreads();
                     if (tid == 0) B3_PROF(7);
-                    // out_2: few rows, one warp per (row, utterance), lanes split k
-                    for (int e = warp; e < n2 * BS; e += SWN_NWARPS) {
-                        const int rr = e / BS, b = e - rr * BS;
-                        const float v = warp_sum(dot_row(w2 + (size_t)rr * n1p, x2 + (size_t)b * n1p, n1p, lane));
-                        if (lane == 0) oc[b * n2p + rr] = v + b2s[rr];
+                    // out_2: few rows; 8 lanes per (row, utterance), each an interleaved eighth of k
+                    for (int e0 = 0; e0 < n2 * BS; e0 += SWN_NTHREADS / 8) {
+                        const int e = e0 + (tid >> 3), kq = tid & 7;
+                        float v = 0.f;
+                        int rr = 0, b = 0;
+                        if (e < n2 * BS) {
+                            rr = e / BS; b = e - rr * BS;
+                            const float4* w4 = reinterpret_cast<const float4*>(w2 + (size_t)rr * n1p);
+                            const float4* x4 = reinterpret_cast<const float4*>(x2 + (size_t)b * n1p);
+                            float a0 = 0.f, a1 = 0.f;
+                            for (int c = kq; c < (n1p >> 2); c += 8) {
+                                const float4 w = w4[c], x = x4[c];
+                                a0 = fmaf(w.x, x.x, fmaf(w.y, x.y, a0));
+                                a1 = fmaf(w.z, x.z, fmaf(w.w, x.w, a1));
+                            }
+                            v = a0 + a1;
+                        }
+                        v += __shfl_xor_sync(0xffffffffu, v, 4);
+                        v += __shfl_xor_sync(0xffffffffu, v, 2);
+                        v += __shfl_xor_sync(0xffffffffu, v, 1);
+                        if (kq == 0 && e < n2 * BS) oc[b * n2p + rr] = v + b2s[rr];
                     }
                 } else {
                     for (int e = tid; e < n2 * BS; e += SWN_NTHREADS) {
@@ -732,6 +874,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                         for (int j = 0; j < SEG; ++j) {
                             const float fed = forced ? forced[j] : smp[j];
                             hs[b * B3_HIST + (int)((nbase + j) % B3_HIST)] = fed;
+                            if (P.build_x) __stcg(P.hist_g + ((size_t)m * BS + b) * B3_HIST + (int)((nbase + j) % B3_HIST), fed);
                             if (real) ((float*)P.out)[(size_t)bglob * P.n_out + nbase + j] = smp[j];
                         }
                     }
