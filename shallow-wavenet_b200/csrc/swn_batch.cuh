@@ -29,6 +29,11 @@ constexpr int B3_LOADER = 4;              // warp 4: lane 0 is the loader
 constexpr int B3_EPI0 = 5;                // epilogue warps 5..15
 constexpr int B3_CNT_STRIDE = 8;          // one counter per 32-byte sector
 constexpr int B3_HIST = 32;
+// Packed fp32 FMA (FFMA2, sm_100) in the GEMM inner loop.  Measured on B200: 7.4 us per 128x192x40 tile against
+// 6.8 us with scalar FFMA (the packed form halves the issue slots but not the FMA-pipe cycles), so it stays off.
+#ifndef B3_FFMA2
+#define B3_FFMA2 0
+#endif
 constexpr int B3_NBW = 4;                 // cell 0 with build_x: warps 5..8 build the input tile, 9..15 are the epilogue
 
 enum { ROLE_DENSE = 3 };                  // besides ROLE_LAYER (gated cell), ROLE_HEAD (tail), ROLE_IDLE
@@ -273,24 +278,26 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
             for (int rb = slot; rb < nrb; rb += nslot) {
                 const int r0 = (rb * RGW + rg) * TR;
                 const bool act = lane_ok && r0 < RP;
+                float acc[TR][TC];
+#if B3_FFMA2
                 // packed fp32 FMA (FFMA2): one instruction updates the accumulators of two adjacent rows
                 unsigned long long acc2[TR / 2][TC];
 #pragma unroll
                 for (int i = 0; i < TR / 2; ++i)
 #pragma unroll
                     for (int j = 0; j < TC; ++j) acc2[i][j] = 0ull;
+#else
+#pragma unroll
+                for (int i = 0; i < TR; ++i)
+#pragma unroll
+                    for (int j = 0; j < TC; ++j) acc[i][j] = 0.f;
+#endif
                 if (act) {
                     const float* wp = Wt + r0;
                     const float* xp = X + cg * TC;
 #pragma unroll 2
                     for (int k = kb; k < ke; ++k) {
-                        unsigned long long w2[TR / 2];
                         float x[TC];
-#pragma unroll
-                        for (int i = 0; i < TR; i += 4) {
-                            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(wp + (size_t)k * RP + i);
-                            w2[i / 2] = v.x; w2[i / 2 + 1] = v.y;
-                        }
                         if constexpr (TC % 4 == 0) {
 #pragma unroll
                             for (int j = 0; j < TC; j += 4) {
@@ -307,6 +314,13 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
 #pragma unroll
                             for (int j = 0; j < TC; ++j) x[j] = xp[k * NC + j];
                         }
+#if B3_FFMA2
+                        unsigned long long w2[TR / 2];
+#pragma unroll
+                        for (int i = 0; i < TR; i += 4) {
+                            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(wp + (size_t)k * RP + i);
+                            w2[i / 2] = v.x; w2[i / 2 + 1] = v.y;
+                        }
 #pragma unroll
                         for (int j = 0; j < TC; ++j) {
                             unsigned long long xx;
@@ -315,14 +329,27 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
                             for (int i = 0; i < TR / 2; ++i)
                                 asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][j]) : "l"(xx), "l"(w2[i]));
                         }
+#else
+                        float w[TR];
+#pragma unroll
+                        for (int i = 0; i < TR; i += 4) {
+                            const float4 v = *reinterpret_cast<const float4*>(wp + (size_t)k * RP + i);
+                            w[i] = v.x; w[i + 1] = v.y; w[i + 2] = v.z; w[i + 3] = v.w;
+                        }
+#pragma unroll
+                        for (int i = 0; i < TR; ++i)
+#pragma unroll
+                            for (int j = 0; j < TC; ++j) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
+#endif
                     }
                 }
-                float acc[TR][TC];
+#if B3_FFMA2
 #pragma unroll
                 for (int i = 0; i < TR / 2; ++i)
 #pragma unroll
                     for (int j = 0; j < TC; ++j)
                         asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * i][j]), "=f"(acc[2 * i + 1][j]) : "l"(acc2[i][j]));
+#endif
                 if (first) {
                     first = false;
                     if (tid == 0) B3_PROF(2);
