@@ -119,7 +119,7 @@ struct swn_model {
     swn::CoreParams core_tmpl;
     size_t core_n_hin = 0, core_n_hacc = 0;
     // ---- v3: pipelined batch kernel (swn_batch.cuh)
-    struct L3Cta { int pair0, npairs, skip0, nskip, rows, RP; int64_t w_off, b_off; };
+    struct L3Cta { int pair0, npairs, skip0, nskip, rows, RP; int64_t w_off, b_off, wr_off; };
     struct D3Cta { int64_t w_off, b_off; };
     std::vector<D3Cta> dense3;
     std::vector<float> wbuf3_h;
@@ -492,6 +492,15 @@ static int pack_v3(swn_model* m, int geff) {
                 W[c.b_off + pi * 2] = y->data[c.pair0 + pi];
                 W[c.b_off + pi * 2 + 1] = y->data[H + c.pair0 + pi];
             }
+            // the same rows row-major [128][Hp] for the tensor-memory resident form (tcgen05 contraction)
+            c.wr_off = 0;
+            if (c.RP <= 128) {
+                c.wr_off = alloc((size_t)128 * Hp);
+                const float* wt2 = W.data() + c.w_off;
+                float* wr = W.data() + c.wr_off;
+                for (int r = 0; r < c.rows; ++r)
+                    for (int k = 0; k < H; ++k) wr[(size_t)r * Hp + k] = wt2[(size_t)k * c.RP + r];
+            }
             m->l3[l].push_back(c);
         }
     }
@@ -536,14 +545,16 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
     std::vector<int> cand;
     if (a->batch_tile > 0) {
         for (const int* t = tiles; *t; ++t) if (*t == a->batch_tile) cand.push_back(*t);
-        if (cand.empty()) return a->kernel_sel == 3 ? fail("swn_generate: batch_tile=%d is not instantiated for the batch kernel at seg=%d", a->batch_tile, seg) : 2;
+        if (cand.empty()) return a->kernel_sel >= 3 ? fail("swn_generate: batch_tile=%d is not instantiated for the batch kernel at seg=%d", a->batch_tile, seg) : 2;
     } else {
         int first = -1;
         for (const int* t = tiles; *t; ++t) if (first < 0 && (B + *t - 1) / *t >= 12) first = *t;
         for (const int* t = tiles; *t; ++t) if (first < 0 ? true : *t <= first) cand.push_back(*t);
         if (first < 0) std::reverse(cand.begin(), cand.end());     // small batches: smallest tile first
     }
-    int BS = 0, M = 0, NT = 0, grid = 0, geff = 0;
+    int BS = 0, M = 0, NT = 0, grid = 0, geff = 0, NPsel = 0;
+    bool umma = false;
+    const bool want_umma = a->kernel_sel != 4 && !(getenv("SWN_NO_UMMA") && atoi(getenv("SWN_NO_UMMA")) == 1);
     size_t smem_max = 0, ring_total = 0, tiles_total = 0;
     std::vector<int> nd(ND, 1);
     std::vector<swn::BCta> desc;
@@ -576,6 +587,12 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
             if (pack_v3(m, ge)) return 1;
         }
         const int Hp = m->Hp3;
+        // tensor-core contraction for the gated cells: rows fit one M=128 tile, weights (tf32 hi + lo) and two
+        // accumulator tiles fit the 512 columns of tensor memory
+        const int NPc = round_up(NC, 16);
+        bool um = want_umma && H % 8 == 0 && Hp == H && 2 * H + 2 * NPc <= 512;
+        for (int l = 0; l < L && um; ++l)
+            for (int g = 0; g < ge; ++g) if (m->l3[l][g].RP > 128) um = false;
         int left = m->n_sm - L * ge - nd_min_total;              // >= 1
         int nt = std::max(1, std::min(std::min(Mx, 2), left));
         left -= nt;
@@ -589,7 +606,8 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
         // tiles: cell inputs [H][NC] x L, last-column tile [H][bs], dense outputs
         tile_off.assign(L + ND + 1, 0);
         size_t tt = 0;
-        for (int l = 0; l < L; ++l) { tile_off[l] = (int64_t)tt; tt += (size_t)Mx * H * NC; }
+        const size_t cell_tile_f = um ? (size_t)2 * H * NPc : (size_t)H * NC;
+        for (int l = 0; l < L; ++l) { tile_off[l] = (int64_t)tt; tt += (size_t)Mx * cell_tile_f; }
         tile_off[L] = (int64_t)tt; tt += (size_t)Mx * H * bs;
         for (int d = 0; d < ND; ++d) { tile_off[L + 1 + d] = (int64_t)tt; tt += (size_t)Mx * dst[d].rows * bs; }
         int cta = 0;
@@ -605,14 +623,14 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
                 d.cnt_in = l; d.cnt_out = l + 1;
                 d.nprod_in = l == 0 ? 1 : ge;
                 d.is_last = l == L - 1;
-                d.in_off = tile_off[l]; d.in_slot_f = H * NC;
-                d.out_off = tile_off[l + 1]; d.out_slot_f = d.is_last ? H * bs : H * NC;
-                d.w_off = c.w_off; d.b_off = c.b_off;
+                d.in_off = tile_off[l]; d.in_slot_f = (int32_t)cell_tile_f;
+                d.out_off = tile_off[l + 1]; d.out_slot_f = d.is_last ? H * bs : (int32_t)cell_tile_f;
+                d.w_off = c.w_off; d.b_off = c.b_off; d.wr_off = c.wr_off;
                 size_t u = 0;
                 auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
-                d.sm_w = take((size_t)Hp * c.RP);
-                d.sm_x = take((size_t)2 * Hp * NC);
-                d.sm_o = take((size_t)c.RP * OS);
+                d.sm_w = take(um ? 0 : (size_t)Hp * c.RP);
+                d.sm_x = take(um ? 2 * cell_tile_f : (size_t)2 * Hp * NC);
+                d.sm_o = take((size_t)(um ? 128 : c.RP) * OS);
                 d.sm_pre = take((size_t)c.npairs * NC * 4);
                 d.sm_bar = take(32);
                 d.sm_build = take((build_x && l == 0) ? (size_t)K * 2 * H + 2 * H + 2 * (size_t)bs * (seg + 7) : 0);
@@ -671,6 +689,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
         }
         if (!fits) continue;
         BS = bs; M = Mx; NT = nt; grid = cta; geff = ge; smem_max = used_max * 4; ring_total = rt; tiles_total = tt;
+        umma = um; NPsel = NPc;
         break;
     }
     if (!BS) return 2;
@@ -714,7 +733,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
             for (int i = 0; i < nd[sd]; ++i, ++cta, ++di) { desc[cta].w_off = m->dense3[di].w_off; desc[cta].b_off = m->dense3[di].b_off; }
     }
     const int NC = BS * seg;
-    const long long key = ((long long)B << 32) | ((long long)BS << 16) | ((long long)geff << 8) | (long long)NT;
+    const long long key = ((long long)B << 32) | ((long long)BS << 16) | ((long long)geff << 8) | ((long long)NT << 1) | (umma ? 1 : 0);
     if (key != m->plan3_key) {
         CUDA_OK(cudaStreamSynchronize(st));
         if (upload(m->desc3, desc)) return 1;
@@ -726,6 +745,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
         m->hist3.ensure((size_t)M * BS * swn::B3_HIST) ||
         m->ring3.ensure(std::max<size_t>(ring_total, 4))) return 1;
     CUDA_OK(cudaMemsetAsync(m->cnt3.p, 0, n_cnt * sizeof(unsigned int), st));
+    if (umma) CUDA_OK(cudaMemsetAsync(m->tiles3.p, 0, tiles_total * sizeof(float), st));     // padding columns of the tiles must be finite
     if (ring_total) CUDA_OK(cudaMemsetAsync(m->ring3.p, 0, ring_total * sizeof(float), st));
     CUDA_OK(cudaMemsetAsync(m->status.p, 0, 8 * sizeof(int32_t), st));
 
@@ -746,7 +766,8 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
     P.P = m->ptab.p; P.pconst = m->pconst.p; P.gain = m->gain.p;
     P.in_tab = m->in_tab.p; P.in_bias = m->in_bias.p;
     P.w2_off = m->w2_off3; P.b2_off = m->b2_off3; P.cs_off = m->cs_off3;
-    P.hist_g = m->hist3.p; P.build_x = build_x ? 1 : 0;
+    P.hist_g = m->hist3.p; P.build_x = (build_x && !umma) ? 1 : 0;
+    P.umma = umma ? 1 : 0; P.NP = NPsel;
     P.tiles = m->tiles3.p; P.cnt = m->cnt3.p; P.skipbuf = m->skip3.p; P.ring_scratch = m->ring3.p;
     P.noise = a->noise_dev; P.seed = a->seed; P.forced = a->forced_dev; P.seedw = a->seed_dev; P.out = a->out_dev; P.head_out = a->head_dev;
     P.status = m->status.p;
@@ -764,7 +785,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
     m->info.batch_tile = BS;
     m->info.n_slots = M;
     m->info.grid = grid;
-    m->info.kernel_variant = 3;
+    m->info.kernel_variant = umma ? 3 : 4;          // 3: tensor-core cells (tcgen05), 4: fp32 FFMA cells
     m->info.ctas_per_layer = geff;
     m->info.head_ctas = grid - L * geff;
     return 0;
@@ -1146,7 +1167,7 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
     if (n_iter + m->R + 2 > 0x7fffffffLL) return fail("swn_generate: too many steps");
 
     // ---- small batches, one sample per step: the cluster kernel (v2); everything else: layer groups (v1)
-    if (m->core_ok && a->kernel_sel != 1 && a->kernel_sel != 3) {
+    if (m->core_ok && a->kernel_sel != 1 && a->kernel_sel < 3) {
         const int rc = generate_core(m, a, st, B, Tf, n_iter);
         if (rc == 0) return 0;
         if (rc == 1) return 1;
@@ -1155,11 +1176,11 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
         return fail("swn_generate: the cluster kernel is not applicable to this configuration");
     }
     // ---- batches: the pipelined batch kernel (v3)
-    if (a->kernel_sel == 3 || (a->kernel_sel == 0 && B > 4)) {
+    if (a->kernel_sel == 3 || a->kernel_sel == 4 || (a->kernel_sel == 0 && B > 4)) {
         const int rc = generate_batch(m, a, st, B, Tf, n_iter);
         if (rc == 0) return 0;
         if (rc == 1) return 1;
-        if (a->kernel_sel == 3) return fail("swn_generate: the batch kernel is not applicable to this configuration/batch");
+        if (a->kernel_sel >= 3) return fail("swn_generate: the batch kernel is not applicable to this configuration/batch");
     }
     // ---- batch tile
     int BS = 0;

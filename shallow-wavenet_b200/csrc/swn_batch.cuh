@@ -55,6 +55,7 @@ struct BCta {
     int32_t sm_w, sm_x, sm_o, sm_pre, sm_ring, sm_bar, sm_build;
     int64_t in_off, out_off;              // float offsets of slot 0 inside BatchParams::tiles
     int64_t w_off;                        // [kp][RP]
+    int64_t wr_off;                       // umma: the same rows row-major [128][kp] (zero padded), loaded into tensor memory
     int64_t b_off;                        // gated cell: [np][2]; dense: [nrows]
     int64_t ring_off;                     // [RL][2*np][Bp] in ring_scratch
     // tail CTA shared-memory layout
@@ -83,6 +84,7 @@ struct BatchParams {
     float* skipbuf;                       // [L-1][M][S][BS]
     float* hist_g;                        // build_x: [M][BS][HIST] fed-back samples (written by the tail, read by cell 0)
     int32_t build_x;                      // 1: the CTAs of cell 0 evaluate the causal input stage themselves
+    int32_t umma, NP;                     // 1: the gated cells contract on the tensor cores (tcgen05, 3 x tf32); NP = columns padded to 16
     float* ring_scratch;
     const float* noise;
     unsigned long long seed;
@@ -156,6 +158,30 @@ __device__ __forceinline__ void b3_signal(unsigned int* p) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
 
+// ---- tcgen05 pieces (validated stand-alone by tools/microbench/umma_tf32.cu)
+// Tile layout of a cell input in UMMA mode: B operand [n][k], K-major, no swizzle: 128-byte core matrices of
+// 8 columns x 4 k; float offset of (column n, channel k) inside one (hi or lo) tile of NP columns:
+__device__ __forceinline__ int b3_uoff(int n, int k, int NP) { return (((k >> 2) * (NP >> 3) + (n >> 3)) << 5) + ((n & 7) << 2) + (k & 3); }
+__device__ __forceinline__ uint64_t b3_udesc(uint32_t saddr, int NP) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((((NP >> 3) * 128) >> 4) & 0x3FFF) << 16;     // leading byte offset: next core matrix along k
+    d |= (uint64_t)((128 >> 4) & 0x3FFF) << 32;                   // stride byte offset: next 8-column group
+    d |= (uint64_t)1 << 46;                                       // descriptor version (Blackwell)
+    return d;                                                     // layout type 0: no swizzle
+}
+__device__ __forceinline__ void b3_umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void b3_umma_commit(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b3_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void b3_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void b3_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ float b3_tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 #define B3_PROF(ev)                                                                                      \
     do {                                                                                                 \
         if (P.prof && it >= P.prof_start && it < P.prof_start + P.prof_count)                            \
@@ -185,7 +211,23 @@ struct B3Tile {
 
 // MODE 0: gated cell (cswnv_shift1.py:275-285) over NC = SEG*BS columns; MODE 1: dense head stage over BS columns.
 template <int SEG, int BS, int MODE>
+__device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem);
+
+template <int SEG, int BS, int MODE>
 __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
+    b3_stage_body<SEG, BS, MODE>(P, D, smem);            // every role returns here, also after an abort
+    if (MODE == 0 && P.umma) {
+        b3_tc_fence_before();
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const uint32_t tb = *reinterpret_cast<const uint32_t*>(reinterpret_cast<unsigned long long*>(smem + D.sm_bar) + 14);
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
+        }
+    }
+}
+
+template <int SEG, int BS, int MODE>
+__device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) {
     constexpr int NC = MODE == 0 ? SEG * BS : BS;
     using T = B3Tile<NC>;
     constexpr int TC = T::TC, NCG = T::NCG, RGW = T::RGW, TR = T::TR, RPW = T::RPW, OS = T::OS, KS = T::KS;
@@ -208,22 +250,30 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
     unsigned long long* kbar = bars + 7;            // [SLOTS] first k-split stored its partial sums
     unsigned long long* kback = bars + 7 + SLOTS;   // [SLOTS] second k-split added its own (only waited for between passes)
 
-    const bool build = MODE == 0 && P.build_x && l == 0;      // this CTA evaluates the causal input stage itself
-    const int epi0 = build ? B3_EPI0 + B3_NBW : B3_EPI0;      // first epilogue warp
+    const bool umma = MODE == 0 && P.umma;                    // tensor-core contraction (weights in tensor memory)
+    const int NP = P.NP, utile = D.kdim * NP;                 // umma: floats of one (hi or lo) input tile
+    const bool build = MODE == 0 && P.build_x && l == 0 && !umma;   // this CTA evaluates the causal input stage itself
+    const int epi0 = build ? B3_EPI0 + B3_NBW : (umma ? B3_EPI0 + 1 : B3_EPI0);      // first epilogue warp
+    unsigned long long* d_full = bars + 7;          // umma: [2] accumulator tile complete (tcgen05.commit)
+    unsigned long long* d_empty = bars + 9;         // umma: [2] accumulator tile drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
     const int nepi = (SWN_NWARPS - epi0) * 32;
     unsigned long long* bbar = bars + 15;           // barrier among the builder warps
 
     const int nrb = (RP + RPW - 1) / RPW;
     const int nslot = nrb < SLOTS ? nrb : SLOTS;    // row-block slots in use
-    const int ngwa = nslot * KS;                    // GEMM warps that own work
+    const int ngwa = umma ? 4 : nslot * KS;         // GEMM warps that own work (umma: the four drain warps)
 
     // ---- one-time staging
     {
-        const float4* src = reinterpret_cast<const float4*>(P.wbuf + D.w_off);
-        float4* dst = reinterpret_cast<float4*>(Wt);
-        const int n4 = kp * RP / 4;
-        for (int i = tid; i < n4; i += SWN_NTHREADS) dst[i] = src[i];
-        for (int i = tid; i < 2 * kp * NC; i += SWN_NTHREADS) Xs[i] = 0.f;
+        if (!umma) {
+            const float4* src = reinterpret_cast<const float4*>(P.wbuf + D.w_off);
+            float4* dst = reinterpret_cast<float4*>(Wt);
+            const int n4 = kp * RP / 4;
+            for (int i = tid; i < n4; i += SWN_NTHREADS) dst[i] = src[i];
+        }
+        const int nx = umma ? 4 * utile : 2 * kp * NC;
+        for (int i = tid; i < nx; i += SWN_NTHREADS) Xs[i] = 0.f;
         if (build) {
             // in_tab [K][2][H], then cst[r] = in_bias[r] + sum_j cb_j[r] (all taps inside the sequence)
             float* itab = smem + D.sm_build;
@@ -242,23 +292,110 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
         if (tid == 0) {
             b3_mbar_init(&x_full[0], build ? B3_NBW : 1); b3_mbar_init(&x_full[1], build ? B3_NBW : 1);
             b3_mbar_init(bbar, B3_NBW);
-            b3_mbar_init(&x_empty[0], ngwa + 1); b3_mbar_init(&x_empty[1], ngwa + 1);
+            b3_mbar_init(&x_empty[0], umma ? 2 : ngwa + 1); b3_mbar_init(&x_empty[1], umma ? 2 : ngwa + 1);
             b3_mbar_init(o_full, ngwa); b3_mbar_init(o_empty, 1);
             b3_mbar_init(ebar, SWN_NWARPS - epi0);
-            for (int i = 0; i < SLOTS; ++i) { b3_mbar_init(&kbar[i], 1); b3_mbar_init(&kback[i], 1); }
+            if (umma) {
+                b3_mbar_init(&d_full[0], 1); b3_mbar_init(&d_full[1], 1);
+                b3_mbar_init(&d_empty[0], 4); b3_mbar_init(&d_empty[1], 4);
+            } else {
+                for (int i = 0; i < SLOTS; ++i) { b3_mbar_init(&kbar[i], 1); b3_mbar_init(&kback[i], 1); }
+            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
+    if (umma && warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(b3_smem(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
     b3_fence_proxy_async();         // the zeroed X buffers are overwritten by the async proxy later
+    b3_tc_fence_before();
     __syncthreads();
+    b3_tc_fence_after();
+    const uint32_t tbase = umma ? *tmem_slot : 0u;
+    if (umma && warp < 4) {
+        // weights -> tensor memory: row = lane, channel k = column; tf32 high halves at [0,kp), low halves at [kp,2kp)
+        const float* wr = P.wbuf + D.wr_off + (size_t)tid * kp;
+        const uint32_t lb = tbase + ((uint32_t)(warp * 32) << 16);
+        for (int k0 = 0; k0 < kp; k0 += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(wr + k0);
+            const float h0 = b3_tf32_hi(w.x), h1 = b3_tf32_hi(w.y), h2 = b3_tf32_hi(w.z), h3 = b3_tf32_hi(w.w);
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(lb + k0), "r"(__float_as_uint(h0)),
+                         "r"(__float_as_uint(h1)), "r"(__float_as_uint(h2)), "r"(__float_as_uint(h3)) : "memory");
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(lb + kp + k0), "r"(__float_as_uint(w.x - h0)),
+                         "r"(__float_as_uint(w.y - h1)), "r"(__float_as_uint(w.z - h2)), "r"(__float_as_uint(w.w - h3)) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    if (umma) {
+        b3_tc_fence_before();
+        __syncthreads();
+        b3_tc_fence_after();
+    }
 
     const int nq = P.n_it * M;
-    const uint32_t tile_bytes = (uint32_t)(D.kdim * NC * sizeof(float));
+    const uint32_t tile_bytes = umma ? (uint32_t)(2 * utile * sizeof(float)) : (uint32_t)(D.kdim * NC * sizeof(float));
+    const int xbuf_f = umma ? 2 * utile : kp * NC;          // floats of one input buffer
     const float* tile_in = P.tiles + D.in_off;
     float* tile_out = P.tiles + D.out_off;
     const unsigned int* cnt_in = P.cnt + (size_t)D.cnt_in * M * B3_CNT_STRIDE;
     unsigned int* cnt_out = P.cnt + (size_t)D.cnt_out * M * B3_CNT_STRIDE;
 
+    if (umma && warp < 4) {
+        // =============================== drain warps: accumulator tile (tensor memory) -> Os; thread = row
+        const uint32_t lb = tbase + ((uint32_t)(warp * 32) << 16) + 2 * kp;
+        for (int q = 0; q < nq; ++q) {
+            const int db = q & 1;
+            if (!b3_wait_warp(&d_full[db], (q >> 1) & 1, P.status)) return;
+            b3_tc_fence_after();
+            const int it = q / M, m = q - it * M;
+            if (tid == 0) B3_PROF(2);
+            if (q > 0 && !b3_wait_warp(o_empty, (q - 1) & 1, P.status)) return;
+            for (int c0 = 0; c0 < NC; c0 += 16) {
+                uint32_t v[16];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                               "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(lb + db * NP + c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (tid < RP) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < NC) Os[tid * OS + c0 + i] = __uint_as_float(v[i]);
+                }
+            }
+            b3_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { b3_mbar_arrive(&d_empty[db]); b3_mbar_arrive(o_full); }
+        }
+        return;
+    }
+    if (umma && warp == B3_EPI0) {
+        // =============================== MMA issuer: D = W_hi.X_hi + W_lo.X_hi + W_hi.X_lo (fp32-equivalent, 3 x tf32)
+        if (lane != 0) return;
+        // instruction descriptor: D fp32, A/B tf32, both K-major, N = NP, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const int kstep_bytes = 2 * (NP >> 3) * 128;                 // 8 channels = two core matrices along k
+        for (int q = 0; q < nq; ++q) {
+            const int buf = q & 1, db = q & 1;
+            if (!b3_mbar_wait(&x_full[buf], (q >> 1) & 1, P.status)) return;
+            const int it = q / M, m = q - it * M;
+            B3_PROF(1);
+            if (q >= 2 && !b3_mbar_wait(&d_empty[db], ((q >> 1) - 1) & 1, P.status)) return;
+            b3_tc_fence_after();
+            const uint32_t xs = b3_smem(Xs + buf * xbuf_f);
+            const uint32_t d_tmem = tbase + 2 * kp + db * NP;
+            for (int ks = 0; ks < (kp >> 3); ++ks) {
+                const uint64_t dh = b3_udesc(xs + ks * kstep_bytes, NP), dl = b3_udesc(xs + utile * 4 + ks * kstep_bytes, NP);
+                b3_umma_tf32_ts(d_tmem, tbase + ks * 8, dh, idesc, ks > 0);
+                b3_umma_tf32_ts(d_tmem, tbase + kp + ks * 8, dh, idesc, 1);
+                b3_umma_tf32_ts(d_tmem, tbase + ks * 8, dl, idesc, 1);
+            }
+            b3_umma_commit(&d_full[db]);
+            b3_umma_commit(&x_empty[buf]);
+        }
+        return;
+    }
     if (warp < B3_NGW) {
         // =============================== GEMM warps: warp = (row-block slot, k-split)
         const int slot = warp % SLOTS, ks = warp / SLOTS;
@@ -464,7 +601,7 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
             B3_PROF(0);
             b3_fence_proxy_async();
             b3_mbar_arm(&x_full[buf], tile_bytes);
-            b3_tma_load(Xs + buf * kp * NC, tile_in + (size_t)m * D.in_slot_f, tile_bytes, &x_full[buf]);
+            b3_tma_load(Xs + buf * xbuf_f, tile_in + (size_t)m * D.in_slot_f, tile_bytes, &x_full[buf]);
         }
         return;
     }
@@ -561,7 +698,7 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
             sk_prev = __ldcg(P.skipbuf + ((size_t)(l - 2) * M + m) * P.S * BS + (size_t)D.skip0 * BS + te);
         if (!b3_wait_warp(o_full, q & 1, P.status)) return;
         if (te == 0) B3_PROF(4);
-        const float* X = Xs + buf * kp * NC;
+        const float* X = Xs + buf * xbuf_f;
         float* tout = tile_out + (size_t)m * D.out_slot_f;
         // ---- P2: gate (cswnv_shift1.py:281-285) and publish
         for (int item = te; item < nitems; item += nepi) {
@@ -583,10 +720,18 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
                 const float ez = __expf(-gz), ec = __expf(-2.f * fabsf(gc));
                 const float z = __frcp_rn(1.f + ez);
                 const float th = copysignf((1.f - ec) * __frcp_rn(1.f + ec), gc);
-                hv = (1.f - z) * th + z * X[(D.pair0 + pi) * NC + col];
+                float carry;
+                if (umma) { const int xo = b3_uoff(col, D.pair0 + pi, NP); carry = X[xo] + X[utile + xo]; }
+                else carry = X[(D.pair0 + pi) * NC + col];
+                hv = (1.f - z) * th + z * carry;
             }
-            if (!D.is_last) __stcg(tout + (size_t)(D.pair0 + pi) * NC + col, hv);
-            else if (s == SEG - 1) __stcg(tout + (size_t)(D.pair0 + pi) * BS + b, hv);     // the head only needs the last column
+            if (!D.is_last) {
+                if (umma) {      // exact split into tf32 halves for the next cell's tensor-core passes
+                    const int xo = b3_uoff(col, D.pair0 + pi, NP);
+                    const float hh = b3_tf32_hi(hv);
+                    __stcg(tout + xo, hh); __stcg(tout + utile + xo, hv - hh);
+                } else __stcg(tout + (size_t)(D.pair0 + pi) * NC + col, hv);
+            } else if (s == SEG - 1) __stcg(tout + (size_t)(D.pair0 + pi) * BS + b, hv);     // the head only needs the last column
         }
         // rows of out_skip[l-1] applied to the last time column of every utterance, added to the running sum
         if (l >= 1) {
@@ -722,7 +867,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
         }
         const int t0n = P.t_first + itn * SEG;
         const float* hs = hist + (size_t)ml * BS * B3_HIST;
-        float* dst = P.tiles + (size_t)m * H * NC;                   // layer 0 input (tile offset 0)
+        float* dst = P.tiles + (size_t)m * (P.umma ? 2 * H * P.NP : H * NC);      // layer 0 input (tile offset 0)
         if (K <= 8) {
             for (int e = tid; e < H * BS; e += SWN_NTHREADS) {
                 const int r = e / BS, b = e - r * BS;
@@ -776,8 +921,14 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                         for (int j = 0; j < 8; ++j) acc[s] += g[s][j];
                 }
 #pragma unroll
-                for (int s = 0; s < SEG; ++s)
-                    __stcg(dst + (size_t)r * NC + s * BS + b, (t0n + s >= 0) ? softsignf_(acc[s]) : 0.f);
+                for (int s = 0; s < SEG; ++s) {
+                    const float v = (t0n + s >= 0) ? softsignf_(acc[s]) : 0.f;
+                    if (P.umma) {
+                        const int xo = b3_uoff(s * BS + b, r, P.NP);
+                        const float hh = b3_tf32_hi(v);
+                        __stcg(dst + xo, hh); __stcg(dst + H * P.NP + xo, v - hh);
+                    } else __stcg(dst + (size_t)r * NC + s * BS + b, v);
+                }
             }
         } else {
             for (int e = tid; e < H * NC; e += SWN_NTHREADS) {
@@ -797,7 +948,11 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                     }
                     v = softsignf_(acc);
                 }
-                __stcg(dst + e, v);
+                if (P.umma) {
+                    const int xo = b3_uoff(c, r, P.NP);
+                    const float hh = b3_tf32_hi(v);
+                    __stcg(dst + xo, hh); __stcg(dst + H * P.NP + xo, v - hh);
+                } else __stcg(dst + e, v);
             }
         }
         const int it = itn - 1;

@@ -348,17 +348,18 @@ def test_full_size_cfg1_on_gpu_tail_property():
 _V3_FIXTURES = [n for n in golden_names() if n != "dswnv_audio_in"]      # audio_in_flag stays on variant 1
 
 
+@pytest.mark.parametrize("engine", [3, 4])          # 3: tensor-core cells where they apply, 4: fp32 FFMA cells
 @pytest.mark.parametrize("tile", [1, 2])
 @pytest.mark.parametrize("name", _V3_FIXTURES)
-def test_batch_kernel_teacher_forced_matches_reference_fixture(name, tile):
+def test_batch_kernel_teacher_forced_matches_reference_fixture(name, tile, engine):
     g = load_golden(name)
     m = _model_from_golden(g)
     B, N = g["samples"].shape
     outs, heads = m.batch_fast_generate(_seed_audio(g["kind"], B, g["cfg"].eff_seg), torch.from_numpy(g["aux"]),
                                         [N] * B, noise=g["noise"], forced=g["samples"], return_heads=True,
-                                        kernel_sel=3, batch_tile=tile)
+                                        kernel_sel=engine, batch_tile=tile)
     info = m.engine().info
-    assert info["kernel_variant"] == 3 and info["batch_tile"] == tile and info["n_slots"] == -(-B // tile)
+    assert info["kernel_variant"] == engine and info["batch_tile"] == tile and info["n_slots"] == -(-B // tile)
     _head_close(heads, g["heads"], "%s v3 tile %d" % (name, tile))
     smp = np.stack(outs)
     if g["kind"] == "dswnv":
@@ -374,7 +375,7 @@ def test_batch_kernel_free_running_matches_reference_fixture(name):
     B, N = g["samples"].shape
     outs = m.batch_fast_generate(_seed_audio(g["kind"], B, g["cfg"].eff_seg), torch.from_numpy(g["aux"]),
                                  g["n_samples_list"], noise=g["noise"], kernel_sel=3)
-    assert m.engine().info["kernel_variant"] == 3
+    assert m.engine().info["kernel_variant"] == 3          # every fixture is small enough for the tensor-core cells
     for b, o in enumerate(outs):
         ref = g["samples"][b, :len(o)]
         if g["kind"] == "dswnv":
@@ -403,7 +404,7 @@ def test_batch_kernel_many_slots_free_running_vs_oracle(name, B, tile):
     outs, heads = m.batch_fast_generate(_seed_audio(g["kind"], B, cfg.eff_seg), torch.from_numpy(aux), [N] * B,
                                         noise=noise, return_heads=True, batch_tile=tile)
     info = m.engine().info
-    assert info["kernel_variant"] == 3 and info["n_slots"] == -(-B // info["batch_tile"])
+    assert info["kernel_variant"] in (3, 4) and info["n_slots"] == -(-B // info["batch_tile"])
     ref_smp, ref_heads = O.generate(cfg, g["sd"], aux, N, noise, return_heads=True)
     _head_close(heads, ref_heads, "%s B=%d" % (name, B))
     if g["kind"] == "dswnv":
@@ -412,12 +413,16 @@ def test_batch_kernel_many_slots_free_running_vs_oracle(name, B, tile):
         assert float(np.abs(np.stack(outs) - ref_smp).max()) <= 5e-5
 
 
-@pytest.mark.parametrize("kind,fs,B,tile,over", [("cswnv", 22050, 9, 4, dict(seg=5, lpc=4)),
-                                                  ("cswnv", 22050, 17, 8, dict(seg=5, lpc=4)),
-                                                  ("cswnv", 22050, 6, 2, dict(seg=10, lpc=4)),
-                                                  ("dswnv", 24000, 20, 8, dict()),
-                                                  ("dswnv", 16000, 33, 8, dict())])
-def test_batch_kernel_recipe_size_teacher_forced_vs_oracle(kind, fs, B, tile, over):
+@pytest.mark.parametrize("kind,fs,B,tile,over,variant", [("cswnv", 22050, 9, 4, dict(seg=5, lpc=4), 3),
+                                                          ("cswnv", 22050, 17, 8, dict(seg=5, lpc=4), 3),
+                                                          ("cswnv", 22050, 17, 8, dict(seg=5, lpc=4), 4),
+                                                          ("cswnv", 22050, 6, 2, dict(seg=10, lpc=4), 3),
+                                                          ("cswnv", 22050, 12, 4, dict(seg=1, lpc=4), 3),
+                                                          ("dswnv", 24000, 20, 8, dict(), 4),
+                                                          ("dswnv", 16000, 33, 8, dict(), 4)])
+def test_batch_kernel_recipe_size_teacher_forced_vs_oracle(kind, fs, B, tile, over, variant):
+    """Recipe sizes: CSWNV (H=192) runs its cells on the tensor cores (variant 3: tcgen05, three tf32 passes,
+    weights in tensor memory); DSWNV (H=256) does not fit tensor memory and stays on the fp32 FFMA cells (4)."""
     model, cfg, sd, aux, kw = _recipe_case(kind, fs, B, 2, 21, **over)
     seg = cfg.eff_seg
     N = 2 * kw["upsampling_factor"]
@@ -429,9 +434,9 @@ def test_batch_kernel_recipe_size_teacher_forced_vs_oracle(kind, fs, B, tile, ov
         forced = rng.integers(0, 256, (B, N)).astype(np.int64)
         noise = rng.exponential(1.0, (B, N, 256)).astype(np.float32)
     outs, heads = model.batch_fast_generate(_seed_audio(kind, B, seg), torch.from_numpy(aux), [N] * B, noise=noise,
-                                            forced=forced, return_heads=True, batch_tile=tile)
+                                            forced=forced, return_heads=True, batch_tile=tile, kernel_sel=variant)
     info = model.engine().info
-    assert info["kernel_variant"] == 3 and info["batch_tile"] == tile
+    assert info["kernel_variant"] == variant and info["batch_tile"] == tile
     ref_heads = O.teacher_forced(cfg, sd, aux, forced)
     _head_close(heads, ref_heads, "%s recipe B=%d" % (kind, B))
     if kind == "dswnv":

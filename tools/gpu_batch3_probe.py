@@ -25,7 +25,7 @@ for kind, fs, over, B, tile in cases:
     try:
         for rep in range(2):
             eng.condition(aux)
-            out, _ = eng.generate(n, seed=rep, batch_tile=tile, kernel_sel=3)
+            out, _ = eng.generate(n, seed=rep, batch_tile=tile, kernel_sel=int(os.environ.get("ENGINE", "3")))
         info = eng.info
         seg = info["eff_seg"]
         steps = n // seg + info["receptive_field"] // seg + 1

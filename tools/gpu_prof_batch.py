@@ -17,13 +17,13 @@ aux = torch.from_numpy(synth.synth_aux(kw["n_aux"], frames, B)).cuda()
 eng = model.engine()
 n = frames * kw["upsampling_factor"]
 eng.condition(aux)
-eng.generate(n, seed=0, batch_tile=tile, kernel_sel=3)
+eng.generate(n, seed=0, batch_tile=tile, kernel_sel=int(os.environ.get('ENGINE', '3')))
 info = eng.info
 M, grid, G, NHEAD, L = info["n_slots"], info["grid"], info["ctas_per_layer"], info["head_ctas"], 6
 start, count = (info["receptive_field"] // info["eff_seg"]) + 60, 3
 prof = torch.zeros((count, M * grid // 2, 32), dtype=torch.int64, device="cuda")
 eng.condition(aux)
-eng.generate(n, seed=0, batch_tile=tile, kernel_sel=3, prof=prof, prof_start=start)
+eng.generate(n, seed=0, batch_tile=tile, kernel_sel=int(os.environ.get('ENGINE', '3')), prof=prof, prof_start=start)
 p = prof.cpu().numpy().reshape(count, M, grid, 16).astype(np.float64)
 print("%s B=%d tile=%d slots=%d grid=%d G=%d head CTAs=%d kernel %.2f ms" % (kind, B, tile, M, grid, G, NHEAD, eng.info["last_gen_ms"]))
 stamps = p[..., :8]
