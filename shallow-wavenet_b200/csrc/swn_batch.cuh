@@ -815,8 +815,8 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
     float* tin = smem + D.sm_tin;                   // [H][NC]
     float* itab = smem + D.sm_itab;                 // CSWNV: in_tab [K][2][H]; then (both kinds) in_bias [H], out_2 bias [n2]
     float* ibias = itab + (is_c ? K * 2 * H : 0);
-    float* b2s = ibias + H;
-    float* cst = b2s + n2;                          // CSWNV: in_bias[r] + sum_j cb_j[r]
+    float* cst = ibias + H;                         // CSWNV: in_bias[r] + sum_j cb_j[r]
+    float* b2s = cst + H;
     float2* ain = reinterpret_cast<float2*>(smem + D.sm_ain);     // [NC][K]
     float* nz = smem + D.sm_noise;                  // CSWNV: eps [BS][SEG]; DSWNV: -log q [BS][Q]
     float* hist = smem + D.sm_hist;                 // [MO][BS][HIST]
@@ -868,7 +868,68 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
         const int t0n = P.t_first + itn * SEG;
         const float* hs = hist + (size_t)ml * BS * B3_HIST;
         float* dst = P.tiles + (size_t)m * (P.umma ? 2 * H * P.NP : H * NC);      // layer 0 input (tile offset 0)
-        if (K <= 8) {
+        if (P.umma && K <= 8) {
+            // tensor-core tile layout: a thread owns 4 consecutive channels of one column and writes them as one
+            // 16-byte word (hi) + one (lo); 8 consecutive columns fill a 128-byte core matrix
+            const int utile = H * P.NP;
+            const bool allv = t0n - (K - 1) >= 0;
+            for (int e = tid; e < (H >> 2) * NC; e += SWN_NTHREADS) {
+                const int kq = e / NC, n = e - kq * NC;
+                const int s = n / BS, b = n - s * BS;
+                const int r0 = kq * 4;
+                float a[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int nn = t0n + s - (K - 1) + j - P.R - 1;         // newest sample seen by tap j of this column
+                    a[j] = (j < K && nn >= -SEG) ? hs[b * B3_HIST + ((nn + 64 * B3_HIST) % B3_HIST)] : (is_c ? 0.f : __int_as_float(P.Q / 2));
+                }
+                float acc[4];
+                if (is_c && allv) {
+                    const float4 c0 = *reinterpret_cast<const float4*>(cst + r0);
+                    acc[0] = c0.x; acc[1] = c0.y; acc[2] = c0.z; acc[3] = c0.w;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < K) {
+                            const float4 cv = *reinterpret_cast<const float4*>(itab + (j * 2 + 1) * H + r0);
+                            acc[0] = fmaf(a[j], cv.x, acc[0]); acc[1] = fmaf(a[j], cv.y, acc[1]);
+                            acc[2] = fmaf(a[j], cv.z, acc[2]); acc[3] = fmaf(a[j], cv.w, acc[3]);
+                        }
+                } else {
+                    const float4 bi = *reinterpret_cast<const float4*>(ibias + r0);
+                    acc[0] = bi.x; acc[1] = bi.y; acc[2] = bi.z; acc[3] = bi.w;
+                    if (is_c) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < K && t0n + s - (K - 1) + j >= 0) {
+                                const float4 cb = *reinterpret_cast<const float4*>(itab + (j * 2) * H + r0);
+                                const float4 cv = *reinterpret_cast<const float4*>(itab + (j * 2 + 1) * H + r0);
+                                acc[0] += cb.x + cv.x * a[j]; acc[1] += cb.y + cv.y * a[j];
+                                acc[2] += cb.z + cv.z * a[j]; acc[3] += cb.w + cv.w * a[j];
+                            }
+                    } else {
+                        float4 g[8];                         // all gathers in flight before the first add
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            g[j] = (j < K && t0n + s - (K - 1) + j >= 0)
+                                       ? __ldg(reinterpret_cast<const float4*>(P.in_tab + ((size_t)j * P.Q + __float_as_int(a[j])) * H + r0))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { acc[0] += g[j].x; acc[1] += g[j].y; acc[2] += g[j].z; acc[3] += g[j].w; }
+                    }
+                }
+                float4 vh, vl;
+                {
+                    const bool tv = t0n + s >= 0;
+                    const float v0 = tv ? softsignf_(acc[0]) : 0.f, v1 = tv ? softsignf_(acc[1]) : 0.f;
+                    const float v2 = tv ? softsignf_(acc[2]) : 0.f, v3 = tv ? softsignf_(acc[3]) : 0.f;
+                    vh = make_float4(b3_tf32_hi(v0), b3_tf32_hi(v1), b3_tf32_hi(v2), b3_tf32_hi(v3));
+                    vl = make_float4(v0 - vh.x, v1 - vh.y, v2 - vh.z, v3 - vh.w);
+                }
+                const int xo = b3_uoff(n, r0, P.NP);
+                __stcg(reinterpret_cast<float4*>(dst + xo), vh);
+                __stcg(reinterpret_cast<float4*>(dst + utile + xo), vl);
+            }
+        } else if (K <= 8) {
             for (int e = tid; e < H * BS; e += SWN_NTHREADS) {
                 const int r = e / BS, b = e - r * BS;
                 // samples / indices seen by hidden times t0n-(K-1) .. t0n+SEG-1 (newest sample of hidden time tau: tau-R-1)

@@ -43,7 +43,7 @@ for m in range(min(M, nshow)):
         e = p[it, m, c]
         if e[0] == 0:
             continue
-        if e[3] == 0 and e[4] == 0:      # dense stage CTA (the tail stamps 3 / 4)
+        if e[7] == 0:      # dense stage CTA (only the tail stamps event 7)
             hd.append("D%d in %7.2f g[%5.2f %5.2f] pub %5.2f" % (c - L * G, (e[0] - t00) / 1e3, (e[1] - e[0]) / 1e3, (e[2] - e[0]) / 1e3, (e[5] - e[0]) / 1e3))
         else:
             hd.append("tail in %7.2f x2-loaded %5.2f logits %5.2f sampled %5.2f input: computed %5.2f synced %5.2f signalled %5.2f" % (
