@@ -37,7 +37,13 @@ WORKLOADS = {
     "cfg3": ("cswnv", 22050, dict(seg=5, lpc=4), 64, 1000,
              "cfg3: CSWNV Laplace seg=5 lpc=4 H=192, 22.05 kHz, batch 64 x 5 s (110000 samples each)"),
     "cfg4": ("cswnv", 22050, dict(seg=5, lpc=4), 64, 2000,
-             "cfg4: CSWNV Laplace seg=5 lpc=4 H=192, 22.05 kHz, batch 64 per GPU x 10 s"),
+             "cfg4: CSWNV Laplace seg=5 lpc=4 H=192, 22.05 kHz, batch 64 per GPU x 10 s (the 8-GPU shard of batch 512)"),
+    "cfg4_256": ("cswnv", 22050, dict(seg=5, lpc=4), 256, 2000,
+                 "cfg4: CSWNV Laplace seg=5 lpc=4 H=192, 22.05 kHz, batch 256 per GPU x 10 s (the 2-GPU shard of batch 512)"),
+    "cfg3s": ("cswnv", 22050, dict(seg=5, lpc=4), 64, 40,
+              "cfg3 short: CSWNV seg=5 lpc=4 H=192, 22.05 kHz, batch 64 x 0.2 s (4400 samples each)"),
+    "cfg5s": ("dswnv", 24000, dict(), 128, 40,
+              "cfg5 short: DSWNV H=256, 24 kHz, batch 128 x 0.2 s (4800 samples each)"),
     "cfg5": ("dswnv", 24000, dict(), 128, 12000,
              "cfg5: DSWNV mu-law softmax H=256, 24 kHz, batch 128 per GPU x 60 s"),
     "cfg2s": ("dswnv", 16000, dict(), 1, 100,
@@ -282,17 +288,39 @@ def main():
             pass
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
         flops = 2.0 * macs * B * n_gen / (kern_ms * 1e-3)
+        variant = info.get("kernel_variant")
         kname = {1: "swn_generate_kernel (layer groups over the chip, persistent)",
-                 2: "swn_core_kernel (16-CTA core cluster + helper CTAs, persistent)"}.get(info.get("kernel_variant"), "?")
-        roofline = {"bound": "smem", "kernel": kname + ", 1 launch per step",
-                    "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
-                    "peak_source": "measured live: aggregate LDS.128 bandwidth, 1 CTA/SM (swn_measure_smem_bandwidth)",
-                    "algorithmic_bytes_per_time_step": weight_bytes, "time_steps_per_launch": seg_steps * n_slots,
-                    "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms * args.steps / total_ms,
-                    "achieved_tflops_fp32": flops / 1e12,
-                    "vs_hbm": {"peak": peaks.get("hbm_gbs"), "frac": (achieved / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
-                               "note": "weights are SMEM-resident; HBM is not the bound (frac>1 = residency pays)"},
-                    "traffic": None}
+                 2: "swn_core_kernel (16-CTA core cluster + helper CTAs, persistent)",
+                 3: "swn_batch_kernel (ring pipeline of slots; gated cells on tcgen05 kind::tf32 x3, weights in tensor memory)",
+                 4: "swn_batch_kernel (ring pipeline of slots; gated cells as register-tiled fp32 FFMA GEMMs)"}.get(variant, "?")
+        if variant in (3, 4):
+            # batched step: dense contraction [rows x H].[H x columns] -> tensor-pipe bound.  The
+            # algorithmic flops count every multiply-add of the reference once (no tf32 pass multiplicity).
+            tf = flops / 1e12
+            peak_bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
+            sm_mhz = clocks.get("sm_mhz") or 1965.0
+            fp32_peak = info["n_sm"] * 128 * 2 * sm_mhz * 1e6 / 1e12
+            roofline = {"bound": "tensor", "kernel": kname + ", 1 launch per step",
+                        "achieved": tf, "peak": peak_bf16, "unit": "TFLOP/s", "frac": tf / peak_bf16,
+                        "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, long loop)" if peaks.get("bf16_tflops_sustained")
+                                        else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"),
+                        "note": "fp32 parity (1e-4) forbids bf16: the cells run three tf32 passes (tf32 dense = bf16/2), so the "
+                                "same-precision tensor ceiling is peak/6; variant 4 (H=256 does not fit tensor memory) is bounded by fp32 FFMA",
+                        "peak_tf32x3_equivalent": peak_bf16 / 6.0, "frac_of_tf32x3_equivalent": tf / (peak_bf16 / 6.0),
+                        "fp32_ffma_peak_at_clock": fp32_peak, "frac_of_fp32_ffma_peak": tf / fp32_peak,
+                        "algorithmic_flop_per_sample": 2.0 * macs, "samples_per_launch": B * n_gen,
+                        "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms * args.steps / total_ms,
+                        "us_per_loop_iteration": kern_ms * 1e3 / seg_steps, "traffic": None}
+        else:
+            roofline = {"bound": "smem", "kernel": kname + ", 1 launch per step",
+                        "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
+                        "peak_source": "measured live: aggregate LDS.128 bandwidth, 1 CTA/SM (swn_measure_smem_bandwidth)",
+                        "algorithmic_bytes_per_time_step": weight_bytes, "time_steps_per_launch": seg_steps * n_slots,
+                        "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms * args.steps / total_ms,
+                        "achieved_tflops_fp32": flops / 1e12,
+                        "vs_hbm": {"peak": peaks.get("hbm_gbs"), "frac": (achieved / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
+                                   "note": "weights are SMEM-resident; HBM is not the bound (frac>1 = residency pays)"},
+                        "traffic": None}
         line = dict(common)
         line.update({"value": value, "ms_per_step": total_ms / args.steps, "rtf": value / fs, "config": config,
                      "rtf_per_utterance": value / fs / (world * B),
