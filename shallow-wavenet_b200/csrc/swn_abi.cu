@@ -535,7 +535,8 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
     const bool tail_gemm = n2 <= 32;
     // cell 0 can evaluate the causal input stage itself (CSWNV: the table is tiny).  Measured slower on B200: the
     // builder warps compete with the GEMM warps for issue slots, so the tail builds the tile unless asked otherwise
-    const bool build_x = is_c && K <= 8 && getenv("SWN_BUILD_X") && atoi(getenv("SWN_BUILD_X")) == 1;
+    const bool build_env = getenv("SWN_BUILD_X") != nullptr;
+    const bool build_x = is_c && K <= 8 && H % 4 == 0 && (!build_env || atoi(getenv("SWN_BUILD_X")) == 1);
     // dense head stages: {input depth, output rows}
     struct DenseSt { int kdim, rows; };
     std::vector<DenseSt> dst = {{H, S}, {S, n1}};
@@ -633,7 +634,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
                 d.sm_o = take((size_t)(um ? 128 : c.RP) * OS);
                 d.sm_pre = take((size_t)c.npairs * NC * 4);
                 d.sm_bar = take(32);
-                d.sm_build = take((build_x && l == 0) ? (size_t)K * 2 * H + 2 * H + 2 * (size_t)bs * (seg + 7) : 0);
+                d.sm_build = take((build_x && l == 0) ? (size_t)K * 2 * H + 2 * H + 4 * (size_t)bs * (seg + 7) : 0);
                 const size_t ring_f = (size_t)d.ring_len * 2 * c.npairs * Bp;
                 d.sm_ring = (int32_t)u;
                 d.ring_in_smem = u + ring_f <= (size_t)smem_floats;
@@ -766,7 +767,9 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
     P.P = m->ptab.p; P.pconst = m->pconst.p; P.gain = m->gain.p;
     P.in_tab = m->in_tab.p; P.in_bias = m->in_bias.p;
     P.w2_off = m->w2_off3; P.b2_off = m->b2_off3; P.cs_off = m->cs_off3;
-    P.hist_g = m->hist3.p; P.build_x = (build_x && !umma) ? 1 : 0;
+    // cell 0 building its own input tile (builder warps / the drain warps in tensor-core mode) measured SLOWER than the
+    // tail doing it (few warps, serial dependent code: ~9 us per tile against ~4 us): only when SWN_BUILD_X=1
+    P.hist_g = m->hist3.p; P.build_x = (build_x && build_env) ? 1 : 0;
     P.umma = umma ? 1 : 0; P.NP = NPsel;
     P.tiles = m->tiles3.p; P.cnt = m->cnt3.p; P.skipbuf = m->skip3.p; P.ring_scratch = m->ring3.p;
     P.noise = a->noise_dev; P.seed = a->seed; P.forced = a->forced_dev; P.seedw = a->seed_dev; P.out = a->out_dev; P.head_out = a->head_dev;

@@ -34,6 +34,9 @@ constexpr int B3_HIST = 32;
 #ifndef B3_FFMA2
 #define B3_FFMA2 0
 #endif
+#ifndef B3_WAIT_SLEEP_NS
+#define B3_WAIT_SLEEP_NS 64
+#endif
 constexpr int B3_NBW = 4;                 // cell 0 with build_x: warps 5..8 build the input tile, 9..15 are the epilogue
 
 enum { ROLE_DENSE = 3 };                  // besides ROLE_LAYER (gated cell), ROLE_HEAD (tail), ROLE_IDLE
@@ -119,6 +122,9 @@ __device__ __forceinline__ bool b3_mbar_try(unsigned long long* b, uint32_t pari
 __device__ __forceinline__ bool b3_mbar_wait(unsigned long long* b, uint32_t parity, const int32_t* status) {
     uint32_t spins = 0;
     while (!b3_mbar_try(b, parity)) {
+#if B3_WAIT_SLEEP_NS
+        __nanosleep(B3_WAIT_SLEEP_NS);       // waiting warps must not take issue slots from the working ones
+#endif
         if (((++spins) & 63u) == 0 && ((volatile const int32_t*)status)[0] != 0) return false;
     }
     return true;
@@ -253,6 +259,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
     const bool umma = MODE == 0 && P.umma;                    // tensor-core contraction (weights in tensor memory)
     const int NP = P.NP, utile = D.kdim * NP;                 // umma: floats of one (hi or lo) input tile
     const bool build = MODE == 0 && P.build_x && l == 0 && !umma;   // this CTA evaluates the causal input stage itself
+    const bool ubuild = umma && P.build_x && l == 0;          // same, tensor-core mode: done by the (mostly idle) drain warps
     const int epi0 = build ? B3_EPI0 + B3_NBW : (umma ? B3_EPI0 + 1 : B3_EPI0);      // first epilogue warp
     unsigned long long* d_full = bars + 7;          // umma: [2] accumulator tile complete (tcgen05.commit)
     unsigned long long* d_empty = bars + 9;         // umma: [2] accumulator tile drained
@@ -274,7 +281,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         }
         const int nx = umma ? 4 * utile : 2 * kp * NC;
         for (int i = tid; i < nx; i += SWN_NTHREADS) Xs[i] = 0.f;
-        if (build) {
+        if (build || ubuild) {
             // in_tab [K][2][H], then cst[r] = in_bias[r] + sum_j cb_j[r] (all taps inside the sequence)
             float* itab = smem + D.sm_build;
             for (int i = tid; i < K * 2 * H; i += SWN_NTHREADS) itab[i] = P.in_tab[i];
@@ -290,7 +297,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
             for (int i = tid; i < RL * np2 * Bp; i += SWN_NTHREADS) rg[i] = 0.f;
         }
         if (tid == 0) {
-            b3_mbar_init(&x_full[0], build ? B3_NBW : 1); b3_mbar_init(&x_full[1], build ? B3_NBW : 1);
+            b3_mbar_init(&x_full[0], (build || ubuild) ? B3_NBW : 1); b3_mbar_init(&x_full[1], (build || ubuild) ? B3_NBW : 1);
             b3_mbar_init(bbar, B3_NBW);
             b3_mbar_init(&x_empty[0], umma ? 2 : ngwa + 1); b3_mbar_init(&x_empty[1], umma ? 2 : ngwa + 1);
             b3_mbar_init(o_full, ngwa); b3_mbar_init(o_empty, 1);
@@ -341,6 +348,121 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
     const unsigned int* cnt_in = P.cnt + (size_t)D.cnt_in * M * B3_CNT_STRIDE;
     unsigned int* cnt_out = P.cnt + (size_t)D.cnt_out * M * B3_CNT_STRIDE;
 
+    if (ubuild && warp < 4) {
+        // =============================== cell 0, tensor-core mode: the drain warps also evaluate the causal input stage
+        // softsign(causal(wav_conv(samples))) (cswnv_shift1.py:352) straight into the B-operand buffer, from the samples
+        // the tail published.  Two independent progress counters (tiles built / tiles drained) and non-blocking checks:
+        // waiting for the next slot's samples must never hold back the drain of the current accumulator.
+        constexpr int NA = SEG + 7;
+        const uint32_t lb = tbase + ((uint32_t)(warp * 32) << 16) + 2 * kp;
+        const float* itab = smem + D.sm_build;
+        const float* cst = itab + K * 2 * H;
+        const float* ibias = cst + H;
+        float* av = smem + D.sm_build + K * 2 * H + 2 * H + warp * (BS * NA);      // per-warp copy of the slot's taps
+        int qb = 0, qd = 0;
+        uint32_t idle = 0;
+        while (qd < nq) {
+            bool progress = false;
+            if (qd < qb && b3_mbar_try(&d_full[qd & 1], (qd >> 1) & 1)) {
+                const int db = qd & 1;
+                b3_tc_fence_after();
+                if (qd > 0 && !b3_wait_warp(o_empty, (qd - 1) & 1, P.status)) return;
+                for (int c0 = 0; c0 < NC; c0 += 16) {
+                    uint32_t v[16];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                                 : "r"(lb + db * NP + c0));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (tid < RP) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < NC) Os[tid * OS + c0 + i] = __uint_as_float(v[i]);
+                    }
+                }
+                b3_tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { b3_mbar_arrive(&d_empty[db]); b3_mbar_arrive(o_full); }
+                ++qd;
+                progress = true;
+            }
+            if (qb < nq && qb < qd + 2) {
+                const int it = qb / M, m = qb - it * M, buf = qb & 1;
+                int ready = 1;
+                if (lane == 0) {
+                    if (qb >= 2 && !b3_mbar_try(&x_empty[buf], ((qb >> 1) - 1) & 1)) ready = 0;
+                    if (ready) {
+                        unsigned int v;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt_in + (size_t)m * B3_CNT_STRIDE) : "memory");
+                        ready = v >= (unsigned)(it + 1);
+                    }
+                }
+                ready = __shfl_sync(0xffffffffu, ready, 0);
+                if (ready) {
+                    if (qb >= 2 && !b3_wait_warp(&x_empty[buf], ((qb >> 1) - 1) & 1, P.status)) return;     // every lane observes it
+                    if (tid == 0) B3_PROF(0);
+                    const int t0 = P.t_first + it * SEG;
+                    for (int e = lane; e < BS * NA; e += 32) {
+                        const int b = e / NA, i = e - b * NA;
+                        const int n = t0 - (K - 1) + i - P.R - 1;           // newest sample seen by hidden time t0-(K-1)+i
+                        av[e] = (i < SEG + K - 1 && n >= -SEG) ? __ldcg(P.hist_g + ((size_t)m * BS + b) * B3_HIST + ((n + 64 * B3_HIST) % B3_HIST)) : 0.f;
+                    }
+                    __syncwarp();
+                    if (tid == 0) B3_PROF(7);
+                    float* X = Xs + buf * xbuf_f;
+                    const bool allv = t0 - (K - 1) >= 0;
+                    for (int e = tid; e < (H >> 2) * NC; e += 128) {
+                        const int kq = e / NC, n = e - kq * NC;
+                        const int s2 = n / BS, b = n - s2 * BS;
+                        const int r0 = kq * 4;
+                        float acc[4];
+                        if (allv) {
+                            const float4 c0 = *reinterpret_cast<const float4*>(cst + r0);
+                            acc[0] = c0.x; acc[1] = c0.y; acc[2] = c0.z; acc[3] = c0.w;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (j < K) {
+                                    const float a = av[b * NA + s2 + j];
+                                    const float4 cv = *reinterpret_cast<const float4*>(itab + (j * 2 + 1) * H + r0);
+                                    acc[0] = fmaf(a, cv.x, acc[0]); acc[1] = fmaf(a, cv.y, acc[1]);
+                                    acc[2] = fmaf(a, cv.z, acc[2]); acc[3] = fmaf(a, cv.w, acc[3]);
+                                }
+                        } else {
+                            const float4 bi = *reinterpret_cast<const float4*>(ibias + r0);
+                            acc[0] = bi.x; acc[1] = bi.y; acc[2] = bi.z; acc[3] = bi.w;
+                            for (int j = 0; j < K; ++j)
+                                if (t0 + s2 - (K - 1) + j >= 0) {
+                                    const float a = av[b * NA + s2 + j];
+                                    const float4 cb = *reinterpret_cast<const float4*>(itab + (j * 2) * H + r0);
+                                    const float4 cv = *reinterpret_cast<const float4*>(itab + (j * 2 + 1) * H + r0);
+                                    acc[0] += cb.x + cv.x * a; acc[1] += cb.y + cv.y * a;
+                                    acc[2] += cb.z + cv.z * a; acc[3] += cb.w + cv.w * a;
+                                }
+                        }
+                        const bool tv = t0 + s2 >= 0;
+                        const float v0 = tv ? softsignf_(acc[0]) : 0.f, v1 = tv ? softsignf_(acc[1]) : 0.f;
+                        const float v2 = tv ? softsignf_(acc[2]) : 0.f, v3 = tv ? softsignf_(acc[3]) : 0.f;
+                        const float4 vh = make_float4(b3_tf32_hi(v0), b3_tf32_hi(v1), b3_tf32_hi(v2), b3_tf32_hi(v3));
+                        const int xo = b3_uoff(n, r0, NP);
+                        *reinterpret_cast<float4*>(X + xo) = vh;
+                        *reinterpret_cast<float4*>(X + utile + xo) = make_float4(v0 - vh.x, v1 - vh.y, v2 - vh.z, v3 - vh.w);
+                    }
+                    if (tid == 0) B3_PROF(8);
+                    b3_fence_proxy_async();          // generic writes -> the tensor core's (async proxy) reads
+                    __syncwarp();
+                    if (lane == 0) b3_mbar_arrive(&x_full[buf]);
+                    if (tid == 0) B3_PROF(9);
+                    ++qb;
+                    progress = true;
+                }
+            }
+            if (!progress && ((++idle) & 255u) == 0) {
+                int dead = ((volatile const int32_t*)P.status)[0] != 0;
+                if (__any_sync(0xffffffffu, dead)) return;
+            }
+        }
+        return;
+    }
     if (umma && warp < 4) {
         // =============================== drain warps: accumulator tile (tensor memory) -> Os; thread = row
         const uint32_t lb = tbase + ((uint32_t)(warp * 32) << 16) + 2 * kp;
@@ -593,7 +715,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
 
     if (warp == B3_LOADER) {
         // =============================== loader
-        if (lane != 0 || build) return;
+        if (lane != 0 || build || ubuild) return;
         for (int q = 0; q < nq; ++q) {
             const int it = q / M, m = q - it * M, buf = q & 1;
             if (q >= 2 && !b3_mbar_wait(&x_empty[buf], ((q >> 1) - 1) & 1, P.status)) return;

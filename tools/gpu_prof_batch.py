@@ -38,6 +38,10 @@ for m in range(min(M, nshow)):
         row.append("L%d in %7.2f g[%5.2f %5.2f] pub %5.2f P3 %5.2f" % (
             l, (e[0] - t00) / 1e3, (e[1] - e[0]) / 1e3, (e[2] - e[0]) / 1e3, (e[5] - e[0]) / 1e3, (e[6] - e[0]) / 1e3))
     print("slot %2d | " % m + " | ".join(row))
+    e = p[it, m, 0]
+    if e[8] > 0 and e[7] > 0:
+        print("        | cell-0 builder (warp 0): samples ready 0, taps staged %.2f, tile computed %.2f, fenced+arrived %.2f, MMA start %.2f" % (
+            (e[7] - e[0]) / 1e3, (e[8] - e[0]) / 1e3, (e[9] - e[0]) / 1e3, (e[1] - e[0]) / 1e3))
     hd = []
     for c in range(L * G, grid):
         e = p[it, m, c]
