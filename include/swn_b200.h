@@ -79,7 +79,9 @@ typedef struct swn_gen_args {
     uint64_t* prof_dev;       /* optional instrumentation: [prof_count][grid][32] %globaltimer stamps */
     int32_t prof_start;       /* first loop iteration stamped */
     int32_t prof_count;
-    int32_t kernel_sel;       /* 0 = auto, 1 = force the layer-group kernel, 2 = force the cluster kernel */
+    int32_t kernel_sel;       /* 0 = auto (B <= 4: cluster / layer-group kernel, B > 4: pipelined batch kernel),
+                                 1 = force the layer-group kernel, 2 = force the cluster kernel,
+                                 3 = force the batch kernel (tensor-core cells where they fit), 4 = batch kernel, FFMA cells */
     int32_t reserved;
 } swn_gen_args;
 
@@ -89,8 +91,8 @@ typedef struct swn_info {
     int32_t eff_seg;          /* samples per loop step */
     int32_t head_dim;
     int32_t n_sm;             /* SMs used by the persistent kernel */
-    int32_t ctas_per_layer;   /* variant 1: CTAs per layer group; variant 2: CTAs of the core cluster (16) */
-    int32_t head_ctas;        /* variant 1: head CTAs; variant 2: helper CTAs */
+    int32_t ctas_per_layer;   /* variant 1, 3, 4: CTAs per layer group; variant 2: CTAs of the core cluster (16) */
+    int32_t head_ctas;        /* variant 1: head CTAs; variant 2: helper CTAs; variant 3, 4: dense head stage + tail CTAs */
     int32_t smem_bytes;       /* dynamic shared memory per CTA of the last launch */
     int32_t batch_tile;       /* of the last launch */
     int32_t n_slots;          /* pipeline slots (ceil(B / batch_tile)) of the last launch */
@@ -100,7 +102,8 @@ typedef struct swn_info {
     float last_gen_ms;        /* device time of the last swn_generate persistent kernel */
     int64_t kernel_launches;  /* kernels launched by this handle so far */
     int32_t grid;             /* CTAs of the last persistent launch */
-    int32_t kernel_variant;   /* 1 = layer groups over the chip, 2 = core cluster + helpers */
+    int32_t kernel_variant;   /* 1 = layer groups over the chip, 2 = core cluster + helpers,
+                                 3 = pipelined batch kernel with tcgen05 (tf32 x3) cells, 4 = the same with fp32 FFMA cells */
 } swn_info;
 
 /* CSWNV(...) / DSWNV(...) followed by model.cuda() (decode_cswnv_laplace-shift1.py:208-223,

@@ -442,3 +442,52 @@ def test_batch_kernel_recipe_size_teacher_forced_vs_oracle(kind, fs, B, tile, ov
     if kind == "dswnv":
         mine = O.gumbel_argmax(heads.reshape(-1, 256), noise.reshape(-1, 256)).reshape(B, N)
         assert np.array_equal(np.stack(outs), mine)
+
+
+def _tail_check(cfg, sd, aux, smp, heads, picks, frames_tail, U, n_tail, what):
+    """Finite receptive field: the heads of the last steps only depend on the last frames of aux and the last
+    samples, so the oracle is evaluated on that window (seconds instead of the reference's O(N^2) loop)."""
+    for b in picks:
+        ref_tail = O.teacher_forced_tail(cfg, sd, aux[b:b + 1, :, -frames_tail:], smp[b:b + 1, -frames_tail * U:], n_tail)
+        _head_close(heads[b:b + 1, -n_tail:], ref_tail, "%s utterance %d tail" % (what, b))
+
+
+def test_full_size_cfg3_batch64_properties():
+    """BASELINE.json configs[2]: CSWNV seg=5 lpc=4, 22.05 kHz, batch 64 x 5 s (110000 samples each), free
+    running on Philox noise through the pipelined batch kernel with tensor-core cells."""
+    B, frames = 64, 1000
+    model, cfg, sd, aux, kw = _recipe_case("cswnv", 22050, B, frames, 3)
+    U = kw["upsampling_factor"]
+    N = frames * U
+    outs, heads = model.batch_fast_generate(torch.zeros(B, 5), torch.from_numpy(aux), [N] * B, seed=21, return_heads=True)
+    info = model.engine().info
+    assert info["kernel_variant"] == 3 and info["n_slots"] * info["batch_tile"] >= B
+    smp = np.stack(outs)
+    assert smp.shape == (B, N) and np.isfinite(smp).all() and np.abs(smp).max() <= 1.0
+    assert np.isfinite(heads).all()
+    assert len({smp[b, -2000:].tobytes() for b in range(B)}) == B          # every utterance is its own stream
+    assert float(np.abs(smp[:, -20000:]).mean()) > 1e-4                     # not silent
+    _tail_check(cfg, sd, aux, smp, heads, (0, 37, 63), 20, U, 6, "cfg3")
+
+
+def test_cfg5_shape_batch128_properties():
+    """BASELINE.json configs[4] shape per GPU (DSWNV, 24 kHz, 128 utterances), 2 s instead of 60 s: indices are the
+    arg-max recomputed from the kernel's own logits and the replicated Philox stream; tail heads equal the oracle's."""
+    from shallow_wavenet_b200 import engine as E
+    B, frames = 128, 400
+    model, cfg, sd, aux, kw = _recipe_case("dswnv", 24000, B, frames, 4)
+    U = kw["upsampling_factor"]
+    N = frames * U
+    outs, heads = model.batch_fast_generate(torch.full((B, 1), 128, dtype=torch.long), torch.from_numpy(aux), [N] * B,
+                                            seed=31, return_heads=True)
+    info = model.engine().info
+    assert info["kernel_variant"] in (3, 4) and info["n_slots"] > 1
+    smp = np.stack(outs)
+    assert smp.shape == (B, N) and smp.min() >= 0 and smp.max() <= 255
+    for b in (0, 77, 127):
+        n0 = N - 4000
+        u = E.philox_uniform(31, "dswnv", b, n0, 4000)
+        with np.errstate(divide="ignore"):
+            g_ = heads[b, n0:] - np.log(-np.log1p(-u.astype(np.float64))).astype(np.float32)
+        assert int((np.argmax(g_, -1) != smp[b, n0:]).sum()) <= 8           # host log vs device logf near-ties only
+    _tail_check(cfg, sd, aux, smp, heads, (0, 127), 20, U, 8, "cfg5 shape")
