@@ -680,7 +680,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
             d.sm_w2 = take(tail_gemm ? (size_t)n2 * m->n1p : 0);
             d.sm_tin = take((size_t)H * NC);
             d.sm_itab = take((is_c ? (size_t)K * 2 * H : 0) + 2 * H + n2);
-            d.sm_ain = take((size_t)NC * K * 2);
+            d.sm_ain = take(std::max((size_t)NC * K * 2, (size_t)bs * ((seg + 7) | 1)));
             d.sm_noise = take(is_c ? (size_t)bs * seg : (size_t)bs * m->Q);
             d.sm_hist = take((size_t)MO * bs * swn::B3_HIST);
             d.sm_lpb = take((size_t)MO * bs * 8);

@@ -977,6 +977,20 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
         __syncthreads();
     }
 
+    // CSWNV, tensor-core tile layout, steady state: thread (channel quad kq, column phase cg) keeps its seven tap
+    // coefficients and constants in registers for the whole utterance and evaluates four columns per slot
+    constexpr int NCQ = NC / 4;
+    const bool fastq = P.umma && is_c && K <= 8 && NC % 4 == 0 && (H >> 2) * NCQ <= SWN_NTHREADS;
+    float4 pcv[8], pcst = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pcv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (fastq && tid < (H >> 2) * NCQ) {
+        const int r0 = (tid / NCQ) * 4;
+        pcst = *reinterpret_cast<const float4*>(cst + r0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < K) pcv[j] = *reinterpret_cast<const float4*>(itab + (j * 2 + 1) * H + r0);
+    }
     // Input stage for iteration `itn` of slot m: h0 = softsign(causal(...)) (cswnv_shift1.py:352 / dswnv.py:345).
     // A thread owns one channel r of one utterance b: the SEG columns of that utterance share their taps.
     auto input_stage = [&](int itn, int m, int ml) {
@@ -990,7 +1004,40 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
         const int t0n = P.t_first + itn * SEG;
         const float* hs = hist + (size_t)ml * BS * B3_HIST;
         float* dst = P.tiles + (size_t)m * (P.umma ? 2 * H * P.NP : H * NC);      // layer 0 input (tile offset 0)
-        if (P.umma && K <= 8) {
+        if (fastq && t0n - (K - 1) >= 0) {
+            constexpr int AST = (SEG + 7) | 1;                       // odd stride: conflict-free tap reads
+            float* as = reinterpret_cast<float*>(ain);
+            for (int e = tid; e < BS * (SEG + 7); e += SWN_NTHREADS) {
+                const int b = e / (SEG + 7), i = e - b * (SEG + 7);
+                const int nn = t0n - (K - 1) + i - P.R - 1;           // newest sample seen by hidden time t0n-(K-1)+i
+                as[b * AST + i] = (i < SEG + K - 1 && nn >= -SEG) ? hs[b * B3_HIST + ((nn + 64 * B3_HIST) % B3_HIST)] : 0.f;
+            }
+            __syncthreads();
+            if (tid < (H >> 2) * NCQ) {
+                const int kq = tid / NCQ, cg = tid - kq * NCQ, r0 = kq * 4;
+                const int utile = H * P.NP;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int n = u * NCQ + cg;                      // lanes write consecutive columns: coalesced 16-byte words
+                    const int s2 = n / BS, b = n - s2 * BS;
+                    float4 acc = pcst;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < K) {
+                            const float a = as[b * AST + s2 + j];
+                            acc.x = fmaf(a, pcv[j].x, acc.x); acc.y = fmaf(a, pcv[j].y, acc.y);
+                            acc.z = fmaf(a, pcv[j].z, acc.z); acc.w = fmaf(a, pcv[j].w, acc.w);
+                        }
+                    // softsign with a correctly rounded reciprocal (<= 1 ulp from the division)
+                    const float v0 = acc.x * __frcp_rn(1.f + fabsf(acc.x)), v1 = acc.y * __frcp_rn(1.f + fabsf(acc.y));
+                    const float v2 = acc.z * __frcp_rn(1.f + fabsf(acc.z)), v3 = acc.w * __frcp_rn(1.f + fabsf(acc.w));
+                    const float4 vh = make_float4(b3_tf32_hi(v0), b3_tf32_hi(v1), b3_tf32_hi(v2), b3_tf32_hi(v3));
+                    const int xo = b3_uoff(n, r0, P.NP);
+                    __stcg(reinterpret_cast<float4*>(dst + xo), vh);
+                    __stcg(reinterpret_cast<float4*>(dst + utile + xo), make_float4(v0 - vh.x, v1 - vh.y, v2 - vh.z, v3 - vh.w));
+                }
+            }
+        } else if (P.umma && K <= 8) {
             // tensor-core tile layout: a thread owns 4 consecutive channels of one column and writes them as one
             // 16-byte word (hi) + one (lo); 8 consecutive columns fill a 128-byte core matrix
             const int utile = H * P.NP;
