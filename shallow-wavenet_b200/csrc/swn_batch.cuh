@@ -203,12 +203,13 @@ __host__ __device__ constexpr int b3_pick_tc(int nc) {
 // RGW row groups; KS warps split k for the same rows (their partial sums are added through the output tile).
 // Shared-memory loads, not FFMA issue, bound small tiles (every LDS.128 costs 4 LSU cycles even when it is a
 // broadcast), hence the large tiles where the column count allows them.
-template <int NCX>
+template <int NCX, bool DENSE = false>
 struct B3Tile {
     static constexpr int TC = (NCX % 10 == 0 && NCX >= 40) ? 10 : (NCX <= 8) ? NCX : b3_pick_tc(NCX);
     static constexpr int NCG = NCX / TC;            // column groups (NCG*TC == NCX)
     static constexpr int RGW = 32 / NCG;            // row groups handled by one warp pass
-    static constexpr int TR = (NCX == 20 || NCX >= 40) ? 8 : 4;
+    // dense head stages own 64..256 rows and few columns: 4-row tiles (2 when a warp pass would cover >= 128 rows)
+    static constexpr int TR = DENSE ? ((32 / NCG) * 4 >= 128 ? 2 : 4) : (NCX == 20 || NCX >= 40) ? 8 : 4;
     static constexpr int RPW = RGW * TR;            // rows per warp pass
     static constexpr int KS = (RPW >= 64) ? 2 : 1;  // k-splits
     static constexpr int OS = NCX | 1;
@@ -235,7 +236,7 @@ __device__ void b3_stage(const BatchParams& P, const BCta& D, float* smem) {
 template <int SEG, int BS, int MODE>
 __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) {
     constexpr int NC = MODE == 0 ? SEG * BS : BS;
-    using T = B3Tile<NC>;
+    using T = B3Tile<NC, MODE == 1>;
     constexpr int TC = T::TC, NCG = T::NCG, RGW = T::RGW, TR = T::TR, RPW = T::RPW, OS = T::OS, KS = T::KS;
     constexpr int SLOTS = B3_NGW / KS;              // row blocks in flight
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -590,10 +591,18 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                         }
 #else
                         float w[TR];
+                        if constexpr (TR % 4 == 0) {
 #pragma unroll
-                        for (int i = 0; i < TR; i += 4) {
-                            const float4 v = *reinterpret_cast<const float4*>(wp + (size_t)k * RP + i);
-                            w[i] = v.x; w[i + 1] = v.y; w[i + 2] = v.z; w[i + 3] = v.w;
+                            for (int i = 0; i < TR; i += 4) {
+                                const float4 v = *reinterpret_cast<const float4*>(wp + (size_t)k * RP + i);
+                                w[i] = v.x; w[i + 1] = v.y; w[i + 2] = v.z; w[i + 3] = v.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < TR; i += 2) {
+                                const float2 v = *reinterpret_cast<const float2*>(wp + (size_t)k * RP + i);
+                                w[i] = v.x; w[i + 1] = v.y;
+                            }
                         }
 #pragma unroll
                         for (int i = 0; i < TR; ++i)
@@ -743,24 +752,43 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
     if constexpr (MODE == 1) {
         // ---- dense head stage: out[row][b] = act(W.x + bias (+ the skips of layers 0..L-2))
         const int nout = D.nrows * BS;
+        constexpr bool V4 = BS % 4 == 0;
+        constexpr int VW = V4 ? 4 : 1;                  // outputs per item
+        const int nitem = nout / VW;
         for (int q = 0; q < nq; ++q) {
             const int it = q / M, m = q - it * M, buf = q & 1;
             if (!b3_wait_warp(&x_full[buf], (q >> 1) & 1, P.status)) return;      // the skips are complete once the input is
-            for (int e = te; e < nout; e += nepi) {
-                const int r = e / BS;
-                float a = bias[r];
-                if (D.add_skips && P.L >= 2)      // running sum of the skips of layers 0..L-2 (chained through the cells)
-                    a += __ldcg(P.skipbuf + ((size_t)(P.L - 2) * M + m) * P.S * BS + (size_t)D.row0 * BS + e);
-                pre1[e] = a;
+            // running sum of the skips of layers 0..L-2 (chained through the cells): up to two items per thread stay
+            // in registers while the GEMM runs, the rest (small CTAs counts / odd shapes) goes through shared memory
+            const bool sk = D.add_skips && P.L >= 2;
+            const float* skp = P.skipbuf + ((size_t)(P.L - 2) * M + m) * P.S * BS + (size_t)D.row0 * BS;
+            float pr[2][VW];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = te + u * nepi;
+#pragma unroll
+                for (int v = 0; v < VW; ++v) pr[u][v] = 0.f;
+                if (sk && e < nitem) {
+                    if constexpr (V4) { const float4 x = __ldcg(reinterpret_cast<const float4*>(skp) + e); pr[u][0] = x.x; pr[u][1] = x.y; pr[u][2] = x.z; pr[u][3] = x.w; }
+                    else pr[u][0] = __ldcg(skp + e);
+                }
             }
+            for (int e = te + 2 * nepi; e < nitem; e += nepi)
+#pragma unroll
+                for (int v = 0; v < VW; ++v) pre1[e * VW + v] = sk ? __ldcg(skp + e * VW + v) : 0.f;
             if (!b3_wait_warp(o_full, q & 1, P.status)) return;
             if (te == 0) B3_PROF(4);
             float* tout = tile_out + (size_t)m * D.out_slot_f + (size_t)D.row0 * BS;
-            for (int e = te; e < nout; e += nepi) {
-                const int r = e / BS, b = e - r * BS;
-                float v = pre1[e] + Os[r * OS + b];
-                if (D.relu) v = fmaxf(v, 0.f);
-                __stcg(tout + e, v);
+            for (int e = te, u = 0; e < nitem; e += nepi, ++u) {
+                const int r = (e * VW) / BS, b = e * VW - r * BS;
+                float o[VW];
+#pragma unroll
+                for (int v = 0; v < VW; ++v) {
+                    float x = bias[r] + Os[r * OS + b + v] + (u == 0 ? pr[0][v] : u == 1 ? pr[1][v] : pre1[e * VW + v]);
+                    o[v] = D.relu ? fmaxf(x, 0.f) : x;
+                }
+                if constexpr (V4) __stcg(reinterpret_cast<float4*>(tout) + e, make_float4(o[0], o[1], o[2], o[3]));
+                else __stcg(tout + e, o[0]);
             }
             if (!epi_sync()) return;
             if (te == 0) {
