@@ -675,8 +675,8 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
             d.role = ROLE_HEAD; d.hindex = hc;
             size_t u = 0;
             auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
-            d.sm_x2 = take((size_t)bs * m->n1p);
-            d.sm_oc = take((size_t)bs * n2p);
+            d.sm_x2 = take((size_t)bs * (m->n1p + 4));
+            d.sm_oc = take((size_t)bs * n2p + (size_t)bs * seg);
             d.sm_w2 = take(tail_gemm ? (size_t)n2 * m->n1p : 0);
             d.sm_tin = take((size_t)H * NC);
             d.sm_itab = take((is_c ? (size_t)K * 2 * H : 0) + 2 * H + n2);

@@ -975,7 +975,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
 
     const int nown = hc < M ? (M - hc + P.NT - 1) / P.NT : 0;       // slots served: m = hc + i*NT
 
-    for (int i = tid; i < BS * n1p; i += SWN_NTHREADS) x2[i] = 0.f;
+    for (int i = tid; i < BS * (n1p + 4); i += SWN_NTHREADS) x2[i] = 0.f;
     for (int i = tid; i < nown * BS * B3_HIST; i += SWN_NTHREADS) hist[i] = is_c ? 0.f : __int_as_float(P.Q / 2);
     for (int i = tid; i < nown * BS * 8; i += SWN_NTHREADS) lpb[i] = 0.f;
     if (is_c)
@@ -1241,7 +1241,9 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                         const int b = e / SEG, j = e - b * SEG;
                         int bglob = m * BS + b; if (bglob >= P.B) bglob = P.B - 1;
                         const long long n = (long long)istep * SEG + j;
-                        nz[e] = P.noise ? P.noise[(size_t)bglob * P.n_out + n] : laplace_eps(P.seed, bglob, n);
+                        const float ev = P.noise ? P.noise[(size_t)bglob * P.n_out + n] : laplace_eps(P.seed, bglob, n);
+                        const float sgn = (ev > 0.f) ? 1.f : ((ev < 0.f) ? -1.f : 0.f);
+                        nz[e] = sgn * log1pf(-2.f * fabsf(ev));      // sign(eps)*log1p(-2|eps|) of cswnv_shift1.py:374
                     }
                 } else {
                     for (int e = tid; e < BS * n2; e += SWN_NTHREADS) {
@@ -1263,7 +1265,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                 if (P.tail_gemm) {
                     for (int e = tid; e < n1 * BS; e += SWN_NTHREADS) {
                         const int k = e / BS, b = e - k * BS;
-                        x2[b * n1p + k] = __ldcg(src + e);
+                        x2[b * (n1p + 4) + k] = __ldcg(src + e);
                     }
                     __syncthreads();
                     if (tid == 0) B3_PROF(7);
@@ -1275,8 +1277,9 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                         if (e < n2 * BS) {
                             rr = e / BS; b = e - rr * BS;
                             const float4* w4 = reinterpret_cast<const float4*>(w2 + (size_t)rr * n1p);
-                            const float4* x4 = reinterpret_cast<const float4*>(x2 + (size_t)b * n1p);
+                            const float4* x4 = reinterpret_cast<const float4*>(x2 + (size_t)b * (n1p + 4));   // +4: the utterances of a warp hit different banks
                             float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
                             for (int c = kq; c < (n1p >> 2); c += 8) {
                                 const float4 w = w4[c], x = x4[c];
                                 a0 = fmaf(w.x, x.x, fmaf(w.y, x.y, a0));
@@ -1299,17 +1302,56 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                 if (tid == 0) B3_PROF(1);
                 float* hs = hist + (size_t)ml * BS * B3_HIST;
                 if (is_c) {
+                    // Laplace / LPC sampler (cswnv_shift1.py:368-391).  Everything but the LP feedback is evaluated by one
+                    // thread per sample: loc - scale*sign(eps)*log1p(-2|eps|); the recursion over the segment is then short
+                    float* sb = oc + BS * n2p;                             // [BS][SEG]
+                    for (int e = tid; e < BS * SEG; e += SWN_NTHREADS) {
+                        const int b = e / SEG, j = e - b * SEG;
+                        const float* o = oc + b * n2p;
+                        sb[e] = o[j] - sigmoidf_(o[SEG + j]) * nz[e];      // scale = exp(logsigmoid(.))
+                    }
+                    __syncthreads();
                     if (tid < BS) {
                         const int b = tid;
                         int bglob = m * BS + b;
                         const bool real = bglob < P.B;
                         if (!real) bglob = P.B - 1;
                         const long long nbase = (long long)istep * SEG;
-                        float eps[SEG], smp[SEG];
-#pragma unroll
-                        for (int j = 0; j < SEG; ++j) eps[j] = nz[b * SEG + j];
+                        const int lpc = P.lpc;
+                        const float* o = oc + b * n2p;
+                        float* lp = lpb + ((size_t)ml * BS + b) * 8;
                         const float* forced = P.forced ? (const float*)P.forced + (size_t)bglob * P.n_out + nbase : nullptr;
-                        laplace_step<SEG>(P.lpc, oc + b * n2p, lpb + ((size_t)ml * BS + b) * 8, eps, forced, smp);
+                        float l[8], ac[8], smp[SEG];
+#pragma unroll
+                        for (int mm = 0; mm < 8; ++mm) {
+                            l[mm] = mm < lpc ? lp[mm] : 0.f;
+                            ac[mm] = mm < lpc ? o[2 * SEG + lpc - 1 - mm] : 0.f;   // a.flip(-1): a[0] multiplies the newest sample
+                        }
+#pragma unroll
+                        for (int j = 0; j < SEG; ++j) {
+                            float lpv = 0.f;
+#pragma unroll
+                            for (int mm = 0; mm < 8; ++mm) lpv += ac[mm] * l[mm];
+                            const float v = fminf(fmaxf(lpv + sb[b * SEG + j], -1.f), 1.f);
+                            smp[j] = v;
+#pragma unroll
+                            for (int mm = 0; mm < 7; ++mm) l[mm] = (mm + 1 < lpc) ? l[mm + 1] : l[mm];
+#pragma unroll
+                            for (int mm = 0; mm < 8; ++mm)
+                                if (mm == lpc - 1) l[mm] = v;
+                        }
+                        if (forced) {
+                            // teacher forcing: inside the segment the recursion ran on its own samples (as the reference's
+                            // sampler would); the history handed to the next step is the forced waveform
+                            for (int j = 0; j < SEG; ++j) {
+                                for (int mm = 0; mm + 1 < lpc; ++mm) lp[mm] = lp[mm + 1];
+                                if (lpc > 0) lp[lpc - 1] = forced[j];
+                            }
+                        } else {
+#pragma unroll
+                            for (int mm = 0; mm < 8; ++mm)
+                                if (mm < lpc) lp[mm] = l[mm];
+                        }
 #pragma unroll
                         for (int j = 0; j < SEG; ++j) {
                             const float fed = forced ? forced[j] : smp[j];
