@@ -20,9 +20,9 @@ def rank_shard(items, rank, world_size):
 
 
 def decode_batches(lengths, batch_size):
-    """decode_generator (:77-84): indices sorted by length (stable argsort), then split into
-    ceil(n / batch_size) nearly equal batches."""
-    idx = np.argsort(np.asarray(lengths), kind="stable")
+    """decode_generator (:77-84): indices sorted by length with numpy's DEFAULT argsort - the order of equal
+    lengths is whatever the reference gets -, then split into ceil(n / batch_size) nearly equal batches."""
+    idx = np.argsort(np.asarray(lengths))
     n_batch = int(math.ceil(len(idx) / float(batch_size)))
     return [b.tolist() for b in np.array_split(idx, n_batch)] if n_batch else []
 
