@@ -491,3 +491,23 @@ def test_cfg5_shape_batch128_properties():
             g_ = heads[b, n0:] - np.log(-np.log1p(-u.astype(np.float64))).astype(np.float32)
         assert int((np.argmax(g_, -1) != smp[b, n0:]).sum()) <= 8           # host log vs device logf near-ties only
     _tail_check(cfg, sd, aux, smp, heads, (0, 127), 20, U, 8, "cfg5 shape")
+
+
+@pytest.mark.parametrize("engine", [3, 4])
+def test_batch_kernel_cell0_builds_its_input_option(engine, monkeypatch):
+    """SWN_BUILD_X=1: the CTAs of cell 0 evaluate the causal input stage themselves from the samples the tail
+    publishes (kept as an option: measured slower than the tail building the tile); same results."""
+    monkeypatch.setenv("SWN_BUILD_X", "1")
+    g = load_golden("cswnv_seg5_lpc4_h64")
+    m = _model_from_golden(g)
+    rng = np.random.default_rng(17)
+    B, Tf, U = 11, 4, g["kw"]["upsampling_factor"]
+    N = Tf * U
+    aux = rng.standard_normal((B, g["kw"]["n_aux"], Tf)).astype(np.float32)
+    eps = rng.uniform(-0.4999, 0.5, (B, N)).astype(np.float32)
+    outs, heads = m.batch_fast_generate(torch.zeros(B, 5), torch.from_numpy(aux), [N] * B, noise=eps, return_heads=True,
+                                        kernel_sel=engine, batch_tile=4)
+    assert m.engine().info["kernel_variant"] == engine
+    ref_smp, ref_heads = O.generate(g["cfg"], g["sd"], aux, N, eps, return_heads=True)
+    _head_close(heads, ref_heads, "build_x engine %d" % engine)
+    assert float(np.abs(np.stack(outs) - ref_smp).max()) <= 5e-5
