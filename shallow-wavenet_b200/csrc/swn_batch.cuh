@@ -264,6 +264,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
     const int epi0 = build ? B3_EPI0 + B3_NBW : (umma ? B3_EPI0 + 1 : B3_EPI0);      // first epilogue warp
     unsigned long long* d_full = bars + 7;          // umma: [2] accumulator tile complete (tcgen05.commit)
     unsigned long long* d_empty = bars + 9;         // umma: [2] accumulator tile drained
+    unsigned long long* x_lo = bars + 11;           // umma: [2] low-half operand tile landed (the high half completes x_full)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
     const int nepi = (SWN_NWARPS - epi0) * 32;
     unsigned long long* bbar = bars + 15;           // barrier among the builder warps
@@ -304,6 +305,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
             b3_mbar_init(o_full, ngwa); b3_mbar_init(o_empty, 1);
             b3_mbar_init(ebar, SWN_NWARPS - epi0);
             if (umma) {
+                b3_mbar_init(&x_lo[0], ubuild ? B3_NBW : 1); b3_mbar_init(&x_lo[1], ubuild ? B3_NBW : 1);
                 b3_mbar_init(&d_full[0], 1); b3_mbar_init(&d_full[1], 1);
                 b3_mbar_init(&d_empty[0], 4); b3_mbar_init(&d_empty[1], 4);
             } else {
@@ -451,7 +453,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                     if (tid == 0) B3_PROF(8);
                     b3_fence_proxy_async();          // generic writes -> the tensor core's (async proxy) reads
                     __syncwarp();
-                    if (lane == 0) b3_mbar_arrive(&x_full[buf]);
+                    if (lane == 0) { b3_mbar_arrive(&x_full[buf]); b3_mbar_arrive(&x_lo[buf]); }
                     if (tid == 0) B3_PROF(9);
                     ++qb;
                     progress = true;
@@ -508,12 +510,16 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
             b3_tc_fence_after();
             const uint32_t xs = b3_smem(Xs + buf * xbuf_f);
             const uint32_t d_tmem = tbase + 2 * kp + db * NP;
+            // the two passes that only read the high half of the activations start as soon as it has landed
             for (int ks = 0; ks < (kp >> 3); ++ks) {
-                const uint64_t dh = b3_udesc(xs + ks * kstep_bytes, NP), dl = b3_udesc(xs + utile * 4 + ks * kstep_bytes, NP);
+                const uint64_t dh = b3_udesc(xs + ks * kstep_bytes, NP);
                 b3_umma_tf32_ts(d_tmem, tbase + ks * 8, dh, idesc, ks > 0);
                 b3_umma_tf32_ts(d_tmem, tbase + kp + ks * 8, dh, idesc, 1);
-                b3_umma_tf32_ts(d_tmem, tbase + ks * 8, dl, idesc, 1);
             }
+            if (!b3_mbar_wait(&x_lo[buf], (q >> 1) & 1, P.status)) return;
+            b3_tc_fence_after();
+            for (int ks = 0; ks < (kp >> 3); ++ks)
+                b3_umma_tf32_ts(d_tmem, tbase + ks * 8, b3_udesc(xs + utile * 4 + ks * kstep_bytes, NP), idesc, 1);
             b3_umma_commit(&d_full[db]);
             b3_umma_commit(&x_empty[buf]);
         }
@@ -731,8 +737,16 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
             if (!b3_cnt_wait(cnt_in + (size_t)m * B3_CNT_STRIDE, (unsigned)D.nprod_in * (unsigned)(it + 1), P, 100 + MODE * 50 + l)) return;
             B3_PROF(0);
             b3_fence_proxy_async();
-            b3_mbar_arm(&x_full[buf], tile_bytes);
-            b3_tma_load(Xs + buf * xbuf_f, tile_in + (size_t)m * D.in_slot_f, tile_bytes, &x_full[buf]);
+            if (umma) {
+                const uint32_t half = tile_bytes >> 1;
+                b3_mbar_arm(&x_full[buf], half);
+                b3_tma_load(Xs + buf * xbuf_f, tile_in + (size_t)m * D.in_slot_f, half, &x_full[buf]);
+                b3_mbar_arm(&x_lo[buf], half);
+                b3_tma_load(Xs + buf * xbuf_f + utile, tile_in + (size_t)m * D.in_slot_f + utile, half, &x_lo[buf]);
+            } else {
+                b3_mbar_arm(&x_full[buf], tile_bytes);
+                b3_tma_load(Xs + buf * xbuf_f, tile_in + (size_t)m * D.in_slot_f, tile_bytes, &x_full[buf]);
+            }
         }
         return;
     }
@@ -841,6 +855,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         }
         if (te == 0) B3_PROF(3);
         if (!b3_wait_warp(&x_full[buf], (q >> 1) & 1, P.status)) return;
+        if (umma && !b3_wait_warp(&x_lo[buf], (q >> 1) & 1, P.status)) return;
         // running sum of the skips of the layers below (complete once the input is): fetch it while the GEMM runs
         const bool sk_pre = D.nskip * BS <= nepi;
         float sk_prev = 0.f;
