@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SWN_ABI_VERSION 1
+#define SWN_ABI_VERSION 2
 
 typedef struct swn_model* swn_handle;
 
@@ -83,6 +83,10 @@ typedef struct swn_gen_args {
                                  1 = force the layer-group kernel, 2 = force the cluster kernel,
                                  3 = force the batch kernel (tensor-core cells where they fit), 4 = batch kernel, FFMA cells */
     int32_t reserved;
+    const int64_t* n_samples_list; /* optional HOST array [B]: samples wanted per utterance (the reference's
+                                 n_samples_list, cswnv_shift1.py:291-295,426-428).  The batch kernel stops a pipeline
+                                 slot once all its utterances are complete; rows of out_dev are only defined up to each
+                                 utterance's own length (rounded up to seg).  NULL = n_samples for everyone. */
 } swn_gen_args;
 
 typedef struct swn_info {

@@ -130,6 +130,8 @@ struct swn_model {
     int64_t w2_off3 = 0, b2_off3 = 0, cs_off3 = 0;
     DevBuf<float> wbuf3, tiles3, skip3, ring3, hist3;
     DevBuf<unsigned int> cnt3;
+    DevBuf<int32_t> slot3;
+    std::vector<int32_t> slot3_h;
     DevBuf<swn::BCta> desc3;
     long long plan3_key = -1;
     int grid3 = 0, nh3 = 0;
@@ -745,6 +747,19 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
     if (m->tiles3.ensure(tiles_total) || m->cnt3.ensure(n_cnt) || m->skip3.ensure(n_skip) ||
         m->hist3.ensure((size_t)M * BS * swn::B3_HIST) ||
         m->ring3.ensure(std::max<size_t>(ring_total, 4))) return 1;
+    // loop steps every slot has to run: the longest of its utterances (ragged batches leave the ring early)
+    m->slot3_h.assign(M, (int32_t)n_iter);
+    if (a->n_samples_list) {
+        for (int s2 = 0; s2 < M; ++s2) {
+            int64_t need = 1;
+            for (int b = s2 * BS; b < std::min(B, (s2 + 1) * BS); ++b)
+                need = std::max<int64_t>(need, (a->n_samples_list[b] + seg - 1) / seg);
+            m->slot3_h[s2] = (int32_t)std::min<int64_t>(need, n_iter);
+        }
+    }
+    if (m->slot3.ensure(M)) return 1;
+    CUDA_OK(cudaStreamSynchronize(st));                  // the previous launch may still read the old steps
+    CUDA_OK(cudaMemcpyAsync(m->slot3.p, m->slot3_h.data(), M * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemsetAsync(m->cnt3.p, 0, n_cnt * sizeof(unsigned int), st));
     if (umma) CUDA_OK(cudaMemsetAsync(m->tiles3.p, 0, tiles_total * sizeof(float), st));     // padding columns of the tiles must be finite
     if (ring_total) CUDA_OK(cudaMemsetAsync(m->ring3.p, 0, ring_total * sizeof(float), st));
@@ -771,6 +786,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
     // tail doing it (few warps, serial dependent code: ~9 us per tile against ~4 us): only when SWN_BUILD_X=1
     P.hist_g = m->hist3.p; P.build_x = (build_x && build_env) ? 1 : 0;
     P.umma = umma ? 1 : 0; P.NP = NPsel;
+    P.slot_nit = m->slot3.p;
     P.tiles = m->tiles3.p; P.cnt = m->cnt3.p; P.skipbuf = m->skip3.p; P.ring_scratch = m->ring3.p;
     P.noise = a->noise_dev; P.seed = a->seed; P.forced = a->forced_dev; P.seedw = a->seed_dev; P.out = a->out_dev; P.head_out = a->head_dev;
     P.status = m->status.p;
@@ -1409,7 +1425,7 @@ int swn_destroy(swn_handle m) {
     m->xa_tab.release(); m->wp.release(); m->act0.release(); m->act1.release(); m->ptab.release();
     m->desc.release(); m->ll.release(); m->ring_scratch.release(); m->status.release();
     m->e2e_aux.release(); m->e2e_out.release();
-    m->wbuf3.release(); m->tiles3.release(); m->skip3.release(); m->ring3.release(); m->hist3.release();
+    m->wbuf3.release(); m->tiles3.release(); m->skip3.release(); m->ring3.release(); m->hist3.release(); m->slot3.release();
     m->cnt3.release(); m->desc3.release();
     m->wbuf2.release(); m->ring2.release(); m->cdesc.release(); m->hdesc.release(); m->ll2.release();
     for (auto& cw : m->aux_convs) { cw.w_t.release(); cw.b.release(); }

@@ -87,6 +87,7 @@ struct BatchParams {
     float* skipbuf;                       // [L-1][M][S][BS]
     float* hist_g;                        // build_x: [M][BS][HIST] fed-back samples (written by the tail, read by cell 0)
     int32_t build_x;                      // 1: the CTAs of cell 0 evaluate the causal input stage themselves
+    const int32_t* slot_nit;              // [M] loop steps slot m still has to generate (utterances of unequal length)
     int32_t umma, NP;                     // 1: the gated cells contract on the tensor cores (tcgen05, 3 x tf32); NP = columns padded to 16
     float* ring_scratch;
     const float* noise;
@@ -187,6 +188,13 @@ __device__ __forceinline__ void b3_umma_commit(unsigned long long* bar) {
 __device__ __forceinline__ void b3_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void b3_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ float b3_tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// Passes of a stage, in ring order (iteration-major, slot-minor).  A slot whose utterances are all complete drops
+// out of the ring: every role of every CTA skips the same passes, `q` counts the passes actually processed
+// (buffer / mbarrier parities follow it), `it` and `m` are the loop iteration and the slot.
+#define B3_FOR_PASSES(q, it, m)                                                        \
+    for (int q##_raw = 0, q = -1, it = 0, m = 0; q##_raw < nq; ++q##_raw)               \
+        if (it = q##_raw / M, m = q##_raw - it * M, (it - P.it0 < __ldg(P.slot_nit + m)) ? (++q, true) : false)
 
 #define B3_PROF(ev)                                                                                      \
     do {                                                                                                 \
@@ -362,9 +370,17 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         const float* cst = itab + K * 2 * H;
         const float* ibias = cst + H;
         float* av = smem + D.sm_build + K * 2 * H + 2 * H + warp * (BS * NA);      // per-warp copy of the slot's taps
-        int qb = 0, qd = 0;
+        auto next_active = [&](int raw) {
+            for (; raw < nq; ++raw) {
+                const int it2 = raw / M;
+                if (it2 - P.it0 < __ldg(P.slot_nit + (raw - it2 * M))) break;
+            }
+            return raw;
+        };
+        int qb = 0, qd = 0;                               // tiles built / drained so far
+        int rb = next_active(0), rd = rb;                 // their positions in the ring order
         uint32_t idle = 0;
-        while (qd < nq) {
+        while (rd < nq) {
             bool progress = false;
             if (qd < qb && b3_mbar_try(&d_full[qd & 1], (qd >> 1) & 1)) {
                 const int db = qd & 1;
@@ -387,10 +403,11 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                 __syncwarp();
                 if (lane == 0) { b3_mbar_arrive(&d_empty[db]); b3_mbar_arrive(o_full); }
                 ++qd;
+                rd = next_active(rd + 1);
                 progress = true;
             }
-            if (qb < nq && qb < qd + 2) {
-                const int it = qb / M, m = qb - it * M, buf = qb & 1;
+            if (rb < nq && qb < qd + 2) {
+                const int it = rb / M, m = rb - it * M, buf = qb & 1;
                 int ready = 1;
                 if (lane == 0) {
                     if (qb >= 2 && !b3_mbar_try(&x_empty[buf], ((qb >> 1) - 1) & 1)) ready = 0;
@@ -456,6 +473,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                     if (lane == 0) { b3_mbar_arrive(&x_full[buf]); b3_mbar_arrive(&x_lo[buf]); }
                     if (tid == 0) B3_PROF(9);
                     ++qb;
+                    rb = next_active(rb + 1);
                     progress = true;
                 }
             }
@@ -469,11 +487,10 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
     if (umma && warp < 4) {
         // =============================== drain warps: accumulator tile (tensor memory) -> Os; thread = row
         const uint32_t lb = tbase + ((uint32_t)(warp * 32) << 16) + 2 * kp;
-        for (int q = 0; q < nq; ++q) {
+        B3_FOR_PASSES(q, it, m) {
             const int db = q & 1;
             if (!b3_wait_warp(&d_full[db], (q >> 1) & 1, P.status)) return;
             b3_tc_fence_after();
-            const int it = q / M, m = q - it * M;
             if (tid == 0) B3_PROF(2);
             if (q > 0 && !b3_wait_warp(o_empty, (q - 1) & 1, P.status)) return;
             for (int c0 = 0; c0 < NC; c0 += 16) {
@@ -501,10 +518,9 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         // instruction descriptor: D fp32, A/B tf32, both K-major, N = NP, M = 128
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const int kstep_bytes = 2 * (NP >> 3) * 128;                 // 8 channels = two core matrices along k
-        for (int q = 0; q < nq; ++q) {
+        B3_FOR_PASSES(q, it, m) {
             const int buf = q & 1, db = q & 1;
             if (!b3_mbar_wait(&x_full[buf], (q >> 1) & 1, P.status)) return;
-            const int it = q / M, m = q - it * M;
             B3_PROF(1);
             if (q >= 2 && !b3_mbar_wait(&d_empty[db], ((q >> 1) - 1) & 1, P.status)) return;
             b3_tc_fence_after();
@@ -534,10 +550,9 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         const int kchunk = (kp + KS - 1) / KS;
         const int kb = ks * kchunk, ke = min(kp, kb + kchunk);
         uint32_t kphase = 0;
-        for (int q = 0; q < nq; ++q) {
+        B3_FOR_PASSES(q, it, m) {
             const int buf = q & 1;
             if (!b3_wait_warp(&x_full[buf], (q >> 1) & 1, P.status)) return;
-            const int it = q / M, m = q - it * M;
             if (tid == 0) B3_PROF(1);
             const float* X = Xs + buf * kp * NC;
             bool first = true;
@@ -671,8 +686,8 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         const float* ibias = cst + H;
         float* av = smem + D.sm_build + K * 2 * H + 2 * H;          // [2][BS][NA]
         uint32_t bp = 0;
-        for (int q = 0; q < nq; ++q) {
-            const int it = q / M, m = q - it * M, buf = q & 1;
+        B3_FOR_PASSES(q, it, m) {
+            const int buf = q & 1;
             const int t0 = P.t_first + it * SEG;
             if (q >= 2 && !b3_wait_warp(&x_empty[buf], ((q >> 1) - 1) & 1, P.status)) return;
             int ok = 1;
@@ -731,8 +746,8 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
     if (warp == B3_LOADER) {
         // =============================== loader
         if (lane != 0 || build || ubuild) return;
-        for (int q = 0; q < nq; ++q) {
-            const int it = q / M, m = q - it * M, buf = q & 1;
+        B3_FOR_PASSES(q, it, m) {
+            const int buf = q & 1;
             if (q >= 2 && !b3_mbar_wait(&x_empty[buf], ((q >> 1) - 1) & 1, P.status)) return;
             if (!b3_cnt_wait(cnt_in + (size_t)m * B3_CNT_STRIDE, (unsigned)D.nprod_in * (unsigned)(it + 1), P, 100 + MODE * 50 + l)) return;
             B3_PROF(0);
@@ -769,8 +784,8 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         constexpr bool V4 = BS % 4 == 0;
         constexpr int VW = V4 ? 4 : 1;                  // outputs per item
         const int nitem = nout / VW;
-        for (int q = 0; q < nq; ++q) {
-            const int it = q / M, m = q - it * M, buf = q & 1;
+        B3_FOR_PASSES(q, it, m) {
+            const int buf = q & 1;
             if (!b3_wait_warp(&x_full[buf], (q >> 1) & 1, P.status)) return;      // the skips are complete once the input is
             // running sum of the skips of layers 0..L-2 (chained through the cells): up to two items per thread stay
             // in registers while the GEMM runs, the rest (small CTAs counts / odd shapes) goes through shared memory
@@ -817,8 +832,8 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
     float* ringG = P.ring_scratch + D.ring_off;
     const int twoH = 2 * H;
     const int nitems = np * NC;
-    for (int q = 0; q < nq; ++q) {
-        const int it = q / M, m = q - it * M, buf = q & 1;
+    B3_FOR_PASSES(q, it, m) {
+        const int buf = q & 1;
         const int t0 = P.t_first + it * SEG;
         // ---- P1: everything the gate needs that does not depend on the GEMM
         for (int item = te; item < nitems; item += nepi) {
@@ -1249,6 +1264,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
         const int istep = it - P.it0;
         for (int ml = 0; ml < nown; ++ml) {
             const int m = hc + ml * P.NT;
+            if (istep >= __ldg(P.slot_nit + m)) continue;          // every utterance of the slot is complete
             // ---- the noise of this step does not depend on the network: draw it while the head is still busy
             if (active) {
                 if (is_c) {

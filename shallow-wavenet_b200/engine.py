@@ -52,7 +52,7 @@ class Engine(object):
         self._B = B
 
     def generate(self, n_samples, seed=0, noise=None, forced=None, seed_audio=None, return_heads=False,
-                 batch_tile=0, sync=True, poll_mode=0, prof=None, prof_start=0, kernel_sel=0):
+                 batch_tile=0, sync=True, poll_mode=0, prof=None, prof_start=0, kernel_sel=0, n_samples_list=None):
         info = self.info
         seg, hd = info["eff_seg"], info["head_dim"]
         B = self._B
@@ -80,6 +80,11 @@ class Engine(object):
         a.batch_tile = int(batch_tile)
         a.poll_mode = int(poll_mode)
         a.kernel_sel = int(kernel_sel) or int(os.environ.get("SWN_KERNEL_SEL", "0"))   # debugging aid
+        if n_samples_list is not None:
+            lens = np.ascontiguousarray(n_samples_list, np.int64)
+            assert lens.shape == (B,), (lens.shape, B)
+            keep.append(lens)
+            a.n_samples_list = lens.ctypes.data_as(ctypes.c_void_p)
         if prof is not None:       # int64 CUDA tensor [count, grid, 32]
             keep.append(prof)
             a.prof_dev = prof.data_ptr()

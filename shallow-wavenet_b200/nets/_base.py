@@ -151,7 +151,8 @@ class _SWNBase(nn.Module):
         start = time.time()
         eng.condition(aux)
         out, heads = eng.generate(max_samples, seed=seed, noise=noise, forced=forced, seed_audio=seed_audio,
-                                  return_heads=return_heads, batch_tile=batch_tile, kernel_sel=kernel_sel)
+                                  return_heads=return_heads, batch_tile=batch_tile, kernel_sel=kernel_sel,
+                                  n_samples_list=n_samples_list)
         samples = out.cpu().numpy()                                  # the reference's single D2H (cswnv:426)
         dt = time.time() - start
         n_gen = samples.shape[1]

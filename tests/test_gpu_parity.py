@@ -511,3 +511,40 @@ def test_batch_kernel_cell0_builds_its_input_option(engine, monkeypatch):
     ref_smp, ref_heads = O.generate(g["cfg"], g["sd"], aux, N, eps, return_heads=True)
     _head_close(heads, ref_heads, "build_x engine %d" % engine)
     assert float(np.abs(np.stack(outs) - ref_smp).max()) <= 5e-5
+
+
+@pytest.mark.parametrize("name,B,tile,engine", [("cswnv_seg5_lpc4_h64", 21, 4, 3), ("cswnv_seg5_lpc4_h64", 21, 4, 4),
+                                                ("dswnv_base", 19, 2, 3), ("cswnv_seg2_lpc3", 7, 1, 3)])
+def test_batch_kernel_ragged_lengths_leave_the_ring_early(name, B, tile, engine):
+    """Utterances of unequal length (decode_generator zero-pads the aux and passes n_samples_list,
+    decode_cswnv_laplace-shift1.py:99-111): a pipeline slot stops once its longest utterance is complete; every
+    utterance still equals the oracle's output truncated to its own length (cswnv_shift1.py:426-428)."""
+    g = load_golden(name)
+    m = _model_from_golden(g)
+    kw, cfg = g["kw"], g["cfg"]
+    rng = np.random.default_rng(B + tile)
+    Tmax, U, seg = 6, kw["upsampling_factor"], cfg.eff_seg
+    frames = np.sort(rng.integers(1, Tmax + 1, B))            # the driver sorts by length
+    frames[-1] = Tmax
+    aux = np.zeros((B, kw["n_aux"], Tmax), np.float32)
+    for b, t in enumerate(frames):
+        aux[b, :, :t] = rng.standard_normal((kw["n_aux"], t))
+    lens = [int(t) * U - (3 if b % 4 == 1 and t * U > 3 else 0) for b, t in enumerate(frames)]   # some not multiples of seg
+    N = Tmax * U
+    n_gen = (N // seg) * seg
+    if g["kind"] == "dswnv":
+        noise = rng.exponential(1.0, (B, n_gen, 256)).astype(np.float32)
+    else:
+        noise = rng.uniform(-0.4999, 0.5, (B, n_gen)).astype(np.float32)
+    outs = m.batch_fast_generate(_seed_audio(g["kind"], B, seg), torch.from_numpy(aux), lens, noise=noise,
+                                 batch_tile=tile, kernel_sel=engine)
+    info = m.engine().info
+    assert info["kernel_variant"] == engine and info["n_slots"] == -(-B // tile)
+    ref_smp = O.generate(cfg, g["sd"], aux, N, noise)
+    for b, o in enumerate(outs):
+        want = min(lens[b], n_gen)
+        assert len(o) == want
+        if g["kind"] == "dswnv":
+            assert np.array_equal(o, ref_smp[b, :want])
+        else:
+            assert float(np.abs(o - ref_smp[b, :want]).max()) <= 5e-5
