@@ -555,7 +555,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
         for (const int* t = tiles; *t; ++t) if (first < 0 ? true : *t <= first) cand.push_back(*t);
         if (first < 0) std::reverse(cand.begin(), cand.end());     // small batches: smallest tile first
     }
-    int BS = 0, M = 0, NT = 0, grid = 0, geff = 0, NPsel = 0;
+    int BS = 0, M = 0, NT = 0, grid = 0, geff = 0, NPsel = 0, ndb_sel = 2;
     bool umma = false;
     const bool want_umma = a->kernel_sel != 4 && !(getenv("SWN_NO_UMMA") && atoi(getenv("SWN_NO_UMMA")) == 1);
     size_t smem_max = 0, ring_total = 0, tiles_total = 0;
@@ -575,7 +575,10 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
             int n = 1;
             for (;; ++n) {
                 const int rows = (dst[d].rows + n - 1) / n, RP = round_up(rows, 8);
-                const size_t u = (size_t)kp * RP + 2 * (size_t)kp * bs + (size_t)RP * OSd + (size_t)rows * bs + 64;
+                const size_t vw = bs % 4 == 0 ? 4 : 1;
+                // a single operand buffer is enough to make one CTA hold the whole stage (e.g. out_skip[L-1] at 16 utterances)
+                const size_t u = (size_t)kp * RP + (size_t)kp * bs + (size_t)RP * OSd +
+                                 ((size_t)rows * bs / vw > 4 * 352 ? (size_t)rows * bs : 0) + 64;
                 if (u <= (size_t)smem_floats) break;
                 if (n >= dst[d].rows) { ok = false; break; }
             }
@@ -593,7 +596,8 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
         // tensor-core contraction for the gated cells: rows fit one M=128 tile, weights (tf32 hi + lo) and two
         // accumulator tiles fit the 512 columns of tensor memory
         const int NPc = round_up(NC, 16);
-        bool um = want_umma && H % 8 == 0 && Hp == H && 2 * H + 2 * NPc <= 512;
+        bool um = want_umma && H % 8 == 0 && Hp == H && 2 * H + NPc <= 512 && NPc <= 256;
+        const int ndb = 2 * H + 2 * NPc <= 512 ? 2 : 1;        // accumulator tiles that fit beside the weights
         for (int l = 0; l < L && um; ++l)
             for (int g = 0; g < ge; ++g) if (m->l3[l][g].RP > 128) um = false;
         int left = m->n_sm - L * ge - nd_min_total;              // >= 1
@@ -632,7 +636,9 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
                 size_t u = 0;
                 auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
                 d.sm_w = take(um ? 0 : (size_t)Hp * c.RP);
-                d.sm_x = take(um ? 2 * cell_tile_f : (size_t)2 * Hp * NC);
+                // two operand buffers (prefetch of the next slot) unless two large tensor-core tiles do not fit
+                d.nxb = (um && 2 * cell_tile_f + (size_t)128 * OS + (size_t)c.npairs * NC * 4 + 64 > (size_t)smem_floats) ? 1 : 2;
+                d.sm_x = take(um ? d.nxb * cell_tile_f : (size_t)2 * Hp * NC);
                 d.sm_o = take((size_t)(um ? 128 : c.RP) * OS);
                 d.sm_pre = take((size_t)c.npairs * NC * 4);
                 d.sm_bar = take(32);
@@ -662,9 +668,17 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
                 size_t u = 0;
                 auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
                 d.sm_w = take((size_t)d.kp * d.RP);
-                d.sm_x = take((size_t)2 * d.kp * bs);
+                {
+                    const size_t vw = bs % 4 == 0 ? 4 : 1;
+                    const size_t rest = (size_t)d.kp * d.RP + (size_t)d.RP * OSd + ((size_t)d.nrows * bs / vw > 4 * 352 ? (size_t)d.nrows * bs : 0) + 64;
+                    d.nxb = rest + 2 * (size_t)d.kp * bs <= (size_t)smem_floats ? 2 : 1;
+                }
+                d.sm_x = take((size_t)d.nxb * d.kp * bs);
                 d.sm_o = take((size_t)d.RP * OSd);
-                d.sm_pre = take((size_t)d.nrows * bs);
+                {   // the epilogue keeps 4 items per thread in registers; shared memory only for what is beyond
+                    const size_t vw = bs % 4 == 0 ? 4 : 1, nitem = (size_t)d.nrows * bs / vw;
+                    d.sm_pre = take(nitem > 4 * 352 ? (size_t)d.nrows * bs : 0);
+                }
                 d.sm_bar = take(32);
                 if (u > (size_t)smem_floats) { fits = false; break; }
                 used_max = std::max(used_max, u);
@@ -692,7 +706,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
         }
         if (!fits) continue;
         BS = bs; M = Mx; NT = nt; grid = cta; geff = ge; smem_max = used_max * 4; ring_total = rt; tiles_total = tt;
-        umma = um; NPsel = NPc;
+        umma = um; NPsel = NPc; ndb_sel = ndb;
         break;
     }
     if (!BS) return 2;
@@ -785,7 +799,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
     // cell 0 building its own input tile (builder warps / the drain warps in tensor-core mode) measured SLOWER than the
     // tail doing it (few warps, serial dependent code: ~9 us per tile against ~4 us): only when SWN_BUILD_X=1
     P.hist_g = m->hist3.p; P.build_x = (build_x && build_env) ? 1 : 0;
-    P.umma = umma ? 1 : 0; P.NP = NPsel;
+    P.umma = umma ? 1 : 0; P.NP = NPsel; P.ndb = ndb_sel;
     P.slot_nit = m->slot3.p;
     P.tiles = m->tiles3.p; P.cnt = m->cnt3.p; P.skipbuf = m->skip3.p; P.ring_scratch = m->ring3.p;
     P.noise = a->noise_dev; P.seed = a->seed; P.forced = a->forced_dev; P.seedw = a->seed_dev; P.out = a->out_dev; P.head_out = a->head_dev;

@@ -53,6 +53,7 @@ struct BCta {
     int32_t kdim, kp;                     // GEMM depth (input channels) and its padding to 4
     int32_t ring_len, ring_in_smem;
     int32_t cnt_in, cnt_out, nprod_in;    // counter rows ([.][M]) of the input / output tile; producers of the input
+    int32_t nxb;                          // input buffers in shared memory (2, or 1 when two large tiles do not fit)
     int32_t is_last, relu, add_skips;
     int32_t in_slot_f, out_slot_f;        // floats per slot of the input / output tile
     int32_t sm_w, sm_x, sm_o, sm_pre, sm_ring, sm_bar, sm_build;
@@ -88,6 +89,7 @@ struct BatchParams {
     float* hist_g;                        // build_x: [M][BS][HIST] fed-back samples (written by the tail, read by cell 0)
     int32_t build_x;                      // 1: the CTAs of cell 0 evaluate the causal input stage themselves
     const int32_t* slot_nit;              // [M] loop steps slot m still has to generate (utterances of unequal length)
+    int32_t ndb;                          // umma: accumulator tiles in tensor memory (2, or 1 when 2H + 2NP > 512 columns)
     int32_t umma, NP;                     // 1: the gated cells contract on the tensor cores (tcgen05, 3 x tf32); NP = columns padded to 16
     float* ring_scratch;
     const float* noise;
@@ -266,6 +268,12 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
     unsigned long long* kback = bars + 7 + SLOTS;   // [SLOTS] second k-split added its own (only waited for between passes)
 
     const bool umma = MODE == 0 && P.umma;                    // tensor-core contraction (weights in tensor memory)
+    // buffer index / use count of pass q for the input buffers (nxb of them) and the accumulator tiles (ndb)
+    const int nxb = D.nxb, ndb = P.ndb;
+    auto XB = [nxb](int q) { return nxb == 2 ? (q & 1) : 0; };
+    auto XU = [nxb](int q) { return (uint32_t)(nxb == 2 ? (q >> 1) : q); };
+    auto DB = [ndb](int q) { return ndb == 2 ? (q & 1) : 0; };
+    auto DU = [ndb](int q) { return (uint32_t)(ndb == 2 ? (q >> 1) : q); };
     const int NP = P.NP, utile = D.kdim * NP;                 // umma: floats of one (hi or lo) input tile
     const bool build = MODE == 0 && P.build_x && l == 0 && !umma;   // this CTA evaluates the causal input stage itself
     const bool ubuild = umma && P.build_x && l == 0;          // same, tensor-core mode: done by the (mostly idle) drain warps
@@ -289,7 +297,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
             const int n4 = kp * RP / 4;
             for (int i = tid; i < n4; i += SWN_NTHREADS) dst[i] = src[i];
         }
-        const int nx = umma ? 4 * utile : 2 * kp * NC;
+        const int nx = umma ? nxb * 2 * utile : nxb * kp * NC;
         for (int i = tid; i < nx; i += SWN_NTHREADS) Xs[i] = 0.f;
         if (build || ubuild) {
             // in_tab [K][2][H], then cst[r] = in_bias[r] + sum_j cb_j[r] (all taps inside the sequence)
@@ -382,8 +390,8 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         uint32_t idle = 0;
         while (rd < nq) {
             bool progress = false;
-            if (qd < qb && b3_mbar_try(&d_full[qd & 1], (qd >> 1) & 1)) {
-                const int db = qd & 1;
+            if (qd < qb && b3_mbar_try(&d_full[DB(qd)], DU(qd) & 1)) {
+                const int db = DB(qd);
                 b3_tc_fence_after();
                 if (qd > 0 && !b3_wait_warp(o_empty, (qd - 1) & 1, P.status)) return;
                 for (int c0 = 0; c0 < NC; c0 += 16) {
@@ -406,11 +414,11 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                 rd = next_active(rd + 1);
                 progress = true;
             }
-            if (rb < nq && qb < qd + 2) {
-                const int it = rb / M, m = rb - it * M, buf = qb & 1;
+            if (rb < nq && qb < qd + nxb) {
+                const int it = rb / M, m = rb - it * M, buf = XB(qb);
                 int ready = 1;
                 if (lane == 0) {
-                    if (qb >= 2 && !b3_mbar_try(&x_empty[buf], ((qb >> 1) - 1) & 1)) ready = 0;
+                    if (qb >= nxb && !b3_mbar_try(&x_empty[buf], (XU(qb) - 1) & 1)) ready = 0;
                     if (ready) {
                         unsigned int v;
                         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt_in + (size_t)m * B3_CNT_STRIDE) : "memory");
@@ -419,7 +427,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                 }
                 ready = __shfl_sync(0xffffffffu, ready, 0);
                 if (ready) {
-                    if (qb >= 2 && !b3_wait_warp(&x_empty[buf], ((qb >> 1) - 1) & 1, P.status)) return;     // every lane observes it
+                    if (qb >= nxb && !b3_wait_warp(&x_empty[buf], (XU(qb) - 1) & 1, P.status)) return;     // every lane observes it
                     if (tid == 0) B3_PROF(0);
                     const int t0 = P.t_first + it * SEG;
                     for (int e = lane; e < BS * NA; e += 32) {
@@ -488,8 +496,8 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         // =============================== drain warps: accumulator tile (tensor memory) -> Os; thread = row
         const uint32_t lb = tbase + ((uint32_t)(warp * 32) << 16) + 2 * kp;
         B3_FOR_PASSES(q, it, m) {
-            const int db = q & 1;
-            if (!b3_wait_warp(&d_full[db], (q >> 1) & 1, P.status)) return;
+            const int db = DB(q);
+            if (!b3_wait_warp(&d_full[db], DU(q) & 1, P.status)) return;
             b3_tc_fence_after();
             if (tid == 0) B3_PROF(2);
             if (q > 0 && !b3_wait_warp(o_empty, (q - 1) & 1, P.status)) return;
@@ -519,10 +527,10 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const int kstep_bytes = 2 * (NP >> 3) * 128;                 // 8 channels = two core matrices along k
         B3_FOR_PASSES(q, it, m) {
-            const int buf = q & 1, db = q & 1;
-            if (!b3_mbar_wait(&x_full[buf], (q >> 1) & 1, P.status)) return;
+            const int buf = XB(q), db = DB(q);
+            if (!b3_mbar_wait(&x_full[buf], XU(q) & 1, P.status)) return;
             B3_PROF(1);
-            if (q >= 2 && !b3_mbar_wait(&d_empty[db], ((q >> 1) - 1) & 1, P.status)) return;
+            if (q >= ndb && !b3_mbar_wait(&d_empty[db], (DU(q) - 1) & 1, P.status)) return;
             b3_tc_fence_after();
             const uint32_t xs = b3_smem(Xs + buf * xbuf_f);
             const uint32_t d_tmem = tbase + 2 * kp + db * NP;
@@ -532,7 +540,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                 b3_umma_tf32_ts(d_tmem, tbase + ks * 8, dh, idesc, ks > 0);
                 b3_umma_tf32_ts(d_tmem, tbase + kp + ks * 8, dh, idesc, 1);
             }
-            if (!b3_mbar_wait(&x_lo[buf], (q >> 1) & 1, P.status)) return;
+            if (!b3_mbar_wait(&x_lo[buf], XU(q) & 1, P.status)) return;
             b3_tc_fence_after();
             for (int ks = 0; ks < (kp >> 3); ++ks)
                 b3_umma_tf32_ts(d_tmem, tbase + ks * 8, b3_udesc(xs + utile * 4 + ks * kstep_bytes, NP), idesc, 1);
@@ -551,8 +559,8 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         const int kb = ks * kchunk, ke = min(kp, kb + kchunk);
         uint32_t kphase = 0;
         B3_FOR_PASSES(q, it, m) {
-            const int buf = q & 1;
-            if (!b3_wait_warp(&x_full[buf], (q >> 1) & 1, P.status)) return;
+            const int buf = XB(q);
+            if (!b3_wait_warp(&x_full[buf], XU(q) & 1, P.status)) return;
             if (tid == 0) B3_PROF(1);
             const float* X = Xs + buf * kp * NC;
             bool first = true;
@@ -687,9 +695,9 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         float* av = smem + D.sm_build + K * 2 * H + 2 * H;          // [2][BS][NA]
         uint32_t bp = 0;
         B3_FOR_PASSES(q, it, m) {
-            const int buf = q & 1;
+            const int buf = XB(q);
             const int t0 = P.t_first + it * SEG;
-            if (q >= 2 && !b3_wait_warp(&x_empty[buf], ((q >> 1) - 1) & 1, P.status)) return;
+            if (q >= nxb && !b3_wait_warp(&x_empty[buf], (XU(q) - 1) & 1, P.status)) return;
             int ok = 1;
             if (lane == 0) ok = b3_cnt_wait(cnt_in + (size_t)m * B3_CNT_STRIDE, (unsigned)(it + 1), P, 100) ? 1 : 0;
             ok = __shfl_sync(0xffffffffu, ok, 0);
@@ -747,8 +755,8 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         // =============================== loader
         if (lane != 0 || build || ubuild) return;
         B3_FOR_PASSES(q, it, m) {
-            const int buf = q & 1;
-            if (q >= 2 && !b3_mbar_wait(&x_empty[buf], ((q >> 1) - 1) & 1, P.status)) return;
+            const int buf = XB(q);
+            if (q >= nxb && !b3_mbar_wait(&x_empty[buf], (XU(q) - 1) & 1, P.status)) return;
             if (!b3_cnt_wait(cnt_in + (size_t)m * B3_CNT_STRIDE, (unsigned)D.nprod_in * (unsigned)(it + 1), P, 100 + MODE * 50 + l)) return;
             B3_PROF(0);
             b3_fence_proxy_async();
@@ -785,15 +793,15 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         constexpr int VW = V4 ? 4 : 1;                  // outputs per item
         const int nitem = nout / VW;
         B3_FOR_PASSES(q, it, m) {
-            const int buf = q & 1;
-            if (!b3_wait_warp(&x_full[buf], (q >> 1) & 1, P.status)) return;      // the skips are complete once the input is
+            const int buf = XB(q);
+            if (!b3_wait_warp(&x_full[buf], XU(q) & 1, P.status)) return;      // the skips are complete once the input is
             // running sum of the skips of layers 0..L-2 (chained through the cells): up to two items per thread stay
             // in registers while the GEMM runs, the rest (small CTAs counts / odd shapes) goes through shared memory
             const bool sk = D.add_skips && P.L >= 2;
             const float* skp = P.skipbuf + ((size_t)(P.L - 2) * M + m) * P.S * BS + (size_t)D.row0 * BS;
-            float pr[2][VW];
+            float pr[4][VW];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < 4; ++u) {
                 const int e = te + u * nepi;
 #pragma unroll
                 for (int v = 0; v < VW; ++v) pr[u][v] = 0.f;
@@ -802,7 +810,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                     else pr[u][0] = __ldcg(skp + e);
                 }
             }
-            for (int e = te + 2 * nepi; e < nitem; e += nepi)
+            for (int e = te + 4 * nepi; e < nitem; e += nepi)
 #pragma unroll
                 for (int v = 0; v < VW; ++v) pre1[e * VW + v] = sk ? __ldcg(skp + e * VW + v) : 0.f;
             if (!b3_wait_warp(o_full, q & 1, P.status)) return;
@@ -813,7 +821,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                 float o[VW];
 #pragma unroll
                 for (int v = 0; v < VW; ++v) {
-                    float x = bias[r] + Os[r * OS + b + v] + (u == 0 ? pr[0][v] : u == 1 ? pr[1][v] : pre1[e * VW + v]);
+                    float x = bias[r] + Os[r * OS + b + v] + (u == 0 ? pr[0][v] : u == 1 ? pr[1][v] : u == 2 ? pr[2][v] : u == 3 ? pr[3][v] : pre1[e * VW + v]);
                     o[v] = D.relu ? fmaxf(x, 0.f) : x;
                 }
                 if constexpr (V4) __stcg(reinterpret_cast<float4*>(tout) + e, make_float4(o[0], o[1], o[2], o[3]));
@@ -833,7 +841,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
     const int twoH = 2 * H;
     const int nitems = np * NC;
     B3_FOR_PASSES(q, it, m) {
-        const int buf = q & 1;
+        const int buf = XB(q);
         const int t0 = P.t_first + it * SEG;
         // ---- P1: everything the gate needs that does not depend on the GEMM
         for (int item = te; item < nitems; item += nepi) {
@@ -869,8 +877,8 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
             pre[item] = v;
         }
         if (te == 0) B3_PROF(3);
-        if (!b3_wait_warp(&x_full[buf], (q >> 1) & 1, P.status)) return;
-        if (umma && !b3_wait_warp(&x_lo[buf], (q >> 1) & 1, P.status)) return;
+        if (!b3_wait_warp(&x_full[buf], XU(q) & 1, P.status)) return;
+        if (umma && !b3_wait_warp(&x_lo[buf], XU(q) & 1, P.status)) return;
         // running sum of the skips of the layers below (complete once the input is): fetch it while the GEMM runs
         const bool sk_pre = D.nskip * BS <= nepi;
         float sk_prev = 0.f;
@@ -924,7 +932,11 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
             }
         }
         if (!epi_sync()) return;
-        if (te == 0) { b3_signal(cnt_out + (size_t)m * B3_CNT_STRIDE); B3_PROF(5); }
+        if (te == 0) {
+            b3_signal(cnt_out + (size_t)m * B3_CNT_STRIDE);
+            b3_mbar_arrive(&x_empty[buf]);          // the carry has been read: P3 below only needs the GEMM output
+            B3_PROF(5);
+        }
         // ---- P3 (off the critical path): delayed taps into the ring of partial sums; the BS utterances of one
         // (tap, row, time column) are contiguous in the GEMM output and in the ring
         {
@@ -973,7 +985,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
             }
         }
         if (!epi_sync()) return;
-        if (te == 0) { b3_mbar_arrive(o_empty); b3_mbar_arrive(&x_empty[buf]); B3_PROF(6); }
+        if (te == 0) { b3_mbar_arrive(o_empty); B3_PROF(6); }
     }
     }
 }
@@ -1037,13 +1049,15 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
 
     // CSWNV, tensor-core tile layout, steady state: thread (channel quad kq, column phase cg) keeps its seven tap
     // coefficients and constants in registers for the whole utterance and evaluates four columns per slot
-    constexpr int NCQ = NC / 4;
-    const bool fastq = P.umma && is_c && K <= 8 && NC % 4 == 0 && (H >> 2) * NCQ <= SWN_NTHREADS;
+    constexpr int NCQ = NC / 4;                      // column phases of one channel quad
+    constexpr int CPT = NCQ > 10 && NCQ % 2 == 0 ? 2 : 1;     // column groups of 4 per thread and pass (8 columns when the tile is wide)
+    constexpr int TPQ = NCQ / CPT;                   // threads per channel quad
+    const bool fastq = P.umma && is_c && K <= 8 && NC % 4 == 0 && (H >> 2) * TPQ <= SWN_NTHREADS;
     float4 pcv[8], pcst = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) pcv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (fastq && tid < (H >> 2) * NCQ) {
-        const int r0 = (tid / NCQ) * 4;
+    if (fastq && tid < (H >> 2) * TPQ) {
+        const int r0 = (tid / TPQ) * 4;
         pcst = *reinterpret_cast<const float4*>(cst + r0);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -1071,12 +1085,12 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                 as[b * AST + i] = (i < SEG + K - 1 && nn >= -SEG) ? hs[b * B3_HIST + ((nn + 64 * B3_HIST) % B3_HIST)] : 0.f;
             }
             __syncthreads();
-            if (tid < (H >> 2) * NCQ) {
-                const int kq = tid / NCQ, cg = tid - kq * NCQ, r0 = kq * 4;
+            if (tid < (H >> 2) * TPQ) {
+                const int kq = tid / TPQ, cg = tid - kq * TPQ, r0 = kq * 4;
                 const int utile = H * P.NP;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int n = u * NCQ + cg;                      // lanes write consecutive columns: coalesced 16-byte words
+                for (int u = 0; u < 4 * CPT; ++u) {
+                    const int n = u * TPQ + cg;                      // lanes write consecutive columns: coalesced 16-byte words
                     const int s2 = n / BS, b = n - s2 * BS;
                     float4 acc = pcst;
 #pragma unroll

@@ -32,7 +32,7 @@ batch_launch_fn SWN_CAT(find_batch_kernel_seg, SWN_SEG)(int bs) {
 #if SWN_SEG == 1 || SWN_SEG == 2 || SWN_SEG == 5
     B3_CASE(8)
 #endif
-#if SWN_SEG == 1
+#if SWN_SEG == 1 || SWN_SEG == 5
     B3_CASE(16)
 #endif
     return nullptr;

@@ -49,8 +49,8 @@ inline const int* batch3_tiles_for_seg(int seg) {
     static const int c[] = {4, 2, 1, 0};
     static const int none[] = {0};
     switch (seg) {
-        case 1: return a;
-        case 2: case 5: return b;
+        case 1: case 5: return a;
+        case 2: return b;
         case 3: case 4: case 10: return c;
         default: return none;
     }

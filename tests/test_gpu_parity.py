@@ -416,6 +416,7 @@ def test_batch_kernel_many_slots_free_running_vs_oracle(name, B, tile):
 @pytest.mark.parametrize("kind,fs,B,tile,over,variant", [("cswnv", 22050, 9, 4, dict(seg=5, lpc=4), 3),
                                                           ("cswnv", 22050, 17, 8, dict(seg=5, lpc=4), 3),
                                                           ("cswnv", 22050, 17, 8, dict(seg=5, lpc=4), 4),
+                                                          ("cswnv", 22050, 35, 16, dict(seg=5, lpc=4), 3),
                                                           ("cswnv", 22050, 6, 2, dict(seg=10, lpc=4), 3),
                                                           ("cswnv", 22050, 12, 4, dict(seg=1, lpc=4), 3),
                                                           ("dswnv", 24000, 20, 8, dict(), 4),

@@ -7,7 +7,7 @@ from shallow_wavenet_b200 import synth
 
 frames = int(os.environ.get("FRAMES", "20"))
 cases = []
-for B, tiles in ((64, (2, 4, 8)), (256, (4, 8))):
+for B, tiles in ((64, (4, 8, 16)), (256, (8, 16))):
     for t in tiles:
         cases.append(("cswnv", 22050, dict(seg=5, lpc=4), B, t))
 for B, tiles in ((128, (4, 8)),):
