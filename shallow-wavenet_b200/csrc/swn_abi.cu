@@ -555,7 +555,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
         for (const int* t = tiles; *t; ++t) if (first < 0 ? true : *t <= first) cand.push_back(*t);
         if (first < 0) std::reverse(cand.begin(), cand.end());     // small batches: smallest tile first
     }
-    int BS = 0, M = 0, NT = 0, grid = 0, geff = 0, NPsel = 0, ndb_sel = 2;
+    int BS = 0, M = 0, NT = 0, grid = 0, geff = 0, NPsel = 0, ndb_sel = 2, tinst_sel = 1;
     bool umma = false;
     const bool want_umma = a->kernel_sel != 4 && !(getenv("SWN_NO_UMMA") && atoi(getenv("SWN_NO_UMMA")) == 1);
     size_t smem_max = 0, ring_total = 0, tiles_total = 0;
@@ -684,7 +684,13 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
                 used_max = std::max(used_max, u);
             }
         if (!fits) continue;
-        const int MO = (Mx + nt - 1) / nt;
+        // two half-size tail instances per tail CTA once the ring is throughput-bound (their short dependent phases hide each other)
+        int tinst = Mx >= 16 ? 2 : 1;
+        if (getenv("SWN_TAIL_INST")) tinst = atoi(getenv("SWN_TAIL_INST")) == 2 ? 2 : 1;
+        const int cta_tail0 = cta;
+      retry_tail:
+        cta = cta_tail0;
+        const int MO = (Mx + nt * tinst - 1) / (nt * tinst);
         for (int hc = 0; hc < nt; ++hc, ++cta) {
             swn::BCta& d = desc[cta];
             memset(&d, 0, sizeof(d));
@@ -701,10 +707,14 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
             d.sm_hist = take((size_t)MO * bs * swn::B3_HIST);
             d.sm_lpb = take((size_t)MO * bs * 8);
             d.sm_misc = take(8);
+            d.tail_stride = (int32_t)u;
+            u *= tinst;
+            if (u > (size_t)smem_floats && tinst == 2) { tinst = 1; goto retry_tail; }     // two instances do not fit: one
             if (u > (size_t)smem_floats) { fits = false; break; }
             used_max = std::max(used_max, u);
         }
         if (!fits) continue;
+        tinst_sel = tinst;
         BS = bs; M = Mx; NT = nt; grid = cta; geff = ge; smem_max = used_max * 4; ring_total = rt; tiles_total = tt;
         umma = um; NPsel = NPc; ndb_sel = ndb;
         break;
@@ -750,7 +760,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
             for (int i = 0; i < nd[sd]; ++i, ++cta, ++di) { desc[cta].w_off = m->dense3[di].w_off; desc[cta].b_off = m->dense3[di].b_off; }
     }
     const int NC = BS * seg;
-    const long long key = ((long long)B << 32) | ((long long)BS << 16) | ((long long)geff << 8) | ((long long)NT << 1) | (umma ? 1 : 0);
+    const long long key = ((long long)B << 32) | ((long long)BS << 16) | ((long long)geff << 8) | ((long long)NT << 2) | ((long long)(tinst_sel - 1) << 1) | (umma ? 1 : 0);
     if (key != m->plan3_key) {
         CUDA_OK(cudaStreamSynchronize(st));
         if (upload(m->desc3, desc)) return 1;
@@ -788,7 +798,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
     P.it0 = (m->R + 1 - P.t_first) / seg - 1;
     P.n_iter = (int)n_iter;
     P.n_it = P.it0 + P.n_iter;
-    P.NT = NT; P.tail_gemm = tail_gemm ? 1 : 0;
+    P.NT = NT; P.tail_inst = tinst_sel; P.tail_gemm = tail_gemm ? 1 : 0;
     P.tail_cnt = L + ND; P.tail_nprod = nd[ND - 1];
     P.tail_in_off = tile_off[L + ND]; P.tail_slot_f = dst[ND - 1].rows * BS;
     P.n_out = n_iter * seg;

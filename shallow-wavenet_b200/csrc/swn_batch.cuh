@@ -67,12 +67,14 @@ struct BCta {
     int64_t ring_off;                     // [RL][2*np][Bp] in ring_scratch
     // tail CTA shared-memory layout
     int32_t sm_x2, sm_oc, sm_w2, sm_tin, sm_itab, sm_ain, sm_noise, sm_hist, sm_lpb, sm_misc;
+    int32_t tail_stride;                  // floats of one tail instance's shared-memory block
 };
 
 struct BatchParams {
     int32_t kind, H, S, K, L, lpc, n1, n1p, n2, n2p, Q, U, R, B, M, Tf;
     int32_t t_first, it0, n_it, n_iter;
     int32_t NT;                           // tail CTAs
+    int32_t tail_inst;                    // tail instances per tail CTA (1 x 512 threads or 2 x 256)
     int32_t tail_gemm;                    // 1: the tail evaluates out_2 itself (few rows); 0: out_2 is dense stage C
     int32_t tail_cnt, tail_nprod, tail_slot_f;   // counter row / producers / floats per slot of the tail's input
     int64_t tail_in_off;
@@ -1000,12 +1002,17 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
 // ------------------------------------------------------------------ tail CTA
 // Serves whole slots (m = hindex, hindex + NT, ...): [out_2 when it is small] -> sampler -> causal input stage
 // of the next step.  The noise of the step is drawn before the wait for the head (off the critical path).
-template <int SEG, int BS>
-__device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
+// NTT threads form one tail instance; a tail CTA runs one instance of 512 threads or two of 256 side by side (the
+// phases of a tail are short dependent chains: two instances on different slots hide each other's latency).
+template <int SEG, int BS, int NTT>
+__device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem_cta, const int inst, const int ninst) {
     constexpr int NC = SEG * BS;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x - inst * NTT, lane = tid & 31, warp = tid >> 5;
+    float* smem = smem_cta + (size_t)inst * D.tail_stride;
+    const int NVT = P.NT * ninst;                    // tail instances of the whole grid
+    auto tsync = [inst]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + inst), "n"(NTT) : "memory"); };
     const int H = P.H, K = P.K, n1 = P.n1, n1p = P.n1p, n2 = P.n2, n2p = P.n2p, M = P.M;
-    const int hc = D.hindex;
+    const int hc = D.hindex * ninst + inst;
     const bool is_c = P.kind == 0;
 
     float* x2 = smem + D.sm_x2;                     // tail_gemm: [BS][n1p] relu(out_1), utterance-major
@@ -1022,44 +1029,46 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
     float* lpb = smem + D.sm_lpb;                   // [MO][BS][8]
     int* flag = reinterpret_cast<int*>(smem + D.sm_misc);
 
-    const int nown = hc < M ? (M - hc + P.NT - 1) / P.NT : 0;       // slots served: m = hc + i*NT
+    const int nown = hc < M ? (M - hc + NVT - 1) / NVT : 0;       // slots served: m = hc + i*NT
 
-    for (int i = tid; i < BS * (n1p + 4); i += SWN_NTHREADS) x2[i] = 0.f;
-    for (int i = tid; i < nown * BS * B3_HIST; i += SWN_NTHREADS) hist[i] = is_c ? 0.f : __int_as_float(P.Q / 2);
-    for (int i = tid; i < nown * BS * 8; i += SWN_NTHREADS) lpb[i] = 0.f;
+    for (int i = tid; i < BS * (n1p + 4); i += NTT) x2[i] = 0.f;
+    for (int i = tid; i < nown * BS * B3_HIST; i += NTT) hist[i] = is_c ? 0.f : __int_as_float(P.Q / 2);
+    for (int i = tid; i < nown * BS * 8; i += NTT) lpb[i] = 0.f;
     if (is_c)
-        for (int i = tid; i < K * 2 * H; i += SWN_NTHREADS) itab[i] = P.in_tab[i];
-    for (int i = tid; i < H; i += SWN_NTHREADS) ibias[i] = P.in_bias[i];
-    for (int i = tid; i < n2; i += SWN_NTHREADS) b2s[i] = P.wbuf[P.b2_off + i];
+        for (int i = tid; i < K * 2 * H; i += NTT) itab[i] = P.in_tab[i];
+    for (int i = tid; i < H; i += NTT) ibias[i] = P.in_bias[i];
+    for (int i = tid; i < n2; i += NTT) b2s[i] = P.wbuf[P.b2_off + i];
     if (is_c)
-        for (int r = tid; r < H; r += SWN_NTHREADS) {
+        for (int r = tid; r < H; r += NTT) {
             float c = P.in_bias[r];
             for (int j = 0; j < K; ++j) c += P.in_tab[(j * 2) * H + r];
             cst[r] = c;
         }
     if (P.tail_gemm)
-        for (int i = tid; i < n2 * n1p; i += SWN_NTHREADS) w2[i] = P.wbuf[P.w2_off + i];
-    __syncthreads();
+        for (int i = tid; i < n2 * n1p; i += NTT) w2[i] = P.wbuf[P.w2_off + i];
+    tsync();
     if (P.seedw) {
-        for (int e = tid; e < nown * BS * SEG; e += SWN_NTHREADS) {
+        for (int e = tid; e < nown * BS * SEG; e += NTT) {
             const int mb = e / SEG, j = e - mb * SEG;
             const int ml = mb / BS, b = mb - ml * BS;
-            int bglob = (hc + ml * P.NT) * BS + b; if (bglob >= P.B) bglob = P.B - 1;
+            int bglob = (hc + ml * NVT) * BS + b; if (bglob >= P.B) bglob = P.B - 1;
             const float v = is_c ? ((const float*)P.seedw)[(size_t)bglob * SEG + j]
                                  : __int_as_float((int)(((const long long*)P.seedw)[bglob] % P.Q));
             hist[(size_t)mb * B3_HIST + ((j - SEG + B3_HIST) % B3_HIST)] = v;
             const int mm = P.lpc - SEG + j;
             if (is_c && mm >= 0) lpb[(size_t)mb * 8 + mm] = v;
         }
-        __syncthreads();
+        tsync();
     }
 
     // CSWNV, tensor-core tile layout, steady state: thread (channel quad kq, column phase cg) keeps its seven tap
     // coefficients and constants in registers for the whole utterance and evaluates four columns per slot
     constexpr int NCQ = NC / 4;                      // column phases of one channel quad
-    constexpr int CPT = NCQ > 10 && NCQ % 2 == 0 ? 2 : 1;     // column groups of 4 per thread and pass (8 columns when the tile is wide)
+    // column groups of 4 per thread and pass: as few as keep (H/4) x (NCQ/CPT) threads inside the instance at H = 192
+    constexpr int CPT = NTT >= 512 ? (NCQ > 10 && NCQ % 2 == 0 ? 2 : 1)
+                                   : (NCQ > 10 && NCQ % 4 == 0 ? 4 : (NCQ > 5 && NCQ % 2 == 0 ? 2 : 1));
     constexpr int TPQ = NCQ / CPT;                   // threads per channel quad
-    const bool fastq = P.umma && is_c && K <= 8 && NC % 4 == 0 && (H >> 2) * TPQ <= SWN_NTHREADS;
+    const bool fastq = P.umma && is_c && K <= 8 && NC % 4 == 0 && (H >> 2) * TPQ <= NTT;
     float4 pcv[8], pcst = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) pcv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1074,7 +1083,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
     // A thread owns one channel r of one utterance b: the SEG columns of that utterance share their taps.
     auto input_stage = [&](int itn, int m, int ml) {
         if (P.build_x) {                              // cell 0 builds its own input from the published samples
-            __syncthreads();
+            tsync();
             const int it = itn - 1;
             if (tid == 0 && itn > 0) B3_PROF(6);
             if (tid == 0) b3_signal(P.cnt + (size_t)m * B3_CNT_STRIDE);
@@ -1086,12 +1095,12 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
         if (fastq && t0n - (K - 1) >= 0) {
             constexpr int AST = (SEG + 7) | 1;                       // odd stride: conflict-free tap reads
             float* as = reinterpret_cast<float*>(ain);
-            for (int e = tid; e < BS * (SEG + 7); e += SWN_NTHREADS) {
+            for (int e = tid; e < BS * (SEG + 7); e += NTT) {
                 const int b = e / (SEG + 7), i = e - b * (SEG + 7);
                 const int nn = t0n - (K - 1) + i - P.R - 1;           // newest sample seen by hidden time t0n-(K-1)+i
                 as[b * AST + i] = (i < SEG + K - 1 && nn >= -SEG) ? hs[b * B3_HIST + ((nn + 64 * B3_HIST) % B3_HIST)] : 0.f;
             }
-            __syncthreads();
+            tsync();
             if (tid < (H >> 2) * TPQ) {
                 const int kq = tid / TPQ, cg = tid - kq * TPQ, r0 = kq * 4;
                 const int utile = H * P.NP;
@@ -1121,7 +1130,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
             // 16-byte word (hi) + one (lo); 8 consecutive columns fill a 128-byte core matrix
             const int utile = H * P.NP;
             const bool allv = t0n - (K - 1) >= 0;
-            for (int e = tid; e < (H >> 2) * NC; e += SWN_NTHREADS) {
+            for (int e = tid; e < (H >> 2) * NC; e += NTT) {
                 const int kq = e / NC, n = e - kq * NC;
                 const int s = n / BS, b = n - s * BS;
                 const int r0 = kq * 4;
@@ -1178,7 +1187,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                 __stcg(reinterpret_cast<float4*>(dst + utile + xo), vl);
             }
         } else if (K <= 8) {
-            for (int e = tid; e < H * BS; e += SWN_NTHREADS) {
+            for (int e = tid; e < H * BS; e += NTT) {
                 const int r = e / BS, b = e - r * BS;
                 // samples / indices seen by hidden times t0n-(K-1) .. t0n+SEG-1 (newest sample of hidden time tau: tau-R-1)
                 float a[SEG + 7];
@@ -1240,7 +1249,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                 }
             }
         } else {
-            for (int e = tid; e < H * NC; e += SWN_NTHREADS) {
+            for (int e = tid; e < H * NC; e += NTT) {
                 const int r = e / NC, c = e - r * NC;
                 const int s = c / BS, b = c - s * BS;
                 const int t = t0n + s;
@@ -1266,30 +1275,30 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
         }
         const int it = itn - 1;
         if (tid == 0 && itn > 0) B3_PROF(5);
-        __syncthreads();
+        tsync();
         if (tid == 0 && itn > 0) B3_PROF(6);
         if (tid == 0) b3_signal(P.cnt + (size_t)m * B3_CNT_STRIDE);
     };
 
     if (P.build_x) {
-        for (int e = tid; e < nown * BS * B3_HIST; e += SWN_NTHREADS) {
+        for (int e = tid; e < nown * BS * B3_HIST; e += NTT) {
             const int ml = e / (BS * B3_HIST), rest = e - ml * (BS * B3_HIST);
-            __stcg(P.hist_g + (size_t)(hc + ml * P.NT) * BS * B3_HIST + rest, hist[e]);
+            __stcg(P.hist_g + (size_t)(hc + ml * NVT) * BS * B3_HIST + rest, hist[e]);
         }
     }
-    for (int i = 0; i < nown; ++i) input_stage(0, hc + i * P.NT, i);
+    for (int i = 0; i < nown; ++i) input_stage(0, hc + i * NVT, i);
 
     const unsigned int* cnt_in = P.cnt + (size_t)P.tail_cnt * M * B3_CNT_STRIDE;
     for (int it = 0; it < P.n_it; ++it) {
         const bool active = it >= P.it0;
         const int istep = it - P.it0;
         for (int ml = 0; ml < nown; ++ml) {
-            const int m = hc + ml * P.NT;
+            const int m = hc + ml * NVT;
             if (istep >= __ldg(P.slot_nit + m)) continue;          // every utterance of the slot is complete
             // ---- the noise of this step does not depend on the network: draw it while the head is still busy
             if (active) {
                 if (is_c) {
-                    for (int e = tid; e < BS * SEG; e += SWN_NTHREADS) {
+                    for (int e = tid; e < BS * SEG; e += NTT) {
                         const int b = e / SEG, j = e - b * SEG;
                         int bglob = m * BS + b; if (bglob >= P.B) bglob = P.B - 1;
                         const long long n = (long long)istep * SEG + j;
@@ -1298,7 +1307,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                         nz[e] = sgn * log1pf(-2.f * fabsf(ev));      // sign(eps)*log1p(-2|eps|) of cswnv_shift1.py:374
                     }
                 } else {
-                    for (int e = tid; e < BS * n2; e += SWN_NTHREADS) {
+                    for (int e = tid; e < BS * n2; e += NTT) {
                         const int b = e / n2, rr = e - b * n2;
                         int bglob = m * BS + b; if (bglob >= P.B) bglob = P.B - 1;
                         const float qv = P.noise ? P.noise[((size_t)bglob * P.n_out + istep) * P.Q + rr] : softmax_q(P.seed, bglob, istep, rr);
@@ -1309,20 +1318,20 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
             // ---- wait for the head (flow control during warm-up, data when active)
             if (tid == 0)
                 *flag = b3_cnt_wait(cnt_in + (size_t)m * B3_CNT_STRIDE, (unsigned)P.tail_nprod * (unsigned)(it + 1), P, 200) ? 1 : 0;
-            __syncthreads();
+            tsync();
             if (*flag == 0) return;
             if (tid == 0) B3_PROF(0);
             if (active) {
                 const float* src = P.tiles + P.tail_in_off + (size_t)m * P.tail_slot_f;      // [rows][BS]
                 if (P.tail_gemm) {
-                    for (int e = tid; e < n1 * BS; e += SWN_NTHREADS) {
+                    for (int e = tid; e < n1 * BS; e += NTT) {
                         const int k = e / BS, b = e - k * BS;
                         x2[b * (n1p + 4) + k] = __ldcg(src + e);
                     }
-                    __syncthreads();
+                    tsync();
                     if (tid == 0) B3_PROF(7);
                     // out_2: few rows; 8 lanes per (row, utterance), each an interleaved eighth of k
-                    for (int e0 = 0; e0 < n2 * BS; e0 += SWN_NTHREADS / 8) {
+                    for (int e0 = 0; e0 < n2 * BS; e0 += NTT / 8) {
                         const int e = e0 + (tid >> 3), kq = tid & 7;
                         float v = 0.f;
                         int rr = 0, b = 0;
@@ -1345,24 +1354,24 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                         if (kq == 0 && e < n2 * BS) oc[b * n2p + rr] = v + b2s[rr];
                     }
                 } else {
-                    for (int e = tid; e < n2 * BS; e += SWN_NTHREADS) {
+                    for (int e = tid; e < n2 * BS; e += NTT) {
                         const int rr = e / BS, b = e - rr * BS;
                         oc[b * n2p + rr] = __ldcg(src + e);
                     }
                 }
-                __syncthreads();
+                tsync();
                 if (tid == 0) B3_PROF(1);
                 float* hs = hist + (size_t)ml * BS * B3_HIST;
                 if (is_c) {
                     // Laplace / LPC sampler (cswnv_shift1.py:368-391).  Everything but the LP feedback is evaluated by one
                     // thread per sample: loc - scale*sign(eps)*log1p(-2|eps|); the recursion over the segment is then short
                     float* sb = oc + BS * n2p;                             // [BS][SEG]
-                    for (int e = tid; e < BS * SEG; e += SWN_NTHREADS) {
+                    for (int e = tid; e < BS * SEG; e += NTT) {
                         const int b = e / SEG, j = e - b * SEG;
                         const float* o = oc + b * n2p;
                         sb[e] = o[j] - sigmoidf_(o[SEG + j]) * nz[e];      // scale = exp(logsigmoid(.))
                     }
-                    __syncthreads();
+                    tsync();
                     if (tid < BS) {
                         const int b = tid;
                         int bglob = m * BS + b;
@@ -1413,7 +1422,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                         }
                     }
                     if (P.head_out) {
-                        for (int e = tid; e < BS * n2; e += SWN_NTHREADS) {
+                        for (int e = tid; e < BS * n2; e += NTT) {
                             const int b = e / n2, rr = e - b * n2;
                             const int bglob = m * BS + b;
                             if (bglob < P.B) P.head_out[((size_t)bglob * P.n_iter + istep) * n2 + rr] = oc[b * n2p + rr];
@@ -1421,7 +1430,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                     }
                 } else {
                     // Gumbel-max: argmax_k(logit_k - log q_k)  (dswnv.py:363-369)
-                    for (int b = warp; b < BS; b += SWN_NWARPS) {
+                    for (int b = warp; b < BS; b += (NTT / 32)) {
                         int bglob = m * BS + b;
                         const bool real = bglob < P.B;
                         if (!real) bglob = P.B - 1;
@@ -1448,7 +1457,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem) {
                         }
                     }
                 }
-                __syncthreads();
+                tsync();
                 if (tid == 0) B3_PROF(3);
             }
             if (it + 1 < P.n_it) input_stage(it + 1, m, ml);
@@ -1464,7 +1473,10 @@ __global__ void __launch_bounds__(SWN_NTHREADS, 1) swn_batch_kernel(const __grid
     const BCta& D = P.desc[blockIdx.x];
     if (D.role == ROLE_LAYER) b3_stage<SEG, BS, 0>(P, D, smem);
     else if (D.role == ROLE_DENSE) b3_stage<SEG, BS, 1>(P, D, smem);
-    else if (D.role == ROLE_HEAD) b3_tail<SEG, BS>(P, D, smem);
+    else if (D.role == ROLE_HEAD) {
+        if (P.tail_inst == 2) b3_tail<SEG, BS, SWN_NTHREADS / 2>(P, D, smem, threadIdx.x / (SWN_NTHREADS / 2), 2);
+        else b3_tail<SEG, BS, SWN_NTHREADS>(P, D, smem, 0, 1);
+    }
 }
 
 }  // namespace swn
