@@ -637,11 +637,11 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
                 auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
                 d.sm_w = take(um ? 0 : (size_t)Hp * c.RP);
                 // two operand buffers (prefetch of the next slot) unless two large tensor-core tiles do not fit
-                d.nxb = (um && 2 * cell_tile_f + (size_t)128 * OS + (size_t)c.npairs * NC * 4 + 64 > (size_t)smem_floats) ? 1 : 2;
+                d.nxb = (um && 2 * cell_tile_f + (size_t)128 * OS + (size_t)2 * c.npairs * NC * 4 + 64 > (size_t)smem_floats) ? 1 : 2;
                 d.sm_x = take(um ? d.nxb * cell_tile_f : (size_t)2 * Hp * NC);
                 d.sm_o = take((size_t)(um ? 128 : c.RP) * OS);
-                d.sm_pre = take((size_t)c.npairs * NC * 4);
-                d.sm_bar = take(32);
+                d.sm_pre = take((size_t)2 * c.npairs * NC * 4);
+                d.sm_bar = take(48);
                 d.sm_build = take((build_x && l == 0) ? (size_t)K * 2 * H + 2 * H + 4 * (size_t)bs * (seg + 7) : 0);
                 const size_t ring_f = (size_t)d.ring_len * 2 * c.npairs * Bp;
                 d.sm_ring = (int32_t)u;
@@ -679,7 +679,7 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
                     const size_t vw = bs % 4 == 0 ? 4 : 1, nitem = (size_t)d.nrows * bs / vw;
                     d.sm_pre = take(nitem > 4 * 352 ? (size_t)d.nrows * bs : 0);
                 }
-                d.sm_bar = take(32);
+                d.sm_bar = take(48);
                 if (u > (size_t)smem_floats) { fits = false; break; }
                 used_max = std::max(used_max, u);
             }
@@ -798,6 +798,8 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
     P.it0 = (m->R + 1 - P.t_first) / seg - 1;
     P.n_iter = (int)n_iter;
     P.n_it = P.it0 + P.n_iter;
+    P.p1_split = M >= 16 ? 1 : 0;
+    if (getenv("SWN_P1_SPLIT")) P.p1_split = atoi(getenv("SWN_P1_SPLIT")) ? 1 : 0;
     P.NT = NT; P.tail_inst = tinst_sel; P.tail_gemm = tail_gemm ? 1 : 0;
     P.tail_cnt = L + ND; P.tail_nprod = nd[ND - 1];
     P.tail_in_off = tile_off[L + ND]; P.tail_slot_f = dst[ND - 1].rows * BS;

@@ -40,6 +40,7 @@ constexpr int B3_HIST = 32;
 #ifndef B3_WAIT_SLEEP_NS
 #define B3_WAIT_SLEEP_NS 64
 #endif
+constexpr int B3_P1W = 3;                 // warps of the gate-operand prefetch team (p1_split)
 constexpr int B3_NBW = 4;                 // cell 0 with build_x: warps 5..8 build the input tile, 9..15 are the epilogue
 
 enum { ROLE_DENSE = 3 };                  // besides ROLE_LAYER (gated cell), ROLE_HEAD (tail), ROLE_IDLE
@@ -75,6 +76,7 @@ struct BatchParams {
     int32_t t_first, it0, n_it, n_iter;
     int32_t NT;                           // tail CTAs
     int32_t tail_inst;                    // tail instances per tail CTA (1 x 512 threads or 2 x 256)
+    int32_t p1_split;                     // gated cells: a separate 3-warp team prefetches the gate operands one pass ahead
     int32_t tail_gemm;                    // 1: the tail evaluates out_2 itself (few rows); 0: out_2 is dense stage C
     int32_t tail_cnt, tail_nprod, tail_slot_f;   // counter row / producers / floats per slot of the tail's input
     int64_t tail_in_off;
@@ -282,7 +284,12 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
     const int NP = P.NP, utile = D.kdim * NP;                 // umma: floats of one (hi or lo) input tile
     const bool build = MODE == 0 && P.build_x && l == 0 && !umma;   // this CTA evaluates the causal input stage itself
     const bool ubuild = umma && P.build_x && l == 0;          // same, tensor-core mode: done by the (mostly idle) drain warps
-    const int epi0 = build ? B3_EPI0 + B3_NBW : (umma ? B3_EPI0 + 1 : B3_EPI0);      // first epilogue warp
+    // throughput-bound rings: three warps (p1w0 ..) prefetch the gate operands of the NEXT pass while the others gate this one
+    const bool psplit = MODE == 0 && P.p1_split && M >= 2;
+    const int p1w0 = build ? B3_EPI0 + B3_NBW : (umma ? B3_EPI0 + 1 : B3_EPI0);
+    const int epi0 = p1w0 + (psplit ? B3_P1W : 0);            // first warp of the (main) epilogue team
+    unsigned long long* pre_full = bars + 16;       // [2] psplit: operands of a pass prefetched
+    unsigned long long* pre_empty = bars + 18;      // [2] psplit: ... consumed
     unsigned long long* d_full = bars + 7;          // umma: [2] accumulator tile complete (tcgen05.commit)
     unsigned long long* d_empty = bars + 9;         // umma: [2] accumulator tile drained
     unsigned long long* x_lo = bars + 11;           // umma: [2] low-half operand tile landed (the high half completes x_full)
@@ -325,6 +332,8 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
             b3_mbar_init(&x_empty[0], umma ? 2 : ngwa + 1); b3_mbar_init(&x_empty[1], umma ? 2 : ngwa + 1);
             b3_mbar_init(o_full, ngwa); b3_mbar_init(o_empty, 1);
             b3_mbar_init(ebar, SWN_NWARPS - epi0);
+            b3_mbar_init(&pre_full[0], B3_P1W); b3_mbar_init(&pre_full[1], B3_P1W);
+            b3_mbar_init(&pre_empty[0], 1); b3_mbar_init(&pre_empty[1], 1);
             if (umma) {
                 b3_mbar_init(&x_lo[0], ubuild ? B3_NBW : 1); b3_mbar_init(&x_lo[1], ubuild ? B3_NBW : 1);
                 b3_mbar_init(&d_full[0], 1); b3_mbar_init(&d_full[1], 1);
@@ -689,7 +698,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         return;
     }
 
-    if (MODE == 0 && build && warp >= B3_EPI0 && warp < epi0) {
+    if (MODE == 0 && build && warp >= B3_EPI0 && warp < p1w0) {
         // =============================== builders (cell 0): softsign(causal(wav_conv(samples))) straight into the
         // GEMM operand buffer (cswnv_shift1.py:352); a thread owns channel r of utterance b, whose SEG columns share taps
         constexpr int NA = SEG + 7;
@@ -849,11 +858,10 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
     float* ringG = P.ring_scratch + D.ring_off;
     const int twoH = 2 * H;
     const int nitems = np * NC;
-    B3_FOR_PASSES(q, it, m) {
-        const int buf = XB(q);
+    // ---- P1: everything the gate needs that does not depend on the GEMM (conditioning, ring of partial sums, bias)
+    auto p1 = [&](const int it, const int m, float4* dst, const int t_id, const int t_n) {
         const int t0 = P.t_first + it * SEG;
-        // ---- P1: everything the gate needs that does not depend on the GEMM
-        for (int item = te; item < nitems; item += nepi) {
+        for (int item = t_id; item < nitems; item += t_n) {
             const int pi = item / NC, col = item - pi * NC;
             const int s = col / BS, b = col - s * BS;
             const int t = t0 + s;
@@ -883,8 +891,32 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                 else { rz = __ldcg(ringG + ro); rc = __ldcg(ringG + ro + Bp); __stcg(ringG + ro, 0.f); __stcg(ringG + ro + Bp, 0.f); }
                 v = make_float4(az, ac, rz + bias[pi * 2], rc + bias[pi * 2 + 1]);
             }
-            pre[item] = v;
+            dst[item] = v;
         }
+    };
+    if (psplit && warp < epi0) {
+        // =============================== prefetch team: one pass ahead of the gate.  pre_empty is released after P3 of the
+        // pass two behind, so the ring slots read (and cleared) here are never ones a running P3 still adds to (M >= 2)
+        const int tp = tid - p1w0 * 32;
+        int m_prev = -1;
+        B3_FOR_PASSES(q, it, m) {
+            const int pb = q & 1;
+            if (q >= 2 && !b3_wait_warp(&pre_empty[pb], ((q >> 1) - 1) & 1, P.status)) return;
+            // a ragged batch can leave a single slot in the ring: then the previous pass is the same utterances and its
+            // scatter into the ring must be complete before the ring is read here
+            if (q >= 1 && m == m_prev && !b3_wait_warp(&pre_empty[pb ^ 1], ((q - 1) >> 1) & 1, P.status)) return;
+            m_prev = m;
+            p1(it, m, pre + pb * nitems, tp, B3_P1W * 32);
+            __syncwarp();
+            if (lane == 0) b3_mbar_arrive(&pre_full[pb]);
+        }
+        return;
+    }
+    B3_FOR_PASSES(q, it, m) {
+        const int buf = XB(q);
+        const int t0 = P.t_first + it * SEG;
+        float4* prq = pre + (psplit ? (q & 1) * nitems : 0);
+        if (!psplit) p1(it, m, prq, te, nepi);
         if (te == 0) B3_PROF(3);
         if (!b3_wait_warp(&x_full[buf], XU(q) & 1, P.status)) return;
         if (umma && !b3_wait_warp(&x_lo[buf], XU(q) & 1, P.status)) return;
@@ -894,6 +926,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
         if (l >= 2 && sk_pre && te < D.nskip * BS)
             sk_prev = __ldcg(P.skipbuf + ((size_t)(l - 2) * M + m) * P.S * BS + (size_t)D.skip0 * BS + te);
         if (!b3_wait_warp(o_full, q & 1, P.status)) return;
+        if (psplit && !b3_wait_warp(&pre_full[q & 1], (q >> 1) & 1, P.status)) return;
         if (te == 0) B3_PROF(4);
         const float* X = Xs + buf * xbuf_f;
         float* tout = tile_out + (size_t)m * D.out_slot_f;
@@ -904,7 +937,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
             const int t = t0 + s;
             float hv = 0.f;
             if (t >= 0) {
-                const float4 v = pre[item];
+                const float4 v = prq[item];
                 float qz = v.z, qc = v.w;
                 for (int j = K - 1; j >= 0; --j) {
                     const int delta = (K - 1 - j) * dil;
@@ -994,7 +1027,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
             }
         }
         if (!epi_sync()) return;
-        if (te == 0) { b3_mbar_arrive(o_empty); B3_PROF(6); }
+        if (te == 0) { b3_mbar_arrive(o_empty); if (psplit) b3_mbar_arrive(&pre_empty[q & 1]); B3_PROF(6); }
     }
     }
 }

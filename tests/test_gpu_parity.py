@@ -549,3 +549,15 @@ def test_batch_kernel_ragged_lengths_leave_the_ring_early(name, B, tile, engine)
             assert np.array_equal(o, ref_smp[b, :want])
         else:
             assert float(np.abs(o - ref_smp[b, :want]).max()) <= 5e-5
+
+
+@pytest.mark.parametrize("engine", [3, 4])
+def test_batch_kernel_throughput_options_forced_on_small_rings(engine, monkeypatch):
+    """The prefetch team of the gated cells (SWN_P1_SPLIT) and the two half-size tail instances (SWN_TAIL_INST=2) are
+    switched on by the plan from 16 slots up; forced here on small, ragged rings (incl. the case where a single slot
+    remains in the ring) so that their hand-offs are exercised by the regular suite."""
+    monkeypatch.setenv("SWN_P1_SPLIT", "1")
+    monkeypatch.setenv("SWN_TAIL_INST", "2")
+    test_batch_kernel_ragged_lengths_leave_the_ring_early("cswnv_seg5_lpc4_h64", 21, 4, engine)
+    test_batch_kernel_ragged_lengths_leave_the_ring_early("cswnv_seg2_lpc3", 7, 1, engine)
+    test_batch_kernel_ragged_lengths_leave_the_ring_early("dswnv_base", 19, 2, engine)
