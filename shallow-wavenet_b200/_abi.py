@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libswn_b200.so")
+# SWN_B200_LIB selects another build of the same library (kernel A/B timing, tools/ab_build.sh); never a fallback
+LIB_PATH = os.environ.get("SWN_B200_LIB") or os.path.join(_HERE, "lib", "libswn_b200.so")
 
 KIND_CSWNV = 0
 KIND_DSWNV = 1

@@ -117,6 +117,9 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arm(unsigned long long* b, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try(unsigned long long* b, uint32_t parity) {
     uint32_t done;
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
@@ -199,16 +202,44 @@ __device__ __forceinline__ float reduce8(const float (&v)[8], int lane) {
     return sres;
 }
 
+#ifndef SWN_FINE_PROF
+#define SWN_FINE_PROF 0      // 1: clock64 stamps inside the stages (tools/gpu_prof_core.py); they cost ~1.4 us per step
+#endif
+#if SWN_FINE_PROF
 #define SWN_CCLK(ev)                                                                               \
     do {                                                                                           \
         if (P.prof && threadIdx.x == 0 && l == 3 && it >= P.prof_start && it < P.prof_start + P.prof_count) \
             P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + (ev)] = (unsigned long long)clock64(); \
     } while (0)
+#define SWN_HCLK(ev)                                                                               \
+    do {                                                                                           \
+        if (P.prof && threadIdx.x == 0 && it >= P.prof_start && it < P.prof_start + P.prof_count) \
+            P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + (ev)] = (unsigned long long)clock64(); \
+    } while (0)
+#else
+#define SWN_CCLK(ev) do {} while (0)
+#define SWN_HCLK(ev) do {} while (0)
+#endif
 #define SWN_CPROF(ev)                                                                              \
     do {                                                                                           \
         if (P.prof && threadIdx.x == 0 && it >= P.prof_start && it < P.prof_start + P.prof_count) \
             P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + (ev)] = gtime();  \
     } while (0)
+
+#ifndef SWN_ABL
+#define SWN_ABL 0            // dev only: ablation timing (tools/ab_build.sh), results are wrong when non-zero
+#endif
+#ifndef SWN_HELP_L2
+#define SWN_HELP_L2 1        // helper sums fetched with L2-scope loads instead of cp.async.ca (stale L1 lines)
+#endif
+#ifndef SWN_RELAY
+#define SWN_RELAY 0          // background warps are released by a local relay barrier instead of the exchange mbarrier
+#endif
+#ifndef SWN_DEFER_BG
+#define SWN_DEFER_BG 0      // 1 measured slower (11.31 vs 10.82 us per step on cfg2): the deferred work collides with the next stage
+#endif
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // Sleep on a local mbarrier until the phase with `parity` has completed (with the watchdog).
 static __device__ __noinline__ bool mbar_wait_slow(unsigned long long* b, uint32_t parity, const CoreParams& P, int where) {
@@ -390,6 +421,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + D.sm_tmem_slot);
     unsigned long long* mb = reinterpret_cast<unsigned long long*>(tmem_slot + 2);     // [L+1] h vectors, then x1, x2, gx
     unsigned long long* mb_x1 = mb + (L + 1), *mb_x2 = mb + (L + 2), *mb_gx = mb + (L + 3);
+    unsigned long long* mbg = mb + (L + 4);                // [L] relay barriers (SWN_RELAY)
     const uint32_t bytes_h = (uint32_t)(H * NC * 4), bytes_x1 = (uint32_t)(S * NC * 4), bytes_x2 = (uint32_t)(n1 * NC * 4),
                    bytes_gx = (uint32_t)(Q * NC * 4);
 
@@ -429,6 +461,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
     }
     if (tid == 0) {
         for (int i = 0; i < L + 4; ++i) mbar_init(mb + i, 1);
+        for (int i = 0; i < L; ++i) mbar_init(mbg + i, 1);
         mbar_fence_init();
         for (int i = 0; i <= L; ++i) mbar_arm(mb + i, bytes_h);          // phase 0 of every vector
         mbar_arm(mb_x1, bytes_x1); mbar_arm(mb_x2, bytes_x2); mbar_arm(mb_gx, bytes_gx);
@@ -507,12 +540,28 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
             PreSlot* ps = pre + (((tt & 1) * L + l) * 16 + plocal) * NC + sub;
             cp_async4(&ps->pz, prow + l * twoH);
             cp_async4(&ps->pc, prow + l * twoH + H);
+#if !SWN_HELP_L2
             if (P.has_help[l] && tt >= P.hdmin[l]) {
                 const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + ((tt & (P.hacc_nt[l] - 1)) * twoH + my_i) * NC + sub;
                 cp_async8(&ps->hz, src);
                 cp_async8(&ps->hc, src + H * NC);
             }
+#endif
         }
+    };
+    // The helpers' partial sums are re-written every ring period, and cp.async of 8 bytes can only be `.ca`: a line
+    // still sitting in this SM's (incoherent) L1 from the previous period comes back with the old tag and sends the
+    // chain warp into the slow polling path.  So they are fetched with L2-scope loads by the delay-1 warps, after
+    // their own work for the stage.
+    auto prefetch_help = [&](int l, int tt) {
+#if SWN_HELP_L2
+        if (pf_lane && tt < P.n_it && P.has_help[l] && tt >= P.hdmin[l]) {
+            PreSlot* ps = pre + (((tt & 1) * L + l) * 16 + plocal) * NC + sub;
+            const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + ((tt & (P.hacc_nt[l] - 1)) * twoH + my_i) * NC + sub;
+            const unsigned long long a = ld_ll(src), b = ld_ll(src + H * NC);
+            ps->hz = a; ps->hc = b;
+        }
+#endif
     };
 
     // ---- input stage: h0 rows of this CTA (row = i0 + warp), published into every peer's hx[0].
@@ -570,7 +619,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                 st_ll(P.hin_ll + P.hin_off[0] + ((itn & (P.hslots[0] - 1)) * NC + c) * H + in_row, v, tagn);
         }
     };
-    for (int l = 0; l < L; ++l) prefetch_gate(l, 0, ptab_b);
+    for (int l = 0; l < L; ++l) { prefetch_gate(l, 0, ptab_b); prefetch_help(l, 0); }
     cp_async_commit();
     int fc = 0, jc = 0;                                            // frame / phase of the current time step
     input_publish(0);                                              // time 0 sees only its own (padding) sample
@@ -639,9 +688,39 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                 }
             }
             // ---- sleep until the layer input has landed in local shared memory
+            SWN_CCLK(14);
+#if SWN_DEFER_BG
+            // Background warps (delay-1 taps, prefetch, out_skip rows) start their share of stage l only after the
+            // chain warps of this CTA have published: the critical path has the LDS / issue slots to itself, the
+            // background work runs while the chain warps sleep on the next hop.  Not for the last layer (the head's
+            // CTA barrier would wait for it).  Nobody leaves the layer loop early (named barriers need every warp).
+            const bool defer = l + 1 < L;
+            if (defer && warp >= 4) named_bar_sync(1 + (l % 15), SWN_NTHREADS);
+            ok = ok && mbar_wait(mb + l, par, P, 500 + l);
+            ok = __all_sync(0xffffffffu, ok);
+            if (!ok) {
+                if (defer && warp < 4) named_bar_arrive(1 + (l % 15), SWN_NTHREADS);
+                continue;
+            }
+#elif SWN_RELAY
+            // Experiment: only the chain warps and warp 4 sleep on the exchange barrier; warp 4 re-arms it and releases
+            // the other background warps.  (tools/microbench/mbar_wake.cu: 15 sleepers are released within 30 cycles
+            // of each other, so there is little to gain.)
+            if (warp <= 4) {
+                ok = mbar_wait(mb + l, par, P, 500 + l) && ok;
+                if (tid == 128) { mbar_arm(mb + l, bytes_h); mbar_arrive(mbg + l); }
+            } else {
+                ok = mbar_wait(mbg + l, par, P, 600 + l) && ok;
+            }
+            if (!__all_sync(0xffffffffu, ok)) { ok = false; break; }
+#else
             ok = mbar_wait(mb + l, par, P, 500 + l) && ok;
             if (!__all_sync(0xffffffffu, ok)) { ok = false; break; }
+#endif
+            SWN_CCLK(15);
+#if !SWN_RELAY
             if (tid == 0) mbar_arm(mb + l, bytes_h);               // next phase (next time step)
+#endif
             if (l < 6) SWN_CPROF(1 + l);
             float2 h[NC][NCH];
 #pragma unroll
@@ -649,6 +728,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
             if (warp < 4) {
                 // ================= chain warp: delay-0 tap of 4 gate pairs, gate, publish =================
                 tmem_wait_ld();
+                SWN_CCLK(16);
                 float myqz = 0.f, myqc = 0.f;                      // lane (pair group, sub = column) keeps its column's sums
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
@@ -663,11 +743,17 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                         }
                         v8[rr] = a + b;
                     }
+#if SWN_ABL & 2
+                    const float mine = v8[0] + v8[1] + v8[2] + v8[3] + v8[4] + v8[5] + v8[6] + v8[7];
+                    const float other = mine;
+#else
                     const float mine = reduce8(v8, lane);          // lane holds row (lane >> 2): even = z, odd = candidate
                     const float other = __shfl_xor_sync(0xffffffffu, mine, 4);
+#endif
                     const float qz = (lane & 4) ? other : mine, qc = (lane & 4) ? mine : other;
                     if (sub == c) { myqz = qz; myqc = qc; }
                 }
+                SWN_CCLK(17);
                 // ---- gate (cswnv_shift1.py:281-285), all columns at once (lane sub = column sub)
                 float hn = 0.f;
                 if (sub < NC) {
@@ -675,12 +761,17 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                     const float gc = (myqc + bc + rc + hcv) * pc;
                     // sigmoid / tanh through ex2.approx + rcp (abs. error ~1e-7, inside the 1e-4 head tolerance);
                     // both exponentials are independent, so their latencies overlap
+#if SWN_ABL & 4
+                    hn = gz * 1e-3f + gc * 1e-3f;
+#else
                     const float ez = __expf(-gz), ec = __expf(-2.f * fabsf(gc));
                     const float z = __frcp_rn(1.f + ez);
                     const float th = copysignf((1.f - ec) * __frcp_rn(1.f + ec), gc);
                     const float carry = hx[(l * NC + sub) * HP + (pvalid ? my_i : 0)];
                     hn = (1.f - z) * th + z * carry;
+#endif
                 }
+                SWN_CCLK(18);
                 // ---- fan out: in every pair group, lane sub writes CTAs sub and sub+8; lane sub==0 feeds the helpers
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
@@ -694,11 +785,16 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                             st_ll(P.hin_ll + P.hin_off[l + 1] + ((it & (P.hslots[l + 1] - 1)) * NC + c) * H + my_i, v, tag);
                     }
                 }
+                SWN_CCLK(19);
+#if SWN_DEFER_BG
+                if (defer) named_bar_arrive(1 + (l % 15), SWN_NTHREADS);
+#endif
                 if (l + 1 < L) tmem_ldw<TCOLS>(taddr0 + P.tap_base[l + 1] * TCOLS, w);
+                SWN_CCLK(20);
             } else if (warp < 8) {
                 // ================= delay-1 tap of dilation-1 layers (for the next step) + operand prefetch =================
-                prefetch_gate(l, t + 1, prow_next);
-                if (ld1 && K >= 2) {
+                if (!(SWN_ABL & 32)) prefetch_gate(l, t + 1, prow_next);
+                if (ld1 && K >= 2 && !(SWN_ABL & 8)) {
                     tmem_ldw<TCOLS>(taddr0 + (P.tap_base[l] + 1) * TCOLS, w);
                     tmem_wait_ld();
 #pragma unroll
@@ -719,7 +815,8 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                             ring[(((l * 2 + (int)(par ^ 1u)) * 16 + plocal) * 2 + ((lane >> 2) & 1)) * BS + c] = mine;
                     }
                 }
-            } else if (active && l >= 1) {
+                prefetch_help(l, t + 1);
+            } else if (active && l >= 1 && !(SWN_ABL & 16)) {
                 // ================= two rows of out_skip[l-1] applied to the input of layer l =================
                 if (skr0 < D.nskip) {
                     float2 ws[NCH];
@@ -744,6 +841,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
         // the output of the last layer (always consumed, so that its barrier advances every step)
         ok = mbar_wait(mb + L, par, P, 510) && ok;
         if (tid == 0) mbar_arm(mb + L, bytes_h);
+        SWN_HCLK(31);
         if (active) {
             // ---- out_skip[L-1] on the output of the last layer; relu(sum of skips) -> x1 on every CTA
             if (warp >= 8) {
@@ -758,7 +856,11 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                         load_frag<NCH>(ws, sSkip + ((L - 1) * D.nskip + row) * HP, lane);
 #pragma unroll
                         for (int c = 0; c < NC; ++c) {
+#if SWN_ABL & 256
+                            const float v = (half ? sk1[c] : sk0[c]) + ws[0].x * hl[c][0].x + (half ? cst1 : cst0);
+#else
                             const float v = warp_sum((half ? sk1[c] : sk0[c]) + dot_frag<NCH>(ws, hl[c])) + (half ? cst1 : cst0);
+#endif
                             if (lane < CORE_CL)
                                 st_async_f32(x1_peer + (uint32_t)((c * Sp + D.skip0 + row) * 4), fmaxf(v, 0.f), mb_peer + (uint32_t)((L + 1) * 8));
                         }
@@ -768,11 +870,13 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
             SWN_CPROF(8);
             // ---- out_1 row of this warp (relu) -> x2 on every CTA
             if (warp < D.nb) {
+                SWN_HCLK(21);
                 ok = mbar_wait(mb_x1, hpar, P, 520) && ok;
+                SWN_HCLK(22);
                 float acc1[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) acc1[c] = 0.f;
-                for (int cc = 0; cc < (Sp >> 6); ++cc) {
+                for (int cc = 0; cc < ((SWN_ABL & 64) ? 1 : (Sp >> 6)); ++cc) {
                     const float2 wv = reinterpret_cast<const float2*>(sW1 + (size_t)warp * Sp)[cc * 32 + lane];
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
@@ -784,20 +888,22 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                 const float b1 = b1w;
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    const float v = warp_sum(acc1[c]) + b1;
+                    const float v = ((SWN_ABL & 64) ? acc1[c] : warp_sum(acc1[c])) + b1;
                     if (lane < CORE_CL)
                         st_async_f32(x2_peer + (uint32_t)((c * n1p + D.b0 + warp) * 4), fmaxf(v, 0.f), mb_peer + (uint32_t)((L + 2) * 8));
                 }
             }
             SWN_CPROF(9);
+            SWN_HCLK(23);
             // ---- out_2 rows
             if (warp < D.nc) ok = mbar_wait(mb_x2, hpar, P, 530) && ok;
+            SWN_HCLK(24);
             if (warp < D.nc) {
                 const int r = warp;
                 float acc2[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) acc2[c] = 0.f;
-                for (int cc = 0; cc < (n1p >> 6); ++cc) {
+                for (int cc = 0; cc < ((SWN_ABL & 128) ? 1 : (n1p >> 6)); ++cc) {
                     const float2 wv = reinterpret_cast<const float2*>(sW2 + r * n1p)[cc * 32 + lane];
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
@@ -808,7 +914,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                 }
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    const float o = warp_sum(acc2[c]) + b2w;
+                    const float o = ((SWN_ABL & 128) ? acc2[c] : warp_sum(acc2[c])) + b2w;
                     if (is_c) {
                         if (lane == 0) o2[c * 16 + r] = o;
                     } else {
@@ -835,7 +941,9 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                 }
             } else if (warp == 0) {
                 // ---- argmax over the 256 published Gumbel scores (first maximum wins), one warp per CTA
+                SWN_HCLK(25);
                 ok = mbar_wait(mb_gx, hpar, P, 540) && ok;
+                SWN_HCLK(26);
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     float best = -CUDART_INF_F; int bi = 0x7fffffff;
@@ -861,13 +969,17 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                     }
                 }
             }
+            SWN_HCLK(27);
             if (__syncthreads_or(!ok)) { ok = false; break; }
+            SWN_HCLK(28);
             // every consumer of this step's head vectors is past them: arm their next phase
             if (tid == 0) { mbar_arm(mb_x1, bytes_x1); mbar_arm(mb_x2, bytes_x2); if (!is_c) mbar_arm(mb_gx, bytes_gx); }
         }
         SWN_CPROF(10);
+        SWN_HCLK(29);
         if (it + 1 < P.n_it) {
             input_publish(it + 1);
+            SWN_HCLK(30);
             SWN_CPROF(11);
             feed(it + 1);
             cp_async_commit();

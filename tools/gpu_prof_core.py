@@ -20,6 +20,9 @@ for sel in (2, 1):
     except Exception as e:
         print("kernel_sel", sel, "failed:", e); continue
     grid = eng.info["grid"]
+    i0 = eng.info
+    print("== %s kernel_variant=%d unprofiled: kernel %.2f ms, %.3f us/step" % (
+        wl, i0["kernel_variant"], i0["last_gen_ms"], i0["last_gen_ms"] * 1e3 / (n + i0["receptive_field"] + 1)))
     cnt = 64
     prof = torch.zeros((cnt, grid, 32), dtype=torch.int64, device="cuda")
     eng.condition(aux)
@@ -42,3 +45,15 @@ for sel in (2, 1):
     print("   step period %.0f ns" % per)
     for e, nme in enumerate(names):
         print("   %-20s mean %.0f ns  (min CTA %.0f, max CTA %.0f)" % (nme, rel[:, :, e].mean(), rel[:, :, e].mean(0).min(), rel[:, :, e].mean(0).max()))
+    # clock64 stamps of thread 0 (chain warp 0): layer 3 stage and the head, cycles
+    c = pall
+    lay = ["before wait", "woken", "h frags + taps in regs", "taps reduced", "gated", "published", "next taps issued"]
+    print("   layer-3 stage of chain warp 0, cycles since 'before wait' (mean over core CTAs):")
+    for i, nme in enumerate(lay):
+        print("      %-26s %7.0f" % (nme, (c[:, :, 14 + i] - c[:, :, 14]).mean()))
+    hd = [(31, "last layer output landed"), (21, "before x1 wait"), (22, "x1 landed"), (23, "out_1 row published"), (24, "x2 landed"),
+          (25, "out_2 row published"), (26, "scores landed"), (27, "argmax done"), (28, "CTA barrier"), (29, "barriers re-armed"),
+          (30, "next h0 published")]
+    print("   head of warp 0, cycles since the last layer output landed:")
+    for e, nme in hd:
+        print("      %-26s %7.0f" % (nme, (c[:, :, e] - c[:, :, 31]).mean()))
