@@ -131,6 +131,11 @@ __device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint
                  ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_mbar) : "memory");
 }
 
+__device__ __forceinline__ void st_async_f32x2(uint32_t remote_addr, float lo, float hi, uint32_t remote_mbar) {
+    const unsigned long long w = ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(remote_addr), "l"(w), "r"(remote_mbar) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_all(uint32_t* slot) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -229,6 +234,29 @@ __device__ __forceinline__ float reduce8(const float (&v)[8], int lane) {
 #ifndef SWN_ABL
 #define SWN_ABL 0            // dev only: ablation timing (tools/ab_build.sh), results are wrong when non-zero
 #endif
+#ifndef SWN_NOSYNC_L
+#define SWN_NOSYNC_L 1       // no CTA barrier between the layer loop and the head
+#endif
+#ifndef SWN_FWD_HELP
+#define SWN_FWD_HELP 0       // helper inputs forwarded by the helper-prefetch team instead of the chain warps
+#endif
+#ifndef SWN_PFG_W
+#define SWN_PFG_W 4          // first warp of the team that prefetches the conditioning rows (4 = the delay-1 warps)
+#endif
+#ifndef SWN_PFH_W
+#define SWN_PFH_W 4         // first warp of the team that fetches the helper sums (4 = the delay-1 warps)
+#endif
+#ifndef SWN_PUB64
+#define SWN_PUB64 0          // layer outputs published as 8-byte messages (two rows each)
+#endif
+#ifndef SWN_HEAD2
+#define SWN_HEAD2 1          // head: weight rows in registers before the vectors land, interleaved reductions, re-arming off warp 0
+#endif
+#ifndef SWN_GATE1
+#define SWN_GATE1 1          // gate with one reciprocal (see the chain warp)
+#endif
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #ifndef SWN_HELP_L2
 #define SWN_HELP_L2 1        // helper sums fetched with L2-scope loads instead of cp.async.ca (stale L1 lines)
 #endif
@@ -520,6 +548,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
     const int my_i = D.pair0 + plocal;                             // row index in H
     const int sub = lane & 7;                                      // lane inside the pair group
     const int skr0 = 2 * (warp - 8), skr1 = skr0 + 1;              // skip rows of warps 8..15
+    const bool pub64 = ((np | D.pair0) & 1) == 0;                  // rows come in aligned pairs (SWN_PUB64)
     const uint32_t hxp0 = mapa(smem_u32(hx), (uint32_t)sub), hxp1 = mapa(smem_u32(hx), (uint32_t)sub + 8);
     const uint32_t mbp0 = mapa(smem_u32(mb), (uint32_t)sub), mbp1 = mapa(smem_u32(mb), (uint32_t)sub + 8);
     const float b1w = (warp < D.nb) ? __ldg(P.wbuf + D.b1_off + warp) : 0.f;
@@ -532,7 +561,9 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
 
     // ---- prefetch (cp.async) of the gate operands of (layer l, time tt) into pre[tt&1][l][pair][col], done by the
     // delay-1 warps (4-7): lane sub < NC of every pair group handles column sub
-    const bool pf_lane = warp >= 4 && warp < 8 && pvalid && sub < NC;
+    // which warp team prefetches (any team of four warps covers the four quarters: quarter = warp & 3)
+    const bool pf_lane = warp >= SWN_PFG_W && warp < SWN_PFG_W + 4 && pvalid && sub < NC;     // conditioning rows (cp.async)
+    const bool pfh_lane = warp >= SWN_PFH_W && warp < SWN_PFH_W + 4 && pvalid && sub < NC;    // helper sums (L2 loads)
     const int bg_col = min(sub, P.B - 1);
     const float* ptab_b = P.P + (size_t)bg_col * P.Tf * L * twoH + my_i;
     auto prefetch_gate = [&](int l, int tt, const float* prow) {
@@ -555,7 +586,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
     // their own work for the stage.
     auto prefetch_help = [&](int l, int tt) {
 #if SWN_HELP_L2
-        if (pf_lane && tt < P.n_it && P.has_help[l] && tt >= P.hdmin[l]) {
+        if ((SWN_HELP_L2 ? pfh_lane : pf_lane) && tt < P.n_it && P.has_help[l] && tt >= P.hdmin[l]) {
             PreSlot* ps = pre + (((tt & 1) * L + l) * 16 + plocal) * NC + sub;
             const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + ((tt & (P.hacc_nt[l] - 1)) * twoH + my_i) * NC + sub;
             const unsigned long long a = ld_ll(src), b = ld_ll(src + H * NC);
@@ -666,7 +697,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
             const bool ld1 = P.dil[l] == 1;
             // ---- chain warps: gate operands that do not depend on the layer input (one pair group = 8 lanes)
             float pz = 0.f, pc = 0.f, hz = 0.f, hcv = 0.f, rz = 0.f, rc = 0.f, bz = 0.f, bc = 0.f;
-            if (warp < 4 && pvalid && sub < NC) {
+            if (warp < 4 && pvalid && sub < NC && !(SWN_ABL & 1024)) {
                 const PreSlot ps = pre[((par * L + l) * 16 + plocal) * NC + sub];
                 const float4 c4 = lc[l * 16 + plocal];
                 pz = fmaf(gq, ps.pz, c4.x); pc = fmaf(gq, ps.pc, c4.y); bz = c4.z; bc = c4.w;
@@ -719,12 +750,12 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
 #endif
             SWN_CCLK(15);
 #if !SWN_RELAY
-            if (tid == 0) mbar_arm(mb + l, bytes_h);               // next phase (next time step)
+            if (tid == (SWN_HEAD2 ? 128 : 0)) mbar_arm(mb + l, bytes_h);   // next phase (next time step); not by a chain warp
 #endif
             if (l < 6) SWN_CPROF(1 + l);
             float2 h[NC][NCH];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) load_frag<NCH>(h[c], hx + (l * NC + c) * HP, lane);
+            for (int c = 0; c < NC; ++c) load_frag<NCH>(h[c], hx + (((SWN_ABL & 2048) ? 0 : l) * NC + c) * HP, lane);
             if (warp < 4) {
                 // ================= chain warp: delay-0 tap of 4 gate pairs, gate, publish =================
                 tmem_wait_ld();
@@ -737,7 +768,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                     for (int rr = 0; rr < 8; ++rr) {
                         float a = 0.f, b = 0.f;
 #pragma unroll
-                        for (int cc = 0; cc < NCH; ++cc) {
+                        for (int cc = 0; cc < ((SWN_ABL & 1) ? 1 : NCH); ++cc) {
                             a = fmaf(w[rr * FPT + 2 * cc], h[c][cc].x, a);
                             b = fmaf(w[rr * FPT + 2 * cc + 1], h[c][cc].y, b);
                         }
@@ -763,6 +794,16 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                     // both exponentials are independent, so their latencies overlap
 #if SWN_ABL & 4
                     hn = gz * 1e-3f + gc * 1e-3f;
+#elif SWN_GATE1
+                    // (1-z) tanh(gc) + z carry over one common denominator: two ex2, one rcp on the dependent chain
+                    //   z = 1/(1+ez), tanh = sign(gc) (1-ec)/(1+ec)  ->  [ez sign(gc) (1-ec) + carry (1+ec)] / [(1+ez)(1+ec)]
+                    // ez is capped at 2^43 (gz >= -30: z differs from 0 by < 1e-13 either way) so the product stays finite.
+                    const float carry = hx[(l * NC + sub) * HP + (pvalid ? my_i : 0)];
+                    const float ez = ex2_approx(fmaxf(gz, -30.f) * -1.4426950408889634f);
+                    const float ec = ex2_approx(fabsf(gc) * -2.8853900817779268f);
+                    const float den = (1.f + ez) * (1.f + ec);
+                    const float num = fmaf(ez, copysignf(1.f - ec, gc), carry * (1.f + ec));
+                    hn = num * rcp_approx(den);
 #else
                     const float ez = __expf(-gz), ec = __expf(-2.f * fabsf(gc));
                     const float z = __frcp_rn(1.f + ez);
@@ -776,12 +817,27 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     const float v = __shfl_sync(0xffffffffu, hn, (lane & 24) + c);
+#if SWN_PUB64
+                    // two adjacent rows per message: half as many remote stores and barrier transactions per hop
+                    // (tools/microbench/a2a_hop.cu).  Even pair groups serve CTAs 0-7, odd ones CTAs 8-15.
+                    const float vo = __shfl_xor_sync(0xffffffffu, v, 8);
+                    if (pub64) {
+                        if (pvalid) {
+                            const uint32_t off = (uint32_t)((((l + 1) * NC + c) * HP + (my_i & ~1)) * 4);
+                            const uint32_t mbo = (uint32_t)((l + 1) * 8);
+                            st_async_f32x2((pslot & 1) ? hxp1 + off : hxp0 + off, (pslot & 1) ? vo : v, (pslot & 1) ? v : vo,
+                                           (pslot & 1) ? mbp1 + mbo : mbp0 + mbo);
+                            if (!SWN_FWD_HELP && sub == 0 && l + 1 < L && P.has_help[l + 1])
+                                st_ll(P.hin_ll + P.hin_off[l + 1] + ((it & (P.hslots[l + 1] - 1)) * NC + c) * H + my_i, v, tag);
+                        }
+                    } else
+#endif
                     if (pvalid) {
                         const uint32_t off = (uint32_t)((((l + 1) * NC + c) * HP + my_i) * 4);
                         const uint32_t mbo = (uint32_t)((l + 1) * 8);
                         st_async_f32(hxp0 + off, v, mbp0 + mbo);
                         st_async_f32(hxp1 + off, v, mbp1 + mbo);
-                        if (sub == 0 && l + 1 < L && P.has_help[l + 1])
+                        if (!SWN_FWD_HELP && sub == 0 && l + 1 < L && P.has_help[l + 1])
                             st_ll(P.hin_ll + P.hin_off[l + 1] + ((it & (P.hslots[l + 1] - 1)) * NC + c) * H + my_i, v, tag);
                     }
                 }
@@ -789,11 +845,11 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
 #if SWN_DEFER_BG
                 if (defer) named_bar_arrive(1 + (l % 15), SWN_NTHREADS);
 #endif
-                if (l + 1 < L) tmem_ldw<TCOLS>(taddr0 + P.tap_base[l + 1] * TCOLS, w);
+                if (l + 1 < L && !(SWN_ABL & 512)) tmem_ldw<TCOLS>(taddr0 + P.tap_base[l + 1] * TCOLS, w);
                 SWN_CCLK(20);
             } else if (warp < 8) {
                 // ================= delay-1 tap of dilation-1 layers (for the next step) + operand prefetch =================
-                if (!(SWN_ABL & 32)) prefetch_gate(l, t + 1, prow_next);
+                if (SWN_PFG_W == 4 && !(SWN_ABL & 32)) prefetch_gate(l, t + 1, prow_next);
                 if (ld1 && K >= 2 && !(SWN_ABL & 8)) {
                     tmem_ldw<TCOLS>(taddr0 + (P.tap_base[l] + 1) * TCOLS, w);
                     tmem_wait_ld();
@@ -815,9 +871,18 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                             ring[(((l * 2 + (int)(par ^ 1u)) * 16 + plocal) * 2 + ((lane >> 2) & 1)) * BS + c] = mine;
                     }
                 }
-                prefetch_help(l, t + 1);
-            } else if (active && l >= 1 && !(SWN_ABL & 16)) {
+                if (SWN_PFH_W == 4) prefetch_help(l, t + 1);
+            } else {
+                if (SWN_PFG_W != 4 && !(SWN_ABL & 32)) prefetch_gate(l, t + 1, prow_next);
+#if SWN_FWD_HELP
+                // the helpers of layer l get this CTA's rows of the layer input from here (one hop later than from the
+                // producing chain warp; the helpers have a whole step of slack).  Layer 0 is fed by the input stage.
+                if (l >= 1 && P.has_help[l] && pfh_lane)
+                    st_ll(P.hin_ll + P.hin_off[l] + ((it & (P.hslots[l] - 1)) * NC + sub) * H + my_i,
+                          hx[(l * NC + sub) * HP + my_i], tag);
+#endif
                 // ================= two rows of out_skip[l-1] applied to the input of layer l =================
+                if (active && l >= 1 && !(SWN_ABL & 16)) {
                 if (skr0 < D.nskip) {
                     float2 ws[NCH];
                     load_frag<NCH>(ws, sSkip + ((l - 1) * D.nskip + skr0) * HP, lane);
@@ -830,17 +895,23 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
 #pragma unroll
                     for (int c = 0; c < NC; ++c) sk1[c] += dot_frag<NCH>(ws, h[c]);
                 }
+                }
+                if (SWN_PFH_W != 4) prefetch_help(l, t + 1);
             }
             __syncwarp();
         }
         cp_async_commit();
+#if !SWN_NOSYNC_L
         if (__syncthreads_or(!ok)) { ok = false; break; }
+#endif
+        // (no CTA barrier here: nothing below depends on another warp's layer work, and the background warps' last
+        // L2 loads would otherwise be exposed in front of the head; a failed wait is voted on at the end of the step)
         SWN_CPROF(7);
         if (P.prof && threadIdx.x == 0 && it >= P.prof_start && it < P.prof_start + P.prof_count)
             P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + 13] = (unsigned long long)hwait;
         // the output of the last layer (always consumed, so that its barrier advances every step)
         ok = mbar_wait(mb + L, par, P, 510) && ok;
-        if (tid == 0) mbar_arm(mb + L, bytes_h);
+        if (tid == (SWN_HEAD2 ? 128 : 0)) mbar_arm(mb + L, bytes_h);
         SWN_HCLK(31);
         if (active) {
             // ---- out_skip[L-1] on the output of the last layer; relu(sum of skips) -> x1 on every CTA
@@ -848,6 +919,28 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                 float2 hl[NC][NCH];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) load_frag<NCH>(hl[c], hx + (L * NC + c) * HP, lane);
+#if SWN_HEAD2
+                // both rows' partial sums first, then the two reductions interleaved (independent shuffle chains)
+                {
+                    const bool v0 = skr0 < D.nskip, v1 = skr1 < D.nskip;
+                    float2 ws0[NCH], ws1[NCH];
+                    load_frag<NCH>(ws0, sSkip + ((L - 1) * D.nskip + (v0 ? skr0 : 0)) * HP, lane);
+                    load_frag<NCH>(ws1, sSkip + ((L - 1) * D.nskip + (v1 ? skr1 : 0)) * HP, lane);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        float a = sk0[c] + dot_frag<NCH>(ws0, hl[c]), b = sk1[c] + dot_frag<NCH>(ws1, hl[c]);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            a += __shfl_xor_sync(0xffffffffu, a, o);
+                            b += __shfl_xor_sync(0xffffffffu, b, o);
+                        }
+                        if (lane < CORE_CL) {
+                            if (v0) st_async_f32(x1_peer + (uint32_t)((c * Sp + D.skip0 + skr0) * 4), fmaxf(a + cst0, 0.f), mb_peer + (uint32_t)((L + 1) * 8));
+                            if (v1) st_async_f32(x1_peer + (uint32_t)((c * Sp + D.skip0 + skr1) * 4), fmaxf(b + cst1, 0.f), mb_peer + (uint32_t)((L + 1) * 8));
+                        }
+                    }
+                }
+#else
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int row = half ? skr1 : skr0;
@@ -866,17 +959,40 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                         }
                     }
                 }
+#endif
             }
             SWN_CPROF(8);
             // ---- out_1 row of this warp (relu) -> x2 on every CTA
             if (warp < D.nb) {
                 SWN_HCLK(21);
-                ok = mbar_wait(mb_x1, hpar, P, 520) && ok;
-                SWN_HCLK(22);
                 float acc1[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) acc1[c] = 0.f;
+#if SWN_HEAD2
+                // the weight row is in registers before the vector lands (up to 256 columns; longer rows continue below)
+                float2 wpre[4];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+                    wpre[cc] = (cc * 64 < Sp) ? reinterpret_cast<const float2*>(sW1 + (size_t)warp * Sp)[cc * 32 + lane] : make_float2(0.f, 0.f);
+                ok = mbar_wait(mb_x1, hpar, P, 520) && ok;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    float a = 0.f, b = 0.f;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        if (cc * 64 < Sp) {
+                            const float2 v = reinterpret_cast<const float2*>(x1 + (size_t)c * Sp)[cc * 32 + lane];
+                            a = fmaf(wpre[cc].x, v.x, a); b = fmaf(wpre[cc].y, v.y, b);
+                        }
+                    }
+                    acc1[c] = a + b;
+                }
+                for (int cc = 4; cc < (Sp >> 6); ++cc) {
+#else
+                ok = mbar_wait(mb_x1, hpar, P, 520) && ok;
+                SWN_HCLK(22);
                 for (int cc = 0; cc < ((SWN_ABL & 64) ? 1 : (Sp >> 6)); ++cc) {
+#endif
                     const float2 wv = reinterpret_cast<const float2*>(sW1 + (size_t)warp * Sp)[cc * 32 + lane];
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
@@ -896,6 +1012,12 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
             SWN_CPROF(9);
             SWN_HCLK(23);
             // ---- out_2 rows
+#if SWN_HEAD2
+            float2 wpre2[4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+                wpre2[cc] = (warp < D.nc && cc * 64 < n1p) ? reinterpret_cast<const float2*>(sW2 + warp * n1p)[cc * 32 + lane] : make_float2(0.f, 0.f);
+#endif
             if (warp < D.nc) ok = mbar_wait(mb_x2, hpar, P, 530) && ok;
             SWN_HCLK(24);
             if (warp < D.nc) {
@@ -903,7 +1025,23 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                 float acc2[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) acc2[c] = 0.f;
+#if SWN_HEAD2
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    float a = 0.f, b = 0.f;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        if (cc * 64 < n1p) {
+                            const float2 v = reinterpret_cast<const float2*>(x2 + c * n1p)[cc * 32 + lane];
+                            a = fmaf(wpre2[cc].x, v.x, a); b = fmaf(wpre2[cc].y, v.y, b);
+                        }
+                    }
+                    acc2[c] = a + b;
+                }
+                for (int cc = 4; cc < (n1p >> 6); ++cc) {
+#else
                 for (int cc = 0; cc < ((SWN_ABL & 128) ? 1 : (n1p >> 6)); ++cc) {
+#endif
                     const float2 wv = reinterpret_cast<const float2*>(sW2 + r * n1p)[cc * 32 + lane];
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
@@ -973,7 +1111,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
             if (__syncthreads_or(!ok)) { ok = false; break; }
             SWN_HCLK(28);
             // every consumer of this step's head vectors is past them: arm their next phase
-            if (tid == 0) { mbar_arm(mb_x1, bytes_x1); mbar_arm(mb_x2, bytes_x2); if (!is_c) mbar_arm(mb_gx, bytes_gx); }
+            if (tid == (SWN_HEAD2 ? 32 * 15 : 0)) { mbar_arm(mb_x1, bytes_x1); mbar_arm(mb_x2, bytes_x2); if (!is_c) mbar_arm(mb_gx, bytes_gx); }
         }
         SWN_CPROF(10);
         SWN_HCLK(29);
