@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SWN_ABI_VERSION 2
+#define SWN_ABI_VERSION 3
 
 typedef struct swn_model* swn_handle;
 
@@ -132,6 +132,16 @@ int swn_condition(swn_handle h, const float* aux_dev, int32_t B, int32_t T_f, vo
 /* The hot loop.  Requires a preceding swn_condition with the same B. Asynchronous on
  * `stream` except for argument validation. */
 int swn_generate(swn_handle h, const swn_gen_args* args, void* stream);
+
+/* Teacher-forced evaluation of the same recurrence (SURVEY.md 8b `swn_teacher_forced`): the given samples are fed
+ * back instead of sampled ones and the raw out_2 rows of every loop step are returned - the per-step outputs that
+ * the parity tests compare with the reference module run on the same samples (a forward hook on out_2 around
+ * cswnv_shift1.py:367 / dswnv.py:361).  Time alignment is that of batch_fast_generate (warm-up over the padded
+ * seed, cswnv_shift1.py:314-334), not of the training-time forward() (cswnv_shift1.py:191-267).
+ * samples_dev: float [B][n_gen] (CSWNV) / int64 [B][n_gen] (DSWNV); head_dev: float [B][n_gen/seg][head_dim];
+ * n_gen = (n_samples/seg)*seg.  Requires a preceding swn_condition with the same B.  Asynchronous on `stream`;
+ * equivalent to swn_generate with forced_dev / head_dev set and the sampled output discarded. */
+int swn_teacher_forced(swn_handle h, const void* samples_dev, int64_t n_samples, float* head_dev, void* stream);
 
 /* Blocks until the stream is idle and reports a device-side failure of the last
  * swn_generate (e.g. the in-kernel watchdog fired) as a non-zero status. */

@@ -17,7 +17,7 @@ KIND_CSWNV = 0
 KIND_DSWNV = 1
 
 # every symbol include/swn_b200.h declares (checked by tests/test_abi_symbols.py)
-SYMBOLS = ("swn_create", "swn_set_tensor", "swn_finalize", "swn_condition", "swn_generate", "swn_sync",
+SYMBOLS = ("swn_create", "swn_set_tensor", "swn_finalize", "swn_condition", "swn_generate", "swn_teacher_forced", "swn_sync",
            "swn_generate_host", "swn_get_info", "swn_philox_uniform", "swn_measure_smem_bandwidth", "swn_destroy",
            "swn_last_error")
 
@@ -71,6 +71,7 @@ def load():
     lib.swn_finalize.argtypes = [vp]
     lib.swn_condition.argtypes = [vp, vp, i32, i32, vp]
     lib.swn_generate.argtypes = [vp, ctypes.POINTER(SwnGenArgs), vp]
+    lib.swn_teacher_forced.argtypes = [vp, vp, i64, vp, vp]
     lib.swn_sync.argtypes = [vp, vp]
     lib.swn_generate_host.argtypes = [vp, vp, i32, i32, i64, u64, vp]
     lib.swn_get_info.argtypes = [vp, ctypes.POINTER(SwnInfo)]

@@ -99,6 +99,7 @@ struct swn_model {
     DevBuf<int32_t> status;
     DevBuf<float> e2e_aux;
     DevBuf<char> e2e_out;
+    DevBuf<char> tf_out;        // swn_teacher_forced: where the discarded samples go
     // ---- v2: core cluster + helpers (swn_core.cuh)
     bool core_ok = false;
     int n_core_taps = 0;
@@ -1382,6 +1383,20 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
     return 0;
 }
 
+int swn_teacher_forced(swn_handle m, const void* samples_dev, int64_t n_samples, float* head_dev, void* stream) {
+    if (!m || !samples_dev || !head_dev) return fail("swn_teacher_forced: null argument");
+    if (!m->finalized) return fail("swn_teacher_forced: call swn_finalize first");
+    if (m->condB <= 0) return fail("swn_teacher_forced: call swn_condition first");
+    CUDA_OK(cudaSetDevice(m->device));
+    const int64_t n_gen = (n_samples / m->seg) * m->seg;
+    const size_t esz = m->cfg.kind == SWN_KIND_CSWNV ? sizeof(float) : sizeof(long long);
+    if (m->tf_out.ensure((size_t)m->condB * (size_t)std::max<int64_t>(n_gen, 1) * esz)) return 1;   // the sampler's own draws, discarded
+    swn_gen_args a;
+    memset(&a, 0, sizeof(a));
+    a.n_samples = n_samples; a.forced_dev = samples_dev; a.head_dev = head_dev; a.out_dev = m->tf_out.p;
+    return swn_generate(m, &a, stream);
+}
+
 int swn_sync(swn_handle m, void* stream) {
     if (!m) return fail("swn_sync: null handle");
     CUDA_OK(cudaSetDevice(m->device));
@@ -1450,7 +1465,7 @@ int swn_destroy(swn_handle m) {
     m->wbuf.release(); m->pconst.release(); m->gain.release(); m->in_tab.release(); m->in_bias.release();
     m->xa_tab.release(); m->wp.release(); m->act0.release(); m->act1.release(); m->ptab.release();
     m->desc.release(); m->ll.release(); m->ring_scratch.release(); m->status.release();
-    m->e2e_aux.release(); m->e2e_out.release();
+    m->e2e_aux.release(); m->e2e_out.release(); m->tf_out.release();
     m->wbuf3.release(); m->tiles3.release(); m->skip3.release(); m->ring3.release(); m->hist3.release(); m->slot3.release();
     m->cnt3.release(); m->desc3.release();
     m->wbuf2.release(); m->ring2.release(); m->cdesc.release(); m->hdesc.release(); m->ll2.release();

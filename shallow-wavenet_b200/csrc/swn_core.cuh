@@ -234,6 +234,9 @@ __device__ __forceinline__ float reduce8(const float (&v)[8], int lane) {
 #ifndef SWN_ABL
 #define SWN_ABL 0            // dev only: ablation timing (tools/ab_build.sh), results are wrong when non-zero
 #endif
+#ifndef SWN_GOP
+#define SWN_GOP 1            // gate operands combined by the delay-1 warps one step ahead: one LDS.128 per stage in the chain
+#endif
 #ifndef SWN_NOSYNC_L
 #define SWN_NOSYNC_L 1       // no CTA barrier between the layer loop and the head
 #endif
@@ -438,6 +441,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
     float* x2 = smem + D.sm_x2;                            // [NC][n1p] relu(out_1)
     float* gx = smem + D.sm_gx;                            // [NC][256] Gumbel scores
     PreSlot* pre = reinterpret_cast<PreSlot*>(smem + D.sm_pre);                        // [2][L][16][NC]
+    float4* gop = reinterpret_cast<float4*>(smem + D.sm_pre);                          // [2][L][16][NC] (SWN_GOP, same region)
     float* misc = smem + D.sm_misc;
     float* hist = misc;                                    // [NC][HIST] fed-back samples / indices
     float* lpb = hist + NC * HIST;                         // [NC][8]
@@ -595,6 +599,45 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
 #endif
     };
 
+    // ---- SWN_GOP: everything the gate of (layer l, time tt) needs besides the newest-tap product is known one step
+    // ahead: conditioning row (x gain + constant), biases, helper sums, delay-1 sums.  The delay-1 warps fetch the
+    // global parts (L2-scope loads, issued before their own FMA work), wait for a late helper themselves, and leave
+    //   { pz, (bz + rz + hz) * pz, pc, (bc + rc + hc) * pc }
+    // in gop[tt & 1][l][pair][col]; the chain warp's stage then needs one LDS.128 and two FMAs before the gate.
+    long long hwait = 0;
+    bool gok = true;
+    auto gop_issue = [&](int l, int tt, const float* prow, float& prz, float& prc, unsigned long long& ha, unsigned long long& hb) {
+        prz = 0.f; prc = 0.f; ha = 0ull; hb = 0ull;
+        if (pf_lane && tt < P.n_it) {
+            prz = __ldg(prow + l * twoH); prc = __ldg(prow + l * twoH + H);
+            if (P.has_help[l] && tt >= P.hdmin[l]) {
+                const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + ((tt & (P.hacc_nt[l] - 1)) * twoH + my_i) * NC + sub;
+                ha = ld_ll(src); hb = ld_ll(src + H * NC);
+            }
+        }
+    };
+    auto gop_commit = [&](int l, int tt, float gain_tt, float prz, float prc, unsigned long long ha, unsigned long long hb,
+                          float rz, float rc) {
+        if (pf_lane && tt < P.n_it) {
+            float hz = 0.f, hc = 0.f;
+            if (P.has_help[l] && tt >= P.hdmin[l]) {
+                const uint32_t tg = (uint32_t)tt + 1u;
+                uint32_t a = (uint32_t)ha, b = (uint32_t)hb;
+                if ((uint32_t)(ha >> 32) != tg || (uint32_t)(hb >> 32) != tg) {      // the helper is late: wait for it here
+                    const long long tw0 = clock64();
+                    const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + ((tt & (P.hacc_nt[l] - 1)) * twoH + my_i) * NC + sub;
+                    gok = wait_gword(src, tg, a, P, 400 + l) && gok;
+                    gok = wait_gword(src + H * NC, tg, b, P, 400 + l) && gok;
+                    hwait += clock64() - tw0;
+                }
+                hz = __uint_as_float(a); hc = __uint_as_float(b);
+            }
+            const float4 c4 = lc[l * 16 + plocal];
+            const float pz = fmaf(gain_tt, prz, c4.x), pc = fmaf(gain_tt, prc, c4.y);
+            gop[(((tt & 1) * L + l) * 16 + plocal) * NC + sub] = make_float4(pz, (c4.z + rz + hz) * pz, pc, (c4.w + rc + hc) * pc);
+        }
+    };
+
     // ---- input stage: h0 rows of this CTA (row = i0 + warp), published into every peer's hx[0].
     // Scatter form again: the sample fed at time tau adds tap (K-1-d) into the partial sum of time tau+d
     // (cacc ring).  Lane d-1 handles delay d >= 1; delay 0 (the newest tap) is added at publish time from
@@ -650,7 +693,16 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                 st_ll(P.hin_ll + P.hin_off[0] + ((itn & (P.hslots[0] - 1)) * NC + c) * H + in_row, v, tagn);
         }
     };
+#if SWN_GOP
+    __syncthreads();                                               // lc[] is complete
+    for (int l = 0; l < L; ++l) {
+        float prz, prc; unsigned long long ha, hb;
+        gop_issue(l, 0, ptab_b, prz, prc, ha, hb);
+        gop_commit(l, 0, __ldg(P.gain), prz, prc, ha, hb, 0.f, 0.f);
+    }
+#else
     for (int l = 0; l < L; ++l) { prefetch_gate(l, 0, ptab_b); prefetch_help(l, 0); }
+#endif
     cp_async_commit();
     int fc = 0, jc = 0;                                            // frame / phase of the current time step
     input_publish(0);                                              // time 0 sees only its own (padding) sample
@@ -670,11 +722,12 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
         for (int c = 0; c < NC; ++c) { sk0[c] = 0.f; sk1[c] = 0.f; }
         float w[TCOLS];
         if (warp < 4) tmem_ldw<TCOLS>(taddr0 + P.tap_base[0] * TCOLS, w);
-        long long hwait = 0;
+        hwait = 0;
         const float gq = __ldg(P.gain + jc);
         int fn = fc, jn = jc;                                      // frame / phase of time t+1
         if (t + 1 > P.R && ++jn == P.U) { jn = 0; ++fn; }
         const float* prow_next = ptab_b + (size_t)fn * L * twoH;
+        const float gq_next = __ldg(P.gain + jn);
         // Gumbel noise of this warp's logit row: independent of the data, so it is drawn before the chain starts
         float gn[NC];
 #pragma unroll
@@ -697,6 +750,31 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
             const bool ld1 = P.dil[l] == 1;
             // ---- chain warps: gate operands that do not depend on the layer input (one pair group = 8 lanes)
             float pz = 0.f, pc = 0.f, hz = 0.f, hcv = 0.f, rz = 0.f, rc = 0.f, bz = 0.f, bc = 0.f;
+#if SWN_GOP
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (warp < 4 && pvalid && sub < NC) g4 = gop[((par * L + l) * 16 + plocal) * NC + sub];
+            if (false) {
+                const PreSlot ps = pre[((par * L + l) * 16 + plocal) * NC + sub];
+                const float4 c4 = lc[l * 16 + plocal];
+                pz = fmaf(gq, ps.pz, c4.x); pc = fmaf(gq, ps.pc, c4.y); bz = c4.z; bc = c4.w;
+                if (P.has_help[l] && t >= P.hdmin[l]) {
+                    uint32_t a = (uint32_t)ps.hz, b = (uint32_t)ps.hc;
+                    if ((uint32_t)(ps.hz >> 32) != tag || (uint32_t)(ps.hc >> 32) != tag) {
+                        // the helper was late when the prefetch was issued: wait for it here
+                        const long long tw0 = clock64();
+                        const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + ((t & (P.hacc_nt[l] - 1)) * twoH + my_i) * NC + sub;
+                        ok = wait_gword(src, tag, a, P, 400 + l) && ok;
+                        ok = wait_gword(src + H * NC, tag, b, P, 400 + l) && ok;
+                        hwait += clock64() - tw0;
+                    }
+                    hz = __uint_as_float(a); hcv = __uint_as_float(b);
+                }
+                if (ld1) {
+                    const float* r0 = ring + (((l * 2 + (int)par) * 16 + plocal) * 2) * BS + sub;
+                    rz = r0[0]; rc = r0[BS];
+                }
+            }
+#else
             if (warp < 4 && pvalid && sub < NC && !(SWN_ABL & 1024)) {
                 const PreSlot ps = pre[((par * L + l) * 16 + plocal) * NC + sub];
                 const float4 c4 = lc[l * 16 + plocal];
@@ -718,6 +796,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                     rz = r0[0]; rc = r0[BS];
                 }
             }
+#endif
             // ---- sleep until the layer input has landed in local shared memory
             SWN_CCLK(14);
 #if SWN_DEFER_BG
@@ -788,8 +867,13 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                 // ---- gate (cswnv_shift1.py:281-285), all columns at once (lane sub = column sub)
                 float hn = 0.f;
                 if (sub < NC) {
+#if SWN_GOP
+                    const float gz = fmaf(myqz, g4.x, g4.y);
+                    const float gc = fmaf(myqc, g4.z, g4.w);
+#else
                     const float gz = (myqz + bz + rz + hz) * pz;
                     const float gc = (myqc + bc + rc + hcv) * pc;
+#endif
                     // sigmoid / tanh through ex2.approx + rcp (abs. error ~1e-7, inside the 1e-4 head tolerance);
                     // both exponentials are independent, so their latencies overlap
 #if SWN_ABL & 4
@@ -849,7 +933,12 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                 SWN_CCLK(20);
             } else if (warp < 8) {
                 // ================= delay-1 tap of dilation-1 layers (for the next step) + operand prefetch =================
+#if SWN_GOP
+                float prz, prc, rz1 = 0.f, rc1 = 0.f; unsigned long long ha, hb;
+                gop_issue(l, t + 1, prow_next, prz, prc, ha, hb);
+#else
                 if (SWN_PFG_W == 4 && !(SWN_ABL & 32)) prefetch_gate(l, t + 1, prow_next);
+#endif
                 if (ld1 && K >= 2 && !(SWN_ABL & 8)) {
                     tmem_ldw<TCOLS>(taddr0 + (P.tap_base[l] + 1) * TCOLS, w);
                     tmem_wait_ld();
@@ -867,13 +956,23 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                             v8[rr] = a + b;
                         }
                         const float mine = reduce8(v8, lane);
+#if SWN_GOP
+                        // row (lane >> 2) = 2 * pair slot + {z, c}: hand both sums of the pair to the lane of column c
+                        const float mz = __shfl_sync(0xffffffffu, mine, lane & 24), mc = __shfl_sync(0xffffffffu, mine, (lane & 24) + 4);
+                        if (sub == c) { rz1 = mz; rc1 = mc; }
+#else
                         if ((lane & 3) == 0 && pvalid)             // row (lane >> 2) = 2 * pair slot + {z, c}
                             ring[(((l * 2 + (int)(par ^ 1u)) * 16 + plocal) * 2 + ((lane >> 2) & 1)) * BS + c] = mine;
+#endif
                     }
                 }
+#if SWN_GOP
+                gop_commit(l, t + 1, gq_next, prz, prc, ha, hb, rz1, rc1);
+#else
                 if (SWN_PFH_W == 4) prefetch_help(l, t + 1);
+#endif
             } else {
-                if (SWN_PFG_W != 4 && !(SWN_ABL & 32)) prefetch_gate(l, t + 1, prow_next);
+                if (!SWN_GOP && SWN_PFG_W != 4 && !(SWN_ABL & 32)) prefetch_gate(l, t + 1, prow_next);
 #if SWN_FWD_HELP
                 // the helpers of layer l get this CTA's rows of the layer input from here (one hop later than from the
                 // producing chain warp; the helpers have a whole step of slack).  Layer 0 is fed by the input stage.
@@ -896,7 +995,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                     for (int c = 0; c < NC; ++c) sk1[c] += dot_frag<NCH>(ws, h[c]);
                 }
                 }
-                if (SWN_PFH_W != 4) prefetch_help(l, t + 1);
+                if (!SWN_GOP && SWN_PFH_W != 4) prefetch_help(l, t + 1);
             }
             __syncwarp();
         }
@@ -907,8 +1006,9 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
         // (no CTA barrier here: nothing below depends on another warp's layer work, and the background warps' last
         // L2 loads would otherwise be exposed in front of the head; a failed wait is voted on at the end of the step)
         SWN_CPROF(7);
-        if (P.prof && threadIdx.x == 0 && it >= P.prof_start && it < P.prof_start + P.prof_count)
+        if (P.prof && threadIdx.x == (SWN_GOP ? 128 : 0) && it >= P.prof_start && it < P.prof_start + P.prof_count)
             P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + 13] = (unsigned long long)hwait;
+        ok = ok && gok;
         // the output of the last layer (always consumed, so that its barrier advances every step)
         ok = mbar_wait(mb + L, par, P, 510) && ok;
         if (tid == (SWN_HEAD2 ? 128 : 0)) mbar_arm(mb + L, bytes_h);

@@ -96,6 +96,22 @@ class Engine(object):
             self.sync()
         return out, heads
 
+    def teacher_forced(self, samples, sync=True):
+        """Per-step out_2 rows of the recurrence fed with `samples` (swn_teacher_forced): [B, n_gen // seg, head_dim]."""
+        info = self.info
+        seg, hd = info["eff_seg"], info["head_dim"]
+        is_c = self.kind == "cswnv"
+        t = torch.as_tensor(samples).to(self.device, torch.float32 if is_c else torch.int64).contiguous()
+        assert t.dim() == 2 and t.shape[0] == self._B, (tuple(t.shape), self._B)
+        n_gen = (int(t.shape[1]) // seg) * seg
+        assert n_gen == t.shape[1], "the number of samples must be a multiple of seg"
+        heads = torch.empty((self._B, n_gen // seg, hd), dtype=torch.float32, device=self.device)
+        _abi.check(self.lib.swn_teacher_forced(self.h, t.data_ptr(), n_gen, heads.data_ptr(), self._stream()))
+        self._keep = [t]
+        if sync:
+            self.sync()
+        return heads
+
     def sync(self):
         _abi.check(self.lib.swn_sync(self.h, self._stream()))
         self.info = self.get_info()

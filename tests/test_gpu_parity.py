@@ -74,6 +74,17 @@ def test_teacher_forced_matches_reference_fixture(name):
 
 
 @pytest.mark.parametrize("name", golden_names())
+def test_swn_teacher_forced_entry_point_matches_reference_fixture(name):
+    """swn_teacher_forced: the reference's own samples in, the reference's per-step out_2 rows out."""
+    g = load_golden(name)
+    m = _model_from_golden(g)
+    eng = m.engine()
+    eng.condition(torch.from_numpy(g["aux"]).cuda())
+    heads = eng.teacher_forced(g["samples"]).cpu().numpy()
+    _head_close(heads, g["heads"], name)
+
+
+@pytest.mark.parametrize("name", golden_names())
 def test_free_running_matches_reference_fixture(name):
     g = load_golden(name)
     m = _model_from_golden(g)
