@@ -234,6 +234,12 @@ __device__ __forceinline__ float reduce8(const float (&v)[8], int lane) {
 #ifndef SWN_ABL
 #define SWN_ABL 0            // dev only: ablation timing (tools/ab_build.sh), results are wrong when non-zero
 #endif
+#ifndef SWN_GN_TEAM
+#define SWN_GN_TEAM 1        // Gumbel noise drawn one step ahead by a few lanes of warps 8-11
+#endif
+#ifndef SWN_LDTM_EARLY
+#define SWN_LDTM_EARLY 0     // next layer's taps requested right after the FMA block instead of after the publish
+#endif
 #ifndef SWN_GOP
 #define SWN_GOP 1            // gate operands combined by the delay-1 warps one step ahead: one LDS.128 per stage in the chain
 #endif
@@ -450,6 +456,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
     float* cacc = reinterpret_cast<float*>(lc + L * 16);   // [8][16][NC]  input-stage partial sums by time slot
     float* cstage = cacc + 8 * 16 * NC;                    // [2][8][16][NC] gathered table entries in flight (cp.async)
     float* sfir = cstage + 2 * 8 * 16 * NC;                // CSWNV [8][2][16] FIR taps (cb, v) of this CTA's rows
+    float* gnz = sfir + 8 * 2 * 16;                        // DSWNV [2][16][NC] Gumbel noise of this CTA's logit rows (SWN_GN_TEAM)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + D.sm_tmem_slot);
     unsigned long long* mb = reinterpret_cast<unsigned long long*>(tmem_slot + 2);     // [L+1] h vectors, then x1, x2, gx
     unsigned long long* mb_x1 = mb + (L + 1), *mb_x2 = mb + (L + 2), *mb_gx = mb + (L + 3);
@@ -638,6 +645,22 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
         }
     };
 
+    // ---- SWN_GN_TEAM: the Gumbel noise of the CTA's 16 logit rows is drawn one step ahead by (16 * NC) lanes of warps
+    // 8-11 while the layers run, instead of by every warp for its own row at the top of the step (a Philox block and
+    // two logarithms per warp, on every scheduler, between the input publish and the first layer).
+    const bool gn_team = SWN_GN_TEAM && !is_c && D.nc <= 16;
+    auto draw_gumbel = [&](int isn) {
+        const int idx = (warp - 8) * 32 + lane;
+        if (gn_team && warp >= 8 && idx < 16 * NC) {
+            const int row = idx & 15, c = idx >> 4, bglob = min(c, P.B - 1);
+            if (row < D.nc) {
+                const float q = P.noise ? __ldg(P.noise + ((size_t)bglob * P.n_out + isn) * Q + D.c0 + row)
+                                        : softmax_q(P.seed, bglob, isn, D.c0 + row);
+                gnz[((isn & 1) * 16 + row) * NC + c] = -logf(q);
+            }
+        }
+    };
+
     // ---- input stage: h0 rows of this CTA (row = i0 + warp), published into every peer's hx[0].
     // Scatter form again: the sample fed at time tau adds tap (K-1-d) into the partial sum of time tau+d
     // (cacc ring).  Lane d-1 handles delay d >= 1; delay 0 (the newest tap) is added at publish time from
@@ -709,6 +732,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
     feed(0);
     cp_async_commit();
 
+    if (P.it0 == 0) draw_gumbel(0);                                // (made visible by the first step's CTA barrier)
     bool ok = true;
     for (int it = 0; it < P.n_it; ++it) {
         const bool active = it >= P.it0;
@@ -723,6 +747,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
         float w[TCOLS];
         if (warp < 4) tmem_ldw<TCOLS>(taddr0 + P.tap_base[0] * TCOLS, w);
         hwait = 0;
+        const bool prof_on = P.prof && threadIdx.x == 0 && it >= P.prof_start && it < P.prof_start + P.prof_count;
         const float gq = __ldg(P.gain + jc);
         int fn = fc, jn = jc;                                      // frame / phase of time t+1
         if (t + 1 > P.R && ++jn == P.U) { jn = 0; ++fn; }
@@ -732,7 +757,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
         float gn[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) gn[c] = 0.f;
-        if (active && !is_c && warp < D.nc) {
+        if (active && !is_c && warp < D.nc && !gn_team) {
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int bglob = min(c, P.B - 1);
@@ -746,6 +771,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
         fold_stage(it);                                            // table entries gathered for the sample of time `it`
         __syncthreads();                                           // pre[] (written by warps 4-7) is read by warps 0-3
         SWN_CPROF(0);
+        if (it + 1 >= P.it0 && it + 1 < P.n_it) draw_gumbel(it + 1 - P.it0);      // for the next step
         for (int l = 0; l < L; ++l) {
             const bool ld1 = P.dil[l] == 1;
             // ---- chain warps: gate operands that do not depend on the layer input (one pair group = 8 lanes)
@@ -831,7 +857,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
 #if !SWN_RELAY
             if (tid == (SWN_HEAD2 ? 128 : 0)) mbar_arm(mb + l, bytes_h);   // next phase (next time step); not by a chain warp
 #endif
-            if (l < 6) SWN_CPROF(1 + l);
+            if (prof_on && l < 6) P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + 1 + l] = gtime();
             float2 h[NC][NCH];
 #pragma unroll
             for (int c = 0; c < NC; ++c) load_frag<NCH>(h[c], hx + (((SWN_ABL & 2048) ? 0 : l) * NC + c) * HP, lane);
@@ -863,6 +889,10 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                     const float qz = (lane & 4) ? other : mine, qc = (lane & 4) ? mine : other;
                     if (sub == c) { myqz = qz; myqc = qc; }
                 }
+#if SWN_LDTM_EARLY
+                // the tap registers are dead from here on: the next layer's taps stream in behind the reduction and the gate
+                if (l + 1 < L) tmem_ldw<TCOLS>(taddr0 + P.tap_base[l + 1] * TCOLS, w);
+#endif
                 SWN_CCLK(17);
                 // ---- gate (cswnv_shift1.py:281-285), all columns at once (lane sub = column sub)
                 float hn = 0.f;
@@ -929,7 +959,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
 #if SWN_DEFER_BG
                 if (defer) named_bar_arrive(1 + (l % 15), SWN_NTHREADS);
 #endif
-                if (l + 1 < L && !(SWN_ABL & 512)) tmem_ldw<TCOLS>(taddr0 + P.tap_base[l + 1] * TCOLS, w);
+                if (!SWN_LDTM_EARLY && l + 1 < L && !(SWN_ABL & 512)) tmem_ldw<TCOLS>(taddr0 + P.tap_base[l + 1] * TCOLS, w);
                 SWN_CCLK(20);
             } else if (warp < 8) {
                 // ================= delay-1 tap of dilation-1 layers (for the next step) + operand prefetch =================
@@ -1118,6 +1148,10 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
             for (int cc = 0; cc < 4; ++cc)
                 wpre2[cc] = (warp < D.nc && cc * 64 < n1p) ? reinterpret_cast<const float2*>(sW2 + warp * n1p)[cc * 32 + lane] : make_float2(0.f, 0.f);
 #endif
+            if (gn_team && warp < D.nc) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) gn[c] = gnz[((istep & 1) * 16 + warp) * NC + c];
+            }
             if (warp < D.nc) ok = mbar_wait(mb_x2, hpar, P, 530) && ok;
             SWN_HCLK(24);
             if (warp < D.nc) {
