@@ -234,6 +234,9 @@ __device__ __forceinline__ float reduce8(const float (&v)[8], int lane) {
 #ifndef SWN_ABL
 #define SWN_ABL 0            // dev only: ablation timing (tools/ab_build.sh), results are wrong when non-zero
 #endif
+#ifndef SWN_ARM_BULK
+#define SWN_ARM_BULK 1       // layer barriers re-armed once per step (after the last one completed) instead of per stage
+#endif
 #ifndef SWN_GN_TEAM
 #define SWN_GN_TEAM 1        // Gumbel noise drawn one step ahead by a few lanes of warps 8-11
 #endif
@@ -772,13 +775,14 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
         __syncthreads();                                           // pre[] (written by warps 4-7) is read by warps 0-3
         SWN_CPROF(0);
         if (it + 1 >= P.it0 && it + 1 < P.n_it) draw_gumbel(it + 1 - P.it0);      // for the next step
+        const float4* gop_rd = gop + ((par * L) * 16 + plocal) * NC + sub;   // this lane's operands of layer 0
         for (int l = 0; l < L; ++l) {
             const bool ld1 = P.dil[l] == 1;
             // ---- chain warps: gate operands that do not depend on the layer input (one pair group = 8 lanes)
             float pz = 0.f, pc = 0.f, hz = 0.f, hcv = 0.f, rz = 0.f, rc = 0.f, bz = 0.f, bc = 0.f;
 #if SWN_GOP
             float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (warp < 4 && pvalid && sub < NC) g4 = gop[((par * L + l) * 16 + plocal) * NC + sub];
+            if (warp < 4 && pvalid && sub < NC) g4 = gop_rd[l * 16 * NC];
             if (false) {
                 const PreSlot ps = pre[((par * L + l) * 16 + plocal) * NC + sub];
                 const float4 c4 = lc[l * 16 + plocal];
@@ -855,7 +859,17 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
 #endif
             SWN_CCLK(15);
 #if !SWN_RELAY
+#if SWN_ARM_BULK
+            // next phase (next time step) of every layer barrier, armed in one go once the last of them has completed:
+            // a per-stage `if (tid == 128)` is predicated, and every warp pays for its operand loads
+            if (l == L - 1 && warp == 4) {
+                if (lane == 0)
+                    for (int i = 0; i < L; ++i) mbar_arm(mb + i, bytes_h);
+                __syncwarp();
+            }
+#else
             if (tid == (SWN_HEAD2 ? 128 : 0)) mbar_arm(mb + l, bytes_h);   // next phase (next time step); not by a chain warp
+#endif
 #endif
             if (prof_on && l < 6) P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + 1 + l] = gtime();
             float2 h[NC][NCH];
