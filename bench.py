@@ -321,6 +321,15 @@ def main():
                         "vs_hbm": {"peak": peaks.get("hbm_gbs"), "frac": (achieved / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
                                    "note": "weights are SMEM-resident; HBM is not the bound (frac>1 = residency pays)"},
                         "traffic": None}
+        # DRAM bytes per launch of the dominant kernel from one `ncu --set full` capture of this workload
+        # (dram__bytes_read.sum + dram__bytes_write.sum), recorded under profiles/; null when none was taken
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+            if cap and cap.get("kernel_variant") == variant:
+                roofline["traffic"] = cap["dram_bytes_per_launch"]
+                roofline["traffic_source"] = cap["source"]
+        except Exception:
+            pass
         line = dict(common)
         line.update({"value": value, "ms_per_step": total_ms / args.steps, "rtf": value / fs, "config": config,
                      "rtf_per_utterance": value / fs / (world * B),

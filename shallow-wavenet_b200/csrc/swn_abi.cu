@@ -332,8 +332,8 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
             lay.sm_x2 = take((size_t)NC * m->n1p);
             lay.sm_gx = take((size_t)NC * 256);
             lay.sm_pre = take((size_t)2 * L * 16 * NC * (sizeof(swn::PreSlot) / 4));
-            lay.sm_misc = take((size_t)NC * (16 + 8 + 16) + (size_t)L * 16 * 4 + (size_t)(8 * 16 + 2 * 8 * 16) * NC + 8 * 2 * 16 + (size_t)2 * 16 * NC);   // ... + Gumbel noise [2][16][NC]
-            lay.sm_tmem_slot = take(4 + 2 * (size_t)(2 * L + 8));  // TMEM base slot, L+4 exchange mbarriers, L+4 relay mbarriers
+            lay.sm_misc = take((size_t)NC * (16 + 8 + 16) + (size_t)L * 16 * 4 + (size_t)(8 * 16 + 2 * 8 * 16) * NC + 8 * 2 * 16 + (size_t)2 * 16 * NC + (size_t)2 * L * 2 * 16 * NC * 2);   // ... + Gumbel noise [2][16][NC] + helper words [2][L][2][16*NC] (u64)
+            lay.sm_tmem_slot = take(4 + 2 * (size_t)(3 * L + 8));  // TMEM base slot, L+4 exchange mbarriers, L relay, L helper-copy mbarriers
             core_used = u;
             for (auto& q : m->ccta) {
                 q.sm_skip = lay.sm_skip; q.sm_w1 = lay.sm_w1; q.sm_w2 = lay.sm_w2; q.sm_tin = lay.sm_tin;

@@ -136,6 +136,10 @@ __device__ __forceinline__ void st_async_f32x2(uint32_t remote_addr, float lo, f
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
                  ::"r"(remote_addr), "l"(w), "r"(remote_mbar) : "memory");
 }
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_all(uint32_t* slot) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -233,6 +237,9 @@ __device__ __forceinline__ float reduce8(const float (&v)[8], int lane) {
 
 #ifndef SWN_ABL
 #define SWN_ABL 0            // dev only: ablation timing (tools/ab_build.sh), results are wrong when non-zero
+#endif
+#ifndef SWN_HBULK
+#define SWN_HBULK 0          // helper sums brought in by bulk copies (TMA): 10.99 vs 8.88 us per step - the latency of a small bulk copy exceeds the stage
 #endif
 #ifndef SWN_ARM_BULK
 #define SWN_ARM_BULK 1       // layer barriers re-armed once per step (after the last one completed) instead of per stage
@@ -464,6 +471,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
     unsigned long long* mb = reinterpret_cast<unsigned long long*>(tmem_slot + 2);     // [L+1] h vectors, then x1, x2, gx
     unsigned long long* mb_x1 = mb + (L + 1), *mb_x2 = mb + (L + 2), *mb_gx = mb + (L + 3);
     unsigned long long* mbg = mb + (L + 4);                // [L] relay barriers (SWN_RELAY)
+    unsigned long long* mbh = mbg + L;                     // [L] completion of the helper-sum bulk copies (SWN_HBULK)
     const uint32_t bytes_h = (uint32_t)(H * NC * 4), bytes_x1 = (uint32_t)(S * NC * 4), bytes_x2 = (uint32_t)(n1 * NC * 4),
                    bytes_gx = (uint32_t)(Q * NC * 4);
 
@@ -503,7 +511,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
     }
     if (tid == 0) {
         for (int i = 0; i < L + 4; ++i) mbar_init(mb + i, 1);
-        for (int i = 0; i < L; ++i) mbar_init(mbg + i, 1);
+        for (int i = 0; i < L; ++i) { mbar_init(mbg + i, 1); mbar_init(mbh + i, 1); }
         mbar_fence_init();
         for (int i = 0; i <= L; ++i) mbar_arm(mb + i, bytes_h);          // phase 0 of every vector
         mbar_arm(mb_x1, bytes_x1); mbar_arm(mb_x2, bytes_x2); mbar_arm(mb_gx, bytes_gx);
@@ -616,14 +624,27 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
     // in gop[tt & 1][l][pair][col]; the chain warp's stage then needs one LDS.128 and two FMAs before the gate.
     long long hwait = 0;
     bool gok = true;
+    // SWN_HBULK: the helper sums of this CTA's rows are two contiguous runs of {value, tag} words (z rows, c rows); one
+    // lane asks for them with two bulk copies (L2 -> shared memory, no L1, no registers, no blocked warp) and the
+    // committing lanes sleep on the copy barrier
+    unsigned long long* hst = reinterpret_cast<unsigned long long*>(gnz + 2 * 16 * NC);   // [2][L][2][16 * NC]
+    const bool hbulk = SWN_HBULK && ((D.pair0 * NC) & 1) == 0 && ((np * NC) & 1) == 0;
     auto gop_issue = [&](int l, int tt, const float* prow, float& prz, float& prc, unsigned long long& ha, unsigned long long& hb) {
         prz = 0.f; prc = 0.f; ha = 0ull; hb = 0ull;
         if (pf_lane && tt < P.n_it) {
             prz = __ldg(prow + l * twoH); prc = __ldg(prow + l * twoH + H);
-            if (P.has_help[l] && tt >= P.hdmin[l]) {
+            if (!hbulk && P.has_help[l] && tt >= P.hdmin[l]) {
                 const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + ((tt & (P.hacc_nt[l] - 1)) * twoH + my_i) * NC + sub;
                 ha = ld_ll(src); hb = ld_ll(src + H * NC);
             }
+        }
+        if (hbulk && tid == 128 && tt < P.n_it && P.has_help[l] && tt >= P.hdmin[l]) {
+            const uint32_t bytes = (uint32_t)(np * NC * 8);
+            const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + ((tt & (P.hacc_nt[l] - 1)) * twoH + D.pair0) * NC;
+            unsigned long long* dst = hst + (size_t)(((tt & 1) * L + l) * 2) * 16 * NC;
+            mbar_arm(mbh + l, 2 * bytes);
+            bulk_g2s(dst, src, bytes, mbh + l);
+            bulk_g2s(dst + 16 * NC, src + H * NC, bytes, mbh + l);
         }
     };
     auto gop_commit = [&](int l, int tt, float gain_tt, float prz, float prc, unsigned long long ha, unsigned long long hb,
@@ -632,6 +653,11 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
             float hz = 0.f, hc = 0.f;
             if (P.has_help[l] && tt >= P.hdmin[l]) {
                 const uint32_t tg = (uint32_t)tt + 1u;
+                if (hbulk) {
+                    gok = mbar_wait(mbh + l, (uint32_t)(tt - P.hdmin[l]) & 1u, P, 700 + l) && gok;
+                    const unsigned long long* d = hst + (size_t)(((tt & 1) * L + l) * 2) * 16 * NC + plocal * NC + sub;
+                    ha = d[0]; hb = d[16 * NC];
+                }
                 uint32_t a = (uint32_t)ha, b = (uint32_t)hb;
                 if ((uint32_t)(ha >> 32) != tg || (uint32_t)(hb >> 32) != tg) {      // the helper is late: wait for it here
                     const long long tw0 = clock64();
