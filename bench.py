@@ -153,6 +153,18 @@ def main():
     ap.add_argument("--cpu-sample-frames", type=int, default=0)
     args = ap.parse_args()
 
+    # stdout carries exactly ONE line (the JSON of rank 0): whatever libraries print there while the run is going on
+    # (NCCL's "NCCL version ..." banner when NCCL_DEBUG=VERSION is set on the box) is sent to stderr instead
+    sys.stdout.flush()
+    _stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(_stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -191,7 +203,7 @@ def main():
                                       "torch_threads": torch.get_num_threads()},
                      "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                      "gpu_launches": 0})
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -348,7 +360,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
                                     "sample": "oracle port of batch_fast_generate, B=1, %d samples (+ the %d-step warm-up), "
                                               "%.1f s wall" % (n, info["receptive_field"] + 1, dt)}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
