@@ -189,6 +189,29 @@ __device__ __forceinline__ void tmem_ldw(uint32_t a, float (&r)[N]) {
     for (int i = 0; i < N; i += 16) tmem_ld16(a + i, &r[i]);
 }
 
+// SWN_LANE8: both rows (z, candidate) of a gate pair live in the 8 lanes of the pair group, lane `sub` holding the
+// weights of k = 4 * (sub + 8 * i) .. + 3, i < 2 * NCH.  w[zc * 8 * NCH + 4 * i + j]; the layer input is read as
+// float4 (the four pair groups read the same 128 bytes: broadcast).  Totals end up in all 8 lanes after 3 butterflies.
+template <int NCH>
+__device__ __forceinline__ void lane8_dot(const float* w, const float* hvec, int sub, float& tz, float& tc) {
+    float az[4] = {0.f, 0.f, 0.f, 0.f}, ac[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 2 * NCH; ++i) {
+        const float4 hv = reinterpret_cast<const float4*>(hvec)[sub + 8 * i];
+        az[0] = fmaf(w[4 * i + 0], hv.x, az[0]); ac[0] = fmaf(w[8 * NCH + 4 * i + 0], hv.x, ac[0]);
+        az[1] = fmaf(w[4 * i + 1], hv.y, az[1]); ac[1] = fmaf(w[8 * NCH + 4 * i + 1], hv.y, ac[1]);
+        az[2] = fmaf(w[4 * i + 2], hv.z, az[2]); ac[2] = fmaf(w[8 * NCH + 4 * i + 2], hv.z, ac[2]);
+        az[3] = fmaf(w[4 * i + 3], hv.w, az[3]); ac[3] = fmaf(w[8 * NCH + 4 * i + 3], hv.w, ac[3]);
+    }
+    float z = (az[0] + az[1]) + (az[2] + az[3]), c = (ac[0] + ac[1]) + (ac[2] + ac[3]);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        z += __shfl_xor_sync(0xffffffffu, z, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    tz = z; tc = c;
+}
+
 // Sum 8 per-lane partials over the 32 lanes: afterwards lane L holds the total of value (L >> 2)
 // (9 shuffles instead of 40).
 __device__ __forceinline__ float reduce8(const float (&v)[8], int lane) {
@@ -237,6 +260,12 @@ __device__ __forceinline__ float reduce8(const float (&v)[8], int lane) {
 
 #ifndef SWN_ABL
 #define SWN_ABL 0            // dev only: ablation timing (tools/ab_build.sh), results are wrong when non-zero
+#endif
+#ifndef SWN_LANE8
+#define SWN_LANE8 0          // chain / delay-1 warps: a row is spread over the 8 lanes of its pair group (3-level reductions)
+#endif
+#ifndef SWN_LANE8_GUARD
+#define SWN_LANE8_GUARD 0
 #endif
 #ifndef SWN_HBULK
 #define SWN_HBULK 0          // helper sums brought in by bulk copies (TMA): 10.99 vs 8.88 us per step - the latency of a small bulk copy exceeds the stage
@@ -524,6 +553,25 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
     const uint32_t taddr0 = tbase + ((uint32_t)(32 * quarter) << 16);
     // ---- tensor memory <- the core taps: warp q < 4 fills its lane quarter with the taps of gate pairs 4q..4q+3
     // (thread-private columns: tap c occupies columns [c*TCOLS, (c+1)*TCOLS), row rr = 2*pair + {z,c} at rr*FPT)
+#if SWN_LANE8
+    if (warp < 4) {
+        for (int c = 0; c < P.n_core_taps; ++c) {
+#pragma unroll
+            for (int zc = 0; zc < 2; ++zc) {
+#pragma unroll
+                for (int i = 0; i < 2 * NCH; ++i) {
+                    const int pl = 4 * quarter + (lane >> 3);
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (pl < np)
+                        a = reinterpret_cast<const float4*>(P.wbuf + D.tap_off + ((size_t)(c * np + pl) * 2 + zc) * HP)[(lane & 7) + 8 * i];
+                    const float wv[4] = {a.x, a.y, a.z, a.w};
+                    tmem_st4(taddr0 + c * TCOLS + zc * 8 * NCH + 4 * i, wv);
+                }
+            }
+        }
+        tmem_wait_st();
+    }
+#else
     if (warp < 4) {
         for (int c = 0; c < P.n_core_taps; ++c) {
 #pragma unroll
@@ -542,6 +590,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
         }
         tmem_wait_st();
     }
+#endif
     if (P.seedw) {
         for (int e = tid; e < NC; e += SWN_NTHREADS) {
             const int bglob = min(e, P.B - 1);
@@ -900,12 +949,21 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
             if (prof_on && l < 6) P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + 1 + l] = gtime();
             float2 h[NC][NCH];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) load_frag<NCH>(h[c], hx + (((SWN_ABL & 2048) ? 0 : l) * NC + c) * HP, lane);
+            for (int c = 0; c < NC; ++c)
+                if (!(SWN_LANE8 && SWN_GOP && SWN_LANE8_GUARD) || warp >= 8) load_frag<NCH>(h[c], hx + (((SWN_ABL & 2048) ? 0 : l) * NC + c) * HP, lane);
             if (warp < 4) {
                 // ================= chain warp: delay-0 tap of 4 gate pairs, gate, publish =================
                 tmem_wait_ld();
                 SWN_CCLK(16);
                 float myqz = 0.f, myqc = 0.f;                      // lane (pair group, sub = column) keeps its column's sums
+#if SWN_LANE8
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    float qz, qc;
+                    lane8_dot<NCH>(w, hx + (l * NC + c) * HP, sub, qz, qc);
+                    if (sub == c) { myqz = qz; myqc = qc; }
+                }
+#else
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     float v8[8];
@@ -929,6 +987,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                     const float qz = (lane & 4) ? other : mine, qc = (lane & 4) ? mine : other;
                     if (sub == c) { myqz = qz; myqc = qc; }
                 }
+#endif
 #if SWN_LDTM_EARLY
                 // the tap registers are dead from here on: the next layer's taps stream in behind the reduction and the gate
                 if (l + 1 < L) tmem_ldw<TCOLS>(taddr0 + P.tap_base[l + 1] * TCOLS, w);
@@ -1012,6 +1071,14 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                 if (ld1 && K >= 2 && !(SWN_ABL & 8)) {
                     tmem_ldw<TCOLS>(taddr0 + (P.tap_base[l] + 1) * TCOLS, w);
                     tmem_wait_ld();
+#if SWN_LANE8 && SWN_GOP
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        float mz, mc;
+                        lane8_dot<NCH>(w, hx + (l * NC + c) * HP, sub, mz, mc);
+                        if (sub == c) { rz1 = mz; rc1 = mc; }
+                    }
+#else
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         float v8[8];
@@ -1035,6 +1102,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                             ring[(((l * 2 + (int)(par ^ 1u)) * 16 + plocal) * 2 + ((lane >> 2) & 1)) * BS + c] = mine;
 #endif
                     }
+#endif
                 }
 #if SWN_GOP
                 gop_commit(l, t + 1, gq_next, prz, prc, ha, hb, rz1, rc1);
