@@ -22,6 +22,9 @@
 #pragma once
 #include "swn_gen.cuh"
 
+#ifndef B3_GATE1
+#define B3_GATE1 0       // gate with one reciprocal (gate_out, swn_gen.cuh): no gain measured in this kernel (78.99 vs 78.10 ms on cfg3s)
+#endif
 namespace swn {
 
 constexpr int B3_NGW = 4;                 // GEMM warps 0..3 (one per SM sub-partition)
@@ -947,13 +950,17 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                 }
                 // sigmoid / tanh through ex2.approx + rcp (abs. error ~1e-7, inside the 1e-4 head tolerance)
                 const float gz = qz * v.x, gc = qc * v.y;
-                const float ez = __expf(-gz), ec = __expf(-2.f * fabsf(gc));
-                const float z = __frcp_rn(1.f + ez);
-                const float th = copysignf((1.f - ec) * __frcp_rn(1.f + ec), gc);
                 float carry;
                 if (umma) { const int xo = b3_uoff(col, D.pair0 + pi, NP); carry = X[xo] + X[utile + xo]; }
                 else carry = X[(D.pair0 + pi) * NC + col];
+#if B3_GATE1
+                hv = gate_out(gz, gc, carry);
+#else
+                const float ez = __expf(-gz), ec = __expf(-2.f * fabsf(gc));
+                const float z = __frcp_rn(1.f + ez);
+                const float th = copysignf((1.f - ec) * __frcp_rn(1.f + ec), gc);
                 hv = (1.f - z) * th + z * carry;
+#endif
             }
             if (!D.is_last) {
                 if (umma) {      // exact split into tf32 halves for the next cell's tensor-core passes

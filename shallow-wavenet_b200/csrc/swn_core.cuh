@@ -303,8 +303,6 @@ __device__ __forceinline__ float reduce8(const float (&v)[8], int lane) {
 #ifndef SWN_GATE1
 #define SWN_GATE1 1          // gate with one reciprocal (see the chain warp)
 #endif
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #ifndef SWN_HELP_L2
 #define SWN_HELP_L2 1        // helper sums fetched with L2-scope loads instead of cp.async.ca (stale L1 lines)
 #endif

@@ -130,6 +130,18 @@ __device__ __forceinline__ float dot_row(const float* __restrict__ wrow, const f
     return a + b;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// Gated-cell output (1 - z) tanh(gc) + z carry with z = sigmoid(gz) (cswnv_shift1.py:276-278), over one common
+// denominator: [ez sgn(gc) (1 - ec) + carry (1 + ec)] / [(1 + ez)(1 + ec)], ez = exp(-gz) (capped: gz >= -30),
+// ec = exp(-2|gc|).  Two ex2.approx and one rcp.approx on the dependent chain (abs. error ~1e-7).
+__device__ __forceinline__ float gate_out(float gz, float gc, float carry) {
+    const float ez = ex2_approx(fmaxf(gz, -30.f) * -1.4426950408889634f);
+    const float ec = ex2_approx(fabsf(gc) * -2.8853900817779268f);
+    const float den = (1.f + ez) * (1.f + ec);
+    const float num = fmaf(ez, copysignf(1.f - ec, gc), carry * (1.f + ec));
+    return num * rcp_approx(den);
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 __device__ __forceinline__ float softsignf_(float x) { return x / (1.f + fabsf(x)); }
 
