@@ -53,6 +53,7 @@ struct HelpCta {                   // one per helper CTA
 struct CoreParams {
     int32_t kind, H, Hp, S, Sp, K, L, lpc, n1, n1p, n2, Q, U, R, B, Tf;
     int32_t it0, n_it, n_iter, n_core_taps, n_help, audio_in;
+    int32_t b0, pad_b0;            // index of this launch's first utterance in the caller's batch (Philox counter)
     int64_t n_out;
     int32_t dil[16];
     int32_t tap_base[16];          // first core tap index of layer l (tap 0 = delay 0, tap 1 = delay 1)
@@ -731,7 +732,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
             const int row = idx & 15, c = idx >> 4, bglob = min(c, P.B - 1);
             if (row < D.nc) {
                 const float q = P.noise ? __ldg(P.noise + ((size_t)bglob * P.n_out + isn) * Q + D.c0 + row)
-                                        : softmax_q(P.seed, bglob, isn, D.c0 + row);
+                                        : softmax_q(P.seed, P.b0 + bglob, isn, D.c0 + row);
                 gnz[((isn & 1) * 16 + row) * NC + c] = -logf(q);
             }
         }
@@ -838,7 +839,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
             for (int c = 0; c < NC; ++c) {
                 const int bglob = min(c, P.B - 1);
                 const float q = P.noise ? __ldg(P.noise + ((size_t)bglob * P.n_out + istep) * Q + D.c0 + warp)
-                                        : softmax_q(P.seed, bglob, istep, D.c0 + warp);
+                                        : softmax_q(P.seed, P.b0 + bglob, istep, D.c0 + warp);
                 gn[c] = -logf(q);
             }
         }
@@ -1307,7 +1308,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                 if (tid < NC) {
                     const int c = tid, bglob = min(c, P.B - 1);
                     float eps[1], smp[1];
-                    eps[0] = P.noise ? P.noise[(size_t)bglob * P.n_out + istep] : laplace_eps(P.seed, bglob, istep);
+                    eps[0] = P.noise ? P.noise[(size_t)bglob * P.n_out + istep] : laplace_eps(P.seed, P.b0 + bglob, istep);
                     const float* forced = P.forced ? (const float*)P.forced + (size_t)bglob * P.n_out + istep : nullptr;
                     laplace_step<1>(P.lpc, o2 + c * 16, lpb + c * 8, eps, forced, smp);
                     hist[c * HIST + (istep % HIST)] = forced ? forced[0] : smp[0];

@@ -245,6 +245,30 @@ def test_philox_stream_is_reproducible_and_matches_host_replica():
     assert np.abs(x).max() <= 1.0
 
 
+@pytest.mark.parametrize("B", [3, 4, 7])
+def test_small_batches_go_through_the_cluster_kernel_two_at_a_time(B):
+    """3-7 utterances (DSWNV): launches of two through the cluster kernel.  Heads against the oracle, the sampled
+    indices against the host replica of the Philox stream (the utterance index of a later launch must be the global one)."""
+    g = load_golden("dswnv_base")
+    m = _model_from_golden(g)
+    rng = np.random.default_rng(100 + B)
+    Tf = 3
+    U = g["kw"]["upsampling_factor"]
+    N = Tf * U
+    aux = rng.standard_normal((B, g["kw"]["n_aux"], Tf)).astype(np.float32)
+    forced = rng.integers(0, 256, (B, N)).astype(np.int64)
+    outs, heads = m.batch_fast_generate(torch.full((B, 1), 128, dtype=torch.long), torch.from_numpy(aux), [N] * B,
+                                        forced=forced, seed=77, return_heads=True)
+    info = m.engine().info
+    assert info["kernel_variant"] == 2 and info["batch_tile"] == 2 and info["n_slots"] == -(-B // 2), info
+    _head_close(heads, O.teacher_forced(g["cfg"], g["sd"], aux, forced), "chunked B=%d" % B)
+    from shallow_wavenet_b200.engine import philox_uniform
+    for b in range(B):
+        u = philox_uniform(77, "dswnv", b, 0, N).reshape(N, 256)
+        gum = heads[b] - np.log(-np.log1p(-u.astype(np.float64))).astype(np.float32)
+        assert (gum.argmax(-1) != outs[b]).mean() < 5e-3, b
+
+
 def test_edge_cases_and_errors():
     from shallow_wavenet_b200._abi import SwnError
     g = load_golden("cswnv_seg5_lpc4_wav")
