@@ -857,27 +857,6 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
 #if SWN_GOP
             float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (warp < 4 && pvalid && sub < NC) g4 = gop_rd[l * 16 * NC];
-            if (false) {
-                const PreSlot ps = pre[((par * L + l) * 16 + plocal) * NC + sub];
-                const float4 c4 = lc[l * 16 + plocal];
-                pz = fmaf(gq, ps.pz, c4.x); pc = fmaf(gq, ps.pc, c4.y); bz = c4.z; bc = c4.w;
-                if (P.has_help[l] && t >= P.hdmin[l]) {
-                    uint32_t a = (uint32_t)ps.hz, b = (uint32_t)ps.hc;
-                    if ((uint32_t)(ps.hz >> 32) != tag || (uint32_t)(ps.hc >> 32) != tag) {
-                        // the helper was late when the prefetch was issued: wait for it here
-                        const long long tw0 = clock64();
-                        const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + ((t & (P.hacc_nt[l] - 1)) * twoH + my_i) * NC + sub;
-                        ok = wait_gword(src, tag, a, P, 400 + l) && ok;
-                        ok = wait_gword(src + H * NC, tag, b, P, 400 + l) && ok;
-                        hwait += clock64() - tw0;
-                    }
-                    hz = __uint_as_float(a); hcv = __uint_as_float(b);
-                }
-                if (ld1) {
-                    const float* r0 = ring + (((l * 2 + (int)par) * 16 + plocal) * 2) * BS + sub;
-                    rz = r0[0]; rc = r0[BS];
-                }
-            }
 #else
             if (warp < 4 && pvalid && sub < NC && !(SWN_ABL & 1024)) {
                 const PreSlot ps = pre[((par * L + l) * 16 + plocal) * NC + sub];
