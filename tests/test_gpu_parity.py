@@ -111,7 +111,7 @@ def _recipe_case(kind, fs, B, frames, seed, **over):
     return model.cuda(), cfg, sd, aux, kw
 
 
-@pytest.mark.parametrize("seg,lpc,B", [(5, 4, 1), (5, 4, 3), (1, 4, 2), (2, 0, 1), (10, 4, 1)])
+@pytest.mark.parametrize("seg,lpc,B", [(5, 4, 1), (5, 4, 3), (1, 4, 2), (1, 4, 3), (1, 0, 4), (2, 0, 1), (10, 4, 1)])
 def test_recipe_size_cswnv_teacher_forced_vs_oracle(seg, lpc, B):
     model, cfg, sd, aux, kw = _recipe_case("cswnv", 22050, B, 2, 7, seg=seg, lpc=lpc)
     N = 2 * kw["upsampling_factor"]
@@ -133,6 +133,15 @@ def test_recipe_size_cswnv_teacher_forced_vs_oracle(seg, lpc, B):
         if lpc:
             lp = torch.cat((lp, ft[:, i * seg:(i + 1) * seg]), 1)[:, -lpc:]
     assert float(np.abs(np.stack(outs) - ref).max()) <= SAMPLE_ATOL
+    if seg == 1 and B >= 3:
+        # launches of two through the cluster kernel; the Philox draws of a later launch use the global utterance index
+        info = model.engine().info
+        assert info["kernel_variant"] == 2 and info["batch_tile"] == 2 and info["n_slots"] == -(-B // 2), info
+        from shallow_wavenet_b200.engine import philox_uniform
+        eps = np.stack([np.float32(-0.4999) + np.float32(0.9999) * philox_uniform(9, "cswnv", b, 0, N) for b in range(B)])
+        a = np.stack(model.batch_fast_generate(torch.zeros(B, seg), torch.from_numpy(aux), [N] * B, seed=9))
+        b_ = np.stack(model.batch_fast_generate(torch.zeros(B, seg), torch.from_numpy(aux), [N] * B, noise=eps.astype(np.float32)))
+        assert float(np.abs(a - b_).max()) <= 1e-6
 
 
 @pytest.mark.parametrize("fs,B", [(16000, 1), (24000, 3)])

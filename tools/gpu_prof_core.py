@@ -8,12 +8,13 @@ from shallow_wavenet_b200 import synth
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2s"
 kind, fs, over, B, frames, desc = bench.WORKLOADS[wl]
+B = int(os.environ.get("SWN_PROF_B", B))          # e.g. SWN_PROF_B=2: the two-column instantiation
 kw = bench.model_kwargs(kind, fs, over)
 model = synth.make_model(kind, **kw).cuda()
 aux = torch.from_numpy(synth.synth_aux(kw["n_aux"], frames, B)).cuda()
 eng = model.engine()
 n = frames * kw["upsampling_factor"]
-for sel in (2, 1):
+for sel in ((2,) if os.environ.get("SWN_PROF_B") else (2, 1)):
     eng.condition(aux)
     try:
         eng.generate(n, seed=1, kernel_sel=sel)
