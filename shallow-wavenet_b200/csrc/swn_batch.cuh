@@ -950,15 +950,18 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                 }
                 // sigmoid / tanh through ex2.approx + rcp (abs. error ~1e-7, inside the 1e-4 head tolerance)
                 const float gz = qz * v.x, gc = qc * v.y;
+#if B3_GATE1
                 float carry;
                 if (umma) { const int xo = b3_uoff(col, D.pair0 + pi, NP); carry = X[xo] + X[utile + xo]; }
                 else carry = X[(D.pair0 + pi) * NC + col];
-#if B3_GATE1
                 hv = gate_out(gz, gc, carry);
 #else
                 const float ez = __expf(-gz), ec = __expf(-2.f * fabsf(gc));
                 const float z = __frcp_rn(1.f + ez);
                 const float th = copysignf((1.f - ec) * __frcp_rn(1.f + ec), gc);
+                float carry;
+                if (umma) { const int xo = b3_uoff(col, D.pair0 + pi, NP); carry = X[xo] + X[utile + xo]; }
+                else carry = X[(D.pair0 + pi) * NC + col];
                 hv = (1.f - z) * th + z * carry;
 #endif
             }
