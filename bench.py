@@ -10,9 +10,10 @@ BASELINE.json configs[1] (DSWNV mu-law softmax, 16 kHz, batch 1, 5 s); with ``--
 rank generates its own copy of that workload (utterances shard with no collective: weak
 scaling).  Rank 0 prints ONE JSON line.
 
-``--impl reference`` times the CPU port of the reference's algorithm (``oracle/``; the Python
-reference itself cannot travel to the GPU box) on the host cores, on a bounded sample of the
-same workload.
+``--impl reference`` times the UNMODIFIED reference (``oracle/_ref``: a verbatim, git-ignored
+copy of its two ``src/nets`` modules made by ``__graft_entry__.build()``; it travels to the GPU
+box with the snapshot) on the host cores, on a bounded sample of the same workload; only when
+that copy is missing does it fall back to the oracle port, and says so (``kind: "port"``).
 """
 import argparse
 import json
@@ -119,18 +120,21 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _cpu_inputs(kind, kw, frames, sample_frames):
+    from shallow_wavenet_b200 import synth
+    model = synth.make_model(kind, **kw)
+    sd = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+    aux = synth.synth_aux(kw["n_aux"], frames, 1)[:, :, :sample_frames]
+    return sd, np.ascontiguousarray(aux), sample_frames * kw["upsampling_factor"]
+
+
 def cpu_port_run(kind, kw, frames, sample_frames, threads):
     """Time the CPU port of the reference algorithm (oracle) on a bounded sample of the workload."""
     import torch
     from oracle import swn_oracle as O
-    from shallow_wavenet_b200 import synth
     torch.set_num_threads(threads)
-    model = synth.make_model(kind, **kw)
-    sd = {k: v.detach().numpy() for k, v in model.state_dict().items()}
-    okw = dict(kw)
-    cfg = O.SWNConfig(kind=kind, **okw)
-    aux = synth.synth_aux(kw["n_aux"], frames, 1)[:, :, :sample_frames]
-    n = sample_frames * kw["upsampling_factor"]
+    sd, aux, n = _cpu_inputs(kind, kw, frames, sample_frames)
+    cfg = O.SWNConfig(kind=kind, **dict(kw))
     rng = np.random.default_rng(0)
     if kind == "cswnv":
         noise = rng.uniform(-0.4999, 0.5, (1, n)).astype(np.float32)
@@ -140,6 +144,55 @@ def cpu_port_run(kind, kw, frames, sample_frames, threads):
     O.generate(cfg, sd, aux, n, noise)
     dt = time.perf_counter() - t0
     return n / dt, n, dt
+
+
+_REF_MODELS = {}
+
+
+def cpu_reference_run(kind, kw, frames, sample_frames, threads):
+    """Time the UNMODIFIED reference (oracle/_ref copy of src/nets, or /root/reference in the build container):
+    ``batch_fast_generate`` on the host CPU, model and inputs on the CPU (the .cuda() identity shim of SURVEY.md 8c),
+    wall time around the call as decode_cswnv_laplace-shift1.py:246-249 does, on a bounded sample of the workload."""
+    import torch
+    from oracle import ref_runner as RR
+    torch.set_num_threads(threads)
+    sd, aux, n = _cpu_inputs(kind, kw, frames, sample_frames)
+    key = (kind, tuple(sorted(kw.items())))
+    if key not in _REF_MODELS:
+        _REF_MODELS[key] = RR.build_model(kind, kw, sd)
+    torch.manual_seed(1)
+    out, _, dt = RR.generate(kind, kw, _REF_MODELS[key], aux, [n])
+    assert len(out) == 1 and len(out[0]) == (n // (kw.get("seg", 1) if kind == "cswnv" else 1)) * (kw.get("seg", 1) if kind == "cswnv" else 1)
+    return n / dt, n, dt
+
+
+def cpu_arm(kind, kw, frames, sample_frames, threads):
+    """(value, n, seconds, kind): the reference itself when its modules are here, else the oracle port (labelled)."""
+    from oracle import ref_runner as RR
+    if RR.available():
+        return cpu_reference_run(kind, kw, frames, sample_frames, threads) + ("reference",)
+    return cpu_port_run(kind, kw, frames, sample_frames, threads) + ("port",)
+
+
+def cpu_baseline_record(kind, kw, frames, sample_frames, receptive_field):
+    """cpu_baseline of the B200 line: all host cores and 1 thread, CPU model stated; the oracle
+    port is reported beside the reference as a second, labelled figure."""
+    import torch
+    from oracle import ref_runner as RR
+    threads = os.cpu_count() or 1
+    v, n, dt, k = cpu_arm(kind, kw, frames, sample_frames, threads)
+    v1, n1, dt1, _ = cpu_arm(kind, kw, frames, max(1, sample_frames // 2), 1)
+    rec = {"value": v, "unit": "samples/s", "cores": threads, "kind": k,
+           "sample": "%s batch_fast_generate on the host CPU, B=1, %d samples (+ the %d-column warm-up), %.1f s wall" % (
+               "unmodified reference" if k == "reference" else "oracle port of", n, receptive_field + 1, dt),
+           "value_1_thread": v1, "sample_1_thread": "%d samples, %.1f s wall" % (n1, dt1),
+           "cpu_model": RR.cpu_model_name(), "nproc": threads, "torch": torch.__version__}
+    if k == "reference":
+        pv, pn, pdt = cpu_port_run(kind, kw, frames, sample_frames, threads)
+        rec["port_value"] = pv
+        rec["port_note"] = "oracle/swn_oracle.py (fixed-size history windows instead of the reference's growing torch.cat), same sample"
+    torch.set_num_threads(threads)
+    return rec
 
 
 def main():
@@ -185,22 +238,29 @@ def main():
         if rank != 0:
             return 0
         import torch
+        from oracle import ref_runner as RR
         threads = os.cpu_count() or 1
-        sf = args.cpu_sample_frames or (40 if kind == "dswnv" else 20)
+        # bounded sample per step: the reference generates O(10^2) samples/s at recipe size, so a step is a few
+        # frames of the workload (3 frames = 240 samples for DSWNV, 10 frames = 1100 samples for CSWNV seg 5)
+        sf = args.cpu_sample_frames or (3 if kind == "dswnv" else 10)
         vals = []
         n = 0
+        arm_kind = "port"
         for i in range(args.warmup + args.steps):
-            v, n, dt = cpu_port_run(kind, kw, frames, sf, threads)
+            v, n, dt, arm_kind = cpu_arm(kind, kw, frames, sf, threads)
             if i >= args.warmup:
                 vals.append((v, dt))
+        v1, n1, dt1, _ = cpu_arm(kind, kw, frames, sf, 1)
         v = float(np.mean([x[0] for x in vals]))
         ms = float(np.mean([x[1] for x in vals]) * 1e3)
-        sample = ("oracle port of %s.batch_fast_generate, B=1, %d samples (%d frames of the workload) incl. its %d-step "
-                  "warm-up, per step" % ("CSWNV" if kind == "cswnv" else "DSWNV", n, sf, 691))
+        sample = ("%s %s.batch_fast_generate on the host CPU, B=1, %d samples (%d frames of the workload) incl. its %d-column "
+                  "warm-up, per step" % ("unmodified reference" if arm_kind == "reference" else "oracle port of",
+                                         "CSWNV" if kind == "cswnv" else "DSWNV", n, sf, 691))
         line = dict(common)
         line.update({"impl": "reference", "value": v, "ms_per_step": ms, "rtf": v / fs, "config": config,
-                     "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
-                                      "torch_threads": torch.get_num_threads()},
+                     "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": arm_kind, "sample": sample,
+                                      "torch_threads": threads, "value_1_thread": v1, "cpu_model": RR.cpu_model_name(),
+                                      "nproc": threads, "torch": torch.__version__},
                      "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                      "gpu_launches": 0})
         emit(line)
@@ -354,12 +414,8 @@ def main():
                      "plan": {k: info[k] for k in ("kernel_variant", "grid", "n_sm", "ctas_per_layer", "head_ctas", "smem_bytes",
                                                    "batch_tile", "n_slots")}})
         if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only (the other ranks would spin in the barrier)
-            threads = os.cpu_count() or 1
-            sf = args.cpu_sample_frames or (40 if kind == "dswnv" else 20)
-            v, n, dt = cpu_port_run(kind, kw, frames, sf, threads)
-            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-                                    "sample": "oracle port of batch_fast_generate, B=1, %d samples (+ the %d-step warm-up), "
-                                              "%.1f s wall" % (n, info["receptive_field"] + 1, dt)}
+            sf = args.cpu_sample_frames or (8 if kind == "dswnv" else 24)
+            line["cpu_baseline"] = cpu_baseline_record(kind, kw, frames, sf, info["receptive_field"])
         emit(line)
     if dist is not None:
         dist.barrier()
