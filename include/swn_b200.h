@@ -129,8 +129,15 @@ int swn_finalize(swn_handle h);
  * as decode_cswnv_laplace-shift1.py:30-48 does). */
 int swn_condition(swn_handle h, const float* aux_dev, int32_t B, int32_t T_f, void* stream);
 
-/* The hot loop.  Requires a preceding swn_condition with the same B. Asynchronous on
- * `stream` except for argument validation. */
+/* The hot loop.  Requires a preceding swn_condition with the same B.  Asynchronous on `stream`
+ * (argument validation aside) in the steady state of a decode loop, i.e. while the PLAN stays
+ * the same.  The plan - CTA roles, packed per-CTA weights, exchange buffers - depends on
+ * (kernel variant, B, batch_tile, T_f class); the first call and every call that changes it
+ * synchronises `stream`, (re)allocates device scratch with cudaMalloc and uploads descriptors
+ * before launching.  The batch kernel (variants 3, 4) additionally synchronises `stream` on
+ * every call that passes n_samples_list, because the per-slot lengths live in one host-written
+ * device buffer.  Nothing is allocated or synchronised when a decode loop repeats the same
+ * (B, T_f, n_samples) shape, which is what bench.py times. */
 int swn_generate(swn_handle h, const swn_gen_args* args, void* stream);
 
 /* Teacher-forced evaluation of the same recurrence (SURVEY.md 8b `swn_teacher_forced`): the given samples are fed

@@ -452,6 +452,13 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
         CUDA_OK(cudaEventRecord(m->ev[2], st));
     }
     cudaError_t e = m_core_launch_dispatch(m, BS, P, st);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
+        // the clusters cannot all be co-resident right now (SMs held by other work): not applicable, the caller goes on
+        // to the cooperatively launched layer-group kernel
+        (void)cudaGetLastError();
+        fail("cluster kernel not launched: %s (grid %d, %zu B smem)", cudaGetErrorString(e), m->core_grid, m->core_smem);
+        return 2;
+    }
     if (e != cudaSuccess) return fail("cluster kernel launch failed: %s (grid %d, %zu B smem)", cudaGetErrorString(e), m->core_grid, m->core_smem);
     if (last) CUDA_OK(cudaEventRecord(m->ev[3], st));
     m->gen_timed = true;
@@ -925,9 +932,14 @@ int swn_create(const swn_config* cfg, int device, swn_handle* out) {
 
 int swn_set_tensor(swn_handle h, const char* key, const float* host, const int64_t* shape, int32_t ndim) {
     if (!h || !key || !host || (!shape && ndim > 0)) return fail("swn_set_tensor: null argument");
+    if (ndim < 0 || ndim > 8) return fail("swn_set_tensor('%s'): ndim %d out of range", key, ndim);
     HostTensor x;
     size_t n = 1;
-    for (int i = 0; i < ndim; ++i) { x.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+    for (int i = 0; i < ndim; ++i) {
+        if (shape[i] <= 0 || shape[i] > (int64_t)1 << 31 || n * (size_t)shape[i] > ((size_t)1 << 32))
+            return fail("swn_set_tensor('%s'): dimension %d has extent %lld", key, i, (long long)shape[i]);
+        x.shape.push_back(shape[i]); n *= (size_t)shape[i];
+    }
     x.data.assign(host, host + n);
     h->t[key] = std::move(x);
     h->finalized = false;

@@ -1096,7 +1096,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem_cta, co
             const int ml = mb / BS, b = mb - ml * BS;
             int bglob = (hc + ml * NVT) * BS + b; if (bglob >= P.B) bglob = P.B - 1;
             const float v = is_c ? ((const float*)P.seedw)[(size_t)bglob * SEG + j]
-                                 : __int_as_float((int)(((const long long*)P.seedw)[bglob] % P.Q));
+                                 : __int_as_float(pos_mod(((const long long*)P.seedw)[bglob], P.Q));
             hist[(size_t)mb * B3_HIST + ((j - SEG + B3_HIST) % B3_HIST)] = v;
             const int mm = P.lpc - SEG + j;
             if (is_c && mm >= 0) lpb[(size_t)mb * 8 + mm] = v;
@@ -1494,7 +1494,7 @@ __device__ void b3_tail(const BatchParams& P, const BCta& D, float* smem_cta, co
                             int fed = bi;
                             if (real) {
                                 ((long long*)P.out)[(size_t)bglob * P.n_out + istep] = bi;
-                                if (P.forced) fed = (int)((const long long*)P.forced)[(size_t)bglob * P.n_out + istep];
+                                if (P.forced) fed = clamp_idx(((const long long*)P.forced)[(size_t)bglob * P.n_out + istep], P.Q);
                             }
                             hs[b * B3_HIST + (istep % B3_HIST)] = __int_as_float(fed);
                         }

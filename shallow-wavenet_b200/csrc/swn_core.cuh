@@ -594,7 +594,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
         for (int e = tid; e < NC; e += SWN_NTHREADS) {
             const int bglob = min(e, P.B - 1);
             const float v = is_c ? ((const float*)P.seedw)[bglob]
-                                 : __int_as_float((int)(((const long long*)P.seedw)[bglob] % Q));
+                                 : __int_as_float(pos_mod(((const long long*)P.seedw)[bglob], Q));
             hist[e * HIST + (HIST - 1)] = v;                       // generated-index -1
             if (is_c && P.lpc > 0) lpb[e * 8 + P.lpc - 1] = v;
         }
@@ -1321,7 +1321,7 @@ __device__ void core_cta(const CoreParams& P, const CoreCta& D, float* smem) {
                         int fed = bi;
                         if (c < P.B) {
                             if (rank == 0) ((long long*)P.out)[(size_t)c * P.n_out + istep] = bi;
-                            if (P.forced) fed = (int)((const long long*)P.forced)[(size_t)c * P.n_out + istep];
+                            if (P.forced) fed = clamp_idx(((const long long*)P.forced)[(size_t)c * P.n_out + istep], Q);
                         }
                         hist[c * HIST + (istep % HIST)] = __int_as_float(fed);
                     }

@@ -40,9 +40,14 @@ static cudaError_t core_launch(const CoreParams& p, int grid, size_t smem, cudaS
     cfg.attrs = at; cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, k, p);
     if (e == cudaSuccess) return e;
-    // some drivers reject cooperative + compile-time cluster dims: the grid never exceeds the
-    // co-resident cluster count (checked by the caller), so a plain launch is equivalent
     (void)cudaGetLastError();
+    // The clusters spin on each other (DSMEM, mbarriers, LL words), so they must all be co-resident: a resource-class
+    // error (too large / out of resources - SMs held by other streams, MPS clients or processes) is returned to the
+    // caller, which falls back to the cooperatively launched layer-group kernel.  Only when the driver rejects the
+    // ATTRIBUTE COMBINATION cooperative + compile-time cluster dims (an argument-class error) is the launch repeated
+    // without the cooperative attribute; the caller has checked the grid against cudaOccupancyMaxActiveClusters, and
+    // a cluster that still fails to become resident trips the in-kernel watchdog instead of hanging.
+    if (e != cudaErrorInvalidValue && e != cudaErrorNotSupported && e != cudaErrorInvalidConfiguration) return e;
     cfg.numAttrs = 0;
     return cudaLaunchKernelEx(&cfg, k, p);
 }

@@ -177,8 +177,16 @@ __device__ __host__ __forceinline__ float laplace_eps(unsigned long long seed, l
 // DSWNV: q ~ Exp(1)  (the variate torch.multinomial divides by, dswnv.py:365)
 __device__ __host__ __forceinline__ float softmax_q(unsigned long long seed, long long b, long long n, int r) {
     float u = philox_uniform(seed, b, n, r);
-    return -logf(1.0f - u);      // 1-u in (0,1]
+    // 1-u in (0,1]: u == 0 (probability 2^-24 per draw) would give q = 0 and a Gumbel score of +inf, i.e. one
+    // uniformly random class every ~2^16 samples.  torch's exponential_ keeps its variate away from 0 the same way
+    // (it returns eps/2 for the largest uniform); q >= 2^-24 caps the score at logit + 16.6.
+    return fmaxf(-logf(1.0f - u), 5.9604645e-8f);
 }
+// non-negative remainder (the reference's OneHot does x % depth with Python semantics, dswnv.py:77)
+__device__ __host__ __forceinline__ int pos_mod(long long x, int q) { const int r = (int)(x % q); return r < 0 ? r + q : r; }
+// fed-back class index: the reference's OneHot would raise on an out-of-range index; the Python API validates
+// `forced`, the kernels clamp so that a bad pointer can never index the gather tables out of bounds
+__device__ __forceinline__ int clamp_idx(long long x, int q) { return x < 0 ? 0 : (x >= q ? q - 1 : (int)x); }
 
 // ------------------------------------------------------------------ layer CTA
 template <int NCH, int SEG, int BS>
@@ -480,7 +488,7 @@ __device__ void head_cta(const GenParams& P, const CtaDesc& D, float* smem) {
             const int mb = e / SEG, j = e - mb * SEG;
             const int bglob = min(mb, P.B - 1);
             const float v = is_c ? ((const float*)P.seedw)[(size_t)bglob * SEG + j]
-                                 : __int_as_float((int)(((const long long*)P.seedw)[bglob] % P.Q));
+                                 : __int_as_float(pos_mod(((const long long*)P.seedw)[bglob], P.Q));
             hist[(size_t)mb * HIST + ((j - SEG + HIST) % HIST)] = v;
             // lp_x_buffer = last lpc samples of the padded seed (cswnv_shift1.py:317-319)
             const int mm = P.lpc - SEG + j;
@@ -688,7 +696,7 @@ __device__ void head_cta(const GenParams& P, const CtaDesc& D, float* smem) {
                         int fed = bi;
                         if (bglob < P.B) {
                             if (hc == 0) ((long long*)P.out)[(size_t)bglob * P.n_out + istep] = bi;
-                            if (P.forced) fed = (int)((const long long*)P.forced)[(size_t)bglob * P.n_out + istep];
+                            if (P.forced) fed = clamp_idx(((const long long*)P.forced)[(size_t)bglob * P.n_out + istep], P.Q);
                         }
                         hs[b * HIST + (istep % HIST)] = __int_as_float(fed);
                     }

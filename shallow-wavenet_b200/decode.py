@@ -66,8 +66,11 @@ def decode_generator(feat_list, batch_size=7, string_path="/feat_org_lf0", seg=1
 
 
 def pcm16(wav):
-    """float [-1, 1] -> int16 the way libsndfile's PCM_16 writer does (scale by 2^15, round, clip)."""
-    return np.clip(np.rint(np.asarray(wav, np.float64) * 32768.0), -32768, 32767).astype(np.int16)
+    """float [-1, 1] -> int16 the way libsndfile writes PCM_16 from floating-point data with its defaults
+    (normalisation on, clipping off: ``lrint(x * 0x7FFF)``, libsndfile pcm.c d2s_array) - what
+    ``sf.write(path, wav, fs, "PCM_16")`` does in decode_cswnv_laplace-shift1.py:253.  The callers clip to [-1, 1]
+    first, as the reference does (:252); the clip here only guards the int16 cast."""
+    return np.clip(np.rint(np.asarray(wav, np.float64) * 32767.0), -32768, 32767).astype(np.int16)
 
 
 def write_wav(path, wav, fs):

@@ -104,7 +104,20 @@ class _SWNBase(nn.Module):
         raise NotImplementedError
 
     def _weights_version(self):
-        return tuple(p._version for p in self.parameters()) + (str(next(self.parameters()).device),)
+        """Key of the packed-weight cache.  ``p._version`` alone misses edits made through ``p.data`` (weight-norm
+        removal, EMA swaps: ``.data`` is a detached alias with its own counter), so the key also carries the storage
+        pointers and a content checksum (one float64 sum per tensor, gathered with a single device->host copy)."""
+        params = list(self.parameters())
+        with torch.no_grad():
+            sums = torch.stack([p.detach().sum(dtype=torch.float64) for p in params]).cpu().numpy().tobytes()
+        return (tuple(p._version for p in params), tuple(p.data_ptr() for p in params), sums, str(params[0].device))
+
+    def refresh_engine(self):
+        """Drop the packed weights on the device; the next generate call re-reads the parameters."""
+        eng = self.__dict__.pop("_engine", None)
+        self.__dict__.pop("_engine_ver", None)
+        if eng is not None:
+            eng.close()
 
     def _engine_for(self, device):
         ver = self._weights_version()
@@ -146,6 +159,11 @@ class _SWNBase(nn.Module):
             default = 0 if self._kind == "cswnv" else self.n_quantize // 2
             if bool((audio != default).any()):
                 seed_audio = audio.reshape(aux.shape[0], -1)
+        if self._kind == "dswnv" and forced is not None:
+            f = torch.as_tensor(forced)
+            if f.numel() and (int(f.min()) < 0 or int(f.max()) >= self.n_quantize):
+                # the reference's OneHot scatter raises on such an index (dswnv.py:92)
+                raise ValueError("forced class indices must lie in [0, %d)" % self.n_quantize)
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())      # follows torch.manual_seed like the reference
         start = time.time()

@@ -65,6 +65,13 @@ def _head_close(a, b, what, g=None, kind=None, kw=None, tol=None):
     return max(errs.values())
 
 
+def _neg_log_q(u):
+    """-log q of the in-kernel sampler for Philox uniforms u in [0, 1): q = max(-log(1 - u), 2^-24) (swn_gen.cuh softmax_q;
+    the floor keeps u == 0 from producing an infinite Gumbel score, as torch's exponential_ does)."""
+    q = np.maximum(-np.log1p(-u.astype(np.float64)), 5.9604645e-8)
+    return (-np.log(q)).astype(np.float32)
+
+
 def _tol(model):
     """Tolerance by the kernel that produced the heads (info of the model's last launch)."""
     return HEAD_TOL_TF32X3 if model.engine().info["kernel_variant"] == 3 else HEAD_TOL
@@ -304,8 +311,7 @@ def test_philox_stream_is_reproducible_and_matches_host_replica():
     assert np.array_equal(a, b) and not np.array_equal(a, c)
     u = np.stack([E.philox_uniform(77, "dswnv", bb, 0, N) for bb in range(B)])          # [B,N,256] in [0,1)
     assert u.min() >= 0.0 and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.02
-    q = (-np.log1p(-u.astype(np.float64))).astype(np.float32)
-    q = np.maximum(q, 1e-30)
+    q = np.maximum(-np.log1p(-u.astype(np.float64)), 5.9604645e-8).astype(np.float32)
     d = np.stack(m.batch_fast_generate(seed_a, aux, [N] * B, noise=q))
     assert (a != d).mean() <= 0.05                                 # same stream up to logf rounding of q
 
@@ -341,7 +347,7 @@ def test_small_batches_go_through_the_cluster_kernel_two_at_a_time(B):
     from shallow_wavenet_b200.engine import philox_uniform
     for b in range(B):
         u = philox_uniform(77, "dswnv", b, 0, N).reshape(N, 256)
-        gum = heads[b] - np.log(-np.log1p(-u.astype(np.float64))).astype(np.float32)
+        gum = heads[b] + _neg_log_q(u)
         assert (gum.argmax(-1) != outs[b]).mean() < 5e-3, b
 
 
@@ -362,6 +368,53 @@ def test_edge_cases_and_errors():
     m.cpu()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.batch_fast_generate(torch.zeros(1, 5), aux, [U], seed=1)
+
+
+def test_zero_noise_variate_and_index_validation():
+    """Injected q == 0 for a class wins whatever its posterior - what the reference's argmax(p / q) does with it
+    (p / 0 = inf); the Philox path never produces it (softmax_q floors q at 2^-24).  Out-of-range forced indices raise
+    like the reference's OneHot scatter; a negative seed index follows Python's % (dswnv.py:77)."""
+    g = load_golden("dswnv_base")
+    m = _model_from_golden(g)
+    B, N = g["samples"].shape
+    aux = torch.from_numpy(g["aux"])
+    seed_a = torch.full((B, 1), 128, dtype=torch.long)
+    q = g["noise"].copy()
+    _, heads = m.batch_fast_generate(seed_a, aux, [N] * B, noise=q, forced=g["samples"], return_heads=True)
+    low = heads.argmin(-1)                                         # least likely class of every step
+    for b in range(B):
+        q[b, np.arange(N), low[b]] = 0.0
+    for sel in (1, 2, 3):
+        outs = m.batch_fast_generate(seed_a, aux, [N] * B, noise=q, forced=g["samples"], kernel_sel=sel)
+        assert np.array_equal(np.stack(outs), low), sel
+    assert np.array_equal(O.gumbel_argmax(heads.reshape(-1, 256), q.reshape(-1, 256)).reshape(B, N), low)
+    bad = g["samples"].copy()
+    bad[0, 3] = 256
+    with pytest.raises(ValueError, match="forced class indices"):
+        m.batch_fast_generate(seed_a, aux, [N] * B, noise=q, forced=bad)
+    bad[0, 3] = -1
+    with pytest.raises(ValueError, match="forced class indices"):
+        m.batch_fast_generate(seed_a, aux, [N] * B, noise=q, forced=bad)
+    a = m.batch_fast_generate(torch.full((B, 1), 128 - 256, dtype=torch.long), aux, [N] * B, noise=g["noise"], return_heads=True)[1]
+    b_ = m.batch_fast_generate(torch.full((B, 1), 128 + 512, dtype=torch.long), aux, [N] * B, noise=g["noise"], return_heads=True)[1]
+    assert np.array_equal(a, b_) and float(np.abs(a - g["heads"]).max()) < 1e-4
+
+
+def test_edits_through_param_data_rebuild_engine():
+    """p.data edits do not bump p._version: the engine cache key carries a content checksum."""
+    g = load_golden("dswnv_base")
+    m = _model_from_golden(g)
+    aux = torch.from_numpy(g["aux"])
+    B, N = g["samples"].shape
+    seed_a = torch.full((B, 1), 128, dtype=torch.long)
+    m.batch_fast_generate(seed_a, aux, [N] * B, noise=g["noise"])
+    m.out_2.bias.data.add_(1.0)
+    _, h2 = m.batch_fast_generate(seed_a, aux, [N] * B, noise=g["noise"], forced=g["samples"], return_heads=True)
+    assert np.allclose(h2 - 1.0, g["heads"], atol=1e-4)
+    m.out_2.bias.data.sub_(1.0)
+    m.refresh_engine()
+    _, h3 = m.batch_fast_generate(seed_a, aux, [N] * B, noise=g["noise"], forced=g["samples"], return_heads=True)
+    assert np.allclose(h3, g["heads"], atol=1e-4)
 
 
 def test_weight_update_rebuilds_engine():
@@ -435,7 +488,7 @@ def test_full_size_cfg2_tail_and_sampler_properties():
     mism = 0
     for n0 in range(0, N, chunk):
         u = E.philox_uniform(11, "dswnv", 0, n0, chunk)
-        g_ = heads[0, n0:n0 + chunk] - np.log(-np.log1p(-u.astype(np.float64))).astype(np.float32)
+        g_ = heads[0, n0:n0 + chunk] + _neg_log_q(u)
         mism += int((np.argmax(g_, -1) != smp[n0:n0 + chunk]).sum())
     assert mism <= N * 1e-3, mism                                  # host log vs device logf near-ties only
     n_tail = 16
@@ -599,8 +652,7 @@ def test_cfg5_shape_batch128_properties():
     for b in (0, 77, 127):
         n0 = N - 4000
         u = E.philox_uniform(31, "dswnv", b, n0, 4000)
-        with np.errstate(divide="ignore"):
-            g_ = heads[b, n0:] - np.log(-np.log1p(-u.astype(np.float64))).astype(np.float32)
+        g_ = heads[b, n0:] + _neg_log_q(u)
         assert int((np.argmax(g_, -1) != smp[b, n0:]).sum()) <= 8           # host log vs device logf near-ties only
     _tail_check(cfg, sd, aux, smp, heads, (0, 127), 20, U, 8, "cfg5 shape", "dswnv", kw, _tol(model))
 
