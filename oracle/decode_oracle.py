@@ -1,10 +1,11 @@
 """TEST INFRASTRUCTURE (oracle): CPU restatement of the batching done by the reference's decode scripts around
 ``batch_fast_generate`` - ``decode_generator`` / ``pad_list`` of src/bin/decode_cswnv_laplace-shift1.py:30-113 and
-src/bin/decode_dswnv_softmax.py:54-117 - over in-memory features (the scripts themselves need h5py / soundfile,
-which this image does not have).  Only tests/ may import this module; the product never does.
-Parity: the mu-law maps are pinned against vectors generated from the reference module
-(tests/golden_aux/mulaw.npz); the batching restatement has no reference fixture (the script cannot be imported)
-and follows the cited lines one to one."""
+src/bin/decode_dswnv_softmax.py:54-117 - over in-memory features.  Only tests/ may import this module; the product
+never does.
+Parity: PINNED.  tests/golden_decode/*.npz are recordings of the reference scripts' own ``main()`` run end to end
+(tests/golden/make_decode_golden.py: h5py / soundfile / torchvision stubbed, everything else unmodified);
+tests/test_decode_driver.py holds both this restatement and the product's driver to them.  The mu-law maps are pinned
+against vectors generated from the reference module (tests/golden_aux/mulaw.npz)."""
 import math
 import os
 

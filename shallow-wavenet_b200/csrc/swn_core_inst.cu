@@ -1,4 +1,6 @@
 // Instantiations of the cluster ("core + helpers") latency kernel for one hidden-size class.
+#include <stdio.h>
+#include <stdlib.h>
 #include "swn_core.cuh"
 #include "swn_launch.h"
 
@@ -39,6 +41,8 @@ static cudaError_t core_launch(const CoreParams& p, int grid, size_t smem, cudaS
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, k, p);
+    static const bool dbg = getenv("SWN_DEBUG_LAUNCH") != nullptr;
+    if (dbg) fprintf(stderr, "[swn] cluster kernel: cooperative launch of %d CTAs -> %s\n", grid, cudaGetErrorName(e));
     if (e == cudaSuccess) return e;
     (void)cudaGetLastError();
     // The clusters spin on each other (DSMEM, mbarriers, LL words), so they must all be co-resident: a resource-class

@@ -7,7 +7,7 @@ plus size-independent properties at BASELINE.json's full sizes.
 Tolerances (north-star: "within a stated fp32 tolerance, e.g. 1e-4 relative"):
   head values, PER COMPONENT (logits | Laplace loc | pre-sigmoid scale | LP coefficients):
       |a-b| <= tol * (max|component of the row| + 0.05), tol = 2e-5 on the fp32 FFMA kernels and
-      1e-4 on the tensor-core cells (three tf32 passes)
+      3e-5 on the tensor-core cells (three tf32 passes)
   Laplace samples given the same head, history and noise: |a-b| <= 2e-5 absolute (range [-1,1])
   mu-law indices: bit-exact given the logits (checked against the argmax recomputed on the host
   from the kernel's own logits and noise, and against the reference's samples on the fixtures).
@@ -25,8 +25,9 @@ from oracle import swn_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-HEAD_TOL = 2e-5            # fp32 FFMA kernels (variants 1, 2, 4): measured <= 1e-6
-HEAD_TOL_TF32X3 = 1e-4     # tensor-core cells (variant 3: W_hi*X_hi + W_lo*X_hi + W_hi*X_lo in tf32): the north-star's 1e-4
+HEAD_TOL = 2e-5            # fp32 FFMA kernels (variants 1, 2, 4): measured <= 5.2e-6
+HEAD_TOL_TF32X3 = 3e-5     # tensor-core cells (variant 3: W_hi*X_hi + W_lo*X_hi + W_hi*X_lo in tf32): measured <= 8e-6
+                           # (profiles/r02_parity_errors.txt); the north-star allows 1e-4
 SAMPLE_ATOL = 2e-5
 
 
