@@ -8,7 +8,11 @@ One "step" = one pass of the hot path over one batch of synthetic utterances: co
 warm-up + the whole autoregressive loop (``batch_fast_generate``).  The default workload is
 BASELINE.json configs[1] (DSWNV mu-law softmax, 16 kHz, batch 1, 5 s); with ``--gpus N`` every
 rank generates its own copy of that workload (utterances shard with no collective: weak
-scaling).  Rank 0 prints ONE JSON line.
+scaling).  Rank 0 prints ONE JSON line; ``value`` / ``e2e`` / ``roofline`` are
+those of the headline workload, and the same line carries two sub-records measured in the same
+run: ``batched.cfg3`` (configs[2]: 64 x 5 s on the tensor-core batch kernel, 2 steps) and, under
+``--gpus N > 1`` (or ``--sharded-at-n1``), ``sharded.cfg4`` (configs[3]: 512 utterances of
+unequal length split over the ranks with ``sharding.split_for_gpus``, STRONG scaling).
 
 ``--impl reference`` times the UNMODIFIED reference (``oracle/_ref``: a verbatim, git-ignored
 copy of its two ``src/nets`` modules made by ``__graft_entry__.build()``; it travels to the GPU
@@ -203,6 +207,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the batched / sharded sub-records")
+    ap.add_argument("--batched-workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--sharded-at-n1", action="store_true", help="also measure the sharded cfg4 sub-record on one GPU (the N=1 figure)")
+    ap.add_argument("--sharded-utterances", type=int, default=512)
     ap.add_argument("--cpu-sample-frames", type=int, default=0)
     args = ap.parse_args()
 
@@ -268,8 +276,8 @@ def main():
 
     # ------------------------------------------------------------------ B200 arm
     import torch
-    import shallow_wavenet_b200 as S
-    from shallow_wavenet_b200 import synth, engine as E
+    import shallow_wavenet_b200 as S  # noqa: F401
+    from shallow_wavenet_b200 import synth, sharding, engine as E
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a B200; there is no CPU fallback")
     dist = None
@@ -279,15 +287,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank if world > 1 else 0)
     torch.cuda.set_device(dev)
-
-    model = synth.make_model(kind, **kw).to(dev)
-    aux_host = torch.from_numpy(synth.synth_aux(kw["n_aux"], frames, B, seed=1234 + rank)).pin_memory()
-    aux_dev = aux_host.to(dev)
-    seg = kw.get("seg", 1) if kind == "cswnv" else 1
-    seed_audio = torch.zeros(B, seg) if kind == "cswnv" else torch.full((B, 1), 128, dtype=torch.long)
-    eng = model.engine()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    n_gen = (n_samples // seg) * seg
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    smem_peak = E.measure_smem_bandwidth(dev.index or 0)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -295,127 +301,226 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def resident_step(i):
-        eng.condition(aux_dev)
-        out, _ = eng.generate(n_samples, seed=1000 + i, sync=False)
-        return out
+    def reduce_max(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
 
-    for i in range(args.warmup):
-        resident_step(i)
-        eng.sync()
+    def reduce_sum(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t]
 
-    # ---- timed: inputs resident in HBM, CUDA events on the launching stream, L2 flushed between steps
-    sampler = ClockSampler(dev.index or 0)
-    sampler.start()
-    barrier()
-    launches0 = eng.get_info()["kernel_launches"]
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    gen_ms, cond_ms = [], []
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)
-        ev[i][0].record()
-        resident_step(args.warmup + i)
-        ev[i][1].record()
-        eng.sync()
-        gen_ms.append(eng.info["last_gen_ms"]); cond_ms.append(eng.info["last_cond_ms"])
-    barrier()
-    launches = eng.get_info()["kernel_launches"] - launches0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(step_ms))
-    clocks = sampler.finish()
+    def measure(kind, kw, aux_np, n_samples_list, steps, warmup, e2e_iters, warm_frames=0):
+        """Times `steps` passes of the hot path over one batch on this rank: (a) inputs resident in HBM, CUDA events on
+        the launching stream, L2 flushed between steps; (b) end to end through batch_fast_generate with pinned host aux
+        in and numpy out.  `warm_frames` > 0: warm-up passes run on the first frames only (same batch, same plan)."""
+        model = synth.make_model(kind, **kw).to(dev)
+        aux_host = torch.from_numpy(aux_np).pin_memory()
+        aux_dev = aux_host.to(dev)
+        B = aux_np.shape[0]
+        seg = kw.get("seg", 1) if kind == "cswnv" else 1
+        seed_audio = torch.zeros(B, seg) if kind == "cswnv" else torch.full((B, 1), 128, dtype=torch.long)
+        eng = model.engine()
+        n_max = max(n_samples_list)
+        ragged = len(set(n_samples_list)) > 1
+        lens = [int(n) for n in n_samples_list]
 
-    # ---- end to end through the public API: pinned host aux in, host samples out, every step
-    e2e_t = []
-    for i in range(max(1, min(args.steps, 3))):
+        def resident_step(i, frames_limit=0):
+            if frames_limit:
+                eng.condition(aux_dev[:, :, :frames_limit].contiguous())
+                n = frames_limit * kw["upsampling_factor"]
+                eng.generate(n, seed=1000 + i, sync=False, n_samples_list=[min(x, n) for x in lens] if ragged else None)
+            else:
+                eng.condition(aux_dev)
+                eng.generate(n_max, seed=1000 + i, sync=False, n_samples_list=lens if ragged else None)
+
+        for i in range(warmup):
+            resident_step(i, warm_frames)
+            eng.sync()
+        sampler = ClockSampler(dev.index or 0)
+        sampler.start()
         barrier()
-        t0 = time.perf_counter()
-        outs = model.batch_fast_generate(seed_audio, aux_host, [n_samples] * B, seed=2000 + i)
-        torch.cuda.synchronize(dev)
-        e2e_t.append(time.perf_counter() - t0)
-        assert len(outs) == B and len(outs[0]) == n_gen
-    e2e_s = float(np.mean(e2e_t))
-
-    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
-    samples_per_step_all = world * B * n_gen
-    value = samples_per_step_all * args.steps / (total_ms * 1e-3)
-    e2e_value = samples_per_step_all / (e2e_ms * 1e-3)
-
-    if rank == 0:
+        launches0 = eng.get_info()["kernel_launches"]
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        gen_ms, cond_ms = [], []
+        for i in range(steps):
+            flush.fill_(i & 0xFF)
+            ev[i][0].record()
+            resident_step(warmup + i)
+            ev[i][1].record()
+            eng.sync()
+            gen_ms.append(eng.info["last_gen_ms"]); cond_ms.append(eng.info["last_cond_ms"])
+        barrier()
+        launches = eng.get_info()["kernel_launches"] - launches0
+        total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+        clocks = sampler.finish()
+        e2e_t = []
+        for i in range(e2e_iters):
+            barrier()
+            t0 = time.perf_counter()
+            outs = model.batch_fast_generate(seed_audio, aux_host, lens, seed=2000 + i)
+            torch.cuda.synchronize(dev)
+            e2e_t.append(time.perf_counter() - t0)
+            assert len(outs) == B and all(len(o) == (n // seg) * seg for o, n in zip(outs, lens))
         info = eng.get_info()
-        # dominant kernel: the persistent generation kernel; per launch it runs n_it sequential steps,
-        # each of which must read every in-loop weight once from on-chip memory
-        kern_ms = float(np.mean(gen_ms))
-        seg_steps = n_gen // seg + info["receptive_field"] // seg + 1
-        weight_bytes = n_weights * 4.0
-        n_slots = info["n_slots"]
-        alg_bytes = weight_bytes * seg_steps * n_slots
-        smem_peak = E.measure_smem_bandwidth(dev.index or 0)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        flops = 2.0 * macs * B * n_gen / (kern_ms * 1e-3)
+        samples = sum((n // seg) * seg for n in lens)
+        res = dict(B=B, seg=seg, samples_per_step=samples, n_gen_max=(n_max // seg) * seg, total_ms=total_ms,
+                   e2e_ms=float(np.mean(e2e_t)) * 1e3, e2e_ms_each=[t * 1e3 for t in e2e_t], kern_ms=float(np.mean(gen_ms)),
+                   cond_ms=float(np.mean(cond_ms)), launches=int(launches), clocks=clocks, info=info,
+                   h2d=int(aux_host.numel() * 4), d2h=int(B * (n_max // seg) * seg * (4 if kind == "cswnv" else 8)))
+        del eng, model, aux_dev
+        torch.cuda.empty_cache()
+        return res
+
+    def roofline_of(kind, kw, r, steps):
+        """Roofline of the dominant kernel (the persistent generation kernel) of a measured workload."""
+        info, kern_ms = r["info"], r["kern_ms"]
+        macs_, n_weights_ = in_loop_macs(kind, kw)
+        seg_ = r["seg"]
+        seg_steps = r["n_gen_max"] // seg_ + info["receptive_field"] // seg_ + 1
+        flops = 2.0 * macs_ * r["samples_per_step"] / (kern_ms * 1e-3)
         variant = info.get("kernel_variant")
         kname = {1: "swn_generate_kernel (layer groups over the chip, persistent)",
                  2: "swn_core_kernel (16-CTA core cluster + helper CTAs, persistent)",
                  3: "swn_batch_kernel (ring pipeline of slots; gated cells on tcgen05 kind::tf32 x3, weights in tensor memory)",
                  4: "swn_batch_kernel (ring pipeline of slots; gated cells as register-tiled fp32 FFMA GEMMs)"}.get(variant, "?")
+        share = kern_ms * steps / r["total_ms"]
         if variant in (3, 4):
             # batched step: dense contraction [rows x H].[H x columns] -> tensor-pipe bound (SURVEY.md 8d).  The
             # algorithmic flops count every multiply-add of the reference once (no tf32 pass multiplicity).
             tf = flops / 1e12
             peak_bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
-            sm_mhz = clocks.get("sm_mhz") or 1965.0
+            sm_mhz = r["clocks"].get("sm_mhz") or 1965.0
             fp32_peak = info["n_sm"] * 128 * 2 * sm_mhz * 1e6 / 1e12
-            roofline = {"bound": "tensor", "kernel": kname + ", 1 launch per step",
-                        "achieved": tf, "peak": peak_bf16, "unit": "TFLOP/s", "frac": tf / peak_bf16,
-                        "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, long loop)" if peaks.get("bf16_tflops_sustained")
-                                        else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"),
-                        "note": "fp32 parity (1e-4) forbids bf16: the cells run three tf32 passes (tf32 dense = bf16/2), so the "
-                                "same-precision tensor ceiling is peak/6; variant 4 (H=256 does not fit tensor memory) is bounded by fp32 FFMA",
-                        "peak_tf32x3_equivalent": peak_bf16 / 6.0, "frac_of_tf32x3_equivalent": tf / (peak_bf16 / 6.0),
-                        "fp32_ffma_peak_at_clock": fp32_peak, "frac_of_fp32_ffma_peak": tf / fp32_peak,
-                        "algorithmic_flop_per_sample": 2.0 * macs, "samples_per_launch": B * n_gen,
-                        "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms * args.steps / total_ms,
-                        "us_per_loop_iteration": kern_ms * 1e3 / seg_steps, "traffic": None}
-        else:
-            roofline = {"bound": "smem", "kernel": kname + ", 1 launch per step",
-                        "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
-                        "peak_source": "measured live: aggregate LDS.128 bandwidth, 1 CTA/SM (swn_measure_smem_bandwidth)",
-                        "algorithmic_bytes_per_time_step": weight_bytes, "time_steps_per_launch": seg_steps * n_slots,
-                        "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms * args.steps / total_ms,
-                        "achieved_tflops_fp32": flops / 1e12,
-                        "vs_hbm": {"peak": peaks.get("hbm_gbs"), "frac": (achieved / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
-                                   "note": "weights are SMEM-resident; HBM is not the bound (frac>1 = residency pays)"},
-                        "traffic": None}
+            return {"bound": "tensor", "kernel": kname + ", 1 launch per step",
+                    "achieved": tf, "peak": peak_bf16, "unit": "TFLOP/s", "frac": tf / peak_bf16,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, long loop)" if peaks.get("bf16_tflops_sustained")
+                                    else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"),
+                    "note": "fp32 parity (1e-4) forbids bf16: the cells run three tf32 passes (tf32 dense = bf16/2), so the "
+                            "same-precision tensor ceiling is peak/6; variant 4 (H=256 does not fit tensor memory) is bounded by fp32 FFMA",
+                    "peak_tf32x3_equivalent": peak_bf16 / 6.0, "frac_of_tf32x3_equivalent": tf / (peak_bf16 / 6.0),
+                    "fp32_ffma_peak_at_clock": fp32_peak, "frac_of_fp32_ffma_peak": tf / fp32_peak,
+                    "algorithmic_flop_per_sample": 2.0 * macs_, "samples_per_launch": r["samples_per_step"],
+                    "kernel_ms": kern_ms, "kernel_share_of_step": share,
+                    "us_per_loop_iteration": kern_ms * 1e3 / seg_steps, "traffic": None}
+        weight_bytes = n_weights_ * 4.0
+        alg_bytes = weight_bytes * seg_steps * info["n_slots"]
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        return {"bound": "smem", "kernel": kname + ", 1 launch per step",
+                "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
+                "peak_source": "measured live: aggregate LDS.128 bandwidth, 1 CTA/SM (swn_measure_smem_bandwidth)",
+                "algorithmic_bytes_per_time_step": weight_bytes, "time_steps_per_launch": seg_steps * info["n_slots"],
+                "us_per_time_step": kern_ms * 1e3 / (seg_steps * info["n_slots"]),
+                "kernel_ms": kern_ms, "kernel_share_of_step": share,
+                "achieved_tflops_fp32": flops / 1e12,
+                "vs_hbm": {"peak": peaks.get("hbm_gbs"), "frac": (achieved / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
+                           "note": "weights are SMEM-resident; HBM is not the bound (frac>1 = residency pays)"},
+                "traffic": None}
+
+    def attach_traffic(roofline, workload, variant):
         # DRAM bytes per launch of the dominant kernel from one `ncu --set full` capture of this workload
         # (dram__bytes_read.sum + dram__bytes_write.sum), recorded under profiles/; null when none was taken
         try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+            cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(workload)
             if cap and cap.get("kernel_variant") == variant:
                 roofline["traffic"] = cap["dram_bytes_per_launch"]
                 roofline["traffic_source"] = cap["source"]
         except Exception:
             pass
+
+    # ---- the headline workload: every rank generates its own copy (weak scaling, no collective on the data path)
+    aux_np = synth.synth_aux(kw["n_aux"], frames, B, seed=1234 + rank)
+    r = measure(kind, kw, aux_np, [n_samples] * B, args.steps, args.warmup, max(1, min(args.steps, 3)))
+    total_ms, e2e_ms = reduce_max([r["total_ms"], r["e2e_ms"]])
+    samples_all = world * r["samples_per_step"]
+    value = samples_all * args.steps / (total_ms * 1e-3)
+    e2e_value = samples_all / (e2e_ms * 1e-3)
+    line = None
+    if rank == 0:
+        roofline = roofline_of(kind, kw, r, args.steps)
+        attach_traffic(roofline, args.workload, r["info"].get("kernel_variant"))
         line = dict(common)
         line.update({"value": value, "ms_per_step": total_ms / args.steps, "rtf": value / fs, "config": config,
                      "rtf_per_utterance": value / fs / (world * B),
-                     "conditioning_ms": float(np.mean(cond_ms)), "kernel_ms": kern_ms,
-                     "clocks": clocks, "roofline": roofline,
-                     "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(aux_host.numel() * 4),
-                             "d2h_bytes_per_step": int(B * n_gen * (4 if kind == "cswnv" else 8)),
+                     "conditioning_ms": r["cond_ms"], "kernel_ms": r["kern_ms"],
+                     "clocks": r["clocks"], "roofline": roofline,
+                     "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                             "ms_each": r["e2e_ms_each"],
                              "api": "%s.batch_fast_generate(pinned host aux) -> list of numpy arrays" % ("CSWNV" if kind == "cswnv" else "DSWNV")},
-                     "gpu_launches": int(launches),
-                     "plan": {k: info[k] for k in ("kernel_variant", "grid", "n_sm", "ctas_per_layer", "head_ctas", "smem_bytes",
-                                                   "batch_tile", "n_slots")}})
+                     "gpu_launches": r["launches"],
+                     "plan": {k: r["info"][k] for k in ("kernel_variant", "grid", "n_sm", "ctas_per_layer", "head_ctas", "smem_bytes",
+                                                        "batch_tile", "n_slots")}})
+
+    # ---- batched sub-record: BASELINE.json configs[2] (tensor-core batched step), measured in the same run
+    if not args.no_extras and args.workload == "cfg2":
+        bk, bfs, bover, bB, bframes, bdesc = WORKLOADS[args.batched_workload]
+        bkw = model_kwargs(bk, bfs, bover)
+        bn = bframes * bkw["upsampling_factor"]
+        rb = measure(bk, bkw, synth.synth_aux(bkw["n_aux"], bframes, bB, seed=4321 + rank), [bn] * bB, 2, 1, 1, warm_frames=40)
+        b_total, b_e2e = reduce_max([rb["total_ms"], rb["e2e_ms"]])
+        if rank == 0:
+            bro = roofline_of(bk, bkw, rb, 2)
+            attach_traffic(bro, args.batched_workload, rb["info"].get("kernel_variant"))
+            bval = world * rb["samples_per_step"] * 2 / (b_total * 1e-3)
+            line["batched"] = {args.batched_workload: {
+                "workload": bdesc, "value": bval, "unit": "samples/s", "rtf": bval / bfs, "rtf_per_utterance": bval / bfs / (world * bB),
+                "steps": 2, "warmup": "1 pass on the first 40 frames (same batch, same plan)", "scaling": "weak",
+                "ms_per_step": b_total / 2, "kernel_ms": rb["kern_ms"], "conditioning_ms": rb["cond_ms"],
+                "e2e": {"value": world * rb["samples_per_step"] / (b_e2e * 1e-3), "unit": "samples/s",
+                        "h2d_bytes_per_step": rb["h2d"], "d2h_bytes_per_step": rb["d2h"]},
+                "roofline": bro, "clocks": rb["clocks"], "gpu_launches": rb["launches"],
+                "plan": {k: rb["info"][k] for k in ("kernel_variant", "grid", "batch_tile", "n_slots", "ctas_per_layer", "head_ctas")}}}
+
+    # ---- sharded sub-record: BASELINE.json configs[3], 512 utterances of unequal length split over the ranks the way
+    # the decode scripts split their list (contiguous np.array_split, decode_cswnv_laplace-shift1.py:200-201), each
+    # rank sorting its share by length (:77-79) and decoding it as one batch.  STRONG scaling: total work is fixed.
+    if not args.no_extras and args.workload == "cfg2" and (world > 1 or args.sharded_at_n1):
+        sk, sfs, sover, _, sframes, sdesc = WORKLOADS["cfg4"]
+        skw = model_kwargs(sk, sfs, sover)
+        U_s = skw["upsampling_factor"]
+        n_utt = args.sharded_utterances
+        lens_all = np.random.default_rng(77).integers(int(0.8 * sframes), int(1.2 * sframes) + 1, n_utt)    # frames, +-20 %
+        mine = [int(i) for i in sharding.rank_shard(list(range(n_utt)), rank, world)]
+        order = [mine[i] for i in sharding.decode_batches([lens_all[i] for i in mine], len(mine))[0]]
+        T_max = int(max(lens_all[i] for i in order))
+        aux_s = np.zeros((len(order), skw["n_aux"], T_max), np.float32)
+        for row, i in enumerate(order):
+            aux_s[row, :, :lens_all[i]] = synth.synth_aux(skw["n_aux"], int(lens_all[i]), 1, seed=9000 + i)[0]
+        n_list = [int(lens_all[i]) * U_s for i in order]
+        rs = measure(sk, skw, aux_s, n_list, 1, 1, 1, warm_frames=40)
+        s_total, s_e2e = reduce_max([rs["total_ms"], rs["e2e_ms"]])
+        s_sum_ms, s_samples = reduce_sum([rs["total_ms"], float(rs["samples_per_step"])])
+        if rank == 0:
+            sval = s_samples / (s_total * 1e-3)
+            sro = roofline_of(sk, skw, rs, 1)
+            rec = {"workload": "cfg4: CSWNV Laplace seg=5 lpc=4 H=192, 22.05 kHz, %d utterances of 8-12 s (10 s +-20 %%) sharded over "
+                               "%d GPU(s) with sharding.split_for_gpus; each rank decodes its share as one length-sorted batch" % (n_utt, world),
+                   "value": sval, "unit": "samples/s", "rtf": sval / sfs, "scaling": "strong", "steps": 1,
+                   "warmup": "1 pass on the first 40 frames (same batch, same plan)",
+                   "utterances_total": n_utt, "utterances_rank0": len(order), "samples_total": s_samples,
+                   "ms_max_over_ranks": s_total, "ms_mean_over_ranks": s_sum_ms / world, "imbalance_max_over_mean": s_total * world / s_sum_ms,
+                   "e2e": {"value": s_samples / (s_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step_rank0": rs["h2d"],
+                           "d2h_bytes_per_step_rank0": rs["d2h"]},
+                   "rank0": {"kernel_ms": rs["kern_ms"], "conditioning_ms": rs["cond_ms"], "roofline": sro,
+                             "conditioning_table_bytes": rs["info"]["cond_bytes"],
+                             "plan": {k: rs["info"][k] for k in ("kernel_variant", "grid", "batch_tile", "n_slots")}}}
+            try:
+                n1 = json.load(open(os.path.join(ROOT, "profiles", "r02_sharded_cfg4_n1.json")))
+                if n1.get("utterances_total") == n_utt:
+                    rec["n1_value"] = n1["value"]
+                    rec["n1_source"] = "profiles/r02_sharded_cfg4_n1.json (same 512 utterances on one GPU)"
+                    rec["efficiency_vs_n1"] = sval / (world * n1["value"])
+            except Exception:
+                pass
+            line["sharded"] = {"cfg4": rec}
+
+    if rank == 0:
         if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only (the other ranks would spin in the barrier)
             sf = args.cpu_sample_frames or (8 if kind == "dswnv" else 24)
-            line["cpu_baseline"] = cpu_baseline_record(kind, kw, frames, sf, info["receptive_field"])
+            line["cpu_baseline"] = cpu_baseline_record(kind, kw, frames, sf, r["info"]["receptive_field"])
         emit(line)
     if dist is not None:
         dist.barrier()
