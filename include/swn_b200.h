@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SWN_ABI_VERSION 3
+#define SWN_ABI_VERSION 4
 
 typedef struct swn_model* swn_handle;
 
@@ -107,7 +107,8 @@ typedef struct swn_info {
     int64_t kernel_launches;  /* kernels launched by this handle so far */
     int32_t grid;             /* CTAs of the last persistent launch */
     int32_t kernel_variant;   /* 1 = layer groups over the chip, 2 = core cluster + helpers,
-                                 3 = pipelined batch kernel with tcgen05 (tf32 x3) cells, 4 = the same with fp32 FFMA cells */
+                                 3 = pipelined batch kernel with tcgen05 (tf32 x3) cells, 4 = the same with fp32 FFMA cells,
+                                 5 = swn_forward (time-parallel tcgen05 GEMMs; last_gen_ms is then the forward's device time) */
 } swn_info;
 
 /* CSWNV(...) / DSWNV(...) followed by model.cuda() (decode_cswnv_laplace-shift1.py:208-223,
@@ -149,6 +150,28 @@ int swn_generate(swn_handle h, const swn_gen_args* args, void* stream);
  * n_gen = (n_samples/seg)*seg.  Requires a preceding swn_condition with the same B.  Asynchronous on `stream`;
  * equivalent to swn_generate with forced_dev / head_dev set and the sampled output discarded. */
 int swn_teacher_forced(swn_handle h, const void* samples_dev, int64_t n_samples, float* head_dev, void* stream);
+
+/* Arguments of swn_forward. */
+typedef struct swn_fwd_args {
+    const void* audio_dev;    /* CSWNV: float [B][T_a] waveform; DSWNV: int64 class indices [B][T_a], or, when
+                                 audio_onehot != 0, the reference's float one-hot tensor [B][n_quantize][T_a] */
+    int32_t audio_onehot;
+    int32_t clip;             /* CSWNV forward(..., clip=True): also fill b_clip_dev / log_b_clip_dev */
+    int64_t T_a;              /* must be T_f * upsampling_factor - seg (seg = 1 for DSWNV) */
+    float* out_dev;           /* raw out_2 rows, [B][T_out][head_dim], T_out = T_f * U - 2 * seg + 1 */
+    float* b_dev;             /* CSWNV: exp(logsigmoid(out[seg:2seg])) [B][T_out][seg] */
+    float* log_b_dev;         /* CSWNV: logsigmoid(out[seg:2seg])      [B][T_out][seg] */
+    float* b_clip_dev;        /* CSWNV, clip: exp(clamp(log_b, log 7.07e-7)) */
+    float* log_b_clip_dev;
+} swn_fwd_args;
+
+/* Training-time / evaluation forward of the modules: CSWNV.forward(aux, audio)
+ * (src/nets/cswnv_shift1.py:191-267) and DSWNV.forward(audio, aux) (src/nets/dswnv.py:250-276) - every time step of
+ * whole utterances at once, zero conv history before the first sample (no warm-up), stride-1 outputs.  Requires a
+ * preceding swn_condition(aux) with the same batch.  Time-parallel: the dilated convs and the 1x1 projections run as
+ * tcgen05 (tf32 x 3) GEMMs over all time steps.  Inference only (no gradients; dropout `do=True` is not available).
+ * Asynchronous on `stream` once its buffers exist (they grow with B * T_out: ~20 KB per time step). */
+int swn_forward(swn_handle h, const swn_fwd_args* args, void* stream);
 
 /* Blocks until the stream is idle and reports a device-side failure of the last
  * swn_generate (e.g. the in-kernel watchdog fired) as a non-zero status. */

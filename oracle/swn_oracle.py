@@ -24,6 +24,7 @@ reference's ``state_dict``:
 * ``generate``             <- the hot loop cswnv_shift1.py:348-402 /
                               dswnv.py:338-374 (fixed-size history windows
                               instead of the reference's growing ``torch.cat``)
+* ``forward_full``         <- the training-time forward, cswnv_shift1.py:191-267 / dswnv.py:250-276
 * ``laplace_sample`` / ``softmax_sample`` <- cswnv_shift1.py:368-391 / dswnv.py:363-369
 * ``encode_mu_law`` / ``decode_mu_law``    <- dswnv.py:19-47
 """
@@ -303,6 +304,50 @@ def teacher_forced_tail(cfg: SWNConfig, sd: Dict, aux, gen, n_tail: int) -> np.n
         first = R + (n_iter - n_tail) * seg - t_lo
         out = out[:, :, first::seg]
     return out.transpose(1, 2).contiguous().numpy()
+
+
+def forward_full(cfg: SWNConfig, sd: Dict, aux, audio, clip: bool = False):
+    """The training-time ``forward`` over whole utterances (cswnv_shift1.py:191-267, dswnv.py:250-276): zero conv
+    history before the first sample (no warm-up), stride-1 outputs.
+
+    CSWNV: ``audio`` float [B, T_a], T_a = T_f*U - seg -> dict(out [B,T,2seg+lpc], mu, b, log_b, a [, b_clip, log_b_clip]),
+    T = T_a - seg + 1.  DSWNV: ``audio`` int [B, T_a] (class indices), T_a = T_f*U - 1 -> dict(out = logits [B,T_a,Q])."""
+    W = _weights(sd)
+    aux = _t(aux)
+    seg = cfg.eff_seg
+    with torch.no_grad():
+        x = upsample(cfg, W, aux_frames(cfg, W, aux))[:, :, seg:]                  # cswnv:193 / dswnv:252
+        if cfg.kind == "cswnv":
+            if seg > 1:
+                if cfg.aux_conv2d_flag:                                              # cswnv:196-198
+                    x = F.conv2d(x.unfold(2, seg, 1).permute(0, 1, 3, 2), W["aux_conv2d.weight"], W["aux_conv2d.bias"]).squeeze(2)
+                else:                                                                # cswnv:199-201
+                    x = x.unfold(2, seg, 1).permute(0, 2, 1, 3)
+                    x = x.reshape(x.size(0), x.size(1), -1).permute(0, 2, 1)
+            u = _t(audio).unsqueeze(1)
+            if cfg.wav_conv_flag:
+                u = F.conv1d(u, W["wav_conv.weight"], W["wav_conv.bias"])
+            h = F.softsign(_causal_conv(u, W["causal.conv.weight"], W["causal.conv.bias"], 1)[:, :, seg - 1:])   # cswnv:204-207
+        else:
+            u = _one_hot(torch.as_tensor(np.asarray(audio)).to(torch.int64), cfg.n_quantize)
+            if cfg.audio_in_flag:
+                x = torch.cat((x, u), 1)                                             # dswnv:254-255
+            if cfg.wav_conv_flag:
+                u = F.conv1d(u, W["wav_conv.weight"], W["wav_conv.bias"])
+            h = F.softsign(_causal_conv(u, W["causal.conv.weight"], W["causal.conv.bias"], 1))            # dswnv:258-261
+        s = None
+        for l in range(len(cfg.dil_facts)):
+            skip, h = _cell(cfg, W, l, x, h)
+            s = skip if s is None else s + skip
+        out = _head(W, s).transpose(1, 2).contiguous()
+    res = {"out": out.numpy()}
+    if cfg.kind == "cswnv":
+        log_b = F.logsigmoid(out[:, :, seg:2 * seg])
+        res.update(mu=out[:, :, :seg].numpy(), b=torch.exp(log_b).numpy(), log_b=log_b.numpy(), a=out[:, :, 2 * seg:].numpy())
+        if clip:
+            lc = torch.clamp(log_b, min=-14.162084148244246758816564788835)
+            res.update(b_clip=torch.exp(lc).numpy(), log_b_clip=lc.numpy())
+    return res
 
 
 # --------------------------------------------------------------------------

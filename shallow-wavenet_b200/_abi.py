@@ -17,7 +17,7 @@ KIND_CSWNV = 0
 KIND_DSWNV = 1
 
 # every symbol include/swn_b200.h declares (checked by tests/test_abi_symbols.py)
-SYMBOLS = ("swn_create", "swn_set_tensor", "swn_finalize", "swn_condition", "swn_generate", "swn_teacher_forced", "swn_sync",
+SYMBOLS = ("swn_create", "swn_set_tensor", "swn_finalize", "swn_condition", "swn_generate", "swn_teacher_forced", "swn_forward", "swn_sync",
            "swn_generate_host", "swn_get_info", "swn_philox_uniform", "swn_measure_smem_bandwidth", "swn_destroy",
            "swn_last_error")
 
@@ -35,6 +35,12 @@ class SwnGenArgs(ctypes.Structure):
                 ("seed_dev", ctypes.c_void_p), ("batch_tile", ctypes.c_int32), ("poll_mode", ctypes.c_int32),
                 ("prof_dev", ctypes.c_void_p), ("prof_start", ctypes.c_int32), ("prof_count", ctypes.c_int32),
                 ("kernel_sel", ctypes.c_int32), ("reserved", ctypes.c_int32), ("n_samples_list", ctypes.c_void_p)]
+
+
+class SwnFwdArgs(ctypes.Structure):
+    _fields_ = [("audio_dev", ctypes.c_void_p), ("audio_onehot", ctypes.c_int32), ("clip", ctypes.c_int32), ("T_a", ctypes.c_int64),
+                ("out_dev", ctypes.c_void_p), ("b_dev", ctypes.c_void_p), ("log_b_dev", ctypes.c_void_p),
+                ("b_clip_dev", ctypes.c_void_p), ("log_b_clip_dev", ctypes.c_void_p)]
 
 
 class SwnInfo(ctypes.Structure):
@@ -72,6 +78,7 @@ def load():
     lib.swn_condition.argtypes = [vp, vp, i32, i32, vp]
     lib.swn_generate.argtypes = [vp, ctypes.POINTER(SwnGenArgs), vp]
     lib.swn_teacher_forced.argtypes = [vp, vp, i64, vp, vp]
+    lib.swn_forward.argtypes = [vp, ctypes.POINTER(SwnFwdArgs), vp]
     lib.swn_sync.argtypes = [vp, vp]
     lib.swn_generate_host.argtypes = [vp, vp, i32, i32, i64, u64, vp]
     lib.swn_get_info.argtypes = [vp, ctypes.POINTER(SwnInfo)]

@@ -18,6 +18,7 @@
 #include "swn_core.cuh"
 #include "swn_batch.cuh"
 #include "swn_launch.h"
+#include "swn_fwd.h"
 
 namespace {
 
@@ -137,6 +138,13 @@ struct swn_model {
     long long plan3_key = -1;
     int grid3 = 0, nh3 = 0;
     size_t smem3 = 0, ring3_total = 0;
+    // ---- time-parallel teacher-forced forward (swn_fwd.cu)
+    bool fwd_ready = false;
+    struct FwdW { DevBuf<float> A, bias; int n_mt = 0, n_kb = 0, C = 0, Cpad = 0, ntaps = 0, rows = 0; std::vector<int> delay; };
+    std::vector<FwdW> fwd_gate;                // [L]
+    FwdW fwd_skip, fwd_out1, fwd_out2;
+    DevBuf<float> fwd_h_hi, fwd_h_lo, fwd_p, fwd_x1_hi, fwd_x1_lo, fwd_x2_hi, fwd_x2_lo;
+    DevBuf<int32_t> fwd_idx, fwd_bad;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool cond_timed = false, gen_timed = false;
     swn_info info;
@@ -858,6 +866,64 @@ static int generate_batch(swn_model* m, const swn_gen_args* a, cudaStream_t st, 
     return 0;
 }
 
+// ---- packing of one forward GEMM operand (weights W[rows][ntaps][C] given through `at(row, tap, c)`)
+template <typename F>
+static int pack_fwd(swn_model::FwdW& w, int rows, int ntaps, int C, bool gate, int H, const std::vector<float>& bias, F at) {
+    const int BK = swn::fwd_bk(), BM = swn::fwd_bm();
+    w.rows = rows; w.ntaps = ntaps; w.C = C; w.Cpad = round_up(C, BK);
+    const int ktot = ntaps * w.Cpad;
+    w.n_kb = ktot / BK;
+    w.n_mt = gate ? (H + BM / 2 - 1) / (BM / 2) : (rows + BM - 1) / BM;
+    std::vector<float> W((size_t)rows * ktot, 0.f);
+    for (int r = 0; r < rows; ++r)
+        for (int j = 0; j < ntaps; ++j)
+            for (int c = 0; c < C; ++c) W[(size_t)r * ktot + (size_t)j * w.Cpad + c] = at(r, j, c);
+    std::vector<int> map((size_t)w.n_mt * BM, -1);
+    for (int i = 0; i < w.n_mt * BM; ++i) {
+        if (gate) { const int pair = (i / BM) * (BM / 2) + (i % BM) / 2; if (pair < H) map[i] = (i & 1) * H + pair; }
+        else if (i < rows) map[i] = i;
+    }
+    std::vector<float> packed((size_t)w.n_mt * w.n_kb * 2 * BM * BK);
+    swn::pack_fwd_weights(W.data(), ktot, w.n_mt, map.data(), packed.data());
+    if (upload(w.A, packed) || upload(w.bias, bias)) return 1;
+    return 0;
+}
+
+static int fwd_prepare(swn_model* m) {
+    if (m->fwd_ready) return 0;
+    const int H = m->H, S = m->S, K = m->K, L = m->L, n1 = m->n1, n2 = m->n2;
+    m->fwd_gate.clear();
+    m->fwd_gate.resize(L);
+    const HostTensor *x, *y;
+    for (int l = 0; l < L; ++l) {
+        if (need(m, "dil_h." + std::to_string(l) + ".conv.weight", {2 * H, H, K}, &x) ||
+            need(m, "dil_h." + std::to_string(l) + ".conv.bias", {2 * H}, &y)) return 1;
+        auto& w = m->fwd_gate[l];
+        if (pack_fwd(w, 2 * H, K, H, true, H, y->data, [&](int r, int j, int c) { return x->data[((size_t)r * H + c) * K + j]; })) return 1;
+        w.delay.resize(K);
+        for (int j = 0; j < K; ++j) w.delay[j] = (K - 1 - j) * m->dil[l];
+    }
+    {   // sum of the L skip projections as one contraction over the stacked layer outputs (cswnv_shift1.py:209-225)
+        std::vector<const HostTensor*> sw(L);
+        std::vector<float> bias(S, 0.f);
+        for (int l = 0; l < L; ++l) {
+            if (need(m, "out_skip." + std::to_string(l) + ".weight", {S, H, 1}, &sw[l]) ||
+                need(m, "out_skip." + std::to_string(l) + ".bias", {S}, &y)) return 1;
+            for (int r = 0; r < S; ++r) bias[r] += y->data[r];
+        }
+        if (pack_fwd(m->fwd_skip, S, L, H, false, H, bias, [&](int r, int j, int c) { return sw[j]->data[(size_t)r * H + c]; })) return 1;
+        m->fwd_skip.delay.assign(L, 0);
+    }
+    if (need(m, "out_1.weight", {n1, S, 1}, &x) || need(m, "out_1.bias", {n1}, &y)) return 1;
+    if (pack_fwd(m->fwd_out1, n1, 1, S, false, H, y->data, [&](int r, int, int c) { return x->data[(size_t)r * S + c]; })) return 1;
+    m->fwd_out1.delay.assign(1, 0);
+    if (need(m, "out_2.weight", {n2, n1, 1}, &x) || need(m, "out_2.bias", {n2}, &y)) return 1;
+    if (pack_fwd(m->fwd_out2, n2, 1, n1, false, H, y->data, [&](int r, int, int c) { return x->data[(size_t)r * n1 + c]; })) return 1;
+    m->fwd_out2.delay.assign(1, 0);
+    m->fwd_ready = true;
+    return 0;
+}
+
 extern "C" {
 
 const char* swn_last_error(void) { return g_err; }
@@ -943,6 +1009,7 @@ int swn_set_tensor(swn_handle h, const char* key, const float* host, const int64
     x.data.assign(host, host + n);
     h->t[key] = std::move(x);
     h->finalized = false;
+    h->fwd_ready = false;
     return 0;
 }
 
@@ -1436,6 +1503,118 @@ int swn_teacher_forced(swn_handle m, const void* samples_dev, int64_t n_samples,
     return swn_generate(m, &a, stream);
 }
 
+int swn_forward(swn_handle m, const swn_fwd_args* a, void* stream) {
+    if (!m || !a) return fail("swn_forward: null argument");
+    if (!m->finalized || m->condB < 1) return fail("swn_forward: call swn_finalize and swn_condition first");
+    if (!a->audio_dev || !a->out_dev) return fail("swn_forward: audio_dev / out_dev is null");
+    CUDA_OK(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool is_c = m->cfg.kind == SWN_KIND_CSWNV;
+    const int B = m->condB, Tf = m->condTf, seg = m->seg, H = m->H, S = m->S, L = m->L, n1 = m->n1, n2 = m->n2, Q = m->Q;
+    const long long T_out = (long long)Tf * m->U - 2 * seg + 1;             // cswnv_shift1.py:193-201, dswnv.py:252
+    if (T_out < 1) return fail("swn_forward: the conditioning is too short (T_f * U = %lld)", (long long)Tf * m->U);
+    if (a->T_a != T_out + seg - 1)
+        return fail("swn_forward: audio length %lld does not match the conditioning: expected T_f*U - seg = %lld",
+                    (long long)a->T_a, T_out + seg - 1);
+    if ((long long)B * T_out > 0x7fffffffLL) return fail("swn_forward: too many time steps in one call");
+    if (is_c && (!a->b_dev || !a->log_b_dev)) return fail("swn_forward: b_dev / log_b_dev is null");
+    if (L + 1 > 16 || m->K > 16) return fail("swn_forward: more than 16 layers / taps");
+    if (!is_c && m->cfg.audio_in_flag && !m->xa_tab.p) return fail("swn_forward: audio_in table missing");
+    if (fwd_prepare(m)) return 1;
+    const int T = (int)T_out, Ta = (int)a->T_a;
+    const size_t rows = (size_t)B * T;
+    const int Hq = round_up(H, 4), Sq = round_up(S, 4), n1q = round_up(n1, 4);
+    const int ldh = (L + 1) * Hq;
+    auto grow = [&](DevBuf<float>& d, size_t n) {
+        if (n <= d.n && d.p) return 0;
+        if (d.ensure(n)) return 1;
+        return cudaMemsetAsync(d.p, 0, n * sizeof(float), st) == cudaSuccess ? 0 : fail("cudaMemsetAsync failed");
+    };
+    if (grow(m->fwd_h_hi, rows * ldh) || grow(m->fwd_h_lo, rows * ldh) || grow(m->fwd_p, rows * 2 * H) ||
+        grow(m->fwd_x1_hi, rows * Sq) || grow(m->fwd_x1_lo, rows * Sq) || grow(m->fwd_x2_hi, rows * n1q) ||
+        grow(m->fwd_x2_lo, rows * n1q)) return 1;
+    CUDA_OK(cudaMemsetAsync(m->status.p, 0, 8 * sizeof(int32_t), st));
+    CUDA_OK(cudaEventRecord(m->ev[2], st));
+    const int32_t* idx = nullptr;
+    if (!is_c) {
+        if (m->fwd_idx.ensure((size_t)B * Ta) || m->fwd_bad.ensure(1)) return 1;
+        CUDA_OK(cudaMemsetAsync(m->fwd_bad.p, 0, sizeof(int32_t), st));
+        if (a->audio_onehot) CUDA_OK(swn::launch_fwd_onehot((const float*)a->audio_dev, B, Q, Ta, m->fwd_idx.p, m->fwd_bad.p, st));
+        else CUDA_OK(swn::launch_fwd_index((const long long*)a->audio_dev, Q, (long long)B * Ta, m->fwd_idx.p, st));
+        idx = m->fwd_idx.p;
+        m->info.kernel_launches++;
+    }
+    {
+        swn::FwdInput I;
+        memset(&I, 0, sizeof(I));
+        I.kind = m->cfg.kind; I.H = H; I.K = m->K; I.Q = Q; I.seg = seg; I.T = T; I.Ta = Ta; I.nbatch = B; I.ld = ldh;
+        I.in_tab = m->in_tab.p; I.in_bias = m->in_bias.p;
+        I.audio_f = is_c ? (const float*)a->audio_dev : nullptr; I.audio_i = idx;
+        I.out_hi = m->fwd_h_hi.p; I.out_lo = m->fwd_h_lo.p;
+        CUDA_OK(swn::launch_fwd_input(I, st));
+        m->info.kernel_launches++;
+    }
+    auto gemm = [&](const swn_model::FwdW& w, swn::FwdGemm& g) {
+        g.A = w.A.p; g.C = w.C; g.Cpad = w.Cpad; g.ntaps = w.ntaps; g.n_kb = w.n_kb; g.n_mt = w.n_mt;
+        for (int j = 0; j < w.ntaps; ++j) g.delay[j] = w.delay[j];
+        g.T = T; g.nbatch = B; g.rows = w.rows; g.H = H; g.bias = w.bias.p; g.status = m->status.p;
+        m->info.kernel_launches++;
+        return swn::launch_fwd_gemm(g, st);
+    };
+    for (int l = 0; l < L; ++l) {
+        swn::FwdCond C;
+        memset(&C, 0, sizeof(C));
+        C.H = H; C.L = L; C.l = l; C.seg = seg; C.U = m->U; C.T = T; C.Tf = Tf; C.Ta = Ta; C.Q = Q; C.nbatch = B;
+        C.P = m->ptab.p; C.pconst = m->pconst.p; C.gain = m->gain.p;
+        C.xa_tab = (!is_c && m->cfg.audio_in_flag) ? m->xa_tab.p : nullptr; C.audio_i = idx;
+        C.out = m->fwd_p.p;
+        CUDA_OK(swn::launch_fwd_cond(C, st));
+        m->info.kernel_launches++;
+        swn::FwdGemm g;
+        memset(&g, 0, sizeof(g));
+        g.mode = swn::FWD_GATE;
+        g.Bhi = m->fwd_h_hi.p; g.Blo = m->fwd_h_lo.p; g.ldb = ldh; g.b_col0 = l * Hq; g.tap_col_stride = 0;
+        g.p = m->fwd_p.p; g.carry_col0 = l * Hq;
+        g.out_hi = m->fwd_h_hi.p; g.out_lo = m->fwd_h_lo.p; g.ldo = ldh; g.out_col0 = (l + 1) * Hq;
+        CUDA_OK(gemm(m->fwd_gate[l], g));
+    }
+    {
+        swn::FwdGemm g;
+        memset(&g, 0, sizeof(g));
+        g.mode = swn::FWD_RELU;
+        g.Bhi = m->fwd_h_hi.p; g.Blo = m->fwd_h_lo.p; g.ldb = ldh; g.b_col0 = Hq; g.tap_col_stride = Hq;
+        g.out_hi = m->fwd_x1_hi.p; g.out_lo = m->fwd_x1_lo.p; g.ldo = Sq; g.out_col0 = 0;
+        CUDA_OK(gemm(m->fwd_skip, g));
+    }
+    {
+        swn::FwdGemm g;
+        memset(&g, 0, sizeof(g));
+        g.mode = swn::FWD_RELU;
+        g.Bhi = m->fwd_x1_hi.p; g.Blo = m->fwd_x1_lo.p; g.ldb = Sq; g.b_col0 = 0; g.tap_col_stride = 0;
+        g.out_hi = m->fwd_x2_hi.p; g.out_lo = m->fwd_x2_lo.p; g.ldo = n1q; g.out_col0 = 0;
+        CUDA_OK(gemm(m->fwd_out1, g));
+    }
+    {
+        swn::FwdGemm g;
+        memset(&g, 0, sizeof(g));
+        g.mode = swn::FWD_LINEAR;
+        g.Bhi = m->fwd_x2_hi.p; g.Blo = m->fwd_x2_lo.p; g.ldb = n1q; g.b_col0 = 0; g.tap_col_stride = 0;
+        g.out_f = a->out_dev; g.ldf = n2;
+        CUDA_OK(gemm(m->fwd_out2, g));
+    }
+    if (is_c) {
+        CUDA_OK(swn::launch_fwd_laplace(a->out_dev, n2, seg, (long long)rows, a->b_dev, a->log_b_dev,
+                                        a->clip ? a->b_clip_dev : nullptr, a->clip ? a->log_b_clip_dev : nullptr, st));
+        m->info.kernel_launches++;
+    }
+    CUDA_OK(cudaEventRecord(m->ev[3], st));
+    m->gen_timed = true;
+    m->info.kernel_variant = 5;
+    m->info.grid = (int32_t)(((T + 255) / 256) * B);
+    m->info.batch_tile = B; m->info.n_slots = 1;
+    return 0;
+}
+
 int swn_sync(swn_handle m, void* stream) {
     if (!m) return fail("swn_sync: null handle");
     CUDA_OK(cudaSetDevice(m->device));
@@ -1447,7 +1626,13 @@ int swn_sync(swn_handle m, void* stream) {
         int32_t stv[8];
         CUDA_OK(cudaMemcpy(stv, m->status.p, sizeof(stv), cudaMemcpyDeviceToHost));
         if (stv[0] != 0)
-            return fail("persistent kernel aborted: watchdog fired at wait site %d (tag %d, CTA %d)", stv[1], stv[2], stv[3]);
+            return fail("%s aborted: watchdog fired at wait site %d (tag %d, CTA %d)", stv[0] == 2 ? "forward GEMM" : "persistent kernel",
+                        stv[1], stv[2], stv[3]);
+        if (m->info.kernel_variant == 5 && m->fwd_bad.p) {
+            int32_t bad = 0;
+            CUDA_OK(cudaMemcpy(&bad, m->fwd_bad.p, sizeof(bad), cudaMemcpyDeviceToHost));
+            if (bad) return fail("swn_forward: %d columns of the audio tensor are not one-hot", bad);
+        }
     }
     return 0;
 }

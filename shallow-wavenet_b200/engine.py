@@ -112,6 +112,44 @@ class Engine(object):
             self.sync()
         return heads
 
+    def forward(self, audio, clip=False, sync=True):
+        """swn_forward: the training-time / evaluation forward over whole utterances (time-parallel tcgen05 GEMMs).
+        audio: CSWNV float [B, T_a]; DSWNV int64 [B, T_a] indices or float one-hot [B, Q, T_a].  Returns a dict of CUDA
+        tensors: ``out`` [B, T, head_dim] raw out_2 rows and, for CSWNV, ``b`` / ``log_b`` (and the clipped pair)."""
+        info = self.info
+        seg, hd = info["eff_seg"], info["head_dim"]
+        is_c = self.kind == "cswnv"
+        B = self._B
+        a = _abi.SwnFwdArgs()
+        if is_c:
+            t = torch.as_tensor(audio).to(self.device, torch.float32).contiguous()
+            assert t.dim() == 2 and t.shape[0] == B, (tuple(t.shape), B)
+            a.audio_onehot = 0
+        elif torch.as_tensor(audio).dtype.is_floating_point:
+            t = torch.as_tensor(audio).to(self.device, torch.float32).contiguous()
+            assert t.dim() == 3 and t.shape[0] == B, (tuple(t.shape), B)
+            a.audio_onehot = 1
+        else:
+            t = torch.as_tensor(audio).to(self.device, torch.int64).contiguous()
+            assert t.dim() == 2 and t.shape[0] == B, (tuple(t.shape), B)
+            a.audio_onehot = 0
+        Ta = int(t.shape[-1])
+        T = Ta - seg + 1
+        res = {"out": torch.empty((B, T, hd), dtype=torch.float32, device=self.device)}
+        a.audio_dev = t.data_ptr()
+        a.T_a = Ta
+        a.clip = 1 if clip else 0
+        a.out_dev = res["out"].data_ptr()
+        if is_c:
+            for k in ("b", "log_b") + (("b_clip", "log_b_clip") if clip else ()):
+                res[k] = torch.empty((B, T, seg), dtype=torch.float32, device=self.device)
+                setattr(a, k + "_dev", res[k].data_ptr())
+        _abi.check(self.lib.swn_forward(self.h, ctypes.byref(a), self._stream()))
+        self._keep = [t]
+        if sync:
+            self.sync()
+        return res
+
     def sync(self):
         _abi.check(self.lib.swn_sync(self.h, self._stream()))
         self.info = self.get_info()

@@ -138,10 +138,16 @@ class _SWNBase(nn.Module):
                                "(no CPU fallback exists)" % type(self).__name__)
         return self._engine_for(dev)
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError(
-            "the teacher-forced training forward is outside the scope of this path (SURVEY.md 8f rank 3); "
-            "use batch_fast_generate(..., forced=...) for teacher-forced head outputs")
+    def _forward_engine(self, aux, audio, do, clip=False):
+        """Shared part of the two ``forward`` methods: conditioning + swn_forward on the model's device."""
+        if do and self.do_prob > 0:
+            raise NotImplementedError("dropout (do=True) is a training-only feature; this forward is inference only")
+        eng = self.engine()
+        aux = torch.as_tensor(aux).to(eng.device, torch.float32).contiguous()
+        if aux.dim() != 3 or aux.shape[1] != self.n_aux:
+            raise ValueError("aux must be [B, n_aux, T]; got %s" % (tuple(aux.shape),))
+        eng.condition(aux)
+        return eng.forward(audio, clip=clip)
 
     # ------------------------------------------------------------------ the generate call
     def _generate(self, audio, aux, n_samples_list, intervals, noise, seed, forced, return_heads, batch_tile,

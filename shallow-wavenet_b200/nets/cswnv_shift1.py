@@ -8,6 +8,8 @@ src/bin/decode_cswnv_laplace-shift1.py:208-248.
 """
 from torch import nn
 
+import torch
+
 from ._base import _SWNBase, _ParamConv, initialize  # noqa: F401
 
 
@@ -52,6 +54,29 @@ class CSWNV(_SWNBase):
                     kernel_size=self.kernel_size, upsampling_factor=self.upsampling_factor, seg=self.seg,
                     lpc=self.lpc, aux_conv2d_flag=self.aux_conv2d_flag, wav_conv_flag=self.wav_conv_flag,
                     audio_in_flag=0)
+
+    def forward(self, aux, audio, do=False, clip=False):
+        """``CSWNV.forward`` of the reference (cswnv_shift1.py:191-267), inference only.  Argument order (aux, audio) as
+        there: ``aux`` [B, n_aux, T_f], ``audio`` [B, 1, T_a] (or [B, T_a]) with T_a = T_f * U - seg.  Returns CUDA tensors in
+        the reference's layouts: ``(mu, b, log_b, a)`` for lpc > 0 (mu / b / log_b [B, T, seg], a [B, T, lpc], T = T_a - seg + 1),
+        ``(mu, b, log_b)`` without LP coefficients ([B, T] each when seg == 1); with ``clip=True`` the clipped scale pair
+        is inserted after ``b`` as the reference does (:233-240).  Computed time-parallel by tcgen05 GEMMs (swn_forward)."""
+        audio = torch.as_tensor(audio)
+        if audio.dim() == 3:
+            if audio.shape[1] != 1:
+                raise ValueError("audio must be [B, 1, T]; got %s" % (tuple(audio.shape),))
+            audio = audio[:, 0]
+        r = self._forward_engine(aux, audio, do, clip)
+        seg, lpc = self.seg, self.lpc
+        out = r["out"]
+        mu = out[:, :, :seg]
+        scale = (r["b"], r["b_clip"], r["log_b_clip"]) if clip else (r["b"], r["log_b"])
+        if lpc > 0:
+            return (mu,) + scale + (out[:, :, 2 * seg:],)
+        if seg > 1:
+            return (mu,) + scale
+        B = out.shape[0]
+        return (mu.reshape(B, -1),) + tuple(x.reshape(B, -1) for x in scale)
 
     def batch_fast_generate(self, audio, aux, n_samples_list, intervals=4410, Laplace=True, *, noise=None,
                             seed=None, forced=None, return_heads=False, batch_tile=0, kernel_sel=0):

@@ -63,6 +63,12 @@ class DSWNV(_SWNBase):
                     kernel_size=self.kernel_size, upsampling_factor=self.upsampling_factor, seg=1, lpc=0,
                     aux_conv2d_flag=0, wav_conv_flag=self.wav_conv_flag, audio_in_flag=self.audio_in_flag)
 
+    def forward(self, audio, aux, do=False, last=False):
+        """``DSWNV.forward`` of the reference (dswnv.py:250-276), inference only: ``audio`` is the one-hot float tensor
+        [B, n_quantize, T_a] (or int64 class indices [B, T_a]), ``aux`` [B, n_aux, T_f] with T_a = T_f * U - 1; returns
+        the logits [B, T_a, n_quantize] as a CUDA tensor.  Computed time-parallel by tcgen05 GEMMs (swn_forward)."""
+        return self._forward_engine(aux, audio, do)["out"]
+
     def batch_fast_generate(self, audio, aux, n_samples_list, intervals=4410, *, noise=None, seed=None,
                             forced=None, return_heads=False, batch_tile=0, kernel_sel=0):
         """Same call as the reference (dswnv.py:296): ``audio`` [B, 1] int64 seed (mu-law index),

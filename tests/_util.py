@@ -88,3 +88,40 @@ def head_errors(a, b, kind, kw, floor=0.05):
         scale = np.abs(b[..., sl]).max(axis=-1, keepdims=True) + floor
         out[name] = float((d / scale).max()) if d.size else 0.0
     return out
+
+
+GOLDEN_FORWARD = os.path.join(ROOT, "tests", "golden_forward")
+
+
+def forward_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_FORWARD, "*.npz")))
+
+
+def load_forward(name):
+    """Fixture of the training-time forward written by tests/golden/make_forward_golden.py from the UNMODIFIED reference.
+    Returns kind, kw, cfg, sd, aux, audio and the reference outputs (``ref``: name -> array)."""
+    z = np.load(os.path.join(GOLDEN_FORWARD, name + ".npz"))
+    if "base" in z.files:
+        g = load_golden(str(z["base"]))
+        kind, kw, cfg, sd, aux = g["kind"], g["kw"], g["cfg"], g["sd"], g["aux"]
+    else:
+        from shallow_wavenet_b200 import synth
+        kw = {k[4:]: z[k].item() for k in z.files if k.startswith("cfg.")}
+        kind = str(z["kind"])
+        model = synth.make_model(kind, seed=int(z["weight_seed"]), **kw)
+        sd = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+        sums = np.array([np.asarray(sd[k], np.float64).sum() for k in sd])
+        assert np.array_equal(sums, z["sd_sums"]), "synth.make_model no longer reproduces the fixture's weights"
+        cfg, aux = SWNConfig(kind=kind, **kw), z["aux"]
+    return dict(name=name, kind=kind, kw=kw, cfg=cfg, sd=sd, aux=aux, audio=z["audio"],
+                ref={k[4:]: z[k] for k in z.files if k.startswith("ref.")})
+
+
+def scaled_err(a, b, floor=0.05):
+    """max|a-b| / (max|b| over the last axis + floor)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.ndim == 2:
+        a, b = a[..., None], b[..., None]
+    return float((np.abs(a - b) / (np.abs(b).max(axis=-1, keepdims=True) + floor)).max())
