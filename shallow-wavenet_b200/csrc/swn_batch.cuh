@@ -132,7 +132,24 @@ __device__ __forceinline__ bool b3_mbar_try(unsigned long long* b, uint32_t pari
     return done != 0;
 }
 // wait with an escape: returns false when another CTA / role aborted
+#ifndef B3_WAIT_TIME
+#define B3_WAIT_TIME 0       // 1: the abort flag is looked at on a time basis (every ~100k cycles) instead of every 64 polls
+#endif
 __device__ __forceinline__ bool b3_mbar_wait(unsigned long long* b, uint32_t parity, const int32_t* status) {
+#if B3_WAIT_TIME
+    // a poll-count based check puts a ~700-cycle L2 load of the flag between two polls every 64 polls: a waiting role
+    // then sees its barrier late (same finding as in the cluster kernel, swn_core2.cuh mbar_wait_slow2)
+    if (b3_mbar_try(b, parity)) return true;
+    long long next = clock64() + 100000;
+    while (!b3_mbar_try(b, parity)) {
+        const long long now = clock64();
+        if (now > next) {
+            if (((volatile const int32_t*)status)[0] != 0) return false;
+            next = now + 100000;
+        }
+    }
+    return true;
+#endif
     uint32_t spins = 0;
     while (!b3_mbar_try(b, parity)) {
 #if B3_WAIT_SLEEP_NS

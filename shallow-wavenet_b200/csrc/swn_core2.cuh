@@ -28,8 +28,18 @@
         if (P.prof && threadIdx.x == 0 && it >= P.prof_start && it < P.prof_start + P.prof_count) \
             P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + (ev)] = gtime();  \
     } while (0)
+// lane 0 of warps 0, 4, 8 and 15 (one per role, plus the last) stamps into slot ev + {0, 1, 2, 3}
+#define SWN_WSTAMP(ev)                                                                             \
+    do {                                                                                           \
+        if (P.prof && (threadIdx.x & 31) == 0 && it >= P.prof_start && it < P.prof_start + P.prof_count) { \
+            const int w_ = threadIdx.x >> 5;                                                       \
+            const int s_ = w_ == 0 ? 0 : (w_ == 4 ? 1 : (w_ == 8 ? 2 : (w_ == 15 ? 3 : -1)));      \
+            if (s_ >= 0) P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + (ev) + s_] = gtime(); \
+        }                                                                                          \
+    } while (0)
 #else
 #define SWN_STAMP(ev) do {} while (0)
+#define SWN_WSTAMP(ev) do {} while (0)
 #endif
 
 namespace swn {
@@ -60,10 +70,31 @@ __device__ __forceinline__ void reduce_pairs(const float (&v)[8], int lane, floa
     qz = z; qc = c;
 }
 
+// Sleep on a local mbarrier until the phase with `parity` has completed.  The watchdog (abort flag in global memory,
+// cycle budget) is consulted on a time basis, every ~50k cycles, so that no L2 load of the flag ever sits between two
+// polls of a warp that is about to be woken (measured neutral against the poll-count based check: try_wait suspends
+// long enough that the count rarely got there; kept because it bounds the worst case).
+static __device__ __noinline__ bool mbar_wait_slow2(unsigned long long* b, uint32_t parity, const CoreParams& P, int where) {
+    const long long t_start = clock64();
+    long long next_check = t_start + 50000;
+    for (;;) {
+        if (mbar_try(b, parity)) return true;
+        const long long now = clock64();
+        if (now > next_check) {
+            next_check = now + 50000;
+            volatile int32_t* st = P.status;
+            if (st[0] != 0) return false;
+            if ((unsigned long long)(now - t_start) > (P.timeout_cycles >> 1)) {
+                if (atomicCAS((int*)P.status, 0, 1) == 0) { st[1] = where; st[2] = (int)parity; st[3] = blockIdx.x; }
+                return false;
+            }
+        }
+    }
+}
 __device__ __forceinline__ bool mbar_wait2(unsigned long long* b, uint32_t parity, const CoreParams& P, int where) {
     if (mbar_try(b, parity)) return true;
-    if (mbar_try(b, parity)) return true;                // (try_wait suspends the warp for a hardware time slice)
-    return mbar_wait_slow(b, parity, P, where);
+    if (mbar_try(b, parity)) return true;
+    return mbar_wait_slow2(b, parity, P, where);
 }
 
 template <int NCH, int BS>
@@ -181,8 +212,7 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
     cluster_sync_all();                                            // every CTA's buffers and barriers are ready
 
     const uint32_t peer = (uint32_t)(lane & (CORE_CL - 1));
-    const uint32_t hx_peer = mapa(smem_u32(hx), peer), x1_peer = mapa(smem_u32(x1), peer),
-                   x2_peer = mapa(smem_u32(x2), peer), gx_peer = mapa(smem_u32(gx), peer), mb_peer = mapa(smem_u32(mb), peer);
+    const uint32_t hx_peer = mapa(smem_u32(hx), peer), mb_peer = mapa(smem_u32(mb), peer);
     const int twoH = 2 * H;
     // ---- roles inside the CTA (one warp group = 4 warps = one warp per SM sub-partition):
     //   warps 0-3   "chain" warps: each evaluates the delay-0 tap of 4 gate pairs (8 rows), gates, publishes
@@ -197,13 +227,31 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
     const int sub = lane & 7;                                      // lane inside the pair group
     const int colc = sub < NC ? sub : 0;                           // column this lane gates (idle lanes shadow column 0)
     const int skr0 = 2 * (warp - 8), skr1 = skr0 + 1;              // skip rows of warps 8..15
-    const float b1w = (warp < D.nb) ? __ldg(P.wbuf + D.b1_off + warp) : 0.f;
-    const float b2w = (warp < D.nc) ? __ldg(P.wbuf + D.b2_off + warp) : 0.f;
-    float cst0 = 0.f, cst1 = 0.f;
-    if (warp >= 8) {
-        if (skr0 < D.nskip) cst0 = __ldg(P.wbuf + D.skipc_off + skr0);
-        if (skr1 < D.nskip) cst1 = __ldg(P.wbuf + D.skipc_off + skr1);
+    // ---- per-warp head record in shared memory: what a head stage needs between its wake-up and its publish (remote byte
+    // offsets relative to hx, biases).  It is fetched BEFORE the stage's wait; taken from the descriptor in global memory or
+    // recomputed, the same values cost an L1/L2 round trip, constant-bank loads and spill reloads after the wake-up
+    // (SASS of the first version of this file: LDG D.c0 -> IMAD -> LDL -> STAS behind the out_2 reduction).
+    uint4* hrec_off = reinterpret_cast<uint4*>(gnz + 2 * 16 * NC);          // [16] {x1 row a, x1 row b, x2 row, score row}
+    float4* hrec_c = reinterpret_cast<float4*>(hrec_off + 16);             // [16] {skip const a, skip const b, out_1 bias, out_2 bias}
+    if (lane == 0) {
+        const uint32_t o_x1 = (uint32_t)((x1 - hx) * 4), o_x2 = (uint32_t)((x2 - hx) * 4), o_gx = (uint32_t)((gx - hx) * 4);
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (warp >= 8) {
+            o.x = o_x1 + (uint32_t)((D.skip0 + skr0) * 4); o.y = o_x1 + (uint32_t)((D.skip0 + skr1) * 4);
+            if (skr0 < D.nskip) c4.x = __ldg(P.wbuf + D.skipc_off + skr0);
+            if (skr1 < D.nskip) c4.y = __ldg(P.wbuf + D.skipc_off + skr1);
+        }
+        o.z = o_x2 + (uint32_t)((D.b0 + warp) * 4); o.w = o_gx + (uint32_t)((D.c0 + warp) * 4);
+        if (warp < D.nb) c4.z = __ldg(P.wbuf + D.b1_off + warp);
+        if (warp < D.nc) c4.w = __ldg(P.wbuf + D.b2_off + warp);
+        hrec_off[warp] = o; hrec_c[warp] = c4;
     }
+    const bool has_b = warp < D.nb, has_c = warp < D.nc;                   // this warp owns a row of out_1 / out_2
+    const bool sk_v0 = skr0 < D.nskip, sk_v1 = skr1 < D.nskip;
+    const int c0row = D.c0 + warp;                                         // logit row of this warp
+    const int ws_stride = D.nskip * HP;                                    // floats between the out_skip blocks of two layers
+    const uint32_t mbh = mb_peer + (uint32_t)((L + 1) * 8);                // x1 barrier of the peer; x2 = +8, scores = +16
     // chain warps: where lane `sub` of a pair group publishes (CTAs sub and sub + 8), layer-0 addresses
     const uint32_t pub0 = mapa(smem_u32(hx), (uint32_t)sub) + (uint32_t)(my_i * 4);
     const uint32_t pub1 = mapa(smem_u32(hx), (uint32_t)sub + 8) + (uint32_t)(my_i * 4);
@@ -304,7 +352,8 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
             else acc += sTin[__float_as_int(fed[c]) * nip + warp];
             __syncwarp();
             if (lane == 0) *slot = 0.f;                              // the slot is reused 8 steps later
-            const float v = softsignf_(acc);
+            // softsign through rcp.approx (1 ulp) instead of the IEEE division sequence: it sits between the arg-max and the publish
+            const float v = acc * rcp_approx(1.f + fabsf(acc));
             if (lane < CORE_CL) st_async_f32(hx_peer + (uint32_t)((c * HP + in_row) * 4), v, mb_peer);
             if (lane == 16 && P.has_help[0])
                 st_ll(P.hin_ll + P.hin_off[0] + ((itn & (P.hslots[0] - 1)) * NC + c) * H + in_row, v, (uint32_t)itn + 1u);
@@ -451,7 +500,8 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
             float sk0[NC], sk1[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) { sk0[c] = 0.f; sk1[c] = 0.f; }
-            const bool v0 = skr0 < D.nskip, v1 = skr1 < D.nskip;
+            const bool v0 = sk_v0, v1 = sk_v1;
+            const int nsk = ws_stride;
             const float* ws_base0 = sSkip + (size_t)(v0 ? skr0 : 0) * HP;
             const float* ws_base1 = sSkip + (size_t)(v1 ? skr1 : 0) * HP;
             for (int l = 0; l < L; ++l) {
@@ -460,8 +510,8 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                     float2 h[NC][NCH], ws0[NCH], ws1[NCH];
 #pragma unroll
                     for (int c = 0; c < NC; ++c) load_frag<NCH>(h[c], hx + (l * NC + c) * HP, lane);
-                    load_frag<NCH>(ws0, ws_base0 + (size_t)(l - 1) * D.nskip * HP, lane);
-                    load_frag<NCH>(ws1, ws_base1 + (size_t)(l - 1) * D.nskip * HP, lane);
+                    load_frag<NCH>(ws0, ws_base0 + (size_t)(l - 1) * nsk, lane);
+                    load_frag<NCH>(ws1, ws_base1 + (size_t)(l - 1) * nsk, lane);
 #pragma unroll
                     for (int c = 0; c < NC; ++c) { sk0[c] += dot_frag<NCH>(ws0, h[c]); sk1[c] += dot_frag<NCH>(ws1, h[c]); }
                 }
@@ -470,8 +520,10 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                 // ---- out_skip[L-1] on the output of the last layer; relu(sum of skips) -> x1 on every CTA.  The weight
                 // rows are in registers before the vector lands.
                 float2 ws0[NCH], ws1[NCH];
-                load_frag<NCH>(ws0, ws_base0 + (size_t)(L - 1) * D.nskip * HP, lane);
-                load_frag<NCH>(ws1, ws_base1 + (size_t)(L - 1) * D.nskip * HP, lane);
+                load_frag<NCH>(ws0, ws_base0 + (size_t)(L - 1) * nsk, lane);
+                load_frag<NCH>(ws1, ws_base1 + (size_t)(L - 1) * nsk, lane);
+                const uint4 ro = hrec_off[warp];
+                const float4 rc = hrec_c[warp];
                 ok = mbar_wait2(mb + L, par, P, 510) && ok;
                 float2 hl[NC][NCH];
 #pragma unroll
@@ -485,13 +537,20 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                         b += __shfl_xor_sync(0xffffffffu, b, o);
                     }
                     if (lane < CORE_CL) {
-                        if (v0) st_async_f32(x1_peer + (uint32_t)((c * Sp + D.skip0 + skr0) * 4), fmaxf(a + cst0, 0.f), mb_peer + (uint32_t)((L + 1) * 8));
-                        if (v1) st_async_f32(x1_peer + (uint32_t)((c * Sp + D.skip0 + skr1) * 4), fmaxf(b + cst1, 0.f), mb_peer + (uint32_t)((L + 1) * 8));
+                        if (v0) st_async_f32(hx_peer + ro.x + (uint32_t)(c * Sp * 4), fmaxf(a + rc.x, 0.f), mbh);
+                        if (v1) st_async_f32(hx_peer + ro.y + (uint32_t)(c * Sp * 4), fmaxf(b + rc.y, 0.f), mbh);
                     }
                 }
             }
         }
         SWN_STAMP(7);
+        SWN_WSTAMP(20);
+        if (it + 1 < P.n_it) {
+            cp_async_wait_all();                                                 // gathers issued one step ago: fold them in before
+            __syncwarp();                                                        // the head, off the sampled -> next h0 path
+            fold_stage(it);
+            __syncwarp();
+        }
         // the output of the last layer (consumed by every warp, so that its barrier advances every step)
         if (warp < 8 || !active) ok = mbar_wait2(mb + L, par, P, 511) && ok;
         if (tid == 128) mbar_arm(mb + L, bytes_h);
@@ -499,15 +558,20 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
         if (active) {
             SWN_STAMP(8);
             // ---- out_1 row of this warp (relu) -> x2 on every CTA
-            if (warp < D.nb) {
-                float acc1[NC];
-                // the weight row is in registers before the vector lands (up to 256 columns; longer rows continue below)
+            if (has_b) {
+                // the weight row (up to 256 columns; longer rows continue below) and the head record are in registers
+                // before the vector lands
+                const float* wrow = sW1 + (size_t)warp * Sp;
                 float2 wpre[4];
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc)
-                    wpre[cc] = (cc * 64 < Sp) ? reinterpret_cast<const float2*>(sW1 + (size_t)warp * Sp)[cc * 32 + lane] : make_float2(0.f, 0.f);
+                    wpre[cc] = (cc * 64 < Sp) ? reinterpret_cast<const float2*>(wrow)[cc * 32 + lane] : make_float2(0.f, 0.f);
+                const uint32_t dst = hx_peer + hrec_off[warp].z;
+                const float bias = hrec_c[warp].z;
                 ok = mbar_wait2(mb_x1, hpar, P, 520) && ok;
+                SWN_STAMP(13);
                 if (tid == 0) mbar_arm(mb_x1, bytes_x1);                          // (its next phase only starts a step later)
+                float acc1[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     float a = 0.f, b = 0.f;
@@ -521,7 +585,7 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                     acc1[c] = a + b;
                 }
                 for (int cc = 4; cc < (Sp >> 6); ++cc) {
-                    const float2 wv = reinterpret_cast<const float2*>(sW1 + (size_t)warp * Sp)[cc * 32 + lane];
+                    const float2 wv = reinterpret_cast<const float2*>(wrow)[cc * 32 + lane];
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         const float2 v = reinterpret_cast<const float2*>(x1 + (size_t)c * Sp)[cc * 32 + lane];
@@ -531,9 +595,8 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                 }
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    const float v = warp_sum(acc1[c]) + b1w;
-                    if (lane < CORE_CL)
-                        st_async_f32(x2_peer + (uint32_t)((c * n1p + D.b0 + warp) * 4), fmaxf(v, 0.f), mb_peer + (uint32_t)((L + 2) * 8));
+                    const float v = warp_sum(acc1[c]) + bias;
+                    if (lane < CORE_CL) st_async_f32(dst + (uint32_t)(c * n1p * 4), fmaxf(v, 0.f), mbh + 8u);
                 }
             } else if (tid == 0) {
                 ok = mbar_wait2(mb_x1, hpar, P, 521) && ok;
@@ -541,15 +604,18 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
             }
             SWN_STAMP(9);
             // ---- out_2 rows
-            float gn[NC];
-#pragma unroll
-            for (int c = 0; c < NC; ++c) gn[c] = 0.f;
-            if (warp < D.nc) {
+            if (has_c) {
                 const int r = warp;
+                const float* wrow = sW2 + r * n1p;
                 float2 wpre2[4];
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc)
-                    wpre2[cc] = (cc * 64 < n1p) ? reinterpret_cast<const float2*>(sW2 + r * n1p)[cc * 32 + lane] : make_float2(0.f, 0.f);
+                    wpre2[cc] = (cc * 64 < n1p) ? reinterpret_cast<const float2*>(wrow)[cc * 32 + lane] : make_float2(0.f, 0.f);
+                const uint32_t dst = hx_peer + hrec_off[warp].w;
+                const float bias = hrec_c[warp].w;
+                float gn[NC];                                                    // the Gumbel noise drawn a step ahead
+#pragma unroll
+                for (int c = 0; c < NC; ++c) gn[c] = 0.f;
                 if (!is_c) {
                     if (gn_team) {
 #pragma unroll
@@ -558,13 +624,14 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
 #pragma unroll
                         for (int c = 0; c < NC; ++c) {
                             const int bglob = min(c, P.B - 1);
-                            const float q = P.noise ? __ldg(P.noise + ((size_t)bglob * P.n_out + istep) * Q + D.c0 + r)
-                                                    : softmax_q(P.seed, P.b0 + bglob, istep, D.c0 + r);
+                            const float q = P.noise ? __ldg(P.noise + ((size_t)bglob * P.n_out + istep) * Q + c0row)
+                                                    : softmax_q(P.seed, P.b0 + bglob, istep, c0row);
                             gn[c] = -logf(q);
                         }
                     }
                 }
                 ok = mbar_wait2(mb_x2, hpar, P, 530) && ok;
+                SWN_STAMP(15);
                 if (tid == 0) mbar_arm(mb_x2, bytes_x2);
                 float acc2[NC];
 #pragma unroll
@@ -580,7 +647,7 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                     acc2[c] = a + b;
                 }
                 for (int cc = 4; cc < (n1p >> 6); ++cc) {
-                    const float2 wv = reinterpret_cast<const float2*>(sW2 + r * n1p)[cc * 32 + lane];
+                    const float2 wv = reinterpret_cast<const float2*>(wrow)[cc * 32 + lane];
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         const float2 v = reinterpret_cast<const float2*>(x2 + c * n1p)[cc * 32 + lane];
@@ -590,19 +657,19 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                 }
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    const float o = warp_sum(acc2[c]) + b2w;
+                    const float o = warp_sum(acc2[c]) + bias;
                     if (is_c) {
                         if (lane == 0) o2[c * 16 + r] = o;
                     } else {
-                        const int row = D.c0 + r;
-                        if (lane < CORE_CL) st_async_f32(gx_peer + (uint32_t)((c * 256 + row) * 4), o + gn[c], mb_peer + (uint32_t)((L + 3) * 8));
-                        if (lane == 16 && P.head_out && c < P.B) P.head_out[((size_t)c * P.n_iter + istep) * n2 + row] = o;
+                        if (lane < CORE_CL) st_async_f32(dst + (uint32_t)(c * 256 * 4), o + gn[c], mbh + 16u);
+                        if (lane == 16 && P.head_out && c < P.B) P.head_out[((size_t)c * P.n_iter + istep) * n2 + c0row] = o;
                     }
                 }
             } else if (tid == 0) {
                 ok = mbar_wait2(mb_x2, hpar, P, 531) && ok;
                 mbar_arm(mb_x2, bytes_x2);
             }
+            SWN_STAMP(16);
             if (is_c) {
                 __syncthreads();
                 if (tid < NC) {
@@ -624,19 +691,24 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                 // ---- arg-max over the 256 published Gumbel scores (first maximum wins), by EVERY warp for itself: the
                 // warp goes straight on to its row of the next input vector, no CTA barrier, no shared-memory round trip
                 ok = mbar_wait2(mb_gx, hpar, P, 540) && ok;
+                SWN_STAMP(17);
                 if (tid == 0) mbar_arm(mb_gx, bytes_gx);
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    float best = -CUDART_INF_F; int bi = 0x7fffffff;
+                    // the lane's 8 scores as a compare tree (depth 3) instead of a chain of 8; ties keep the lower index
+                    float bv[4]; int bx[4];
 #pragma unroll
-                    for (int r0 = 0; r0 < 256; r0 += 64) {
-                        if (r0 < Q) {
-                            const float2 v = reinterpret_cast<const float2*>(gx + c * 256 + r0)[lane];
-                            const int i0 = r0 + 2 * lane;
-                            if (v.x > best) { best = v.x; bi = i0; }
-                            if (v.y > best) { best = v.y; bi = i0 + 1; }
-                        }
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const float2 v = (q4 * 64 < Q) ? reinterpret_cast<const float2*>(gx + c * 256 + q4 * 64)[lane]
+                                                       : make_float2(-CUDART_INF_F, -CUDART_INF_F);
+                        const int i0 = q4 * 64 + 2 * lane;
+                        bv[q4] = v.y > v.x ? v.y : v.x; bx[q4] = v.y > v.x ? i0 + 1 : i0;
                     }
+                    const bool s01 = bv[1] > bv[0], s23 = bv[3] > bv[2];
+                    const float b01 = s01 ? bv[1] : bv[0], b23 = s23 ? bv[3] : bv[2];
+                    const int i01 = s01 ? bx[1] : bx[0], i23 = s23 ? bx[3] : bx[2];
+                    const float best = b23 > b01 ? b23 : b01;
+                    int bi = b23 > b01 ? i23 : i01;
                     // warp arg-max with the integer reduction unit: order-preserving key, redux.max, then the
                     // smallest index among the lanes that hold the maximum (first maximum wins, as torch.argmax)
                     uint32_t key = __float_as_uint(best);
@@ -652,14 +724,11 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                 }
             }
             SWN_STAMP(10);
+            SWN_WSTAMP(24);
         } else {
             fed_from_hist(it + 1, fed);                                          // warm-up: the padded seed
         }
         if (it + 1 < P.n_it) {
-            cp_async_wait_all();                                                 // gathers issued one step ago
-            __syncwarp();
-            fold_stage(it);
-            __syncwarp();
             input_publish(it + 1, fed);
             SWN_STAMP(11);
             feed(it + 1, fed);

@@ -14,7 +14,9 @@
 //     tap j of the block is the same tile read `delay_j` rows earlier (rows before the utterance start are zeros =
 //     the zero padding of CausalConv1d, cswnv_shift1.py:68-92).  Four loader warps gather it in 16-byte pieces
 //     straight into the core-matrix layout;
-//   * 4-stage mbarrier pipeline (loaders -> MMA issuer -> tcgen05.commit frees the stage), one MMA-issuing lane;
+//   * 2-stage mbarrier pipeline (loaders -> MMA issuer -> tcgen05.commit frees the stage), one MMA-issuing lane; two
+//     CTAs per SM (96 KB of shared memory and 256 of the 512 tensor-memory columns each), so that the epilogue of one
+//     tile overlaps the main loop of another (a cp.async-pipelined loader with 4 stages and one CTA per SM measured slower);
 //   * the epilogue (the same four warps, one TMEM lane = one output row each) is fused: gate with the hoisted
 //     conditioning + carry (rows are interleaved z/c so that a lane pair holds one gate pair), or bias + relu, and
 //     writes the next operand already split into tf32 hi / lo planes.
@@ -30,7 +32,7 @@ namespace swn {
 
 namespace {
 
-constexpr int FW_BM = 128, FW_BN = 256, FW_BK = 16, FW_STAGES = 4;
+constexpr int FW_BM = 128, FW_BN = 256, FW_BK = 16, FW_STAGES = 2;
 constexpr int FW_A_PLANE = FW_BM * FW_BK * 4;                  // bytes of one (hi or lo) weight block
 constexpr int FW_B_PLANE = FW_BN * FW_BK * 4;
 constexpr int FW_STAGE_BYTES = 2 * FW_A_PLANE + 2 * FW_B_PLANE; // 48 KB
@@ -107,7 +109,7 @@ __device__ __forceinline__ void fw_tmem_ld16(uint32_t a, float* r) {
 }  // namespace
 
 // ------------------------------------------------------------------ the GEMM
-__global__ void __launch_bounds__(FW_THREADS, 1) fwd_gemm_kernel(const __grid_constant__ FwdGemm G) {
+__global__ void __launch_bounds__(FW_THREADS, 2) fwd_gemm_kernel(const __grid_constant__ FwdGemm G) {
     extern __shared__ __align__(1024) uint8_t fw_smem_raw[];
     uint8_t* stages = fw_smem_raw;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(fw_smem_raw + FW_STAGES * FW_STAGE_BYTES);
@@ -148,47 +150,43 @@ __global__ void __launch_bounds__(FW_THREADS, 1) fwd_gemm_kernel(const __grid_co
         const float* Ablk = G.A + (size_t)mt * n_kb * (2 * FW_BM * FW_BK);
         // piece p of the block: row n = p >> 2 (time), kq = p & 3 (4 channels = 16 bytes); 128 threads cover 32 rows
         const int kq = tid & 3, nr = tid >> 2;
-        // Software pipeline: the copies of k block kb + STAGES - 1 are issued (cp.async, 16 bytes each, zero-filled where
-        // the source row lies before the utterance start) before the thread waits for those of k block kb, so that
-        // STAGES - 1 blocks of loads are in flight per thread; a completed block is made visible to the tensor-core
-        // (async) proxy with fence.proxy.async and handed over through the stage's mbarrier.
-        for (int ki = 0; ki < n_kb + FW_STAGES - 1; ++ki) {
-            if (ki < n_kb && ok) {
-                const int s = ki % FW_STAGES;
-                const uint32_t ph = (uint32_t)(ki / FW_STAGES) & 1u;
-                ok = fw_mbar_wait(&empty[s], ph ^ 1u, G.status, 1);
-                if (ok) {
-                    uint8_t* st = stages + s * FW_STAGE_BYTES;
-                    if (tid == 0) {
-                        fw_mbar_expect(&full[s], 2 * FW_A_PLANE);
-                        fw_bulk_g2s(st, Ablk + (size_t)ki * (2 * FW_BM * FW_BK), 2 * FW_A_PLANE, &full[s]);
-                    }
-                    const int tap = ki / kb_per_tap;
-                    const int c0 = (ki - tap * kb_per_tap) * FW_BK + kq * 4;      // channel of this piece inside the tap
-                    const int delay = G.delay[tap];
-                    const bool cvalid = c0 < G.C;                                  // (buffers are padded to 4 channels with zeros)
-                    const size_t col = (size_t)G.b_col0 + (size_t)tap * G.tap_col_stride + (cvalid ? c0 : 0);
-                    const uint32_t bh = fw_smem(st + 2 * FW_A_PLANE), bl = bh + FW_B_PLANE;
+        for (int kb = 0; kb < n_kb && ok; ++kb) {
+            const int s = kb % FW_STAGES;
+            const uint32_t ph = (uint32_t)(kb / FW_STAGES) & 1u;
+            ok = fw_mbar_wait(&empty[s], ph ^ 1u, G.status, 1);
+            if (!ok) break;
+            uint8_t* st = stages + s * FW_STAGE_BYTES;
+            if (tid == 0) {
+                fw_mbar_expect(&full[s], 2 * FW_A_PLANE);
+                fw_bulk_g2s(st, Ablk + (size_t)kb * (2 * FW_BM * FW_BK), 2 * FW_A_PLANE, &full[s]);
+            }
+            const int tap = kb / kb_per_tap;
+            const int c0 = (kb - tap * kb_per_tap) * FW_BK + kq * 4;          // channel of this piece inside the tap
+            const int delay = G.delay[tap];
+            const bool cvalid = c0 < G.C;                                      // (buffers are padded to 4 channels with zeros)
+            const size_t col = (size_t)G.b_col0 + (size_t)tap * G.tap_col_stride + c0;
+            float4* bh = reinterpret_cast<float4*>(st + 2 * FW_A_PLANE);
+            float4* bl = reinterpret_cast<float4*>(st + 2 * FW_A_PLANE + FW_B_PLANE);
+            float4 vh[FW_BN / 32], vl[FW_BN / 32];
 #pragma unroll
-                    for (int i = 0; i < FW_BN / 32; ++i) {
-                        const int n = nr + 32 * i;
-                        const int ts = t0 + n - delay;                             // source time inside the utterance
-                        const bool v = cvalid && ts >= 0 && ts < G.T;
-                        const size_t off = (size_t)(row_base + (v ? ts : 0)) * G.ldb + col;
-                        const uint32_t o = (uint32_t)(((kq * (FW_BN >> 3) + (n >> 3)) * 8 + (n & 7)) * 16);   // [k/4][n/8][n%8] x 16 B
-                        const uint32_t sz = v ? 16u : 0u;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(bh + o), "l"(G.Bhi + off), "r"(sz) : "memory");
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(bl + o), "l"(G.Blo + off), "r"(sz) : "memory");
-                    }
+            for (int i = 0; i < FW_BN / 32; ++i) {
+                const int n = nr + 32 * i;
+                const int ts = t0 + n - delay;                                 // source time inside the utterance
+                vh[i] = make_float4(0.f, 0.f, 0.f, 0.f); vl[i] = vh[i];
+                if (cvalid && ts >= 0 && ts < G.T) {
+                    const size_t off = (size_t)(row_base + ts) * G.ldb + col;
+                    vh[i] = __ldg(reinterpret_cast<const float4*>(G.Bhi + off));
+                    vl[i] = __ldg(reinterpret_cast<const float4*>(G.Blo + off));
                 }
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            const int kd = ki - (FW_STAGES - 1);
-            if (kd >= 0) {
-                asm volatile("cp.async.wait_group %0;" ::"n"(FW_STAGES - 1) : "memory");
-                asm volatile("fence.proxy.async;" ::: "memory");                   // generic-proxy writes -> visible to the MMA
-                fw_mbar_arrive(&full[kd % FW_STAGES]);
+#pragma unroll
+            for (int i = 0; i < FW_BN / 32; ++i) {
+                const int n = nr + 32 * i;
+                const int o = (kq * (FW_BN >> 3) + (n >> 3)) * 8 + (n & 7);    // float4 index: [k/4][n/8][n%8]
+                bh[o] = vh[i]; bl[o] = vl[i];
             }
+            asm volatile("fence.proxy.async;" ::: "memory");       // generic-proxy stores -> visible to the MMA
+            fw_mbar_arrive(&full[s]);
         }
     } else if (lane == 0) {
         // =============================== MMA issuer: D += A_hi.B_hi + A_lo.B_hi + A_hi.B_lo per 8-wide k step

@@ -46,6 +46,14 @@ for sel in ((2,) if os.environ.get("SWN_PROF_B") else (2, 1)):
     print("   step period %.0f ns" % per)
     for e, nme in enumerate(names):
         print("   %-20s mean %.0f ns  (min CTA %.0f, max CTA %.0f)" % (nme, rel[:, :, e].mean(), rel[:, :, e].mean(0).min(), rel[:, :, e].mean(0).max()))
+    if pall.shape[2] >= 32 and pall[:, :, 16:32].max() > 0:
+        print("   per-role stamps, ns since iter start of the earliest CTA (mean over core CTAs): warp 0 / 4 / 8 / 15")
+        for ev, nme in ((13, "warp 0: x1 landed"), (9, "warp 0: x2 row published"), (15, "warp 0: x2 landed"), (16, "warp 0: score published"),
+                        (17, "warp 0: scores landed"), (10, "warp 0: arg-max done")):
+            print("      %-52s %6.0f" % (nme, (pall[:, :, ev:ev + 1] - base).mean()))
+        for ev, nme in ((20, "leaves its layer section"), (24, "arg-max done")):
+            v = pall[:, :, ev:ev + 4] - base
+            print("      %-52s %s" % (nme, "  ".join("%6.0f" % x for x in v.mean(axis=(0, 1)))))
     # clock64 stamps of thread 0 (chain warp 0): layer 3 stage and the head, cycles
     c = pall
     lay = ["before wait", "woken", "h frags + taps in regs", "taps reduced", "gated", "published", "next taps issued"]
