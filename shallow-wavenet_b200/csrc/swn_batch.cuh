@@ -22,9 +22,6 @@
 #pragma once
 #include "swn_gen.cuh"
 
-#ifndef B3_GATE1
-#define B3_GATE1 0       // gate with one reciprocal (gate_out, swn_gen.cuh): no gain measured in this kernel (78.99 vs 78.10 ms on cfg3s)
-#endif
 namespace swn {
 
 constexpr int B3_NGW = 4;                 // GEMM warps 0..3 (one per SM sub-partition)
@@ -34,9 +31,6 @@ constexpr int B3_CNT_STRIDE = 8;          // one counter per 32-byte sector
 constexpr int B3_HIST = 32;
 // Packed fp32 FMA (FFMA2, sm_100) in the GEMM inner loop.  Measured on B200: 7.4 us per 128x192x40 tile against
 // 6.8 us with scalar FFMA (the packed form halves the issue slots but not the FMA-pipe cycles), so it stays off.
-#ifndef B3_FFMA2
-#define B3_FFMA2 0
-#endif
 #ifndef B3_TMA_SPLIT
 #define B3_TMA_SPLIT 1
 #endif
@@ -132,24 +126,7 @@ __device__ __forceinline__ bool b3_mbar_try(unsigned long long* b, uint32_t pari
     return done != 0;
 }
 // wait with an escape: returns false when another CTA / role aborted
-#ifndef B3_WAIT_TIME
-#define B3_WAIT_TIME 0       // 1: the abort flag is looked at on a time basis (every ~100k cycles) instead of every 64 polls
-#endif
 __device__ __forceinline__ bool b3_mbar_wait(unsigned long long* b, uint32_t parity, const int32_t* status) {
-#if B3_WAIT_TIME
-    // a poll-count based check puts a ~700-cycle L2 load of the flag between two polls every 64 polls: a waiting role
-    // then sees its barrier late (same finding as in the cluster kernel, swn_core2.cuh mbar_wait_slow2)
-    if (b3_mbar_try(b, parity)) return true;
-    long long next = clock64() + 100000;
-    while (!b3_mbar_try(b, parity)) {
-        const long long now = clock64();
-        if (now > next) {
-            if (((volatile const int32_t*)status)[0] != 0) return false;
-            next = now + 100000;
-        }
-    }
-    return true;
-#endif
     uint32_t spins = 0;
     while (!b3_mbar_try(b, parity)) {
 #if B3_WAIT_SLEEP_NS
@@ -602,19 +579,10 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                 const int r0 = (rb * RGW + rg) * TR;
                 const bool act = lane_ok && r0 < RP;
                 float acc[TR][TC];
-#if B3_FFMA2
-                // packed fp32 FMA (FFMA2): one instruction updates the accumulators of two adjacent rows
-                unsigned long long acc2[TR / 2][TC];
-#pragma unroll
-                for (int i = 0; i < TR / 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < TC; ++j) acc2[i][j] = 0ull;
-#else
 #pragma unroll
                 for (int i = 0; i < TR; ++i)
 #pragma unroll
                     for (int j = 0; j < TC; ++j) acc[i][j] = 0.f;
-#endif
                 if (act) {
                     const float* wp = Wt + r0;
                     const float* xp = X + cg * TC;
@@ -637,22 +605,6 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
 #pragma unroll
                             for (int j = 0; j < TC; ++j) x[j] = xp[k * NC + j];
                         }
-#if B3_FFMA2
-                        unsigned long long w2[TR / 2];
-#pragma unroll
-                        for (int i = 0; i < TR; i += 4) {
-                            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(wp + (size_t)k * RP + i);
-                            w2[i / 2] = v.x; w2[i / 2 + 1] = v.y;
-                        }
-#pragma unroll
-                        for (int j = 0; j < TC; ++j) {
-                            unsigned long long xx;
-                            asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x[j]));
-#pragma unroll
-                            for (int i = 0; i < TR / 2; ++i)
-                                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][j]) : "l"(xx), "l"(w2[i]));
-                        }
-#else
                         float w[TR];
                         if constexpr (TR % 4 == 0) {
 #pragma unroll
@@ -671,16 +623,8 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                         for (int i = 0; i < TR; ++i)
 #pragma unroll
                             for (int j = 0; j < TC; ++j) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
-#endif
                     }
                 }
-#if B3_FFMA2
-#pragma unroll
-                for (int i = 0; i < TR / 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < TC; ++j)
-                        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * i][j]), "=f"(acc[2 * i + 1][j]) : "l"(acc2[i][j]));
-#endif
                 if (first) {
                     first = false;
                     if (tid == 0) B3_PROF(2);
@@ -967,12 +911,6 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                 }
                 // sigmoid / tanh through ex2.approx + rcp (abs. error ~1e-7, inside the 1e-4 head tolerance)
                 const float gz = qz * v.x, gc = qc * v.y;
-#if B3_GATE1
-                float carry;
-                if (umma) { const int xo = b3_uoff(col, D.pair0 + pi, NP); carry = X[xo] + X[utile + xo]; }
-                else carry = X[(D.pair0 + pi) * NC + col];
-                hv = gate_out(gz, gc, carry);
-#else
                 const float ez = __expf(-gz), ec = __expf(-2.f * fabsf(gc));
                 const float z = __frcp_rn(1.f + ez);
                 const float th = copysignf((1.f - ec) * __frcp_rn(1.f + ec), gc);
@@ -980,7 +918,6 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                 if (umma) { const int xo = b3_uoff(col, D.pair0 + pi, NP); carry = X[xo] + X[utile + xo]; }
                 else carry = X[(D.pair0 + pi) * NC + col];
                 hv = (1.f - z) * th + z * carry;
-#endif
             }
             if (!D.is_last) {
                 if (umma) {      // exact split into tf32 halves for the next cell's tensor-core passes

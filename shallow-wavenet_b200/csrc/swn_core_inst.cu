@@ -9,20 +9,11 @@
 #error "compile with -DSWN_NCH=<1..4>"
 #endif
 
-#ifndef SWN_CORE_V
-#define SWN_CORE_V 2          // 1: first-generation core CTA (swn_core.cuh), 2: role-specialised core CTA (swn_core2.cuh)
-#endif
-#if SWN_CORE_V == 2
-#define SWN_CORE_KERNEL swn_core_kernel2
-#else
-#define SWN_CORE_KERNEL swn_core_kernel
-#endif
-
 namespace swn {
 
 template <int NCH, int BS>
 static cudaError_t core_prepare(size_t smem, int* max_clusters) {
-    auto k = SWN_CORE_KERNEL<NCH, BS>;
+    auto k = swn_core_kernel2<NCH, BS>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -40,7 +31,7 @@ static cudaError_t core_prepare(size_t smem, int* max_clusters) {
 
 template <int NCH, int BS>
 static cudaError_t core_launch(const CoreParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto k = SWN_CORE_KERNEL<NCH, BS>;
+    auto k = swn_core_kernel2<NCH, BS>;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(SWN_NTHREADS);
