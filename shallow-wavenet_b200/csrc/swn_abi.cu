@@ -345,7 +345,7 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
             lay.sm_gx = take((size_t)NC * 256);
             lay.sm_pre = take((size_t)2 * L * 16 * NC * (sizeof(swn::PreSlot) / 4));
             lay.sm_misc = take((size_t)NC * (16 + 8 + 16) + (size_t)L * 16 * 4 + (size_t)(8 * 16 + 2 * 8 * 16) * NC + 8 * 2 * 16 + (size_t)2 * 16 * NC + (size_t)2 * L * 2 * 16 * NC * 2);   // ... + Gumbel noise [2][16][NC] + helper words [2][L][2][16*NC] (u64)
-            lay.sm_tmem_slot = take(4 + 2 * (size_t)(3 * L + 8));  // TMEM base slot, L+4 exchange mbarriers, L relay, L helper-copy mbarriers
+            lay.sm_tmem_slot = take(4 + 2 * (size_t)((L + 4) * BS + 4));  // TMEM base slot, one exchange mbarrier per (vector, column): (L+4) x BS
             core_used = u;
             for (auto& q : m->ccta) {
                 q.sm_skip = lay.sm_skip; q.sm_w1 = lay.sm_w1; q.sm_w2 = lay.sm_w2; q.sm_tin = lay.sm_tin;

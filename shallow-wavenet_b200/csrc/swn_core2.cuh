@@ -130,10 +130,12 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
     float* sfir = cstage + 2 * 8 * 16 * NC;                // CSWNV [8][2][16] FIR taps (cb, v) of this CTA's rows
     float* gnz = sfir + 8 * 2 * 16;                        // DSWNV [2][16][NC] Gumbel noise of this CTA's logit rows
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + D.sm_tmem_slot);
-    unsigned long long* mb = reinterpret_cast<unsigned long long*>(tmem_slot + 2);     // [L+1] h vectors, then x1, x2, gx
-    unsigned long long* mb_x1 = mb + (L + 1), *mb_x2 = mb + (L + 2), *mb_gx = mb + (L + 3);
-    const uint32_t bytes_h = (uint32_t)(H * NC * 4), bytes_x1 = (uint32_t)(S * NC * 4), bytes_x2 = (uint32_t)(n1 * NC * 4),
-                   bytes_gx = (uint32_t)(Q * NC * 4);
+    // One mbarrier per (exchanged vector, utterance column): the columns of a slot run as independent pipelines, so that
+    // the stage of one column is computed while the hop of another is in flight (a joint barrier per vector made two
+    // columns cost 1.75 x one, profiles/r02k_core_columns_probe.txt).  [L+1][NC] h vectors, then [NC] x1, x2, scores.
+    unsigned long long* mb = reinterpret_cast<unsigned long long*>(tmem_slot + 2);
+    unsigned long long* mb_x1 = mb + (L + 1) * NC, *mb_x2 = mb + (L + 2) * NC, *mb_gx = mb + (L + 3) * NC;
+    const uint32_t bytes_h = (uint32_t)(H * 4), bytes_x1 = (uint32_t)(S * 4), bytes_x2 = (uint32_t)(n1 * 4), bytes_gx = (uint32_t)(Q * 4);
 
     auto stage = [&](float* dst, const float* src, int n) {
         const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -168,10 +170,10 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
         sfir[i] = (is_c && j < K && r < D.ni) ? P.in_tab[(j * 2 + w2) * H + D.i0 + r] : 0.f;
     }
     if (tid == 0) {
-        for (int i = 0; i < L + 4; ++i) mbar_init(mb + i, 1);
+        for (int i = 0; i < (L + 4) * NC; ++i) mbar_init(mb + i, 1);
         mbar_fence_init();
-        for (int i = 0; i <= L; ++i) mbar_arm(mb + i, bytes_h);          // phase 0 of every vector
-        mbar_arm(mb_x1, bytes_x1); mbar_arm(mb_x2, bytes_x2); mbar_arm(mb_gx, bytes_gx);
+        for (int i = 0; i < (L + 1) * NC; ++i) mbar_arm(mb + i, bytes_h);          // phase 0 of every vector
+        for (int c = 0; c < NC; ++c) { mbar_arm(mb_x1 + c, bytes_x1); mbar_arm(mb_x2 + c, bytes_x2); mbar_arm(mb_gx + c, bytes_gx); }
     }
     if (warp == 0) tmem_alloc_all(tmem_slot);
     tmem_fence_before();
@@ -251,7 +253,7 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
     const bool sk_v0 = skr0 < D.nskip, sk_v1 = skr1 < D.nskip;
     const int c0row = D.c0 + warp;                                         // logit row of this warp
     const int ws_stride = D.nskip * HP;                                    // floats between the out_skip blocks of two layers
-    const uint32_t mbh = mb_peer + (uint32_t)((L + 1) * 8);                // x1 barrier of the peer; x2 = +8, scores = +16
+    const uint32_t mbh = mb_peer + (uint32_t)((L + 1) * NC * 8);           // x1 barriers of the peer; x2 = + NC * 8, scores = + 2 * NC * 8
     // chain warps: where lane `sub` of a pair group publishes (CTAs sub and sub + 8), layer-0 addresses
     const uint32_t pub0 = mapa(smem_u32(hx), (uint32_t)sub) + (uint32_t)(my_i * 4);
     const uint32_t pub1 = mapa(smem_u32(hx), (uint32_t)sub + 8) + (uint32_t)(my_i * 4);
@@ -342,22 +344,23 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
             }
         }
     };
-    auto input_publish = [&](int itn, const float (&fed)[NC]) {     // h0 of time itn (its own sample is in `fed`)
+    auto input_publish_col = [&](int itn, int c, float fv) {       // h0 of time itn, column c (its own sample is `fv`)
         if (!has_in) return;
+        float* slot = cacc + ((itn & 7) * 16 + warp) * NC + c;
+        float acc = in_b + *slot;
+        if (is_c) acc += sfir[((K - 1) * 2) * 16 + warp] + sfir[((K - 1) * 2 + 1) * 16 + warp] * fv;
+        else acc += sTin[__float_as_int(fv) * nip + warp];
+        __syncwarp();
+        if (lane == 0) *slot = 0.f;                                  // the slot is reused 8 steps later
+        // softsign through rcp.approx (1 ulp) instead of the IEEE division sequence: it sits between the arg-max and the publish
+        const float v = acc * rcp_approx(1.f + fabsf(acc));
+        if (lane < CORE_CL) st_async_f32(hx_peer + (uint32_t)((c * HP + in_row) * 4), v, mb_peer + (uint32_t)(c * 8));
+        if (lane == 16 && P.has_help[0])
+            st_ll(P.hin_ll + P.hin_off[0] + ((itn & (P.hslots[0] - 1)) * NC + c) * H + in_row, v, (uint32_t)itn + 1u);
+    };
+    auto input_publish = [&](int itn, const float (&fed)[NC]) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            float* slot = cacc + ((itn & 7) * 16 + warp) * NC + c;
-            float acc = in_b + *slot;
-            if (is_c) acc += sfir[((K - 1) * 2) * 16 + warp] + sfir[((K - 1) * 2 + 1) * 16 + warp] * fed[c];
-            else acc += sTin[__float_as_int(fed[c]) * nip + warp];
-            __syncwarp();
-            if (lane == 0) *slot = 0.f;                              // the slot is reused 8 steps later
-            // softsign through rcp.approx (1 ulp) instead of the IEEE division sequence: it sits between the arg-max and the publish
-            const float v = acc * rcp_approx(1.f + fabsf(acc));
-            if (lane < CORE_CL) st_async_f32(hx_peer + (uint32_t)((c * HP + in_row) * 4), v, mb_peer);
-            if (lane == 16 && P.has_help[0])
-                st_ll(P.hin_ll + P.hin_off[0] + ((itn & (P.hslots[0] - 1)) * NC + c) * H + in_row, v, (uint32_t)itn + 1u);
-        }
+        for (int c = 0; c < NC; ++c) input_publish_col(itn, c, fed[c]);
     };
     // what the input stage sees as the sample of time tau (generated index n = tau - R - 1; padding before the seed)
     auto fed_from_hist = [&](int tau, float (&fed)[NC]) {
@@ -398,63 +401,57 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
             // ======================= chain warps: delay-0 tap of 4 gate pairs per layer, gate, publish =======================
             float w[TCOLS];
             tmem_ldw<TCOLS>(taddr0 + P.tap_base[0] * TCOLS, w);
-            const float4* gp = gop + ((par * L) * 16 + plocal) * NC + colc;      // this lane's operands of layer 0
-            const float* hxl = hx;                                               // input vector of layer l
+            const float4* gp = gop + ((par * L) * 16 + plocal) * NC;            // gate operands of layer 0, column 0
+            const float* hxl = hx;                                               // input vector of layer l, column 0
             uint32_t d0 = pub0 + (uint32_t)(NC * HP * 4), d1 = pub1 + (uint32_t)(NC * HP * 4);   // where hx[l+1] rows go
-            uint32_t m0 = pmb0 + 8u, m1 = pmb1 + 8u;
+            uint32_t m0 = pmb0 + (uint32_t)(NC * 8), m1 = pmb1 + (uint32_t)(NC * 8);
             unsigned long long* bar = mb;
             for (int l = 0; l < L; ++l) {
-                const float4 g4 = *gp;                                           // (before the wait: in the shadow of the hop)
-                ok = mbar_wait2(bar, par, P, 500 + l) && ok;
-#if SWN_STAMPS
-                if (P.prof && tid == 0 && l < 6 && it >= P.prof_start && it < P.prof_start + P.prof_count)
-                    P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + 1 + l] = gtime();
-#endif
-                float2 h[NC][NCH];
-#pragma unroll
-                for (int c = 0; c < NC; ++c) load_frag<NCH>(h[c], hxl + c * HP, lane);
-                const float carry = hxl[colc * HP + my_i];
-                tmem_wait_ld();
-                float myqz = 0.f, myqc = 0.f;
+                // the columns one after the other, each behind its own barrier: while the hop of column c is in flight
+                // the stage of column c + 1 is computed
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
+                    const float4 g4 = gp[c];                                     // (before the wait: in the shadow of the hop)
+                    ok = mbar_wait2(bar + c, par, P, 500 + l) && ok;
+#if SWN_STAMPS
+                    if (c == 0 && P.prof && tid == 0 && l < 6 && it >= P.prof_start && it < P.prof_start + P.prof_count)
+                        P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + 1 + l] = gtime();
+#endif
+                    float2 h[NCH];
+                    load_frag<NCH>(h, hxl + c * HP, lane);
+                    const float carry = hxl[c * HP + my_i];
+                    if (c == 0) tmem_wait_ld();
                     float v8[8];
 #pragma unroll
                     for (int rr = 0; rr < 8; ++rr) {
                         float a = 0.f, b = 0.f;
 #pragma unroll
                         for (int cc = 0; cc < NCH; ++cc) {
-                            a = fmaf(w[rr * FPT + 2 * cc], h[c][cc].x, a);
-                            b = fmaf(w[rr * FPT + 2 * cc + 1], h[c][cc].y, b);
+                            a = fmaf(w[rr * FPT + 2 * cc], h[cc].x, a);
+                            b = fmaf(w[rr * FPT + 2 * cc + 1], h[cc].y, b);
                         }
                         v8[rr] = a + b;
                     }
                     float qz, qc;
                     reduce_pairs(v8, lane, qz, qc);
-                    if (NC == 1 || sub == c) { myqz = qz; myqc = qc; }
-                }
-                // ---- gate (cswnv_shift1.py:281-285) by every lane (lanes sub >= NC shadow column 0: no branch).
-                // (1-z) tanh(gc) + z carry over one common denominator: two ex2, one rcp on the dependent chain
-                //   z = 1/(1+ez), tanh = sign(gc) (1-ec)/(1+ec)  ->  [ez sign(gc) (1-ec) + carry (1+ec)] / [(1+ez)(1+ec)]
-                // ez is capped at 2^43 (gz >= -30: z differs from 0 by < 1e-13 either way) so the product stays finite.
-                const float hn = gate_out(fmaf(myqz, g4.x, g4.y), fmaf(myqc, g4.z, g4.w), carry);
-                // ---- fan out: in every pair group, lane sub writes CTAs sub and sub+8
-#pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    const float v = NC == 1 ? hn : __shfl_sync(0xffffffffu, hn, (lane & 24) + c);
+                    // ---- gate (cswnv_shift1.py:281-285) by every lane of the pair group (no branch).
+                    // (1-z) tanh(gc) + z carry over one common denominator: two ex2, one rcp on the dependent chain
+                    //   z = 1/(1+ez), tanh = sign(gc) (1-ec)/(1+ec)  ->  [ez sign(gc) (1-ec) + carry (1+ec)] / [(1+ez)(1+ec)]
+                    // ez is capped at 2^43 (gz >= -30: z differs from 0 by < 1e-13 either way) so the product stays finite.
+                    const float hn = gate_out(fmaf(qz, g4.x, g4.y), fmaf(qc, g4.z, g4.w), carry);
+                    // ---- fan out: in every pair group, lane sub writes CTAs sub and sub+8
                     if (pvalid) {
-                        st_async_f32(d0 + (uint32_t)(c * HP * 4), v, m0);
-                        st_async_f32(d1 + (uint32_t)(c * HP * 4), v, m1);
+                        st_async_f32(d0 + (uint32_t)(c * HP * 4), hn, m0 + (uint32_t)(c * 8));
+                        st_async_f32(d1 + (uint32_t)(c * HP * 4), hn, m1 + (uint32_t)(c * 8));
                     }
+                    // ---- behind the publish (in the shadow of the hop): helper hand-off
+                    if (l + 1 < L && P.has_help[l + 1] && pvalid && sub == 0)
+                        st_ll(P.hin_ll + P.hin_off[l + 1] + ((it & (P.hslots[l + 1] - 1)) * NC + c) * H + my_i, hn, (uint32_t)it + 1u);
                 }
-                // ---- behind the publish (in the shadow of the hop): helper hand-off, next taps, running pointers
-                if (l + 1 < L) {
-                    if (P.has_help[l + 1] && pvalid && sub < NC)
-                        st_ll(P.hin_ll + P.hin_off[l + 1] + ((it & (P.hslots[l + 1] - 1)) * NC + sub) * H + my_i, hn, (uint32_t)it + 1u);
-                    tmem_ldw<TCOLS>(taddr0 + P.tap_base[l + 1] * TCOLS, w);
-                }
-                gp += 16 * NC; hxl += NC * HP; ++bar;
-                d0 += (uint32_t)(NC * HP * 4); d1 += (uint32_t)(NC * HP * 4); m0 += 8u; m1 += 8u;
+                // next taps, running pointers
+                if (l + 1 < L) tmem_ldw<TCOLS>(taddr0 + P.tap_base[l + 1] * TCOLS, w);
+                gp += 16 * NC; hxl += NC * HP; bar += NC;
+                d0 += (uint32_t)(NC * HP * 4); d1 += (uint32_t)(NC * HP * 4); m0 += (uint32_t)(NC * 8); m1 += (uint32_t)(NC * 8);
             }
         } else if (warp < 8) {
             // ======================= delay-1 taps of the dilation-1 layers + next step's gate operands =======================
@@ -462,10 +459,11 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
             const float* prow_next = ptab_b + (size_t)fn * L * twoH;
             const float gq_next = __ldg(P.gain + jn);
             for (int l = 0; l < L; ++l) {
-                ok = mbar_wait2(mb + l, par, P, 600 + l) && ok;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) ok = mbar_wait2(mb + l * NC + c, par, P, 600 + l) && ok;
                 // next phase (next time step) of every layer barrier, armed in one go once the last of them has completed
                 if (l == L - 1 && warp == 4 && lane == 0)
-                    for (int i = 0; i < L; ++i) mbar_arm(mb + i, bytes_h);
+                    for (int i = 0; i < L * NC; ++i) mbar_arm(mb + i, bytes_h);
                 float prz, prc, rz1 = 0.f, rc1 = 0.f; unsigned long long ha, hb;
                 gop_issue(l, it + 1, prow_next, prz, prc, ha, hb);
                 if (P.dil[l] == 1 && K >= 2) {
@@ -505,7 +503,8 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
             const float* ws_base0 = sSkip + (size_t)(v0 ? skr0 : 0) * HP;
             const float* ws_base1 = sSkip + (size_t)(v1 ? skr1 : 0) * HP;
             for (int l = 0; l < L; ++l) {
-                ok = mbar_wait2(mb + l, par, P, 700 + l) && ok;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) ok = mbar_wait2(mb + l * NC + c, par, P, 700 + l) && ok;
                 if (active && l >= 1) {                                          // out_skip[l-1] on the input of layer l
                     float2 h[NC][NCH], ws0[NCH], ws1[NCH];
 #pragma unroll
@@ -524,21 +523,20 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                 load_frag<NCH>(ws1, ws_base1 + (size_t)(L - 1) * nsk, lane);
                 const uint4 ro = hrec_off[warp];
                 const float4 rc = hrec_c[warp];
-                ok = mbar_wait2(mb + L, par, P, 510) && ok;
-                float2 hl[NC][NCH];
-#pragma unroll
-                for (int c = 0; c < NC; ++c) load_frag<NCH>(hl[c], hx + (L * NC + c) * HP, lane);
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    float a = sk0[c] + dot_frag<NCH>(ws0, hl[c]), b = sk1[c] + dot_frag<NCH>(ws1, hl[c]);
+                    ok = mbar_wait2(mb + L * NC + c, par, P, 510) && ok;
+                    float2 hl[NCH];
+                    load_frag<NCH>(hl, hx + (L * NC + c) * HP, lane);
+                    float a = sk0[c] + dot_frag<NCH>(ws0, hl), b = sk1[c] + dot_frag<NCH>(ws1, hl);
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
                         a += __shfl_xor_sync(0xffffffffu, a, o);
                         b += __shfl_xor_sync(0xffffffffu, b, o);
                     }
                     if (lane < CORE_CL) {
-                        if (v0) st_async_f32(hx_peer + ro.x + (uint32_t)(c * Sp * 4), fmaxf(a + rc.x, 0.f), mbh);
-                        if (v1) st_async_f32(hx_peer + ro.y + (uint32_t)(c * Sp * 4), fmaxf(b + rc.y, 0.f), mbh);
+                        if (v0) st_async_f32(hx_peer + ro.x + (uint32_t)(c * Sp * 4), fmaxf(a + rc.x, 0.f), mbh + (uint32_t)(c * 8));
+                        if (v1) st_async_f32(hx_peer + ro.y + (uint32_t)(c * Sp * 4), fmaxf(b + rc.y, 0.f), mbh + (uint32_t)(c * 8));
                     }
                 }
             }
@@ -552,8 +550,12 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
             __syncwarp();
         }
         // the output of the last layer (consumed by every warp, so that its barrier advances every step)
-        if (warp < 8 || !active) ok = mbar_wait2(mb + L, par, P, 511) && ok;
-        if (tid == 128) mbar_arm(mb + L, bytes_h);
+        if (warp < 8 || !active) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) ok = mbar_wait2(mb + L * NC + c, par, P, 511) && ok;
+        }
+        if (tid == 128)
+            for (int c = 0; c < NC; ++c) mbar_arm(mb + L * NC + c, bytes_h);
         float fed[NC];                                                           // what is fed back as the sample of time it+1
         if (active) {
             SWN_STAMP(8);
@@ -568,39 +570,33 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                     wpre[cc] = (cc * 64 < Sp) ? reinterpret_cast<const float2*>(wrow)[cc * 32 + lane] : make_float2(0.f, 0.f);
                 const uint32_t dst = hx_peer + hrec_off[warp].z;
                 const float bias = hrec_c[warp].z;
-                ok = mbar_wait2(mb_x1, hpar, P, 520) && ok;
-                SWN_STAMP(13);
-                if (tid == 0) mbar_arm(mb_x1, bytes_x1);                          // (its next phase only starts a step later)
-                float acc1[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
+                    ok = mbar_wait2(mb_x1 + c, hpar, P, 520) && ok;
+                    if (c == 0) SWN_STAMP(13);
+                    if (tid == 0) mbar_arm(mb_x1 + c, bytes_x1);                  // (its next phase only starts a step later)
+                    const float2* xv = reinterpret_cast<const float2*>(x1 + (size_t)c * Sp);
                     float a = 0.f, b = 0.f;
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
                         if (cc * 64 < Sp) {
-                            const float2 v = reinterpret_cast<const float2*>(x1 + (size_t)c * Sp)[cc * 32 + lane];
+                            const float2 v = xv[cc * 32 + lane];
                             a = fmaf(wpre[cc].x, v.x, a); b = fmaf(wpre[cc].y, v.y, b);
                         }
                     }
-                    acc1[c] = a + b;
-                }
-                for (int cc = 4; cc < (Sp >> 6); ++cc) {
-                    const float2 wv = reinterpret_cast<const float2*>(wrow)[cc * 32 + lane];
-#pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        const float2 v = reinterpret_cast<const float2*>(x1 + (size_t)c * Sp)[cc * 32 + lane];
-                        acc1[c] = fmaf(wv.x, v.x, acc1[c]);
-                        acc1[c] = fmaf(wv.y, v.y, acc1[c]);
+                    for (int cc = 4; cc < (Sp >> 6); ++cc) {
+                        const float2 wv = reinterpret_cast<const float2*>(wrow)[cc * 32 + lane], v = xv[cc * 32 + lane];
+                        a = fmaf(wv.x, v.x, a); b = fmaf(wv.y, v.y, b);
                     }
-                }
-#pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    const float v = warp_sum(acc1[c]) + bias;
-                    if (lane < CORE_CL) st_async_f32(dst + (uint32_t)(c * n1p * 4), fmaxf(v, 0.f), mbh + 8u);
+                    const float v = warp_sum(a + b) + bias;
+                    if (lane < CORE_CL)
+                        st_async_f32(dst + (uint32_t)(c * n1p * 4), fmaxf(v, 0.f), mbh + (uint32_t)((NC + c) * 8));
                 }
             } else if (tid == 0) {
-                ok = mbar_wait2(mb_x1, hpar, P, 521) && ok;
-                mbar_arm(mb_x1, bytes_x1);
+                for (int c = 0; c < NC; ++c) {
+                    ok = mbar_wait2(mb_x1 + c, hpar, P, 521) && ok;
+                    mbar_arm(mb_x1 + c, bytes_x1);
+                }
             }
             SWN_STAMP(9);
             // ---- out_2 rows
@@ -630,44 +626,37 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                         }
                     }
                 }
-                ok = mbar_wait2(mb_x2, hpar, P, 530) && ok;
-                SWN_STAMP(15);
-                if (tid == 0) mbar_arm(mb_x2, bytes_x2);
-                float acc2[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
+                    ok = mbar_wait2(mb_x2 + c, hpar, P, 530) && ok;
+                    if (c == 0) SWN_STAMP(15);
+                    if (tid == 0) mbar_arm(mb_x2 + c, bytes_x2);
+                    const float2* xv = reinterpret_cast<const float2*>(x2 + c * n1p);
                     float a = 0.f, b = 0.f;
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
                         if (cc * 64 < n1p) {
-                            const float2 v = reinterpret_cast<const float2*>(x2 + c * n1p)[cc * 32 + lane];
+                            const float2 v = xv[cc * 32 + lane];
                             a = fmaf(wpre2[cc].x, v.x, a); b = fmaf(wpre2[cc].y, v.y, b);
                         }
                     }
-                    acc2[c] = a + b;
-                }
-                for (int cc = 4; cc < (n1p >> 6); ++cc) {
-                    const float2 wv = reinterpret_cast<const float2*>(wrow)[cc * 32 + lane];
-#pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        const float2 v = reinterpret_cast<const float2*>(x2 + c * n1p)[cc * 32 + lane];
-                        acc2[c] = fmaf(wv.x, v.x, acc2[c]);
-                        acc2[c] = fmaf(wv.y, v.y, acc2[c]);
+                    for (int cc = 4; cc < (n1p >> 6); ++cc) {
+                        const float2 wv = reinterpret_cast<const float2*>(wrow)[cc * 32 + lane], v = xv[cc * 32 + lane];
+                        a = fmaf(wv.x, v.x, a); b = fmaf(wv.y, v.y, b);
                     }
-                }
-#pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    const float o = warp_sum(acc2[c]) + bias;
+                    const float o = warp_sum(a + b) + bias;
                     if (is_c) {
                         if (lane == 0) o2[c * 16 + r] = o;
                     } else {
-                        if (lane < CORE_CL) st_async_f32(dst + (uint32_t)(c * 256 * 4), o + gn[c], mbh + 16u);
+                        if (lane < CORE_CL) st_async_f32(dst + (uint32_t)(c * 256 * 4), o + gn[c], mbh + (uint32_t)((2 * NC + c) * 8));
                         if (lane == 16 && P.head_out && c < P.B) P.head_out[((size_t)c * P.n_iter + istep) * n2 + c0row] = o;
                     }
                 }
             } else if (tid == 0) {
-                ok = mbar_wait2(mb_x2, hpar, P, 531) && ok;
-                mbar_arm(mb_x2, bytes_x2);
+                for (int c = 0; c < NC; ++c) {
+                    ok = mbar_wait2(mb_x2 + c, hpar, P, 531) && ok;
+                    mbar_arm(mb_x2 + c, bytes_x2);
+                }
             }
             SWN_STAMP(16);
             if (is_c) {
@@ -690,11 +679,11 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
             } else {
                 // ---- arg-max over the 256 published Gumbel scores (first maximum wins), by EVERY warp for itself: the
                 // warp goes straight on to its row of the next input vector, no CTA barrier, no shared-memory round trip
-                ok = mbar_wait2(mb_gx, hpar, P, 540) && ok;
-                SWN_STAMP(17);
-                if (tid == 0) mbar_arm(mb_gx, bytes_gx);
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
+                    ok = mbar_wait2(mb_gx + c, hpar, P, 540) && ok;
+                    if (c == 0) SWN_STAMP(17);
+                    if (tid == 0) mbar_arm(mb_gx + c, bytes_gx);
                     // the lane's 8 scores as a compare tree (depth 3) instead of a chain of 8; ties keep the lower index
                     float bv[4]; int bx[4];
 #pragma unroll
@@ -721,6 +710,7 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                         if (P.forced) f = clamp_idx(__ldg((const long long*)P.forced + (size_t)c * P.n_out + istep), Q);
                     }
                     fed[c] = __int_as_float(f);
+                    if (it + 1 < P.n_it) input_publish_col(it + 1, c, fed[c]);   // straight on to this column's next input row
                 }
             }
             SWN_STAMP(10);
@@ -729,7 +719,7 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
             fed_from_hist(it + 1, fed);                                          // warm-up: the padded seed
         }
         if (it + 1 < P.n_it) {
-            input_publish(it + 1, fed);
+            if (is_c || !active) input_publish(it + 1, fed);
             SWN_STAMP(11);
             feed(it + 1, fed);
             cp_async_commit();
