@@ -103,14 +103,21 @@ class _SWNBase(nn.Module):
     def _cfg_kwargs(self):
         raise NotImplementedError
 
+    #: also key the packed-weight cache on the CONTENT of the parameters (one float64 sum per tensor, i.e. ~50 small torch
+    #: reductions on the device per generate call).  Off by default: the generation path launches no torch kernel.
+    check_weight_content = False
+
     def _weights_version(self):
-        """Key of the packed-weight cache.  ``p._version`` alone misses edits made through ``p.data`` (weight-norm
-        removal, EMA swaps: ``.data`` is a detached alias with its own counter), so the key also carries the storage
-        pointers and a content checksum (one float64 sum per tensor, gathered with a single device->host copy)."""
+        """Key of the packed-weight cache: ``p._version`` and the storage pointers of every parameter.  Edits made through
+        ``p.data`` in place (weight-norm removal, EMA swaps: ``.data`` is a detached alias with its own version counter)
+        change neither: call ``refresh_engine()`` after such an edit, or set ``check_weight_content = True`` to have the
+        key carry a content checksum as well."""
         params = list(self.parameters())
-        with torch.no_grad():
-            sums = torch.stack([p.detach().sum(dtype=torch.float64) for p in params]).cpu().numpy().tobytes()
-        return (tuple(p._version for p in params), tuple(p.data_ptr() for p in params), sums, str(params[0].device))
+        key = (tuple(p._version for p in params), tuple(p.data_ptr() for p in params), str(params[0].device))
+        if self.check_weight_content:
+            with torch.no_grad():
+                key += (torch.stack([p.detach().sum(dtype=torch.float64) for p in params]).cpu().numpy().tobytes(),)
+        return key
 
     def refresh_engine(self):
         """Drop the packed weights on the device; the next generate call re-reads the parameters."""

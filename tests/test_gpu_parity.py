@@ -402,9 +402,11 @@ def test_zero_noise_variate_and_index_validation():
 
 
 def test_edits_through_param_data_rebuild_engine():
-    """p.data edits do not bump p._version: the engine cache key carries a content checksum."""
+    """p.data edits do not bump p._version: refresh_engine() after such an edit, or let the engine cache key
+    carry a content checksum (check_weight_content)."""
     g = load_golden("dswnv_base")
     m = _model_from_golden(g)
+    m.check_weight_content = True
     aux = torch.from_numpy(g["aux"])
     B, N = g["samples"].shape
     seed_a = torch.full((B, 1), 128, dtype=torch.long)
