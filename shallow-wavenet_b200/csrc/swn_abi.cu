@@ -104,7 +104,7 @@ struct swn_model {
     // ---- v2: core cluster + helpers (swn_core.cuh)
     bool core_ok = false;
     int n_core_taps = 0;
-    std::vector<int> tap_base;
+    std::vector<int> tap_base, ncore;
     struct HelpLayer { int ntaps = 0, dmin = 0; std::vector<int> delay, tapj; };
     std::vector<HelpLayer> hl;
     std::vector<float> in_tab_h;
@@ -302,6 +302,7 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
                          int b0 = 0, bool first = true, bool last = true, int force_bs = 0) {
     const int H = m->H, Hp = m->Hp, K = m->K, L = m->L, S = m->S, Q = m->Q;
     const bool is_c = m->cfg.kind == SWN_KIND_CSWNV;
+    if (m->seg != 1) return 2;                           // (seg > 1: generate_coreseg)
     int BS = 0;
     for (int t : {1, 2, 4}) if (!BS && t >= B) BS = t;
     if (a->batch_tile > 0) BS = a->batch_tile;
@@ -477,6 +478,174 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
     m->info.grid = m->core_grid;
     m->info.kernel_variant = 2;
     m->info.ctas_per_layer = swn::CORE_CL;          // the core cluster; the other CTAs are helpers
+    m->info.head_ctas = m->core_n_help;
+    return 0;
+}
+
+
+// ---- seg > 1 cluster kernel (swn_coreseg.cuh), utterance b0 of the conditioned batch: 0 = launched, 2 = not applicable, 1 = error
+static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st, int Tf, int64_t n_iter, int b0, bool first,
+                            bool last) {
+    const int H = m->H, Hp = m->Hp, K = m->K, L = m->L, S = m->S, seg = m->seg;
+    swn::core_fns fn = {nullptr, nullptr};
+    switch (m->NCH) {
+        case 1: fn = swn::find_coreseg_kernel_nch1(seg); break;
+        case 2: fn = swn::find_coreseg_kernel_nch2(seg); break;
+        case 3: fn = swn::find_coreseg_kernel_nch3(seg); break;
+        case 4: fn = swn::find_coreseg_kernel_nch4(seg); break;
+    }
+    if (!fn.launch) return 2;
+    const long long key = 1000 + seg;
+    if (key != m->core_plan_key) {
+        CUDA_OK(cudaStreamSynchronize(st));
+        const int smem_floats = SWN_MAX_SMEM / 4;
+        size_t core_used = 0;
+        {
+            int mx_skip = 0, mx_nb = 0, mx_nc = 0;
+            for (auto& q : m->ccta) { mx_skip = std::max(mx_skip, q.nskip); mx_nb = std::max(mx_nb, q.nb); mx_nc = std::max(mx_nc, q.nc); }
+            size_t u = 0;
+            auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
+            swn::CoreCta lay;
+            lay.sm_skip = take((size_t)L * mx_skip * Hp);
+            lay.sm_w1 = take((size_t)mx_nb * m->Sp);
+            lay.sm_w2 = take((size_t)mx_nc * m->n1p);
+            lay.sm_hx = take((size_t)2 * (L + 1) * seg * Hp);       // hx (both parities), x1, x2 stay contiguous
+            lay.sm_x1 = take((size_t)m->Sp);
+            lay.sm_x2 = take((size_t)m->n1p);
+            lay.sm_pre = take((size_t)L * 16 * seg * 4);
+            lay.sm_misc = take((size_t)(32 + 8 + 16 + 8) + (size_t)L * 16 * 4 + 8 * 2 * 16);
+            lay.sm_tmem_slot = take(4 + 2 * (size_t)(2 * L + 3 + 1));
+            core_used = u;
+            for (auto& q : m->ccta) {
+                q.sm_skip = lay.sm_skip; q.sm_w1 = lay.sm_w1; q.sm_w2 = lay.sm_w2; q.sm_tin = 0; q.sm_ring = 0;
+                q.sm_hx = lay.sm_hx; q.sm_x1 = lay.sm_x1; q.sm_x2 = lay.sm_x2; q.sm_gx = 0; q.sm_pre = lay.sm_pre;
+                q.sm_misc = lay.sm_misc; q.sm_tmem_slot = lay.sm_tmem_slot;
+            }
+        }
+        if (core_used > (size_t)smem_floats) return 2;
+        int max_cl = 0;
+        CUDA_OK(fn.prepare(SWN_MAX_SMEM, &max_cl));
+        int n_help_layers = 0, n_help_taps = 0;
+        for (int l = 0; l < L; ++l) { n_help_layers += m->hl[l].ntaps > 0; n_help_taps += m->hl[l].ntaps; }
+        if (max_cl < 1 || (n_help_layers > 0 && max_cl < 2)) return 2;
+        const int n_help = n_help_layers ? (max_cl - 1) * swn::CORE_CL : 0;
+        if (n_help_layers && n_help < n_help_layers) return 2;
+        // ---- helper CTAs: a share of the helper SMs per layer in proportion to its taps (at least one)
+        std::vector<float>& V = m->wbuf2_h;
+        V.resize(m->wbuf2_core_floats);
+        auto alloc2 = [&](size_t n) { size_t off = (V.size() + 3) & ~size_t(3); V.resize(off + n, 0.f); return (int64_t)off; };
+        std::vector<swn::HelpCta> hd;
+        size_t help_used = 0;
+        int spare = n_help - n_help_layers;
+        for (int l = 0; l < L; ++l) {
+            const auto& hl = m->hl[l];
+            if (!hl.ntaps) continue;
+            const HostTensor* x = m->get("dil_h." + std::to_string(l) + ".conv.weight");
+            int GHe = 1 + (int)((long long)(n_help - n_help_layers) * hl.ntaps / n_help_taps);
+            GHe = std::min(GHe, 1 + spare); spare -= GHe - 1;
+            GHe = std::min(GHe, H);
+            for (int g = 0; g < GHe; ++g) {
+                swn::HelpCta d;
+                memset(&d, 0, sizeof(d));
+                d.layer = l; d.dil = m->dil[l]; d.ntaps = hl.ntaps; d.dmin = hl.dmin;
+                split_range(H, GHe, g, &d.pair0, &d.npairs);
+                d.ring_len = 8; while (d.ring_len < hl.delay.back() + 2 * seg + 2) d.ring_len *= 2;      // power of two
+                for (int j = 0; j < hl.ntaps; ++j) d.delay[j] = hl.delay[j];
+                const int np = d.npairs;
+                d.w_off = alloc2((size_t)hl.ntaps * np * 2 * Hp);
+                for (int j = 0; j < hl.ntaps; ++j)
+                    for (int pi = 0; pi < np; ++pi)
+                        for (int zc = 0; zc < 2; ++zc) {
+                            const int row = zc * H + d.pair0 + pi;
+                            float* dst = V.data() + d.w_off + ((size_t)(j * np + pi) * 2 + zc) * Hp;
+                            for (int k = 0; k < H; ++k) dst[k] = x->data[((size_t)row * H + k) * K + hl.tapj[j]];
+                        }
+                size_t u = 0;
+                auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
+                d.sm_w = take((size_t)hl.ntaps * np * 2 * Hp);
+                d.sm_h = take((size_t)seg * Hp);
+                d.sm_ring = take((size_t)d.ring_len * np * 2);
+                d.ring_in_smem = 1;
+                if (u > (size_t)smem_floats) return 2;
+                help_used = std::max(help_used, u);
+                hd.push_back(d);
+            }
+        }
+        const int n_help_used = (int)hd.size();
+        const int grid = swn::CORE_CL * (1 + (n_help_used + swn::CORE_CL - 1) / swn::CORE_CL);
+        if (grid / swn::CORE_CL > max_cl) return 2;
+        m->core_smem = std::max(core_used, help_used) * 4;
+        m->core_grid = grid; m->core_n_help = n_help_used; m->core_ring_total = 0;
+        if (upload(m->wbuf2, V)) return 1;
+        if (upload(m->cdesc, m->ccta)) return 1;
+        if (hd.empty()) hd.push_back(swn::HelpCta());
+        if (upload(m->hdesc, hd)) return 1;
+        swn::CoreParams& P = m->core_tmpl;
+        memset(&P, 0, sizeof(P));
+        size_t n_hin = 0, n_hacc = 0;
+        for (int l = 0; l < L; ++l) {
+            const auto& hl = m->hl[l];
+            P.dil[l] = m->dil[l]; P.tap_base[l] = m->tap_base[l]; P.ncore[l] = m->ncore[l];
+            P.has_help[l] = hl.ntaps > 0; P.hdmin[l] = hl.dmin;
+            int p2 = 4; while (p2 < hl.dmin / seg + 4) p2 *= 2;                 // input ring: steps the core may run ahead
+            P.hslots[l] = p2;
+            p2 = 8; while (p2 < hl.dmin + 3 * seg) p2 *= 2;                     // finished sums: time slots in flight
+            P.hacc_nt[l] = p2;
+            P.hin_off[l] = (int64_t)n_hin; P.hacc_off[l] = (int64_t)n_hacc;
+            if (hl.ntaps) { n_hin += (size_t)P.hslots[l] * seg * H; n_hacc += (size_t)P.hacc_nt[l] * 2 * H; }
+        }
+        m->core_n_hin = n_hin; m->core_n_hacc = n_hacc;
+        if (m->ll2.ensure(n_hin + n_hacc + 8)) return 1;
+        m->core_plan_key = key;
+    }
+    swn::CoreParams P = m->core_tmpl;
+    P.kind = m->cfg.kind; P.H = H; P.Hp = Hp; P.S = S; P.Sp = m->Sp; P.K = K; P.L = L; P.lpc = m->lpc;
+    P.n1 = m->n1; P.n1p = m->n1p; P.n2 = m->n2; P.Q = m->Q; P.U = m->U; P.R = m->R; P.B = 1; P.Tf = Tf;
+    P.seg = seg;
+    const int rem = (m->R + 1) % seg;                      // the time-index contract of the layer-group kernel (swn_generate)
+    P.t_first = rem == 0 ? 0 : rem - seg;
+    P.it0 = (m->R + 1 - P.t_first) / seg - 1;
+    P.n_iter = (int)n_iter; P.n_it = P.it0 + (int)n_iter;
+    P.n_core_taps = m->n_core_taps; P.n_help = m->core_n_help; P.audio_in = 0;
+    P.n_out = n_iter * seg;
+    P.cdesc = m->cdesc.p; P.hdesc = m->hdesc.p; P.wbuf = m->wbuf2.p;
+    P.P = m->ptab.p + (size_t)b0 * Tf * L * seg * 2 * H; P.pconst = m->pconst.p; P.gain = m->gain.p;
+    P.in_tab = m->in_tab.p; P.in_bias = m->in_bias.p; P.xa_tab = nullptr;
+    P.hin_ll = m->ll2.p; P.hacc_ll = m->ll2.p + m->core_n_hin; P.ring_scratch = nullptr;
+    {
+        const size_t off = (size_t)b0 * (size_t)P.n_out;
+        P.b0 = b0;
+        P.noise = a->noise_dev ? a->noise_dev + off : nullptr;
+        P.forced = a->forced_dev ? (const char*)a->forced_dev + off * sizeof(float) : nullptr;
+        P.seedw = a->seed_dev ? (const char*)a->seed_dev + (size_t)b0 * seg * sizeof(float) : nullptr;
+        P.out = (char*)a->out_dev + off * sizeof(float);
+        P.head_out = a->head_dev ? a->head_dev + (size_t)b0 * (size_t)n_iter * m->n2 : nullptr;
+    }
+    P.seed = a->seed; P.status = m->status.p; P.timeout_cycles = 4000000000ULL;
+    P.prof = (unsigned long long*)a->prof_dev; P.prof_start = a->prof_start; P.prof_count = a->prof_dev ? a->prof_count : 0;
+    CUDA_OK(cudaMemsetAsync(m->ll2.p, 0, (m->core_n_hin + m->core_n_hacc) * sizeof(unsigned long long), st));
+    if (first) {
+        CUDA_OK(cudaMemsetAsync(m->status.p, 0, 8 * sizeof(int32_t), st));
+        CUDA_OK(cudaEventRecord(m->ev[2], st));
+    }
+    int max_cl_dummy_ = 0;
+    cudaError_t e = fn.prepare(m->core_smem, &max_cl_dummy_);
+    if (e == cudaSuccess) e = fn.launch(P, m->core_grid, m->core_smem, st);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
+        (void)cudaGetLastError();
+        fail("cluster kernel not launched: %s (grid %d, %zu B smem)", cudaGetErrorString(e), m->core_grid, m->core_smem);
+        return first ? 2 : 1;
+    }
+    if (e != cudaSuccess) return fail("cluster kernel launch failed: %s (grid %d, %zu B smem)", cudaGetErrorString(e), m->core_grid, m->core_smem);
+    if (last) CUDA_OK(cudaEventRecord(m->ev[3], st));
+    m->gen_timed = true;
+    m->info.kernel_launches++;
+    m->info.smem_bytes = (int32_t)m->core_smem;
+    m->info.batch_tile = 1;
+    m->info.n_slots = first ? 1 : m->info.n_slots + 1;     // launches, one after the other
+    m->info.grid = m->core_grid;
+    m->info.kernel_variant = 2;
+    m->info.ctas_per_layer = swn::CORE_CL;
     m->info.head_ctas = m->core_n_help;
     return 0;
 }
@@ -1158,12 +1327,18 @@ int swn_finalize(swn_handle m) {
         const bool audio_in = (!is_c && c.audio_in_flag);
         int nct = 0;
         m->tap_base.assign(L, 0);
+        m->ncore.assign(L, 1);
         m->hl.assign(L, swn_model::HelpLayer());
+        bool help_lanes_ok = true;
         for (int l = 0; l < L; ++l) {
             m->tap_base[l] = nct;
             const int d = m->dil[l];
-            const int ncore = (d == 1 && K >= 2) ? 2 : 1;
+            // one sample per step: delay 0, and delay 1 of the dilation-1 layers (two steps of helper slack);
+            // seg > 1 (swn_coreseg.cuh): every tap whose delay is shorter than a step (one step of helper slack)
+            const int ncore = seg > 1 ? std::min(K, (seg + d - 1) / d) : ((d == 1 && K >= 2) ? 2 : 1);
+            m->ncore[l] = ncore;
             nct += ncore;
+            if (seg > 1 && (K - ncore) * seg > 32) help_lanes_ok = false;
             auto& hl = m->hl[l];
             for (int j = K - 1 - ncore; j >= 0; --j) {          // increasing delay
                 hl.tapj.push_back(j);
@@ -1174,8 +1349,12 @@ int swn_finalize(swn_handle m) {
         }
         m->n_core_taps = nct;
         const int tcols = 2 * 2 * m->NCH;
-        const bool fits = seg == 1 && !audio_in && H <= 256 && S <= 256 && n1 <= 256 && K <= swn::CORE_KMAX && L <= 16 &&
-                          nct * tcols <= 128 && (is_c ? n2 <= 16 : n2 <= 256);
+        const bool fits1 = seg == 1 && !audio_in && H <= 256 && S <= 256 && n1 <= 256 && K <= swn::CORE_KMAX && L <= 16 &&
+                           nct * tcols <= 128 && (is_c ? n2 <= 16 : n2 <= 256);
+        // seg > 1: 4 NCH^2 tensor-memory columns per tap and thread, one (tap, column) per helper lane
+        const bool fits5 = is_c && (seg == 2 || seg == 5) && H <= 256 && S <= 256 && n1 <= 256 && K <= swn::CORE_KMAX &&
+                           L <= 16 && nct * 4 * m->NCH * m->NCH <= 512 && n2 <= 16 && help_lanes_ok;
+        const bool fits = fits1 || fits5;
         if (fits) {
             std::vector<float>& V = m->wbuf2_h;
             V.clear();
@@ -1310,7 +1489,7 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
     // other (measured, DSWNV H=256: 145 k samples/s against 69-92 k for the layer-group kernel at B=3-4 and 111 k for
     // the batch kernel at B=6; from 8 utterances on the batch kernel wins).  CSWNV seg=1 only where the alternative
     // is the layer-group kernel (B <= 4): its batch kernel runs on the tensor cores.
-    if (m->core_ok && a->kernel_sel == 0 && a->batch_tile == 0 && !a->prof_dev && B >= 3 &&
+    if (m->core_ok && seg == 1 && a->kernel_sel == 0 && a->batch_tile == 0 && !a->prof_dev && B >= 3 &&
         B <= (m->cfg.kind == SWN_KIND_DSWNV ? 7 : 4)) {
         int rc = 0;
         for (int b0 = 0; b0 < B && rc == 0; b0 += 2)
@@ -1319,7 +1498,17 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
         if (rc == 1) return 1;
         CUDA_OK(cudaStreamSynchronize(st));                 // not applicable after all: nothing was launched (rc == 2 comes first)
     }
-    if (m->core_ok && a->kernel_sel != 1 && a->kernel_sel < 3) {
+    if (m->core_ok && seg > 1) {
+        // seg > 1: the cluster kernel takes one utterance per launch; small batches run as launches one after the other
+        if (a->kernel_sel == 2 || (a->kernel_sel == 0 && a->batch_tile == 0 && B <= 2)) {
+            int rc = 0;
+            for (int b0 = 0; b0 < B && rc == 0; ++b0) rc = generate_coreseg(m, a, st, Tf, n_iter, b0, b0 == 0, b0 + 1 == B);
+            if (rc == 0) return 0;
+            if (rc == 1) return 1;
+            if (a->kernel_sel == 2) return fail("swn_generate: the cluster kernel is not applicable to this configuration");
+            CUDA_OK(cudaStreamSynchronize(st));
+        }
+    } else if (m->core_ok && a->kernel_sel != 1 && a->kernel_sel < 3) {
         const int rc = generate_core(m, a, st, B, Tf, n_iter);
         if (rc == 0) return 0;
         if (rc == 1) return 1;

@@ -59,6 +59,8 @@ struct CoreParams {
     int64_t n_out;
     int32_t dil[16];
     int32_t tap_base[16];          // first core tap index of layer l (tap 0 = delay 0, tap 1 = delay 1)
+    int32_t ncore[16];             // core taps of layer l (swn_coreseg.cuh: the taps with delay < seg)
+    int32_t t_first, seg;          // swn_coreseg.cuh: time of the first column of block 0 (<= 0), samples per step
     int32_t has_help[16];
     int32_t hslots[16];            // depth of the core->helper input ring of layer l (iterations)
     int32_t hacc_nt[16];           // time slots of the helper->core partial-sum ring of layer l
@@ -85,6 +87,8 @@ __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("m
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
     uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank)); return r;

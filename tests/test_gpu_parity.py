@@ -465,6 +465,50 @@ def test_both_kernel_variants_agree(name):
     assert float(np.abs(res[1][1] - res[2][1]).max()) <= 2e-5
 
 
+SEG_FIXTURES = ["cswnv_seg2_lpc3", "cswnv_seg5_lpc0_conv2d", "cswnv_seg5_lpc4_h64", "cswnv_seg5_lpc4_wav"]
+
+
+@pytest.mark.parametrize("name", SEG_FIXTURES)
+def test_seg_cluster_kernel_matches_reference_fixture(name):
+    """CSWNV with several samples per step on the cluster kernel (swn_coreseg.cuh, variant 2; one utterance per launch):
+    teacher-forced heads and samples, then free running on the reference's own noise with per-utterance lengths."""
+    g = load_golden(name)
+    m = _model_from_golden(g)
+    B, N = g["samples"].shape
+    seed_a = _seed_audio(g["kind"], B, g["cfg"].eff_seg)
+    outs, heads = m.batch_fast_generate(seed_a, torch.from_numpy(g["aux"]), [N] * B, noise=g["noise"],
+                                        forced=g["samples"], return_heads=True, kernel_sel=2)
+    info = m.engine().info
+    assert info["kernel_variant"] == 2 and info["n_slots"] == B
+    _head_close(heads, g["heads"], "%s seg cluster kernel" % name, g)
+    assert float(np.abs(np.stack(outs) - g["samples"]).max()) <= SAMPLE_ATOL
+    outs = m.batch_fast_generate(seed_a, torch.from_numpy(g["aux"]), g["n_samples_list"], noise=g["noise"], kernel_sel=2)
+    assert [len(o) for o in outs] == g["n_samples_list"]
+    for b, o in enumerate(outs):
+        assert float(np.abs(o - g["samples"][b, :len(o)]).max()) <= 5e-5
+
+
+def test_seg_cluster_kernel_recipe_size_reference_fixture():
+    """The recipe model (H=192, seg 5, lpc 4, k=7, L=6, R=690) on the seg cluster kernel against the unmodified reference's
+    outputs (tests/golden_large, oracle/build_ref.py), and against the layer-group kernel on the same inputs."""
+    g = load_large("large_cswnv_seg5_b2")
+    m = g["model"].cuda().eval()
+    B, N = g["samples"].shape
+    seed_a = _seed_audio("cswnv", B, 5)
+    res = {}
+    for sel in (2, 1):
+        outs, heads = m.batch_fast_generate(seed_a, torch.from_numpy(g["aux"]), [N] * B, noise=g["noise"],
+                                            forced=g["samples"], return_heads=True, kernel_sel=sel)
+        assert m.engine().info["kernel_variant"] == sel
+        _head_close(heads, g["heads"], "large_cswnv_seg5_b2 v%d" % sel, g)
+        assert float(np.abs(np.stack(outs) - g["samples"]).max()) <= SAMPLE_ATOL
+        res[sel] = heads
+    assert float(np.abs(res[1] - res[2]).max()) <= 5e-5
+    outs = m.batch_fast_generate(seed_a, torch.from_numpy(g["aux"]), g["n_samples_list"], noise=g["noise"], kernel_sel=2)
+    for b, o in enumerate(outs):
+        assert float(np.abs(o - g["samples"][b, :len(o)]).max()) <= 5e-5
+
+
 def test_cluster_kernel_is_used_for_the_headline_workload():
     model, cfg, sd, aux, kw = _recipe_case("dswnv", 16000, 1, 2, 3)
     N = 2 * kw["upsampling_factor"]
