@@ -492,7 +492,6 @@ static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st
         case 1: fn = swn::find_coreseg_kernel_nch1(seg); break;
         case 2: fn = swn::find_coreseg_kernel_nch2(seg); break;
         case 3: fn = swn::find_coreseg_kernel_nch3(seg); break;
-        case 4: fn = swn::find_coreseg_kernel_nch4(seg); break;
     }
     if (!fn.launch) return 2;
     const long long key = 1000 + seg;
@@ -513,7 +512,7 @@ static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st
             lay.sm_x1 = take((size_t)m->Sp);
             lay.sm_x2 = take((size_t)m->n1p);
             lay.sm_pre = take((size_t)L * 16 * seg * 4);
-            lay.sm_misc = take((size_t)(32 + 8 + 16 + 8) + (size_t)L * 16 * 4 + 8 * 2 * 16);
+            lay.sm_misc = take((size_t)(32 + 16 + 16 + 8) + (size_t)L * 16 * 4 + 8 * 2 * 16 + 20 * 4 + (size_t)L * 8);
             lay.sm_tmem_slot = take(4 + 2 * (size_t)(2 * L + 3 + 1));
             core_used = u;
             for (auto& q : m->ccta) {
@@ -606,7 +605,12 @@ static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st
     P.t_first = rem == 0 ? 0 : rem - seg;
     P.it0 = (m->R + 1 - P.t_first) / seg - 1;
     P.n_iter = (int)n_iter; P.n_it = P.it0 + (int)n_iter;
-    P.n_core_taps = m->n_core_taps; P.n_help = m->core_n_help; P.audio_in = 0;
+    P.n_core_taps = m->n_core_taps; P.n_help = m->core_n_help;
+    {   // (field reused as a flag) per-step cluster barrier also outside the warm-up: some chain warp owns no out_1 row
+        int min_nb = 1 << 30;
+        for (auto& q : m->ccta) min_nb = std::min(min_nb, (int)q.nb);
+        P.audio_in = min_nb < 4 * m->NCH ? 1 : 0;
+    }
     P.n_out = n_iter * seg;
     P.cdesc = m->cdesc.p; P.hdesc = m->hdesc.p; P.wbuf = m->wbuf2.p;
     P.P = m->ptab.p + (size_t)b0 * Tf * L * seg * 2 * H; P.pconst = m->pconst.p; P.gain = m->gain.p;
@@ -1352,7 +1356,7 @@ int swn_finalize(swn_handle m) {
         const bool fits1 = seg == 1 && !audio_in && H <= 256 && S <= 256 && n1 <= 256 && K <= swn::CORE_KMAX && L <= 16 &&
                            nct * tcols <= 128 && (is_c ? n2 <= 16 : n2 <= 256);
         // seg > 1: 4 NCH^2 tensor-memory columns per tap and thread, one (tap, column) per helper lane
-        const bool fits5 = is_c && (seg == 2 || seg == 5) && H <= 256 && S <= 256 && n1 <= 256 && K <= swn::CORE_KMAX &&
+        const bool fits5 = is_c && (seg == 2 || seg == 5) && m->NCH <= 3 && H <= 192 && S <= 256 && n1 <= 256 && K <= swn::CORE_KMAX &&
                            L <= 16 && nct * 4 * m->NCH * m->NCH <= 512 && n2 <= 16 && help_lanes_ok;
         const bool fits = fits1 || fits5;
         if (fits) {

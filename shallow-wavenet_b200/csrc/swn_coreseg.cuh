@@ -12,18 +12,29 @@
 //     steps: they are the helpers', in scatter form with one step of slack;
 //   * tensor memory holds the core taps thread-privately: a thread of TMEM lane quarter q keeps 2*NCH rows (NCH gate
 //     pairs) x 2*NCH weights per tap = 4*NCH^2 columns (36 at H=192: 14 taps of the recipe model = 504 of 512 columns);
-//   * the columns of a stage are spread over TWO warps per quarter (warps q and q+4 read the same TMEM lanes): even
-//     columns / odd columns.  Each warp owns its columns from the first FMA to the publish, so a stage has no
-//     intra-CTA hand-off; the two warps share a scheduler and fill each other's issue gaps;
+//   * a chain warp owns ONE gate pair for all SEG columns (warps q, q+4, q+8 read the same TMEM lane quarter, each
+//     its own pair's columns): every tap is read from tensor memory once per stage (TMEM reads are 64 B/clk per SM:
+//     the first cut, columns split over two warps, read every tap twice and spent 4 us per step on it), the totals
+//     of all columns come out of ONE transposed reduction (18 shuffles), one gate, one publish - no intra-CTA hand-off;
 //   * the last layer only evaluates the last column (the head reads nothing else and no layer follows);
-//   * warps 8-15: the out_skip rows of the last column, and the gate operands (conditioning rows x gain + constant,
+//   * warps 12-15: the out_skip rows of the last column, and the gate operands (conditioning rows x gain + constant,
 //     bias + helper sums) of layer l+2 while layer l runs - late enough for the helpers' one-step slack, early enough
 //     that the L2 latency is never on the chain.  A local mbarrier per layer tells the chain warps the operands are in;
 //   * head as in swn_core2.cuh: x1 = relu(sum of skips) -> out_1 -> out_2 (every CTA all rows) -> Laplace / LPC sampler
-//     (cswnv_shift1.py:368-391) by one thread per CTA (bit-identical in all 16) -> the SEG new input columns.
+//     (cswnv_shift1.py:368-391) by every warp for itself (bit-identical everywhere) -> the SEG new input columns.
 #pragma once
 #include "swn_core.cuh"
 #include "swn_core2.cuh"
+
+#if SWN_STAMPS
+#define SWN_TSTAMP(ev, cond)                                                                        \
+    do {                                                                                            \
+        if (P.prof && (cond) && it >= P.prof_start && it < P.prof_start + P.prof_count)             \
+            P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + (ev)] = gtime();   \
+    } while (0)
+#else
+#define SWN_TSTAMP(ev, cond) do {} while (0)
+#endif
 
 namespace swn {
 
@@ -116,11 +127,49 @@ __device__ void helper_cta_seg(const CoreParams& P, const HelpCta& D, float* sme
 }
 
 // ------------------------------------------------------------------ core CTA
+// Totals of acc[c][z|c] (c < 8 column slots) over the 32 lanes: afterwards every lane of column group lane >> 2 holds
+// both totals of that column.  Three halving levels (16, 8, 4) and two butterflies: 18 shuffles for all columns.
+template <int SEG>
+__device__ __forceinline__ void reduce_columns(const float (&a)[SEG][2], int lane, float& qz, float& qc) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    float u[4][2], v[2][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int zc = 0; zc < 2; ++zc) {
+            const float lo = i < SEG ? a[i < SEG ? i : 0][zc] : 0.f, hi = i + 4 < SEG ? a[i + 4 < SEG ? i + 4 : 0][zc] : 0.f;
+            const float send = b4 ? lo : hi, keep = b4 ? hi : lo;
+            u[i][zc] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int zc = 0; zc < 2; ++zc) {
+            const float send = b3 ? u[i][zc] : u[i + 2][zc], keep = b3 ? u[i + 2][zc] : u[i][zc];
+            v[i][zc] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    float z, c;
+    {
+        const float sz = b2 ? v[0][0] : v[1][0], kz = b2 ? v[1][0] : v[0][0];
+        const float sc = b2 ? v[0][1] : v[1][1], kc = b2 ? v[1][1] : v[0][1];
+        z = kz + __shfl_xor_sync(0xffffffffu, sz, 4);
+        c = kc + __shfl_xor_sync(0xffffffffu, sc, 4);
+    }
+#pragma unroll
+    for (int o = 2; o > 0; o >>= 1) {
+        z += __shfl_xor_sync(0xffffffffu, z, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    qz = z; qc = c;
+}
+
 template <int NCH, int SEG>
 __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem) {
+    static_assert(NCH <= 3 && SEG <= 8, "chain warps 0 .. 4*NCH-1, service warps 12-15; 8 column slots in the reduction");
     constexpr int HP = NCH * 64, NPW = NCH, FPT = 2 * NCH, ROWS = 2 * NPW, TCOLS = ROWS * FPT;
+    constexpr int WT = 2 * FPT;                                 // tensor-memory columns of one warp per tap: 2 rows x FPT weights
     constexpr int HIST = 32;
-    constexpr int NCI = (SEG + 1) / 2;                          // columns per team (team 0: even, team 1: odd)
+    constexpr int NCHAIN = 4 * NCH;                             // chain warps
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = P.H, S = P.S, Sp = P.Sp, K = P.K, L = P.L, n1 = P.n1, n1p = P.n1p, n2 = P.n2;
     const uint32_t rank = cluster_ctarank();
@@ -138,15 +187,15 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     float4* gop = reinterpret_cast<float4*>(smem + D.sm_pre);   // [L][16][SEG] gate operands {pz, bz*pz, pc, bc*pc}
     float* misc = smem + D.sm_misc;
     float* hist = misc;                                    // [HIST] fed-back samples
-    float* lpb = hist + HIST;                              // [8]
-    float* o2 = lpb + 8;                                   // [16] out_2 rows
-    float* epsb = o2 + 16;                                 // [8] the step's uniform noise
+    float* lpb = hist + HIST;                              // [2][8] LPC history, by head-step parity
+    float* o2 = lpb + 16;                                  // [16] out_2 rows
+    float* epsb = o2 + 16;                                 // [8] sign(e) log1p(-2|e|) of the step's noise
     float4* lc = reinterpret_cast<float4*>(epsb + 8);      // [L][16] per (layer, pair): conditioning const z/c, bias z/c
     float* sfir = reinterpret_cast<float*>(lc + L * 16);   // [8][2][16] FIR taps (cb, v) of this CTA's input rows
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + D.sm_tmem_slot);
     unsigned long long* mb = reinterpret_cast<unsigned long long*>(tmem_slot + 2);   // [L+1] layer inputs (+ last layer's output)
     unsigned long long* mb_x1 = mb + (L + 1), *mb_x2 = mb + (L + 2);
-    unsigned long long* gb = mb + (L + 3);                 // [L] "gate operands of layer l are in" (8 arrivals: warps 8-15)
+    unsigned long long* gb = mb + (L + 3);                 // [L] "gate operands of layer l are in" (4 arrivals: warps 12-15)
     const uint32_t bytes_h = (uint32_t)(SEG * H * 4), bytes_last = (uint32_t)(H * 4);
     const uint32_t bytes_x1 = (uint32_t)(S * 4), bytes_x2 = (uint32_t)(n1 * 4);
     const int LS = (L + 1) * SEG * HP;                     // floats per parity copy of hx
@@ -161,7 +210,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     stage(sW2, P.wbuf + D.w2_off, D.nc * n1p);
     for (int i = tid; i < 2 * LS + Sp + n1p; i += SWN_NTHREADS) hx[i] = 0.f;    // hx, x1, x2 are contiguous; pads stay 0
     for (int i = tid; i < L * 16 * SEG; i += SWN_NTHREADS) gop[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = tid; i < HIST + 8 + 16 + 8; i += SWN_NTHREADS) misc[i] = 0.f;
+    for (int i = tid; i < HIST + 16 + 16 + 8; i += SWN_NTHREADS) misc[i] = 0.f;
     __syncthreads();
     for (int i = tid; i < L * 16; i += SWN_NTHREADS) {
         const int l = i >> 4, wv = i & 15;
@@ -178,7 +227,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     }
     if (tid == 0) {
         for (int i = 0; i < L + 3; ++i) mbar_init(mb + i, 1);
-        for (int i = 0; i < L; ++i) mbar_init(gb + i, 8);
+        for (int i = 0; i < L; ++i) mbar_init(gb + i, 4);
         mbar_fence_init();
         for (int i = 0; i < L; ++i) mbar_arm(mb + i, bytes_h);                    // phase 0 of every vector
         mbar_arm(mb + L, bytes_last); mbar_arm(mb_x1, bytes_x1); mbar_arm(mb_x2, bytes_x2);
@@ -190,7 +239,8 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     const uint32_t tbase = *tmem_slot;
     const uint32_t taddr0 = tbase + ((uint32_t)(32 * quarter) << 16);
     // ---- tensor memory <- the core taps: warp q < 4 fills its lane quarter with the taps of gate pairs NPW*q .. +NPW-1
-    // (thread-private columns: tap c occupies columns [c*TCOLS, (c+1)*TCOLS), row rr = 2*pair + {z,c} at rr*FPT)
+    // (thread-private columns: tap c occupies columns [c*TCOLS, (c+1)*TCOLS), row rr = 2*pair + {z,c} at rr*FPT); in the
+    // loop the chain warp of team t reads the 2*FPT columns of pair slot t
     if (warp < 4) {
         for (int c = 0; c < P.n_core_taps; ++c) {
 #pragma unroll
@@ -219,8 +269,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
         if (tid < SEG) {
             const float v = ((const float*)P.seedw)[tid];
             hist[(tid - SEG + HIST) & (HIST - 1)] = v;
-            const int mm = P.lpc - SEG + tid;
-            if (mm >= 0) lpb[mm] = v;
+            if (8 - SEG + tid >= 0) lpb[8 - SEG + tid] = v;            // newest last (slot 7); slots beyond lpc have zero coefficients
         }
     }
     __syncthreads();
@@ -228,56 +277,112 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
 
     const uint32_t peer = (uint32_t)(lane & (CORE_CL - 1));
     const uint32_t hx_peer = mapa(smem_u32(hx), peer), mb_peer = mapa(smem_u32(mb), peer);
-    const int pslot = lane >> 3;                                   // pair slot inside the quarter (valid below NPW)
-    const int plocal = NPW * quarter + pslot;                      // gate pair inside this CTA
-    const bool pvalid = pslot < NPW && plocal < np;
-    const int my_i = D.pair0 + (pvalid ? plocal : 0);              // row index in H (a valid row for idle lanes too)
-    const int sub = lane & 7;                                      // lane inside the pair group: publishes to CTAs sub, sub+8
-    const uint32_t pub0 = mapa(smem_u32(hx), (uint32_t)sub) + (uint32_t)(my_i * 4);
-    const uint32_t pub1 = mapa(smem_u32(hx), (uint32_t)sub + 8) + (uint32_t)(my_i * 4);
-    const uint32_t pmb0 = mapa(smem_u32(mb), (uint32_t)sub), pmb1 = mapa(smem_u32(mb), (uint32_t)sub + 8);
-    const int skr0 = 2 * (warp - 8), skr1 = skr0 + 1;              // skip rows of warps 8..15
-    const bool sk_v0 = warp >= 8 && skr0 < D.nskip, sk_v1 = warp >= 8 && skr1 < D.nskip;
+    // ---- chain warps: warp (quarter q, team t) owns gate pair NPW*q + t of this CTA for all SEG columns
+    const int plocal = NPW * quarter + team;
+    const bool is_chain = warp < NCHAIN;
+    const bool pvalid = is_chain && plocal < np;
+    const int my_i = D.pair0 + (pvalid ? plocal : 0);              // row index in H (a valid row for idle warps too)
+    const int cg = lane >> 2, sub4 = lane & 3;                     // column group of the lane after the reduction; its 4 lanes
+    const int ccl = cg < SEG ? cg : SEG - 1;                       // publish to CTAs sub4, sub4+4, sub4+8, sub4+12
+    const uint32_t hx_mine = smem_u32(hx) + (uint32_t)(my_i * 4), mb_mine = smem_u32(mb);
+    // ---- service warps 12-15: four out_skip rows each (last column only), gate operands
+    const int srow0 = 4 * (warp - 12);
     const bool has_b = warp < D.nb, has_c = warp < D.nc;
+    // per-layer record of the chain stage in shared memory: indexed kernel-parameter loads (LDC c[0][R+imm]) between the
+    // wake-up and the publish showed up as the largest single stall of the stage (profiles/r02u: short scoreboard on the
+    // LDC.64 of P.hin_off[l+1])
+    struct LRec { int32_t nco, dil, tcol, hmask; unsigned long long hin; int32_t nco_next, tcol_next; };
+    LRec* lrec = reinterpret_cast<LRec*>(reinterpret_cast<float4*>(sfir + 8 * 2 * 16) + 20);   // [L] behind wconst
+    if (tid < L) {
+        const int l = tid;
+        LRec r;
+        r.nco = P.ncore[l]; r.dil = P.dil[l]; r.tcol = P.tap_base[l] * TCOLS;
+        const bool hn_ = l + 1 < L && P.has_help[l + 1];
+        r.hmask = hn_ ? P.hslots[l + 1] - 1 : -1;                  // -1: no helper behind this layer's output
+        r.hin = hn_ ? (unsigned long long)(P.hin_ll + P.hin_off[l + 1]) : 0ull;
+        r.nco_next = l + 1 < L ? P.ncore[l + 1] : 0; r.tcol_next = l + 1 < L ? P.tap_base[l + 1] * TCOLS : 0;
+        lrec[l] = r;
+    }
+    __syncthreads();
+    // per-warp constants of the head (out_1 / out_2 bias, input bias, skip constants) live in shared memory and are read
+    // right before the waits they follow: as loop-long registers they pushed the chain section into spills
+    float4* wconst = reinterpret_cast<float4*>(sfir + 8 * 2 * 16);      // [16] {out_1 bias, out_2 bias, input bias, -}, [4] skip constants
     const int in_row = D.i0 + warp;
     const bool has_in = warp < D.ni;
-    const float in_b = has_in ? __ldg(P.in_bias + in_row) : 0.f;
+    if (lane == 0) {
+        wconst[warp] = make_float4(has_b ? __ldg(P.wbuf + D.b1_off + warp) : 0.f, has_c ? __ldg(P.wbuf + D.b2_off + warp) : 0.f,
+                                   has_in ? __ldg(P.in_bias + in_row) : 0.f, 0.f);
+        if (warp >= 12) {
+            float k4[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) k4[r] = (srow0 + r < D.nskip) ? __ldg(P.wbuf + D.skipc_off + srow0 + r) : 0.f;
+            wconst[16 + warp - 12] = make_float4(k4[0], k4[1], k4[2], k4[3]);
+        }
+    }
+    __syncwarp();
+    // the cluster-wide "previous columns are no longer read" barrier (below) is only needed where the head does not couple
+    // every chain warp of every CTA to the next step: in the warm-up, and when some chain warp owns no out_1 row
+    const bool cb_always = P.audio_in != 0;                        // (field reused as a flag by the host plan)
     bool ok = true;
 
-    // ---- gate operands of (step s, layer l), by the 256 lanes of warps 8-15: lane <-> (pair, column)
-    auto prep = [&](int s, int l) {
-        const int idx = (warp - 8) * 32 + lane;
-        if (s < P.n_it && idx < np * SEG) {
-            const int p = idx / SEG, c = idx - p * SEG;
-            const int row = D.pair0 + p;
-            const int t = P.t_first + s * SEG + c;
-            const float4 c4 = lc[l * 16 + p];
-            float az = c4.x, ac = c4.y;
+    // ---- gate operands of target q = step * L + layer, by the 128 lanes of warps 12-15: lane <-> (pair, column).  Issue
+    // (L2 loads into registers) and commit (combine, write gop, signal) are one service-loop iteration apart, so that the
+    // L2 latency is never inside the iteration that feeds the chain.
+    struct PrepRegs { float tv[2 * SEG]; float gn[SEG]; unsigned long long ha, hb; };
+    PrepRegs pr_;                                                  // (only ever named directly: stays in registers)
+    const int pidx = (warp - 12) * 32 + lane;
+    const bool p_lane = warp >= 12 && pidx < np * SEG;
+    const int p_p = p_lane ? pidx / SEG : 0, p_c = p_lane ? pidx - (pidx / SEG) * SEG : 0;
+    const int p_row = D.pair0 + p_p;
+    auto prep_issue = [&](int q) {
+        PrepRegs& r = pr_;
+        const int s_ = q / L, l = q - s_ * L;
+        r.ha = 0ull; r.hb = 0ull;
+#pragma unroll
+        for (int sp = 0; sp < SEG; ++sp) { r.tv[2 * sp] = 0.f; r.tv[2 * sp + 1] = 0.f; r.gn[sp] = 0.f; }
+        if (p_lane && s_ < P.n_it) {
+            const int t = P.t_first + s_ * SEG + p_c;
             int f = 0, j = 0;
             if (t >= P.R) { f = (t - P.R) / P.U; j = (t - P.R) - f * P.U; }
-            const float* pl = P.P + (size_t)l * SEG * twoH + row;
+            const float* pl = P.P + (size_t)l * SEG * twoH + p_row;
             int tau = t;
 #pragma unroll
             for (int sp = 0; sp < SEG; ++sp) {
-                const float g = __ldg(P.gain + j);
+                r.gn[sp] = __ldg(P.gain + j);
                 const float* pr = pl + ((size_t)f * L * SEG + sp) * twoH;
-                az = fmaf(g, __ldg(pr), az);
-                ac = fmaf(g, __ldg(pr + H), ac);
+                r.tv[2 * sp] = __ldg(pr);
+                r.tv[2 * sp + 1] = __ldg(pr + H);
                 ++tau;
                 if (tau > P.R && ++j == P.U) { j = 0; ++f; }
             }
-            float hz = 0.f, hc = 0.f;
-            const int T = s * SEG + c;
+            const int T = s_ * SEG + p_c;
             if (P.has_help[l] && T >= P.hdmin[l]) {
-                const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + (size_t)(T & (P.hacc_nt[l] - 1)) * twoH + row;
+                const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + (size_t)(T & (P.hacc_nt[l] - 1)) * twoH + p_row;
+                r.ha = ld_ll(src); r.hb = ld_ll(src + H);
+            }
+        }
+    };
+    auto prep_commit = [&](int q) {
+        const PrepRegs& r = pr_;
+        const int s_ = q / L, l = q - s_ * L;
+        if (p_lane && s_ < P.n_it) {
+            const float4 c4 = lc[l * 16 + p_p];
+            float az = c4.x, ac = c4.y;
+#pragma unroll
+            for (int sp = 0; sp < SEG; ++sp) { az = fmaf(r.gn[sp], r.tv[2 * sp], az); ac = fmaf(r.gn[sp], r.tv[2 * sp + 1], ac); }
+            float hz = 0.f, hc = 0.f;
+            const int T = s_ * SEG + p_c;
+            if (P.has_help[l] && T >= P.hdmin[l]) {
                 const uint32_t tg = (uint32_t)T + 1u;
-                const unsigned long long va = ld_ll(src), vb = ld_ll(src + H);
-                uint32_t a = (uint32_t)va, b = (uint32_t)vb;
-                if ((uint32_t)(va >> 32) != tg) ok = wait_gword(src, tg, a, P, 400 + l) && ok;       // the helper is late
-                if ((uint32_t)(vb >> 32) != tg) ok = wait_gword(src + H, tg, b, P, 400 + l) && ok;
+                uint32_t a = (uint32_t)r.ha, b = (uint32_t)r.hb;
+                if ((uint32_t)(r.ha >> 32) != tg || (uint32_t)(r.hb >> 32) != tg) {         // the helper was late at issue time
+                    const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + (size_t)(T & (P.hacc_nt[l] - 1)) * twoH + p_row;
+                    ok = wait_gword(src, tg, a, P, 400 + l) && ok;
+                    ok = wait_gword(src + H, tg, b, P, 400 + l) && ok;
+                }
                 hz = __uint_as_float(a); hc = __uint_as_float(b);
             }
-            gop[(l * 16 + p) * SEG + c] = make_float4(az, (c4.z + hz) * az, ac, (c4.w + hc) * ac);
+            gop[(l * 16 + p_p) * SEG + p_c] = make_float4(az, (c4.z + hz) * az, ac, (c4.w + hc) * ac);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(gb + l);
@@ -285,19 +390,32 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
 
     // ---- input stage: the SEG columns of block itn (cswnv_shift1.py:352), rows of this CTA, published into every
     // peer's hx[parity of itn][0].  Gather form over the sample history (tap validity = the conv's zero padding).
+    float cbsum = 0.f;                                             // sum of the taps' constant terms (all taps valid)
+    for (int j = 0; j < K; ++j) cbsum += sfir[(j * 2) * 16 + (warp < 16 ? warp : 0)];
     auto input_stage = [&](int itn) {
         if (!has_in) return;
         const int c = lane < SEG ? lane : SEG - 1;
         const int t = P.t_first + itn * SEG + c;
+        const int t0b = P.t_first + itn * SEG;                     // first column of the block
         float v = 0.f;
-        if (t >= 0) {
-            float acc = in_b;
-            for (int j = 0; j < K; ++j) {
+        if (t0b - (K - 1) >= 0 && t0b - (K - 1) - P.R - 1 >= -SEG) {
+            // steady state (warp-uniform): every tap of every column is valid and inside the sample history
+            float acc = wconst[warp].z + cbsum;
+            const int n0 = t - (K - 1) - P.R - 1 + HIST;
+#pragma unroll
+            for (int j = 0; j < CORE_KMAX; ++j)
+                if (j < K) acc = fmaf(sfir[(j * 2 + 1) * 16 + warp], hist[(n0 + j) & (HIST - 1)], acc);
+            v = acc * rcp_approx(1.f + fabsf(acc));
+        } else if (t >= 0) {
+            float acc = wconst[warp].z;
+#pragma unroll
+            for (int j = 0; j < CORE_KMAX; ++j) {
                 const int tau = t - (K - 1) + j;                             // hidden time of the tap
-                if (tau < 0) continue;                                       // conv zero padding
-                const int n = tau - P.R - 1;                                 // newest sample seen by hidden time tau
-                const float a = (n >= -SEG) ? hist[(n + HIST) & (HIST - 1)] : 0.f;
-                acc += sfir[(j * 2) * 16 + warp] + sfir[(j * 2 + 1) * 16 + warp] * a;
+                if (j < K && tau >= 0) {                                     // (tau < 0: conv zero padding)
+                    const int n = tau - P.R - 1;                             // newest sample seen by hidden time tau
+                    const float a = (n >= -SEG) ? hist[(n + HIST) & (HIST - 1)] : 0.f;
+                    acc += sfir[(j * 2) * 16 + warp] + sfir[(j * 2 + 1) * 16 + warp] * a;
+                }
             }
             v = acc * rcp_approx(1.f + fabsf(acc));
         }
@@ -312,7 +430,11 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     };
 
     // ---- prologue: operands of the first two layers of step 0, inputs of block 0 (padding / seed)
-    if (warp >= 8) { prep(0, 0); if (L > 1) prep(0, 1); }
+    if (warp >= 12) {
+        prep_issue(0); prep_commit(0);
+        prep_issue(1); prep_commit(1);
+        prep_issue(2);                                             // (committed in the first service iteration)
+    }
     input_stage(0);
 
     for (int it = 0; it < P.n_it; ++it) {
@@ -325,128 +447,210 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
         SWN_STAMP(0);
         const float* hcur = hx + par * LS;                                   // this step's columns
         const float* hprev = hx + (par ^ 1u) * LS;                           // the previous step's
-        if (warp < 8) {
-            // ======================= column teams: core taps (gather form), gate, publish =======================
-            float w[TCOLS];
-            tmem_ldn<TCOLS>(taddr0 + P.tap_base[0] * TCOLS, w);
+        if (is_chain) {
+            // ======================= chain warps: one gate pair, all columns: core taps (gather form), gate, publish =======================
+            float w[SEG][WT];
+            tmem_ldn<WT>(taddr0 + P.tap_base[0] * TCOLS + team * WT, w[0]);
+            if (P.ncore[0] > 1) {
+                const int nco0 = P.ncore[0];
+#pragma unroll
+                for (int e = 1; e < SEG; ++e)
+                    if (e < nco0) tmem_ldn<WT>(taddr0 + (P.tap_base[0] + e) * TCOLS + team * WT, w[e]);
+            }
+            const bool t_neg = it == 0 && P.t_first + ccl < 0;               // alignment columns before time 0
             for (int l = 0; l < L; ++l) {
-                const int nco = P.ncore[l], dl = P.dil[l];
+                const LRec lr = lrec[l];
+                const int nco = lr.nco, dl = lr.dil;
                 const bool lastl = l + 1 == L;
+                float acc[SEG][2];
+#pragma unroll
+                for (int c = 0; c < SEG; ++c) { acc[c][0] = 0.f; acc[c][1] = 0.f; }
+                tmem_wait_ld();
+                if (dl == 1) {
+                    // dilation 1: source columns -(SEG-1) .. SEG-1 (negative = the previous step's), each loaded once; tap e
+                    // of source s feeds target column s + e (taps beyond ncore are zero-filled).  The previous step's
+                    // sources do not depend on this step's input: they are done BEFORE the wait, in the shadow of the hop.
+#pragma unroll
+                    for (int e = 1; e < SEG; ++e)
+                        if (e >= nco)
+#pragma unroll
+                            for (int q = 0; q < WT; ++q) w[e][q] = 0.f;
+#pragma unroll
+                    for (int sidx = 0; sidx < SEG - 1; ++sidx) {
+                        const int s = sidx - (SEG - 1);
+                        float2 h[NCH];
+                        load_frag<NCH>(h, hprev + (SEG + s) * HP + l * SEG * HP, lane);
+#pragma unroll
+                        for (int e = 1; e < SEG; ++e) {
+                            const int c = s + e;
+                            if (c >= 0 && c < SEG) {
+#pragma unroll
+                                for (int cc = 0; cc < NCH; ++cc) {
+                                    acc[c][0] = fmaf(w[e][2 * cc], h[cc].x, acc[c][0]);
+                                    acc[c][0] = fmaf(w[e][2 * cc + 1], h[cc].y, acc[c][0]);
+                                    acc[c][1] = fmaf(w[e][FPT + 2 * cc], h[cc].x, acc[c][1]);
+                                    acc[c][1] = fmaf(w[e][FPT + 2 * cc + 1], h[cc].y, acc[c][1]);
+                                }
+                            }
+                        }
+                    }
+                }
+                SWN_TSTAMP(17, tid == 0 && l == 1);
                 ok = mbar_wait2(gb + l, par, P, 480 + l) && ok;
+                SWN_TSTAMP(18, tid == 0 && l == 1);
                 ok = mbar_wait2(mb + l, par, P, 500 + l) && ok;
 #if SWN_STAMPS
                 if (P.prof && tid == 0 && l < 6 && it >= P.prof_start && it < P.prof_start + P.prof_count)
                     P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + 1 + l] = gtime();
 #endif
-                float acc[NCI][ROWS];
+                const float4 g4 = gop[(l * 16 + (pvalid ? plocal : 0)) * SEG + ccl];
+                const float carry = hcur[(l * SEG + ccl) * HP + my_i];
+                if (dl == 1) {
 #pragma unroll
-                for (int ci = 0; ci < NCI; ++ci)
+                    for (int s = 0; s < SEG; ++s) {
+                        float2 h[NCH];
+                        load_frag<NCH>(h, hcur + s * HP + l * SEG * HP, lane);
 #pragma unroll
-                    for (int rr = 0; rr < ROWS; ++rr) acc[ci][rr] = 0.f;
-                for (int e = 0; e < nco; ++e) {
-                    if (e > 0) tmem_ldn<TCOLS>(taddr0 + (P.tap_base[l] + e) * TCOLS, w);
-                    tmem_wait_ld();
-                    const int dly = e * dl;
-#pragma unroll
-                    for (int ci = 0; ci < NCI; ++ci) {
-                        const int c = 2 * ci + team;
-                        if (c < SEG && (!lastl || c == SEG - 1)) {
-                            const int src = c - dly;
-                            const float* hp = (src >= 0 ? hcur + src * HP : hprev + (SEG + src) * HP) + l * SEG * HP;
-                            float2 h[NCH];
-                            load_frag<NCH>(h, hp, lane);
-#pragma unroll
-                            for (int rr = 0; rr < ROWS; ++rr)
+                        for (int e = 0; e < SEG; ++e) {
+                            const int c = s + e;
+                            if (c < SEG) {
 #pragma unroll
                                 for (int cc = 0; cc < NCH; ++cc) {
-                                    acc[ci][rr] = fmaf(w[rr * FPT + 2 * cc], h[cc].x, acc[ci][rr]);
-                                    acc[ci][rr] = fmaf(w[rr * FPT + 2 * cc + 1], h[cc].y, acc[ci][rr]);
+                                    acc[c][0] = fmaf(w[e][2 * cc], h[cc].x, acc[c][0]);
+                                    acc[c][0] = fmaf(w[e][2 * cc + 1], h[cc].y, acc[c][0]);
+                                    acc[c][1] = fmaf(w[e][FPT + 2 * cc], h[cc].x, acc[c][1]);
+                                    acc[c][1] = fmaf(w[e][FPT + 2 * cc + 1], h[cc].y, acc[c][1]);
                                 }
+                            }
+                        }
+                    }
+                } else {
+                    // dilation >= 2: at most (SEG+1)/2 core taps; one fragment load per (tap, target column)
+#pragma unroll
+                    for (int e = 0; e < (SEG + 1) / 2; ++e) {
+                        if (e < nco) {
+                            const int dly = e * dl;
+#pragma unroll
+                            for (int c = 0; c < SEG; ++c) {
+                                if (!lastl || c == SEG - 1) {
+                                    const int src = c - dly;
+                                    const float* hp = (src >= 0 ? hcur + src * HP : hprev + (SEG + src) * HP) + l * SEG * HP;
+                                    float2 h[NCH];
+                                    load_frag<NCH>(h, hp, lane);
+#pragma unroll
+                                    for (int cc = 0; cc < NCH; ++cc) {
+                                        acc[c][0] = fmaf(w[e][2 * cc], h[cc].x, acc[c][0]);
+                                        acc[c][0] = fmaf(w[e][2 * cc + 1], h[cc].y, acc[c][0]);
+                                        acc[c][1] = fmaf(w[e][FPT + 2 * cc], h[cc].x, acc[c][1]);
+                                        acc[c][1] = fmaf(w[e][FPT + 2 * cc + 1], h[cc].y, acc[c][1]);
+                                    }
+                                }
+                            }
                         }
                     }
                 }
-                if (!lastl) tmem_ldn<TCOLS>(taddr0 + P.tap_base[l + 1] * TCOLS, w);    // next layer's first tap, in the shadow
+                SWN_TSTAMP(19, tid == 0 && l == 1);
+                float qz, qc;
+                reduce_columns<SEG>(acc, lane, qz, qc);
+                SWN_TSTAMP(20, tid == 0 && l == 1);
+                float hn = gate_out(fmaf(qz, g4.x, g4.y), fmaf(qc, g4.z, g4.w), carry);
+                if (t_neg) hn = 0.f;
+                if (pvalid && cg < SEG && (!lastl || cg == SEG - 1)) {
+                    // the last layer's output is a single column (slot 0 of hx[.][L])
+                    const uint32_t off = (uint32_t)(((par * (L + 1) + (l + 1)) * SEG + (lastl ? 0 : cg)) * HP * 4);
+                    const uint32_t mo = (uint32_t)((l + 1) * 8);
 #pragma unroll
-                for (int ci = 0; ci < NCI; ++ci) {
-                    const int c = 2 * ci + team;
-                    if (c < SEG && (!lastl || c == SEG - 1)) {
-                        float v8[8];
+                    for (int k = 0; k < 4; ++k)
+                        st_async_f32(mapa(hx_mine + off, (uint32_t)(sub4 + 4 * k)), hn, mapa(mb_mine + mo, (uint32_t)(sub4 + 4 * k)));
+                    if (lr.hmask >= 0 && sub4 == 0)
+                        st_ll(reinterpret_cast<unsigned long long*>(lr.hin) + ((size_t)(it & lr.hmask) * SEG + cg) * H + my_i, hn,
+                              (uint32_t)it + 1u);
+                }
+                SWN_TSTAMP(21, tid == 0 && l == 1);
+                // next layer's taps: requested behind the publish, they land in the shadow of the hop
+                if (!lastl) {
+                    const uint32_t ta = taddr0 + lr.tcol_next + team * WT;
+                    tmem_ldn<WT>(ta, w[0]);
+                    if (lr.nco_next > 1) {
 #pragma unroll
-                        for (int rr = 0; rr < 8; ++rr) v8[rr] = rr < ROWS ? acc[ci][rr] : 0.f;
-                        float qz, qc;
-                        reduce_pairs(v8, lane, qz, qc);
-                        const float4 g4 = gop[(l * 16 + (pvalid ? plocal : 0)) * SEG + c];
-                        const float carry = hcur[(l * SEG + c) * HP + my_i];
-                        float hn = gate_out(fmaf(qz, g4.x, g4.y), fmaf(qc, g4.z, g4.w), carry);
-                        if (it == 0 && P.t_first + c < 0) hn = 0.f;              // alignment columns before time 0
-                        if (pvalid) {
-                            // the last layer's output is a single column (slot 0 of hx[.][L])
-                            const uint32_t off = (uint32_t)(((par * (L + 1) + (l + 1)) * SEG + (lastl ? 0 : c)) * HP * 4);
-                            st_async_f32(pub0 + off, hn, pmb0 + (uint32_t)((l + 1) * 8));
-                            st_async_f32(pub1 + off, hn, pmb1 + (uint32_t)((l + 1) * 8));
-                            if (!lastl && P.has_help[l + 1] && sub == 0)
-                                st_ll(P.hin_ll + P.hin_off[l + 1] + ((size_t)(it & (P.hslots[l + 1] - 1)) * SEG + c) * H + my_i, hn,
-                                      (uint32_t)it + 1u);
-                        }
+                        for (int e = 1; e < SEG; ++e)
+                            if (e < lr.nco_next) tmem_ldn<WT>(ta + e * TCOLS, w[e]);
                     }
                 }
             }
-            tmem_wait_ld();
-        } else {
-            // ======================= warps 8-15: noise, gate operands two layers ahead, out_skip rows of the last column =======================
+        } else if (warp >= 12) {
+            // ======================= service warps: noise, gate operands two layers ahead, out_skip rows of the last column =======================
             if (active && warp == 15 && lane < SEG) {
                 const long long n = (long long)istep * SEG + lane;
-                epsb[lane] = P.noise ? __ldg(P.noise + n) : laplace_eps(P.seed, P.b0, n);
+                const float e = P.noise ? __ldg(P.noise + n) : laplace_eps(P.seed, P.b0, n);
+                const float sgn = (e > 0.f) ? 1.f : ((e < 0.f) ? -1.f : 0.f);
+                epsb[lane] = sgn * log1pf(-2.f * fabsf(e));
             }
-            float sk0 = 0.f, sk1 = 0.f;
-            const float* ws0 = sSkip + (size_t)(sk_v0 ? skr0 : 0) * HP;
-            const float* ws1 = sSkip + (size_t)(sk_v1 ? skr1 : 0) * HP;
+            float sk[4] = {0.f, 0.f, 0.f, 0.f};
             const int nsk = D.nskip * HP;
             for (int l = 0; l < L; ++l) {
-                if (l + 2 < L) prep(it, l + 2);
+                SWN_TSTAMP(24, tid == 384 && l == 1);
+                {   // operands two layers ahead (their loads were issued one iteration ago), loads for three ahead
+                    const int q = it * L + l + 2;
+                    prep_commit(q);
+                    prep_issue(q + 1);
+                }
+                SWN_TSTAMP(25, tid == 384 && l == 1);
                 ok = mbar_wait2(mb + l, par, P, 700 + l) && ok;
+                SWN_TSTAMP(26, tid == 384 && l == 1);
                 if (active && l >= 1) {                                          // out_skip[l-1] on the last column of layer l's input
-                    float2 h[NCH], a0[NCH], a1[NCH];
+                    float2 h[NCH];
                     load_frag<NCH>(h, hcur + (l * SEG + SEG - 1) * HP, lane);
-                    load_frag<NCH>(a0, ws0 + (size_t)(l - 1) * nsk, lane);
-                    load_frag<NCH>(a1, ws1 + (size_t)(l - 1) * nsk, lane);
-                    sk0 += dot_frag<NCH>(a0, h); sk1 += dot_frag<NCH>(a1, h);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        float2 a[NCH];
+                        load_frag<NCH>(a, sSkip + (size_t)(l - 1) * nsk + (size_t)(srow0 + r < D.nskip ? srow0 + r : 0) * HP, lane);
+                        sk[r] += dot_frag<NCH>(a, h);
+                    }
                 }
             }
             {
-                float2 a0[NCH], a1[NCH];
-                load_frag<NCH>(a0, ws0 + (size_t)(L - 1) * nsk, lane);
-                load_frag<NCH>(a1, ws1 + (size_t)(L - 1) * nsk, lane);
-                const float c0 = sk_v0 ? __ldg(P.wbuf + D.skipc_off + skr0) : 0.f, c1 = sk_v1 ? __ldg(P.wbuf + D.skipc_off + skr1) : 0.f;
+                float2 a[4][NCH];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    load_frag<NCH>(a[r], sSkip + (size_t)(L - 1) * nsk + (size_t)(srow0 + r < D.nskip ? srow0 + r : 0) * HP, lane);
+                const float4 k4 = wconst[16 + warp - 12];
+                const float skc[4] = {k4.x, k4.y, k4.z, k4.w};
                 ok = mbar_wait2(mb + L, par, P, 510) && ok;
                 if (active) {
                     float2 hl[NCH];
                     load_frag<NCH>(hl, hcur + (size_t)L * SEG * HP, lane);
-                    float a = sk0 + dot_frag<NCH>(a0, hl), b = sk1 + dot_frag<NCH>(a1, hl);
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        a += __shfl_xor_sync(0xffffffffu, a, o);
-                        b += __shfl_xor_sync(0xffffffffu, b, o);
-                    }
+                    for (int r = 0; r < 4; ++r) sk[r] += dot_frag<NCH>(a[r], hl);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) sk[r] += __shfl_xor_sync(0xffffffffu, sk[r], o);
                     if (lane < CORE_CL) {
-                        const uint32_t dst = hx_peer + (uint32_t)((2 * LS + D.skip0) * 4);
-                        if (sk_v0) st_async_f32(dst + (uint32_t)(skr0 * 4), fmaxf(a + c0, 0.f), mb_peer + (uint32_t)((L + 1) * 8));
-                        if (sk_v1) st_async_f32(dst + (uint32_t)(skr1 * 4), fmaxf(b + c1, 0.f), mb_peer + (uint32_t)((L + 1) * 8));
+                        const uint32_t dst = hx_peer + (uint32_t)((2 * LS + D.skip0 + srow0) * 4);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            if (srow0 + r < D.nskip)
+                                st_async_f32(dst + (uint32_t)(r * 4), fmaxf(sk[r] + skc[r], 0.f), mb_peer + (uint32_t)((L + 1) * 8));
                     }
                 }
                 // every layer barrier of this step has completed (this thread waited for each): arm the next phase
-                if (warp == 8 && lane == 0) {
+                if (warp == 12 && lane == 0) {
                     for (int i = 0; i < L; ++i) mbar_arm(mb + i, bytes_h);
                     mbar_arm(mb + L, bytes_last);
                 }
             }
         }
-        // This thread has read the previous step's columns for the last time.  Nobody overwrites them (the next block's
-        // input columns go into the same parity copy) before every thread of the cluster has said so: arrive here, wait
-        // right before the next block's inputs are published - behind the head the wait is free; in the warm-up, where no
-        // head couples the CTAs, it is what keeps a fast CTA from running a step ahead.
-        cluster_arrive();
+        // The previous step's columns have been read for the last time.  Where the head does not couple every chain warp
+        // of every CTA to the next block's inputs (warm-up; models with fewer out_1 rows than chain warps) a fast CTA could
+        // overwrite them a step early: cluster barrier, arrive here, wait right before the next inputs are published.
+        // (Its acquire side flushes L1, so it is not used where the head already gives the ordering.)
+        const bool cb = !active || cb_always;
+        if (cb) cluster_arrive();
         SWN_STAMP(7);
+        float fed[SEG];
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) fed[j] = 0.f;
         if (active) {
             // ---- out_1 row of this warp (relu) -> x2 on every CTA
             if (has_b) {
@@ -455,7 +659,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc)
                     wpre[cc] = (cc * 64 < Sp) ? reinterpret_cast<const float2*>(wrow)[cc * 32 + lane] : make_float2(0.f, 0.f);
-                const float bias = __ldg(P.wbuf + D.b1_off + warp);
+                const float bias1 = wconst[warp].x;
                 ok = mbar_wait2(mb_x1, hpar, P, 520) && ok;
                 if (tid == 0) mbar_arm(mb_x1, bytes_x1);
                 const float2* xv = reinterpret_cast<const float2*>(x1);
@@ -467,7 +671,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                     const float2 wv = reinterpret_cast<const float2*>(wrow)[cc * 32 + lane], v = xv[cc * 32 + lane];
                     a = fmaf(wv.x, v.x, a); b = fmaf(wv.y, v.y, b);
                 }
-                const float v = warp_sum(a + b) + bias;
+                const float v = warp_sum(a + b) + bias1;
                 if (lane < CORE_CL)
                     st_async_f32(hx_peer + (uint32_t)((2 * LS + Sp + D.b0 + warp) * 4), fmaxf(v, 0.f), mb_peer + (uint32_t)((L + 2) * 8));
             } else if (tid == 0) {
@@ -482,7 +686,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc)
                     wpre2[cc] = (cc * 64 < n1p) ? reinterpret_cast<const float2*>(wrow)[cc * 32 + lane] : make_float2(0.f, 0.f);
-                const float bias = __ldg(P.wbuf + D.b2_off + warp);
+                const float bias2 = wconst[warp].y;
                 ok = mbar_wait2(mb_x2, hpar, P, 530) && ok;
                 if (tid == 0) mbar_arm(mb_x2, bytes_x2);
                 const float2* xv = reinterpret_cast<const float2*>(x2);
@@ -494,42 +698,98 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                     const float2 wv = reinterpret_cast<const float2*>(wrow)[cc * 32 + lane], v = xv[cc * 32 + lane];
                     a = fmaf(wv.x, v.x, a); b = fmaf(wv.y, v.y, b);
                 }
-                const float o = warp_sum(a + b) + bias;
+                const float o = warp_sum(a + b) + bias2;
                 if (lane == 0) o2[warp] = o;
             } else if (tid == 0) {
                 ok = mbar_wait2(mb_x2, hpar, P, 531) && ok;
                 mbar_arm(mb_x2, bytes_x2);
             }
             SWN_STAMP(16);
-            __syncthreads();
-            if (tid == 0) {
-                // Laplace / LPC sampler (cswnv_shift1.py:368-391), identically in every CTA
+            __syncthreads();                                                     // o2[] is complete
+            // ---- Laplace / LPC sampler (cswnv_shift1.py:368-391), by EVERY warp for itself (bit-identical): lane j evaluates
+            // the scale and the noise term of sample j, then all lanes run the LPC recursion on the broadcast values; no
+            // second CTA barrier and no shared-memory round trip between "sampled" and the next block's input columns
+            {
                 const long long nbase = (long long)istep * SEG;
-                float eps[SEG], smp[SEG];
+                const int jj = lane < SEG ? lane : 0;
+                const float bj = sigmoidf_(o2[SEG + jj]);                         // exp(logsigmoid(.))
+                const float bt = bj * epsb[jj];
+                const float mu = o2[jj];
+                // LPC history in 8 slots, newest LAST (slot 7), coefficients aligned to it and zero beyond lpc: the recursion
+                // does not depend on lpc (as code it compiled to a jump table over local memory)
+                const float* lpr = lpb + hpar * 8;
+                float lh[8], aa[8];
 #pragma unroll
-                for (int j = 0; j < SEG; ++j) eps[j] = epsb[j];
+                for (int mm = 0; mm < 8; ++mm) {
+                    lh[mm] = lpr[mm];
+                    // ass = a.flip(-1) times the buffer ordered oldest -> newest: a[0] multiplies the newest
+                    aa[mm] = (7 - mm) < P.lpc ? o2[2 * SEG + (7 - mm)] : 0.f;
+                }
                 const float* forced = P.forced ? (const float*)P.forced + nbase : nullptr;
-                laplace_step<SEG>(P.lpc, o2, lpb, eps, forced, smp);
+                float smp[SEG];
 #pragma unroll
                 for (int j = 0; j < SEG; ++j) {
-                    hist[(int)((nbase + j) & (HIST - 1))] = forced ? forced[j] : smp[j];
-                    if (rank == 0) ((float*)P.out)[nbase + j] = smp[j];
+                    float lpv = 0.f;
+                    // (summation order of the layer-group kernel: newest-last buffer, oldest tap first)
+#pragma unroll
+                    for (int mm = 0; mm < 8; ++mm) lpv += aa[mm] * lh[mm];
+                    float v = lpv + __shfl_sync(0xffffffffu, mu, j) - __shfl_sync(0xffffffffu, bt, j);
+                    v = fminf(fmaxf(v, -1.f), 1.f);
+                    smp[j] = v;
+                    fed[j] = forced ? __ldg(forced + j) : v;
+#pragma unroll
+                    for (int mm = 0; mm < 7; ++mm) lh[mm] = lh[mm + 1];
+                    lh[7] = v;
                 }
-                if (rank == 0 && P.head_out)
-                    for (int r = 0; r < n2; ++r) P.head_out[(size_t)istep * n2 + r] = o2[r];
+                if (forced) {
+                    // teacher forcing: inside the segment the recursion ran on its own samples (as the reference's sampler
+                    // would); the history handed to the next step is the forced waveform
+#pragma unroll
+                    for (int mm = 0; mm < 8; ++mm) lh[mm] = lpr[mm];
+#pragma unroll
+                    for (int j = 0; j < SEG; ++j) {
+#pragma unroll
+                        for (int mm = 0; mm < 7; ++mm) lh[mm] = lh[mm + 1];
+                        lh[7] = fed[j];
+                    }
+                }
+                // every warp files the fed-back samples itself (identical values): its own input rows read them right away
+                if (lane < SEG) {
+                    float f = fed[0];
+#pragma unroll
+                    for (int j = 1; j < SEG; ++j) f = lane == j ? fed[j] : f;
+                    hist[(int)((nbase + lane) & (HIST - 1))] = f;
+                }
+                if (warp == 0) {
+                    if (lane < 8) {
+                        float f = lh[0];
+#pragma unroll
+                        for (int mm = 1; mm < 8; ++mm) f = lane == mm ? lh[mm] : f;
+                        lpb[(hpar ^ 1u) * 8 + lane] = f;
+                    }
+                    if (rank == 0) {
+                        if (lane < SEG) {
+                            float f = smp[0];
+#pragma unroll
+                            for (int j = 1; j < SEG; ++j) f = lane == j ? smp[j] : f;
+                            ((float*)P.out)[nbase + lane] = f;
+                        }
+                        if (P.head_out && lane < n2) P.head_out[(size_t)istep * n2 + lane] = o2[lane];
+                    }
+                }
+                __syncwarp();
             }
-            __syncthreads();
             SWN_STAMP(10);
         }
-        cluster_wait();
+        if (cb) cluster_wait();
         if (it + 1 < P.n_it) {
             input_stage(it + 1);
             SWN_STAMP(11);
-            if (warp >= 8) { prep(it + 1, 0); if (L > 1) prep(it + 1, 1); }
         }
         SWN_STAMP(12);
     }
     // ---- teardown
+    tmem_wait_ld();
     __syncthreads();
     cluster_sync_all();
     if (warp == 0) tmem_free_all(tbase);

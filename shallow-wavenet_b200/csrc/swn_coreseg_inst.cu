@@ -5,7 +5,7 @@
 #include "swn_launch.h"
 
 #ifndef SWN_NCH
-#error "compile with -DSWN_NCH=<1..4>"
+#error "compile with -DSWN_NCH=<1..3>"
 #endif
 
 namespace swn {

@@ -26,7 +26,6 @@ core_fns find_core_kernel_nch4(int bs);
 core_fns find_coreseg_kernel_nch1(int seg);
 core_fns find_coreseg_kernel_nch2(int seg);
 core_fns find_coreseg_kernel_nch3(int seg);
-core_fns find_coreseg_kernel_nch4(int seg);
 
 // ---- variant 3: pipelined batch kernel (swn_batch.cuh), one object file per seg
 typedef cudaError_t (*batch_launch_fn)(const BatchParams& p, int grid, size_t smem, cudaStream_t st);
