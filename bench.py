@@ -474,6 +474,26 @@ def main():
                 "roofline": bro, "clocks": rb["clocks"], "gpu_launches": rb["launches"],
                 "plan": {k: rb["info"][k] for k in ("kernel_variant", "grid", "batch_tile", "n_slots", "ctas_per_layer", "head_ctas")}}}
 
+    # ---- latency sub-record: BASELINE.json configs[0] on the GPU (the Laplace recipe model at batch 1; the seg > 1 cluster
+    # kernel, swn_coreseg.cuh), measured in the same run
+    if not args.no_extras and args.workload == "cfg2":
+        lk, lfs, lover, lB, lframes, ldesc = WORKLOADS["cfg1"]
+        lkw = model_kwargs(lk, lfs, lover)
+        ln = lframes * lkw["upsampling_factor"]
+        rl = measure(lk, lkw, synth.synth_aux(lkw["n_aux"], lframes, lB, seed=2345 + rank), [ln] * lB, 3, 2, 3)
+        l_total, l_e2e = reduce_max([rl["total_ms"], rl["e2e_ms"]])
+        if rank == 0:
+            lro = roofline_of(lk, lkw, rl, 3)
+            lval = world * rl["samples_per_step"] * 3 / (l_total * 1e-3)
+            line["latency"] = {"cfg1": {
+                "workload": ldesc, "value": lval, "unit": "samples/s", "rtf": lval / lfs, "rtf_per_utterance": lval / lfs / (world * lB),
+                "steps": 3, "warmup": 2, "scaling": "weak", "ms_per_step": l_total / 3, "kernel_ms": rl["kern_ms"],
+                "conditioning_ms": rl["cond_ms"],
+                "e2e": {"value": world * rl["samples_per_step"] / (l_e2e * 1e-3), "unit": "samples/s",
+                        "h2d_bytes_per_step": rl["h2d"], "d2h_bytes_per_step": rl["d2h"]},
+                "roofline": lro, "clocks": rl["clocks"], "gpu_launches": rl["launches"],
+                "plan": {k: rl["info"][k] for k in ("kernel_variant", "grid", "batch_tile", "n_slots", "ctas_per_layer", "head_ctas")}}}
+
     # ---- sharded sub-record: BASELINE.json configs[3], 512 utterances of unequal length split over the ranks the way
     # the decode scripts split their list (contiguous np.array_split, decode_cswnv_laplace-shift1.py:200-201), each
     # rank sorting its share by length (:77-79) and decoding it as one batch.  STRONG scaling: total work is fixed.

@@ -26,6 +26,12 @@
 #include "swn_core.cuh"
 #include "swn_core2.cuh"
 
+#ifndef SEG_TMEM_EARLY
+#define SEG_TMEM_EARLY 0        // next layer's taps requested before the reduction (1) or behind the publish (0)
+#endif
+#ifndef SEG_NCO1
+#define SEG_NCO1 1              // fixed-address path for the layers whose only core tap is delay 0
+#endif
 #if SWN_STAMPS
 #define SWN_TSTAMP(ev, cond)                                                                        \
     do {                                                                                            \
@@ -524,8 +530,22 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                             }
                         }
                     }
+                } else if (SEG_NCO1 && nco == 1 && !lastl) {
+                    // dilation >= SEG (the usual case): delay 0 only, column c from column c - fixed addresses, all loads first
+                    float2 h[SEG][NCH];
+#pragma unroll
+                    for (int c = 0; c < SEG; ++c) load_frag<NCH>(h[c], hcur + c * HP + l * SEG * HP, lane);
+#pragma unroll
+                    for (int c = 0; c < SEG; ++c)
+#pragma unroll
+                        for (int cc = 0; cc < NCH; ++cc) {
+                            acc[c][0] = fmaf(w[0][2 * cc], h[c][cc].x, acc[c][0]);
+                            acc[c][0] = fmaf(w[0][2 * cc + 1], h[c][cc].y, acc[c][0]);
+                            acc[c][1] = fmaf(w[0][FPT + 2 * cc], h[c][cc].x, acc[c][1]);
+                            acc[c][1] = fmaf(w[0][FPT + 2 * cc + 1], h[c][cc].y, acc[c][1]);
+                        }
                 } else {
-                    // dilation >= 2: at most (SEG+1)/2 core taps; one fragment load per (tap, target column)
+                    // 2 <= dilation < SEG, or the last layer: at most (SEG+1)/2 core taps; one fragment load per (tap, target column)
 #pragma unroll
                     for (int e = 0; e < (SEG + 1) / 2; ++e) {
                         if (e < nco) {
@@ -550,6 +570,17 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                     }
                 }
                 SWN_TSTAMP(19, tid == 0 && l == 1);
+                // next layer's taps: requested as soon as the registers are free (tensor-memory reads are 64 B/clk per SM: the
+                // five taps of a dilation-1 layer take 0.7 us per CTA, more than the hop alone would hide)
+                if (SEG_TMEM_EARLY && !lastl) {
+                    const uint32_t ta = taddr0 + lr.tcol_next + team * WT;
+                    tmem_ldn<WT>(ta, w[0]);
+                    if (lr.nco_next > 1) {
+#pragma unroll
+                        for (int e = 1; e < SEG; ++e)
+                            if (e < lr.nco_next) tmem_ldn<WT>(ta + e * TCOLS, w[e]);
+                    }
+                }
                 float qz, qc;
                 reduce_columns<SEG>(acc, lane, qz, qc);
                 SWN_TSTAMP(20, tid == 0 && l == 1);
@@ -567,8 +598,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                               (uint32_t)it + 1u);
                 }
                 SWN_TSTAMP(21, tid == 0 && l == 1);
-                // next layer's taps: requested behind the publish, they land in the shadow of the hop
-                if (!lastl) {
+                if (!SEG_TMEM_EARLY && !lastl) {
                     const uint32_t ta = taddr0 + lr.tcol_next + team * WT;
                     tmem_ldn<WT>(ta, w[0]);
                     if (lr.nco_next > 1) {

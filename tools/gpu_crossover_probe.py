@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 from shallow_wavenet_b200 import synth
 
-frames = 20
+frames = int(os.environ.get("SWN_PROBE_FRAMES", 20))
 for kind, fs, over in (("cswnv", 22050, dict(seg=5, lpc=4)), ("dswnv", 16000, dict())):
     kw = synth.cswnv_kwargs(fs) if kind == "cswnv" else synth.dswnv_kwargs(fs)
     kw.update(over)
