@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SWN_ABI_VERSION 4
+#define SWN_ABI_VERSION 5
 
 typedef struct swn_model* swn_handle;
 
@@ -193,6 +193,34 @@ int swn_philox_uniform(uint64_t seed, int32_t kind, int32_t n_quantize, int64_t 
 /* Measurement aid (no reference counterpart): aggregate shared-memory read bandwidth of the
  * device in GB/s, the denominator of the batch-1 step roofline. */
 int swn_measure_smem_bandwidth(int device, double* gb_per_s);
+
+/* Noise-shaping restore filter over a decoded batch (recipe stages 6 / 9): what
+ * src/bin/noise_shaping.py:52-87 (synthesis_diff: pysptk mc2b + MLSADF(order, alpha, pd) + Synthesizer with the frame
+ * shift `hop`) followed by src/bin/feature_extract.py:57-76 (low_cut_filter: lfilter(firwin(255, ...), 1, x)) compute,
+ * in float64 as the reference does.  Not tied to a model handle.  The trailing partial frame is not synthesised (pysptk
+ * leaves it uninitialised; zeros here).  Synchronous with respect to its host arguments; the kernels run on `stream`. */
+typedef struct swn_ns_args {
+    const double* x_dev;          /* [B][stride] waveforms                                                       */
+    double* y_dev;                /* [B][stride] filtered waveforms (may not alias x_dev)                        */
+    double* tmp_dev;              /* [B][stride] scratch between the two filters (unused when fir_taps == 0)     */
+    int64_t stride;
+    int32_t B;
+    int32_t order;                /* mel-cepstrum order m = dim - 1 (2 .. 62)                                    */
+    const int64_t* n_samples;     /* host [B]: valid samples of every waveform                                   */
+    const int32_t* n_frames;      /* host [B]: coefficient frames of every waveform (pyworld.harvest's count,
+                                     noise_shaping.py:160-161); NULL = mcep_frames                               */
+    const double* mcep_host;      /* [mcep_utts][mcep_frames][order + 1] differential mel-cepstrum (:165-170);
+                                     NULL = no MLSA stage, the low-cut FIR alone (x_dev -> y_dev)                */
+    int32_t mcep_utts;            /* 1 = shared by all waveforms, else B                                         */
+    int32_t mcep_frames;          /* 1 = one vector for every frame (the script tiles the mean vector, :170)     */
+    int32_t pade;                 /* 4 (pysptk's default) or 5                                                   */
+    int32_t hop;                  /* int(fs / 1000 * shiftms) (:76)                                              */
+    double alpha;                 /* all-pass constant (--mcep_alpha)                                            */
+    const double* fir_host;       /* low-cut FIR taps (feature_extract.py:73) or NULL                            */
+    int32_t fir_taps;
+    int32_t reserved;
+} swn_ns_args;
+int swn_noise_shaping(int device, const swn_ns_args* args, void* stream);
 
 int swn_destroy(swn_handle h);
 

@@ -18,7 +18,7 @@ KIND_DSWNV = 1
 
 # every symbol include/swn_b200.h declares (checked by tests/test_abi_symbols.py)
 SYMBOLS = ("swn_create", "swn_set_tensor", "swn_finalize", "swn_condition", "swn_generate", "swn_teacher_forced", "swn_forward", "swn_sync",
-           "swn_generate_host", "swn_get_info", "swn_philox_uniform", "swn_measure_smem_bandwidth", "swn_destroy",
+           "swn_generate_host", "swn_get_info", "swn_philox_uniform", "swn_measure_smem_bandwidth", "swn_noise_shaping", "swn_destroy",
            "swn_last_error")
 
 
@@ -41,6 +41,14 @@ class SwnFwdArgs(ctypes.Structure):
     _fields_ = [("audio_dev", ctypes.c_void_p), ("audio_onehot", ctypes.c_int32), ("clip", ctypes.c_int32), ("T_a", ctypes.c_int64),
                 ("out_dev", ctypes.c_void_p), ("b_dev", ctypes.c_void_p), ("log_b_dev", ctypes.c_void_p),
                 ("b_clip_dev", ctypes.c_void_p), ("log_b_clip_dev", ctypes.c_void_p)]
+
+
+class SwnNsArgs(ctypes.Structure):
+    _fields_ = [("x_dev", ctypes.c_void_p), ("y_dev", ctypes.c_void_p), ("tmp_dev", ctypes.c_void_p), ("stride", ctypes.c_int64),
+                ("B", ctypes.c_int32), ("order", ctypes.c_int32), ("n_samples", ctypes.c_void_p), ("n_frames", ctypes.c_void_p),
+                ("mcep_host", ctypes.c_void_p), ("mcep_utts", ctypes.c_int32), ("mcep_frames", ctypes.c_int32),
+                ("pade", ctypes.c_int32), ("hop", ctypes.c_int32), ("alpha", ctypes.c_double), ("fir_host", ctypes.c_void_p),
+                ("fir_taps", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class SwnInfo(ctypes.Structure):
@@ -84,6 +92,7 @@ def load():
     lib.swn_get_info.argtypes = [vp, ctypes.POINTER(SwnInfo)]
     lib.swn_philox_uniform.argtypes = [u64, i32, i32, i64, i64, i64, vp]
     lib.swn_measure_smem_bandwidth.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    lib.swn_noise_shaping.argtypes = [ctypes.c_int, ctypes.POINTER(SwnNsArgs), vp]
     lib.swn_destroy.argtypes = [vp]
     lib.swn_last_error.argtypes = []
     lib.swn_last_error.restype = ctypes.c_char_p

@@ -19,6 +19,7 @@
 #include "swn_batch.cuh"
 #include "swn_launch.h"
 #include "swn_fwd.h"
+#include "swn_post.h"
 
 namespace {
 
@@ -1875,6 +1876,74 @@ int swn_measure_smem_bandwidth(int device, double* gb_per_s) {
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail("swn_measure_smem_bandwidth: device is not sm_100");
     CUDA_OK(swn::measure_smem_bandwidth(prop.multiProcessorCount, gb_per_s, nullptr));
+    return 0;
+}
+
+int swn_noise_shaping(int device, const swn_ns_args* a, void* stream) {
+    if (!a || !a->x_dev || !a->y_dev || !a->n_samples) return fail("swn_noise_shaping: null argument");
+    const bool fir_only = a->mcep_host == nullptr;               // low_cut_filter alone (feature_extract.py:57-76)
+    if (fir_only && a->fir_taps < 1) return fail("swn_noise_shaping: neither a mel-cepstrum nor FIR taps were given");
+    if (a->B < 1 || a->stride < 1) return fail("swn_noise_shaping: B=%d stride=%lld", a->B, (long long)a->stride);
+    if (!fir_only) {
+        if (a->order < 2 || a->order > 62) return fail("swn_noise_shaping: order=%d is outside 2..62", a->order);
+        if (a->pade != 4 && a->pade != 5) return fail("swn_noise_shaping: pade=%d (4 or 5)", a->pade);
+        if (a->hop < 1 || a->mcep_frames < 1 || (a->mcep_utts != 1 && a->mcep_utts != a->B))
+            return fail("swn_noise_shaping: hop=%d mcep_frames=%d mcep_utts=%d (1 or B=%d)", a->hop, a->mcep_frames, a->mcep_utts, a->B);
+    }
+    if (a->fir_taps > 0 && (!a->fir_host || (!fir_only && !a->tmp_dev)))
+        return fail("swn_noise_shaping: fir_taps=%d needs fir_host and tmp_dev", a->fir_taps);
+    CUDA_OK(cudaSetDevice(device));
+    {
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) return fail("swn_noise_shaping: device %d is sm_%d%d, this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = a->B, m = a->order;
+    // mc2b on the host (SPTK mc2b.c: b(m) = c(m), b(i) = c(i) - alpha b(i+1)): a few hundred values
+    std::vector<double> b(fir_only ? 0 : (size_t)a->mcep_utts * a->mcep_frames * (m + 1));
+    for (size_t r = 0; !fir_only && r < (size_t)a->mcep_utts * a->mcep_frames; ++r) {
+        const double* c = a->mcep_host + r * (m + 1);
+        double* o = b.data() + r * (m + 1);
+        o[m] = c[m];
+        for (int i = m - 1; i >= 0; --i) o[i] = c[i] - a->alpha * o[i + 1];
+        for (int i = 0; i <= m; ++i)
+            if (!(o[i] == o[i]) || o[i] > 1e300 || o[i] < -1e300) return fail("swn_noise_shaping: non-finite filter coefficient");
+    }
+    std::vector<long long> ns(B);
+    std::vector<int> nf(B);
+    long long n_max = 0;
+    for (int u = 0; u < B; ++u) {
+        if (a->n_samples[u] < 0 || a->n_samples[u] > a->stride) return fail("swn_noise_shaping: n_samples[%d]=%lld", u, (long long)a->n_samples[u]);
+        ns[u] = a->n_samples[u]; n_max = std::max(n_max, ns[u]);
+        long long f = a->n_frames ? a->n_frames[u] : a->mcep_frames;
+        if (a->mcep_frames > 1 && f > a->mcep_frames) f = a->mcep_frames;
+        nf[u] = (int)std::max<long long>(0, std::min<long long>(f, 0x7fffffff));
+    }
+    DevBuf<double> b_dev, h_dev;
+    DevBuf<long long> ns_dev;
+    DevBuf<int> nf_dev;
+    int rc = 0;
+    if (upload(b_dev, b) || upload(ns_dev, ns) || upload(nf_dev, nf)) rc = 1;
+    if (!rc && a->fir_taps > 0) {
+        std::vector<double> h(a->fir_host, a->fir_host + a->fir_taps);
+        if (upload(h_dev, h)) rc = 1;
+    }
+    cudaError_t e = cudaSuccess;
+    if (!rc && fir_only) {
+        e = swn::launch_fir(a->x_dev, a->y_dev, a->stride, ns_dev.p, n_max, h_dev.p, a->fir_taps, B, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    } else if (!rc) {
+        double* mid = a->fir_taps > 0 ? a->tmp_dev : a->y_dev;
+        e = swn::launch_mlsa(a->x_dev, mid, a->stride, ns_dev.p, nf_dev.p, b_dev.p, a->mcep_utts, a->mcep_frames, m, a->pade, a->alpha,
+                             a->hop, B, st);
+        if (e == cudaSuccess && a->fir_taps > 0)
+            e = swn::launch_fir(mid, a->y_dev, a->stride, ns_dev.p, n_max, h_dev.p, a->fir_taps, B, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);          // the coefficient buffers are released below
+    }
+    b_dev.release(); h_dev.release(); ns_dev.release(); nf_dev.release();
+    if (rc) return 1;
+    if (e != cudaSuccess) return fail("swn_noise_shaping: %s", cudaGetErrorString(e));
     return 0;
 }
 
