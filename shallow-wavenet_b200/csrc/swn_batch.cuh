@@ -22,6 +22,10 @@
 #pragma once
 #include "swn_gen.cuh"
 
+#ifndef B3_ABL
+#define B3_ABL 0     // diagnostic builds only (tools/run_r02_v3abl.sh): 1 = no ring scatter, 2 = no tile stores of the gated cells, 3 = no tile stores of the tail; results are wrong, DRAM traffic is what is measured
+#endif
+
 namespace swn {
 
 constexpr int B3_NGW = 4;                 // GEMM warps 0..3 (one per SM sub-partition)
@@ -919,7 +923,8 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                 else carry = X[(D.pair0 + pi) * NC + col];
                 hv = (1.f - z) * th + z * carry;
             }
-            if (!D.is_last) {
+            if (B3_ABL == 2) {
+            } else if (!D.is_last) {
                 if (umma) {      // exact split into tf32 halves for the next cell's tensor-core passes
                     const int xo = b3_uoff(col, D.pair0 + pi, NP);
                     const float hh = b3_tf32_hi(hv);
@@ -979,6 +984,7 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
                 if (D.ring_in_smem) {
 #pragma unroll
                     for (int b = 0; b < BS; ++b) ringS[ro + b] += val[b];
+                } else if (B3_ABL == 1) {
                 } else if constexpr (BS % 4 == 0) {
 #pragma unroll
                     for (int b = 0; b < BS; b += 4)                         // RED: fire and forget, one writer per element
