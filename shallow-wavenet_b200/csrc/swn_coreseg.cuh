@@ -17,6 +17,8 @@
 //     the first cut, columns split over two warps, read every tap twice and spent 4 us per step on it), the totals
 //     of all columns come out of ONE transposed reduction (18 shuffles), one gate, one publish - no intra-CTA hand-off;
 //   * the last layer only evaluates the last column (the head reads nothing else and no layer follows);
+//     (Measured negative, removed: requesting them before the reduction, +0.25 us per step; requesting taps 1.. of a
+//     dilation-1 layer a whole stage ahead while the single-tap layer before it runs, +0.28 us - profiles/r02z_coreseg_ab_timings.txt.)
 //   * warps 12-15: the out_skip rows of the last column, and the gate operands (conditioning rows x gain + constant,
 //     bias + helper sums) of layer l+2 while layer l runs - late enough for the helpers' one-step slack, early enough
 //     that the L2 latency is never on the chain.  A local mbarrier per layer tells the chain warps the operands are in;
@@ -306,7 +308,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
         const bool hn_ = l + 1 < L && P.has_help[l + 1];
         r.hmask = hn_ ? P.hslots[l + 1] - 1 : -1;                  // -1: no helper behind this layer's output
         r.hin = hn_ ? (unsigned long long)(P.hin_ll + P.hin_off[l + 1]) : 0ull;
-        r.nco_next = l + 1 < L ? P.ncore[l + 1] : 0; r.tcol_next = l + 1 < L ? P.tap_base[l + 1] * TCOLS : 0;
+        r.nco_next = P.ncore[(l + 1) % L]; r.tcol_next = P.tap_base[(l + 1) % L] * TCOLS;     // (the last layer: layer 0 of the next step)
         lrec[l] = r;
     }
     __syncthreads();
@@ -400,7 +402,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     for (int j = 0; j < K; ++j) cbsum += sfir[(j * 2) * 16 + (warp < 16 ? warp : 0)];
     auto input_stage = [&](int itn) {
         if (!has_in) return;
-        const int c = lane < SEG ? lane : SEG - 1;
+        const int c = (lane & 15) < SEG ? (lane & 15) : SEG - 1;          // lanes 16.. mirror lanes 0..: they hand the columns to the helper
         const int t = P.t_first + itn * SEG + c;
         const int t0b = P.t_first + itn * SEG;                     // first column of the block
         float v = 0.f;
@@ -430,9 +432,9 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
         for (int cc = 0; cc < SEG; ++cc) {
             const float vc = __shfl_sync(0xffffffffu, v, cc);
             if (lane < CORE_CL) st_async_f32(base + (uint32_t)(cc * HP * 4), vc, mb_peer);
-            if (lane == 16 && P.has_help[0])
-                st_ll(P.hin_ll + P.hin_off[0] + ((size_t)(itn & (P.hslots[0] - 1)) * SEG + cc) * H + in_row, vc, (uint32_t)itn + 1u);
         }
+        if (lane >= 16 && lane < 16 + SEG && P.has_help[0])
+            st_ll(P.hin_ll + P.hin_off[0] + ((size_t)(itn & (P.hslots[0] - 1)) * SEG + (lane - 16)) * H + in_row, v, (uint32_t)itn + 1u);
     };
 
     // ---- prologue: operands of the first two layers of step 0, inputs of block 0 (padding / seed)
@@ -443,6 +445,14 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     }
     input_stage(0);
 
+    float w[SEG][WT];                                              // chain warps: the core taps of the current layer
+    if (is_chain) {
+        tmem_ldn<WT>(taddr0 + P.tap_base[0] * TCOLS + team * WT, w[0]);
+        const int nco0 = P.ncore[0];
+#pragma unroll
+        for (int e = 1; e < SEG; ++e)
+            if (e < nco0) tmem_ldn<WT>(taddr0 + (P.tap_base[0] + e) * TCOLS + team * WT, w[e]);
+    }
     for (int it = 0; it < P.n_it; ++it) {
         const bool active = it >= P.it0;
         const uint32_t par = (uint32_t)it & 1u;
@@ -455,14 +465,6 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
         const float* hprev = hx + (par ^ 1u) * LS;                           // the previous step's
         if (is_chain) {
             // ======================= chain warps: one gate pair, all columns: core taps (gather form), gate, publish =======================
-            float w[SEG][WT];
-            tmem_ldn<WT>(taddr0 + P.tap_base[0] * TCOLS + team * WT, w[0]);
-            if (P.ncore[0] > 1) {
-                const int nco0 = P.ncore[0];
-#pragma unroll
-                for (int e = 1; e < SEG; ++e)
-                    if (e < nco0) tmem_ldn<WT>(taddr0 + (P.tap_base[0] + e) * TCOLS + team * WT, w[e]);
-            }
             const bool t_neg = it == 0 && P.t_first + ccl < 0;               // alignment columns before time 0
             for (int l = 0; l < L; ++l) {
                 const LRec lr = lrec[l];
@@ -472,6 +474,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
 #pragma unroll
                 for (int c = 0; c < SEG; ++c) { acc[c][0] = 0.f; acc[c][1] = 0.f; }
                 tmem_wait_ld();
+                const bool more = !lastl || it + 1 < P.n_it;                   // a next layer exists (the last layer wraps to the next step)
                 if (dl == 1) {
                     // dilation 1: source columns -(SEG-1) .. SEG-1 (negative = the previous step's), each loaded once; tap e
                     // of source s feeds target column s + e (taps beyond ncore are zero-filled).  The previous step's
@@ -572,7 +575,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                 SWN_TSTAMP(19, tid == 0 && l == 1);
                 // next layer's taps: requested as soon as the registers are free (tensor-memory reads are 64 B/clk per SM: the
                 // five taps of a dilation-1 layer take 0.7 us per CTA, more than the hop alone would hide)
-                if (SEG_TMEM_EARLY && !lastl) {
+                if (SEG_TMEM_EARLY && more) {
                     const uint32_t ta = taddr0 + lr.tcol_next + team * WT;
                     tmem_ldn<WT>(ta, w[0]);
                     if (lr.nco_next > 1) {
@@ -598,7 +601,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                               (uint32_t)it + 1u);
                 }
                 SWN_TSTAMP(21, tid == 0 && l == 1);
-                if (!SEG_TMEM_EARLY && !lastl) {
+                if (!SEG_TMEM_EARLY && more) {
                     const uint32_t ta = taddr0 + lr.tcol_next + team * WT;
                     tmem_ldn<WT>(ta, w[0]);
                     if (lr.nco_next > 1) {
