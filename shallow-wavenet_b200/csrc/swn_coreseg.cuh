@@ -28,8 +28,9 @@
 #include "swn_core.cuh"
 #include "swn_core2.cuh"
 
-#ifndef SEG_TMEM_EARLY
-#define SEG_TMEM_EARLY 0        // next layer's taps requested before the reduction (1) or behind the publish (0)
+#define SEG_TMEM_EARLY 0        // (next layer's taps are requested behind the publish; before the reduction measured slower)
+#ifndef SEG_FAT
+#define SEG_FAT 1               // layers with a single core tap: ONE chain warp per tensor-memory quarter owns all its pairs
 #endif
 #ifndef SEG_NCO1
 #define SEG_NCO1 1              // fixed-address path for the layers whose only core tap is delay 0
@@ -50,6 +51,13 @@ template <int N>
 __device__ __forceinline__ void tmem_ldn(uint32_t a, float (&r)[N]) {
     if constexpr (N % 16 == 0) tmem_ldw<N>(a, r);
     else tmem_ld<N>(a, r);
+}
+// N floats (multiple of 4) into r[O .. O+N) of a larger register array
+template <int N, int O, int M>
+__device__ __forceinline__ void tmem_ld_at(uint32_t a, float (&r)[M]) {
+    static_assert(O + N <= M && N % 4 == 0, "slice of the tap registers");
+#pragma unroll
+    for (int i = 0; i < N; i += 4) tmem_ld4(a + i, &r[O + i]);
 }
 
 // ------------------------------------------------------------------ helper CTA (time-granular targets)
@@ -169,6 +177,43 @@ __device__ __forceinline__ void reduce_columns(const float (&a)[SEG][2], int lan
         c += __shfl_xor_sync(0xffffffffu, c, o);
     }
     qz = z; qc = c;
+}
+
+// Totals of a[slot][z|c] (16 slots) over the 32 lanes: afterwards the two lanes of slot lane >> 1 hold both totals of that
+// slot.  Four halving levels (16, 8, 4, 2) and one butterfly: 32 shuffles for 16 (pair, column) slots.
+__device__ __forceinline__ void reduce_slots16(const float (&a)[16][2], int lane, float& qz, float& qc) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    float u[8][2], v[4][2], w2[2][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int zc = 0; zc < 2; ++zc) {
+            const float send = b4 ? a[i][zc] : a[i + 8][zc], keep = b4 ? a[i + 8][zc] : a[i][zc];
+            u[i][zc] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int zc = 0; zc < 2; ++zc) {
+            const float send = b3 ? u[i][zc] : u[i + 4][zc], keep = b3 ? u[i + 4][zc] : u[i][zc];
+            v[i][zc] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int zc = 0; zc < 2; ++zc) {
+            const float send = b2 ? v[i][zc] : v[i + 2][zc], keep = b2 ? v[i + 2][zc] : v[i][zc];
+            w2[i][zc] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    float z, c;
+    {
+        const float sz = b1 ? w2[0][0] : w2[1][0], kz = b1 ? w2[1][0] : w2[0][0];
+        const float sc = b1 ? w2[0][1] : w2[1][1], kc = b1 ? w2[1][1] : w2[0][1];
+        z = kz + __shfl_xor_sync(0xffffffffu, sz, 2);
+        c = kc + __shfl_xor_sync(0xffffffffu, sc, 2);
+    }
+    qz = z + __shfl_xor_sync(0xffffffffu, z, 1);
+    qc = c + __shfl_xor_sync(0xffffffffu, c, 1);
 }
 
 template <int NCH, int SEG>
@@ -299,7 +344,12 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     // per-layer record of the chain stage in shared memory: indexed kernel-parameter loads (LDC c[0][R+imm]) between the
     // wake-up and the publish showed up as the largest single stall of the stage (profiles/r02u: short scoreboard on the
     // LDC.64 of P.hin_off[l+1])
-    struct LRec { int32_t nco, dil, tcol, hmask; unsigned long long hin; int32_t nco_next, tcol_next; };
+    // fat: this layer has a single core tap and runs on team 0 alone (one warp per quarter, all its pairs).  nxa_*: the next
+    // layer (wrapping into the next step) = what team 0 requests behind its publish; nxb_*: the next layer in the one-pair-per-
+    // warp layout (-1: none) = what teams 1, 2 request behind theirs.
+    struct LRec { int32_t nco, dil, tcol, hmask; unsigned long long hin; int32_t nco_next, tcol_next;
+                  int32_t fat, nxa_fat, nxb_tcol, nxb_nco, nxb_wrap, r0, r1, r2; };
+    static_assert(sizeof(LRec) == 64, "per-layer record: 16 words");
     LRec* lrec = reinterpret_cast<LRec*>(reinterpret_cast<float4*>(sfir + 8 * 2 * 16) + 20);   // [L] behind wconst
     if (tid < L) {
         const int l = tid;
@@ -309,6 +359,13 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
         r.hmask = hn_ ? P.hslots[l + 1] - 1 : -1;                  // -1: no helper behind this layer's output
         r.hin = hn_ ? (unsigned long long)(P.hin_ll + P.hin_off[l + 1]) : 0ull;
         r.nco_next = P.ncore[(l + 1) % L]; r.tcol_next = P.tap_base[(l + 1) % L] * TCOLS;     // (the last layer: layer 0 of the next step)
+        r.fat = SEG_FAT && P.ncore[l] == 1 && NPW * SEG <= 16;
+        r.nxa_fat = SEG_FAT && P.ncore[(l + 1) % L] == 1 && NPW * SEG <= 16;
+        r.nxb_tcol = 0; r.nxb_nco = -1; r.nxb_wrap = 0; r.r0 = r.r1 = r.r2 = 0;
+        for (int k = 1; k <= L; ++k) {
+            const int l2 = (l + k) % L;
+            if (!(SEG_FAT && P.ncore[l2] == 1 && NPW * SEG <= 16)) { r.nxb_tcol = P.tap_base[l2] * TCOLS; r.nxb_nco = P.ncore[l2]; r.nxb_wrap = l + k >= L; break; }
+        }
         lrec[l] = r;
     }
     __syncthreads();
@@ -445,13 +502,29 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     }
     input_stage(0);
 
-    float w[SEG][WT];                                              // chain warps: the core taps of the current layer
+    // The tap registers of a chain warp: [SEG taps][WT] of its pair for a one-pair-per-warp layer, or (team 0, `fat` layer)
+    // the single tap of all NPW pairs of the quarter [TCOLS] - the same registers: a warp only ever holds its next own stage.
+    constexpr int WREGS = SEG * WT > TCOLS ? SEG * WT : TCOLS;
+    float wr[WREGS];
+#define W_(e, q) wr[(e) * WT + (q)]
+    auto request_w = [&](int tcol, int nco_) {
+        const uint32_t ta = taddr0 + tcol + team * WT;
+        tmem_ld_at<WT, 0>(ta, wr);
+        if (nco_ > 1) {
+            if (1 < SEG && 1 < nco_) tmem_ld_at<WT, (1 < SEG ? 1 : 0) * WT>(ta + 1 * TCOLS, wr);
+            if (2 < SEG && 2 < nco_) tmem_ld_at<WT, (2 < SEG ? 2 : 0) * WT>(ta + 2 * TCOLS, wr);
+            if (3 < SEG && 3 < nco_) tmem_ld_at<WT, (3 < SEG ? 3 : 0) * WT>(ta + 3 * TCOLS, wr);
+            if (4 < SEG && 4 < nco_) tmem_ld_at<WT, (4 < SEG ? 4 : 0) * WT>(ta + 4 * TCOLS, wr);
+            static_assert(SEG <= 5, "tap requests are written out for up to five taps");
+        }
+    };
+    auto request_fat = [&](int tcol) { tmem_ld_at<TCOLS, 0>(taddr0 + tcol, wr); };
     if (is_chain) {
-        tmem_ldn<WT>(taddr0 + P.tap_base[0] * TCOLS + team * WT, w[0]);
-        const int nco0 = P.ncore[0];
-#pragma unroll
-        for (int e = 1; e < SEG; ++e)
-            if (e < nco0) tmem_ldn<WT>(taddr0 + (P.tap_base[0] + e) * TCOLS + team * WT, w[e]);
+        const LRec l0 = lrec[0];
+        if (l0.fat) {
+            if (team == 0) request_fat(l0.tcol);
+            else if (l0.nxb_nco > 0) request_w(l0.nxb_tcol, l0.nxb_nco);
+        } else request_w(l0.tcol, l0.nco);
     }
     for (int it = 0; it < P.n_it; ++it) {
         const bool active = it >= P.it0;
@@ -470,6 +543,62 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                 const LRec lr = lrec[l];
                 const int nco = lr.nco, dl = lr.dil;
                 const bool lastl = l + 1 == L;
+                if (lr.fat) {
+                    // ---------- single core tap: team 0 alone, one warp per quarter with all NPW pairs: one 16-slot reduction,
+                    // one gate, one publish per quarter instead of NPW of each on the same scheduler at the same time
+                    if (team != 0) continue;
+                    tmem_wait_ld();
+                    ok = mbar_wait2(gb + l, par, P, 480 + l) && ok;
+                    ok = mbar_wait2(mb + l, par, P, 500 + l) && ok;
+#if SWN_STAMPS
+                    if (P.prof && tid == 0 && l < 6 && it >= P.prof_start && it < P.prof_start + P.prof_count)
+                        P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + 1 + l] = gtime();
+#endif
+                    const int slot = lane >> 1, sj = slot / SEG, sc = slot - sj * SEG;       // (pair of the quarter, column) of this lane
+                    const int prow = NPW * quarter + sj;
+                    const bool svalid = slot < NPW * SEG && prow < np;
+                    const float4 g4 = gop[(l * 16 + (svalid ? prow : 0)) * SEG + (svalid ? sc : 0)];
+                    const float carry = hcur[(l * SEG + (svalid ? sc : 0)) * HP + D.pair0 + (svalid ? prow : 0)];
+                    float a16[16][2];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { a16[i][0] = 0.f; a16[i][1] = 0.f; }
+#pragma unroll
+                    for (int c = 0; c < SEG; ++c) {
+                        if (!lastl || c == SEG - 1) {
+                            float2 h[NCH];
+                            load_frag<NCH>(h, hcur + (l * SEG + c) * HP, lane);
+#pragma unroll
+                            for (int j = 0; j < NPW; ++j)
+#pragma unroll
+                                for (int zc = 0; zc < 2; ++zc)
+#pragma unroll
+                                    for (int cc = 0; cc < NCH; ++cc) {
+                                        a16[j * SEG + c][zc] = fmaf(wr[(2 * j + zc) * FPT + 2 * cc], h[cc].x, a16[j * SEG + c][zc]);
+                                        a16[j * SEG + c][zc] = fmaf(wr[(2 * j + zc) * FPT + 2 * cc + 1], h[cc].y, a16[j * SEG + c][zc]);
+                                    }
+                        }
+                    }
+                    float qz, qc;
+                    reduce_slots16(a16, lane, qz, qc);
+                    float hn = gate_out(fmaf(qz, g4.x, g4.y), fmaf(qc, g4.z, g4.w), carry);
+                    if (it == 0 && P.t_first + sc < 0) hn = 0.f;
+                    if (svalid && (!lastl || sc == SEG - 1)) {
+                        const uint32_t off = (uint32_t)(((par * (L + 1) + (l + 1)) * SEG + (lastl ? 0 : sc)) * HP * 4 + (D.pair0 + prow) * 4);
+                        const uint32_t mo = (uint32_t)((l + 1) * 8);
+                        const uint32_t hx0 = smem_u32(hx), s1 = (uint32_t)(lane & 1);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            st_async_f32(mapa(hx0 + off, s1 + 2 * k), hn, mapa(mb_mine + mo, s1 + 2 * k));
+                        if (lr.hmask >= 0 && s1 == 0)
+                            st_ll(reinterpret_cast<unsigned long long*>(lr.hin) + ((size_t)(it & lr.hmask) * SEG + sc) * H + D.pair0 + prow, hn,
+                                  (uint32_t)it + 1u);
+                    }
+                    if (!lastl || it + 1 < P.n_it) {                          // the next layer's taps (team 0 takes part in every layer)
+                        if (lr.nxa_fat) request_fat(lr.tcol_next);
+                        else request_w(lr.tcol_next, lr.nco_next);
+                    }
+                    continue;
+                }
                 float acc[SEG][2];
 #pragma unroll
                 for (int c = 0; c < SEG; ++c) { acc[c][0] = 0.f; acc[c][1] = 0.f; }
@@ -483,7 +612,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                     for (int e = 1; e < SEG; ++e)
                         if (e >= nco)
 #pragma unroll
-                            for (int q = 0; q < WT; ++q) w[e][q] = 0.f;
+                            for (int q = 0; q < WT; ++q) W_(e, q) = 0.f;
 #pragma unroll
                     for (int sidx = 0; sidx < SEG - 1; ++sidx) {
                         const int s = sidx - (SEG - 1);
@@ -495,10 +624,10 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                             if (c >= 0 && c < SEG) {
 #pragma unroll
                                 for (int cc = 0; cc < NCH; ++cc) {
-                                    acc[c][0] = fmaf(w[e][2 * cc], h[cc].x, acc[c][0]);
-                                    acc[c][0] = fmaf(w[e][2 * cc + 1], h[cc].y, acc[c][0]);
-                                    acc[c][1] = fmaf(w[e][FPT + 2 * cc], h[cc].x, acc[c][1]);
-                                    acc[c][1] = fmaf(w[e][FPT + 2 * cc + 1], h[cc].y, acc[c][1]);
+                                    acc[c][0] = fmaf(W_(e, 2 * cc), h[cc].x, acc[c][0]);
+                                    acc[c][0] = fmaf(W_(e, 2 * cc + 1), h[cc].y, acc[c][0]);
+                                    acc[c][1] = fmaf(W_(e, FPT + 2 * cc), h[cc].x, acc[c][1]);
+                                    acc[c][1] = fmaf(W_(e, FPT + 2 * cc + 1), h[cc].y, acc[c][1]);
                                 }
                             }
                         }
@@ -525,10 +654,10 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                             if (c < SEG) {
 #pragma unroll
                                 for (int cc = 0; cc < NCH; ++cc) {
-                                    acc[c][0] = fmaf(w[e][2 * cc], h[cc].x, acc[c][0]);
-                                    acc[c][0] = fmaf(w[e][2 * cc + 1], h[cc].y, acc[c][0]);
-                                    acc[c][1] = fmaf(w[e][FPT + 2 * cc], h[cc].x, acc[c][1]);
-                                    acc[c][1] = fmaf(w[e][FPT + 2 * cc + 1], h[cc].y, acc[c][1]);
+                                    acc[c][0] = fmaf(W_(e, 2 * cc), h[cc].x, acc[c][0]);
+                                    acc[c][0] = fmaf(W_(e, 2 * cc + 1), h[cc].y, acc[c][0]);
+                                    acc[c][1] = fmaf(W_(e, FPT + 2 * cc), h[cc].x, acc[c][1]);
+                                    acc[c][1] = fmaf(W_(e, FPT + 2 * cc + 1), h[cc].y, acc[c][1]);
                                 }
                             }
                         }
@@ -542,10 +671,10 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                     for (int c = 0; c < SEG; ++c)
 #pragma unroll
                         for (int cc = 0; cc < NCH; ++cc) {
-                            acc[c][0] = fmaf(w[0][2 * cc], h[c][cc].x, acc[c][0]);
-                            acc[c][0] = fmaf(w[0][2 * cc + 1], h[c][cc].y, acc[c][0]);
-                            acc[c][1] = fmaf(w[0][FPT + 2 * cc], h[c][cc].x, acc[c][1]);
-                            acc[c][1] = fmaf(w[0][FPT + 2 * cc + 1], h[c][cc].y, acc[c][1]);
+                            acc[c][0] = fmaf(W_(0, 2 * cc), h[c][cc].x, acc[c][0]);
+                            acc[c][0] = fmaf(W_(0, 2 * cc + 1), h[c][cc].y, acc[c][0]);
+                            acc[c][1] = fmaf(W_(0, FPT + 2 * cc), h[c][cc].x, acc[c][1]);
+                            acc[c][1] = fmaf(W_(0, FPT + 2 * cc + 1), h[c][cc].y, acc[c][1]);
                         }
                 } else {
                     // 2 <= dilation < SEG, or the last layer: at most (SEG+1)/2 core taps; one fragment load per (tap, target column)
@@ -562,10 +691,10 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                                     load_frag<NCH>(h, hp, lane);
 #pragma unroll
                                     for (int cc = 0; cc < NCH; ++cc) {
-                                        acc[c][0] = fmaf(w[e][2 * cc], h[cc].x, acc[c][0]);
-                                        acc[c][0] = fmaf(w[e][2 * cc + 1], h[cc].y, acc[c][0]);
-                                        acc[c][1] = fmaf(w[e][FPT + 2 * cc], h[cc].x, acc[c][1]);
-                                        acc[c][1] = fmaf(w[e][FPT + 2 * cc + 1], h[cc].y, acc[c][1]);
+                                        acc[c][0] = fmaf(W_(e, 2 * cc), h[cc].x, acc[c][0]);
+                                        acc[c][0] = fmaf(W_(e, 2 * cc + 1), h[cc].y, acc[c][0]);
+                                        acc[c][1] = fmaf(W_(e, FPT + 2 * cc), h[cc].x, acc[c][1]);
+                                        acc[c][1] = fmaf(W_(e, FPT + 2 * cc + 1), h[cc].y, acc[c][1]);
                                     }
                                 }
                             }
@@ -575,15 +704,6 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                 SWN_TSTAMP(19, tid == 0 && l == 1);
                 // next layer's taps: requested as soon as the registers are free (tensor-memory reads are 64 B/clk per SM: the
                 // five taps of a dilation-1 layer take 0.7 us per CTA, more than the hop alone would hide)
-                if (SEG_TMEM_EARLY && more) {
-                    const uint32_t ta = taddr0 + lr.tcol_next + team * WT;
-                    tmem_ldn<WT>(ta, w[0]);
-                    if (lr.nco_next > 1) {
-#pragma unroll
-                        for (int e = 1; e < SEG; ++e)
-                            if (e < lr.nco_next) tmem_ldn<WT>(ta + e * TCOLS, w[e]);
-                    }
-                }
                 float qz, qc;
                 reduce_columns<SEG>(acc, lane, qz, qc);
                 SWN_TSTAMP(20, tid == 0 && l == 1);
@@ -601,14 +721,14 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                               (uint32_t)it + 1u);
                 }
                 SWN_TSTAMP(21, tid == 0 && l == 1);
-                if (!SEG_TMEM_EARLY && more) {
-                    const uint32_t ta = taddr0 + lr.tcol_next + team * WT;
-                    tmem_ldn<WT>(ta, w[0]);
-                    if (lr.nco_next > 1) {
-#pragma unroll
-                        for (int e = 1; e < SEG; ++e)
-                            if (e < lr.nco_next) tmem_ldn<WT>(ta + e * TCOLS, w[e]);
-                    }
+                if (!SEG_TMEM_EARLY) {
+                    // behind the publish: the taps of this warp's next own stage
+                    if (team == 0) {
+                        if (more) {
+                            if (lr.nxa_fat) request_fat(lr.tcol_next);
+                            else request_w(lr.tcol_next, lr.nco_next);
+                        }
+                    } else if (lr.nxb_nco > 0 && (!lr.nxb_wrap || it + 1 < P.n_it)) request_w(lr.nxb_tcol, lr.nxb_nco);
                 }
             }
         } else if (warp >= 12) {
