@@ -512,9 +512,9 @@ static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st
             lay.sm_hx = take((size_t)2 * (L + 1) * seg * Hp);       // hx (both parities), x1, x2 stay contiguous
             lay.sm_x1 = take((size_t)m->Sp);
             lay.sm_x2 = take((size_t)m->n1p);
-            lay.sm_pre = take((size_t)L * 16 * seg * 4);
+            lay.sm_pre = take((size_t)2 * L * 16 * seg * 4);
             lay.sm_misc = take((size_t)(32 + 16 + 16 + 8) + (size_t)L * 16 * 4 + 8 * 2 * 16 + 20 * 4 + (size_t)L * 16);
-            lay.sm_tmem_slot = take(4 + 2 * (size_t)(2 * L + 3 + 1));
+            lay.sm_tmem_slot = take(4 + 2 * (size_t)(3 * L + 3 + 1));
             core_used = u;
             for (auto& q : m->ccta) {
                 q.sm_skip = lay.sm_skip; q.sm_w1 = lay.sm_w1; q.sm_w2 = lay.sm_w2; q.sm_tin = 0; q.sm_ring = 0;

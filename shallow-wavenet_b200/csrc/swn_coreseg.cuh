@@ -19,9 +19,10 @@
 //   * the last layer only evaluates the last column (the head reads nothing else and no layer follows);
 //     (Measured negative, removed: requesting them before the reduction, +0.25 us per step; requesting taps 1.. of a
 //     dilation-1 layer a whole stage ahead while the single-tap layer before it runs, +0.28 us - profiles/r02z_coreseg_ab_timings.txt.)
-//   * warps 12-15: the out_skip rows of the last column, and the gate operands (conditioning rows x gain + constant,
-//     bias + helper sums) of layer l+2 while layer l runs - late enough for the helpers' one-step slack, early enough
-//     that the L2 latency is never on the chain.  A local mbarrier per layer tells the chain warps the operands are in;
+//   * warps 12-13: the out_skip rows of the last column (eight each) and x1;  warps 14-15: nothing but the gate operands
+//     (conditioning rows x gain + constant, bias + helper sums), a step ahead - operands and their "are in" mbarriers are
+//     double-buffered by step parity, so these warps may block on L2 and on a late helper without holding up x1 (with
+//     all four warps doing both, the blocking fetch put x1 1.2 us late once the stages had become faster);
 //   * head as in swn_core2.cuh: x1 = relu(sum of skips) -> out_1 -> out_2 (every CTA all rows) -> Laplace / LPC sampler
 //     (cswnv_shift1.py:368-391) by every warp for itself (bit-identical everywhere) -> the SEG new input columns.
 #pragma once
@@ -237,7 +238,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     float* hx = smem + D.sm_hx;                            // [2][L+1][SEG][HP] layer inputs, by step parity
     float* x1 = smem + D.sm_x1;                            // [Sp]
     float* x2 = smem + D.sm_x2;                            // [n1p]
-    float4* gop = reinterpret_cast<float4*>(smem + D.sm_pre);   // [L][16][SEG] gate operands {pz, bz*pz, pc, bc*pc}
+    float4* gop = reinterpret_cast<float4*>(smem + D.sm_pre);   // [2][L][16][SEG] gate operands {pz, bz*pz, pc, bc*pc}, by step parity
     float* misc = smem + D.sm_misc;
     float* hist = misc;                                    // [HIST] fed-back samples
     float* lpb = hist + HIST;                              // [2][8] LPC history, by head-step parity
@@ -248,7 +249,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + D.sm_tmem_slot);
     unsigned long long* mb = reinterpret_cast<unsigned long long*>(tmem_slot + 2);   // [L+1] layer inputs (+ last layer's output)
     unsigned long long* mb_x1 = mb + (L + 1), *mb_x2 = mb + (L + 2);
-    unsigned long long* gb = mb + (L + 3);                 // [L] "gate operands of layer l are in" (4 arrivals: warps 12-15)
+    unsigned long long* gb = mb + (L + 3);                 // [2][L] "gate operands of layer l are in", by step parity (2 arrivals: warps 14, 15)
     const uint32_t bytes_h = (uint32_t)(SEG * H * 4), bytes_last = (uint32_t)(H * 4);
     const uint32_t bytes_x1 = (uint32_t)(S * 4), bytes_x2 = (uint32_t)(n1 * 4);
     const int LS = (L + 1) * SEG * HP;                     // floats per parity copy of hx
@@ -262,7 +263,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     stage(sW1, P.wbuf + D.w1_off, D.nb * Sp);
     stage(sW2, P.wbuf + D.w2_off, D.nc * n1p);
     for (int i = tid; i < 2 * LS + Sp + n1p; i += SWN_NTHREADS) hx[i] = 0.f;    // hx, x1, x2 are contiguous; pads stay 0
-    for (int i = tid; i < L * 16 * SEG; i += SWN_NTHREADS) gop[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < 2 * L * 16 * SEG; i += SWN_NTHREADS) gop[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = tid; i < HIST + 16 + 16 + 8; i += SWN_NTHREADS) misc[i] = 0.f;
     __syncthreads();
     for (int i = tid; i < L * 16; i += SWN_NTHREADS) {
@@ -280,7 +281,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     }
     if (tid == 0) {
         for (int i = 0; i < L + 3; ++i) mbar_init(mb + i, 1);
-        for (int i = 0; i < L; ++i) mbar_init(gb + i, 4);
+        for (int i = 0; i < 2 * L; ++i) mbar_init(gb + i, 2);
         mbar_fence_init();
         for (int i = 0; i < L; ++i) mbar_arm(mb + i, bytes_h);                    // phase 0 of every vector
         mbar_arm(mb + L, bytes_last); mbar_arm(mb_x1, bytes_x1); mbar_arm(mb_x2, bytes_x2);
@@ -339,7 +340,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     const int ccl = cg < SEG ? cg : SEG - 1;                       // publish to CTAs sub4, sub4+4, sub4+8, sub4+12
     const uint32_t hx_mine = smem_u32(hx) + (uint32_t)(my_i * 4), mb_mine = smem_u32(mb);
     // ---- service warps 12-15: four out_skip rows each (last column only), gate operands
-    const int srow0 = 4 * (warp - 12);
+    const int srow0 = 8 * (warp - 12);                              // skip warps 12, 13: eight out_skip rows each
     const bool has_b = warp < D.nb, has_c = warp < D.nc;
     // per-layer record of the chain stage in shared memory: indexed kernel-parameter loads (LDC c[0][R+imm]) between the
     // wake-up and the publish showed up as the largest single stall of the stage (profiles/r02u: short scoreboard on the
@@ -377,11 +378,12 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     if (lane == 0) {
         wconst[warp] = make_float4(has_b ? __ldg(P.wbuf + D.b1_off + warp) : 0.f, has_c ? __ldg(P.wbuf + D.b2_off + warp) : 0.f,
                                    has_in ? __ldg(P.in_bias + in_row) : 0.f, 0.f);
-        if (warp >= 12) {
-            float k4[4];
+        if (warp == 12 || warp == 13) {
+            float k8[8];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) k4[r] = (srow0 + r < D.nskip) ? __ldg(P.wbuf + D.skipc_off + srow0 + r) : 0.f;
-            wconst[16 + warp - 12] = make_float4(k4[0], k4[1], k4[2], k4[3]);
+            for (int r = 0; r < 8; ++r) k8[r] = (srow0 + r < D.nskip) ? __ldg(P.wbuf + D.skipc_off + srow0 + r) : 0.f;
+            wconst[16 + 2 * (warp - 12)] = make_float4(k8[0], k8[1], k8[2], k8[3]);
+            wconst[17 + 2 * (warp - 12)] = make_float4(k8[4], k8[5], k8[6], k8[7]);
         }
     }
     __syncwarp();
@@ -390,68 +392,51 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     const bool cb_always = P.audio_in != 0;                        // (field reused as a flag by the host plan)
     bool ok = true;
 
-    // ---- gate operands of target q = step * L + layer, by the 128 lanes of warps 12-15: lane <-> (pair, column).  Issue
-    // (L2 loads into registers) and commit (combine, write gop, signal) are one service-loop iteration apart, so that the
-    // L2 latency is never inside the iteration that feeds the chain.
-    struct PrepRegs { float tv[2 * SEG]; float gn[SEG]; unsigned long long ha, hb; };
-    PrepRegs pr_;                                                  // (only ever named directly: stays in registers)
-    const int pidx = (warp - 12) * 32 + lane;
-    const bool p_lane = warp >= 12 && pidx < np * SEG;
-    const int p_p = p_lane ? pidx / SEG : 0, p_c = p_lane ? pidx - (pidx / SEG) * SEG : 0;
-    const int p_row = D.pair0 + p_p;
-    auto prep_issue = [&](int q) {
-        PrepRegs& r = pr_;
-        const int s_ = q / L, l = q - s_ * L;
-        r.ha = 0ull; r.hb = 0ull;
-#pragma unroll
-        for (int sp = 0; sp < SEG; ++sp) { r.tv[2 * sp] = 0.f; r.tv[2 * sp + 1] = 0.f; r.gn[sp] = 0.f; }
-        if (p_lane && s_ < P.n_it) {
-            const int t = P.t_first + s_ * SEG + p_c;
+    // ---- gate operands of (step s_, layer l), by the 64 lanes of the operand warps 14, 15: lane <-> (pair, column).  These
+    // warps do nothing else in the layer section and run up to a step ahead (operands and their barriers are double-buffered by
+    // step parity), so they are free to block on L2 and on a late helper.
+    const int pidx = (warp - 14) * 32 + lane;
+    auto prep = [&](int s_, int l) {
+        for (int idx = pidx; idx < np * SEG; idx += 64) {
+            const int p = idx / SEG, c = idx - p * SEG;
+            const int row = D.pair0 + p;
+            const int t = P.t_first + s_ * SEG + c;
+            const float4 c4 = lc[l * 16 + p];
+            float az = c4.x, ac = c4.y;
             int f = 0, j = 0;
             if (t >= P.R) { f = (t - P.R) / P.U; j = (t - P.R) - f * P.U; }
-            const float* pl = P.P + (size_t)l * SEG * twoH + p_row;
+            const float* pl = P.P + (size_t)l * SEG * twoH + row;
+            float hz = 0.f, hc = 0.f;
+            const int T = s_ * SEG + c;
+            const bool hh = P.has_help[l] && T >= P.hdmin[l];
+            const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + (size_t)(T & (P.hacc_nt[l] - 1)) * twoH + row;
+            unsigned long long va = 0ull, vb = 0ull;
+            if (hh) { va = ld_ll(src); vb = ld_ll(src + H); }
             int tau = t;
 #pragma unroll
             for (int sp = 0; sp < SEG; ++sp) {
-                r.gn[sp] = __ldg(P.gain + j);
+                const float g = __ldg(P.gain + j);
                 const float* pr = pl + ((size_t)f * L * SEG + sp) * twoH;
-                r.tv[2 * sp] = __ldg(pr);
-                r.tv[2 * sp + 1] = __ldg(pr + H);
+                az = fmaf(g, __ldg(pr), az);
+                ac = fmaf(g, __ldg(pr + H), ac);
                 ++tau;
                 if (tau > P.R && ++j == P.U) { j = 0; ++f; }
             }
-            const int T = s_ * SEG + p_c;
-            if (P.has_help[l] && T >= P.hdmin[l]) {
-                const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + (size_t)(T & (P.hacc_nt[l] - 1)) * twoH + p_row;
-                r.ha = ld_ll(src); r.hb = ld_ll(src + H);
-            }
-        }
-    };
-    auto prep_commit = [&](int q) {
-        const PrepRegs& r = pr_;
-        const int s_ = q / L, l = q - s_ * L;
-        if (p_lane && s_ < P.n_it) {
-            const float4 c4 = lc[l * 16 + p_p];
-            float az = c4.x, ac = c4.y;
-#pragma unroll
-            for (int sp = 0; sp < SEG; ++sp) { az = fmaf(r.gn[sp], r.tv[2 * sp], az); ac = fmaf(r.gn[sp], r.tv[2 * sp + 1], ac); }
-            float hz = 0.f, hc = 0.f;
-            const int T = s_ * SEG + p_c;
-            if (P.has_help[l] && T >= P.hdmin[l]) {
+            if (hh) {
                 const uint32_t tg = (uint32_t)T + 1u;
-                uint32_t a = (uint32_t)r.ha, b = (uint32_t)r.hb;
-                if ((uint32_t)(r.ha >> 32) != tg || (uint32_t)(r.hb >> 32) != tg) {         // the helper was late at issue time
-                    const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + (size_t)(T & (P.hacc_nt[l] - 1)) * twoH + p_row;
-                    ok = wait_gword(src, tg, a, P, 400 + l) && ok;
-                    ok = wait_gword(src + H, tg, b, P, 400 + l) && ok;
-                }
+                uint32_t a = (uint32_t)va, b = (uint32_t)vb;
+                if ((uint32_t)(va >> 32) != tg) ok = wait_gword(src, tg, a, P, 400 + l) && ok;       // the helper is late
+                if ((uint32_t)(vb >> 32) != tg) ok = wait_gword(src + H, tg, b, P, 400 + l) && ok;
                 hz = __uint_as_float(a); hc = __uint_as_float(b);
             }
-            gop[(l * 16 + p_p) * SEG + p_c] = make_float4(az, (c4.z + hz) * az, ac, (c4.w + hc) * ac);
+            gop[(((s_ & 1) * L + l) * 16 + p) * SEG + c] = make_float4(az, (c4.z + hz) * az, ac, (c4.w + hc) * ac);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(gb + l);
+        if (lane == 0) mbar_arrive(gb + (s_ & 1) * L + l);
     };
+    // a layer is "late" when its helper sums for step s only exist once step s-1 is (nearly) over: one step of helper slack and
+    // not among the first two layers.  Late layers of step s are fetched at the top of step s, everything else a step ahead.
+    auto late = [&](int l) { return l >= 2 && P.has_help[l] && P.hdmin[l] < 2 * SEG; };
 
     // ---- input stage: the SEG columns of block itn (cswnv_shift1.py:352), rows of this CTA, published into every
     // peer's hx[parity of itn][0].  Gather form over the sample history (tap validity = the conv's zero padding).
@@ -495,11 +480,8 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     };
 
     // ---- prologue: operands of the first two layers of step 0, inputs of block 0 (padding / seed)
-    if (warp >= 12) {
-        prep_issue(0); prep_commit(0);
-        prep_issue(1); prep_commit(1);
-        prep_issue(2);                                             // (committed in the first service iteration)
-    }
+    if (warp >= 14)
+        for (int l = 0; l < L; ++l) prep(0, l);                    // every layer of step 0 (nothing to wait for yet)
     input_stage(0);
 
     // The tap registers of a chain warp: [SEG taps][WT] of its pair for a one-pair-per-warp layer, or (team 0, `fat` layer)
@@ -548,7 +530,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                     // one gate, one publish per quarter instead of NPW of each on the same scheduler at the same time
                     if (team != 0) continue;
                     tmem_wait_ld();
-                    ok = mbar_wait2(gb + l, par, P, 480 + l) && ok;
+                    ok = mbar_wait2(gb + par * L + l, (uint32_t)(it >> 1) & 1u, P, 480 + l) && ok;
                     ok = mbar_wait2(mb + l, par, P, 500 + l) && ok;
 #if SWN_STAMPS
                     if (P.prof && tid == 0 && l < 6 && it >= P.prof_start && it < P.prof_start + P.prof_count)
@@ -557,7 +539,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                     const int slot = lane >> 1, sj = slot / SEG, sc = slot - sj * SEG;       // (pair of the quarter, column) of this lane
                     const int prow = NPW * quarter + sj;
                     const bool svalid = slot < NPW * SEG && prow < np;
-                    const float4 g4 = gop[(l * 16 + (svalid ? prow : 0)) * SEG + (svalid ? sc : 0)];
+                    const float4 g4 = gop[((par * L + l) * 16 + (svalid ? prow : 0)) * SEG + (svalid ? sc : 0)];
                     const float carry = hcur[(l * SEG + (svalid ? sc : 0)) * HP + D.pair0 + (svalid ? prow : 0)];
                     float a16[16][2];
 #pragma unroll
@@ -634,14 +616,14 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                     }
                 }
                 SWN_TSTAMP(17, tid == 0 && l == 1);
-                ok = mbar_wait2(gb + l, par, P, 480 + l) && ok;
+                ok = mbar_wait2(gb + par * L + l, (uint32_t)(it >> 1) & 1u, P, 480 + l) && ok;
                 SWN_TSTAMP(18, tid == 0 && l == 1);
                 ok = mbar_wait2(mb + l, par, P, 500 + l) && ok;
 #if SWN_STAMPS
                 if (P.prof && tid == 0 && l < 6 && it >= P.prof_start && it < P.prof_start + P.prof_count)
                     P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + 1 + l] = gtime();
 #endif
-                const float4 g4 = gop[(l * 16 + (pvalid ? plocal : 0)) * SEG + ccl];
+                const float4 g4 = gop[((par * L + l) * 16 + (pvalid ? plocal : 0)) * SEG + ccl];
                 const float carry = hcur[(l * SEG + ccl) * HP + my_i];
                 if (dl == 1) {
 #pragma unroll
@@ -731,31 +713,33 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                     } else if (lr.nxb_nco > 0 && (!lr.nxb_wrap || it + 1 < P.n_it)) request_w(lr.nxb_tcol, lr.nxb_nco);
                 }
             }
-        } else if (warp >= 12) {
-            // ======================= service warps: noise, gate operands two layers ahead, out_skip rows of the last column =======================
+        } else if (warp >= 14) {
+            // ======================= operand warps: noise, then gate operands - the late layers of this step, everything else of the next =======================
             if (active && warp == 15 && lane < SEG) {
                 const long long n = (long long)istep * SEG + lane;
                 const float e = P.noise ? __ldg(P.noise + n) : laplace_eps(P.seed, P.b0, n);
                 const float sgn = (e > 0.f) ? 1.f : ((e < 0.f) ? -1.f : 0.f);
                 epsb[lane] = sgn * log1pf(-2.f * fabsf(e));
             }
-            float sk[4] = {0.f, 0.f, 0.f, 0.f};
+            if (it > 0)
+                for (int l = 0; l < L; ++l) if (late(l)) prep(it, l);
+            if (it + 1 < P.n_it) {
+                for (int l = 2; l < L; ++l) if (!late(l)) prep(it + 1, l);
+                for (int l = 0; l < 2 && l < L; ++l) prep(it + 1, l);          // (their helper inputs are the youngest: last)
+            }
+        } else if (warp >= 12) {
+            // ======================= skip warps: eight out_skip rows each, last column only; x1 =======================
+            float sk[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) sk[r] = 0.f;
             const int nsk = D.nskip * HP;
             for (int l = 0; l < L; ++l) {
-                SWN_TSTAMP(24, tid == 384 && l == 1);
-                {   // operands two layers ahead (their loads were issued one iteration ago), loads for three ahead
-                    const int q = it * L + l + 2;
-                    prep_commit(q);
-                    prep_issue(q + 1);
-                }
-                SWN_TSTAMP(25, tid == 384 && l == 1);
                 ok = mbar_wait2(mb + l, par, P, 700 + l) && ok;
-                SWN_TSTAMP(26, tid == 384 && l == 1);
                 if (active && l >= 1) {                                          // out_skip[l-1] on the last column of layer l's input
                     float2 h[NCH];
                     load_frag<NCH>(h, hcur + (l * SEG + SEG - 1) * HP, lane);
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
+                    for (int r = 0; r < 8; ++r) {
                         float2 a[NCH];
                         load_frag<NCH>(a, sSkip + (size_t)(l - 1) * nsk + (size_t)(srow0 + r < D.nskip ? srow0 + r : 0) * HP, lane);
                         sk[r] += dot_frag<NCH>(a, h);
@@ -763,26 +747,26 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                 }
             }
             {
-                float2 a[4][NCH];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-                    load_frag<NCH>(a[r], sSkip + (size_t)(L - 1) * nsk + (size_t)(srow0 + r < D.nskip ? srow0 + r : 0) * HP, lane);
-                const float4 k4 = wconst[16 + warp - 12];
-                const float skc[4] = {k4.x, k4.y, k4.z, k4.w};
+                const float4 ka = wconst[16 + 2 * (warp - 12)], kb = wconst[17 + 2 * (warp - 12)];
+                const float skc[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
                 ok = mbar_wait2(mb + L, par, P, 510) && ok;
                 if (active) {
                     float2 hl[NCH];
                     load_frag<NCH>(hl, hcur + (size_t)L * SEG * HP, lane);
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) sk[r] += dot_frag<NCH>(a[r], hl);
+                    for (int r = 0; r < 8; ++r) {
+                        float2 a[NCH];
+                        load_frag<NCH>(a, sSkip + (size_t)(L - 1) * nsk + (size_t)(srow0 + r < D.nskip ? srow0 + r : 0) * HP, lane);
+                        sk[r] += dot_frag<NCH>(a, hl);
+                    }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) sk[r] += __shfl_xor_sync(0xffffffffu, sk[r], o);
+                        for (int r = 0; r < 8; ++r) sk[r] += __shfl_xor_sync(0xffffffffu, sk[r], o);
                     if (lane < CORE_CL) {
                         const uint32_t dst = hx_peer + (uint32_t)((2 * LS + D.skip0 + srow0) * 4);
 #pragma unroll
-                        for (int r = 0; r < 4; ++r)
+                        for (int r = 0; r < 8; ++r)
                             if (srow0 + r < D.nskip)
                                 st_async_f32(dst + (uint32_t)(r * 4), fmaxf(sk[r] + skc[r], 0.f), mb_peer + (uint32_t)((L + 1) * 8));
                     }
