@@ -18,7 +18,8 @@
 //     of all columns come out of ONE transposed reduction (18 shuffles), one gate, one publish - no intra-CTA hand-off;
 //   * the last layer only evaluates the last column (the head reads nothing else and no layer follows);
 //     (Measured negative, removed: requesting them before the reduction, +0.25 us per step; requesting taps 1.. of a
-//     dilation-1 layer a whole stage ahead while the single-tap layer before it runs, +0.28 us - profiles/r02z_coreseg_ab_timings.txt.)
+//     dilation-1 layer a whole stage ahead while the single-tap layer before it runs, +0.28 us; requesting the first layer's taps
+//     at the end of the step instead of behind the warp's last own stage, +0.14 us - profiles/r02z_coreseg_ab_timings.txt.)
 //   * warps 12-13: the out_skip rows of the last column (eight each) and x1;  warps 14-15: nothing but the gate operands
 //     (conditioning rows x gain + constant, bias + helper sums), a step ahead - operands and their "are in" mbarriers are
 //     double-buffered by step parity, so these warps may block on L2 and on a late helper without holding up x1 (with
@@ -348,24 +349,24 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
     // fat: this layer has a single core tap and runs on team 0 alone (one warp per quarter, all its pairs).  nxa_*: the next
     // layer (wrapping into the next step) = what team 0 requests behind its publish; nxb_*: the next layer in the one-pair-per-
     // warp layout (-1: none) = what teams 1, 2 request behind theirs.
-    struct LRec { int32_t nco, dil, tcol, hmask; unsigned long long hin; int32_t nco_next, tcol_next;
-                  int32_t fat, nxa_fat, nxb_tcol, nxb_nco, nxb_wrap, r0, r1, r2; };
-    static_assert(sizeof(LRec) == 64, "per-layer record: 16 words");
+    struct LRec { int8_t nco, nco_next, nxb_nco, fat, nxa_fat, nxb_wrap; int16_t dil; int16_t tcol, tcol_next, nxb_tcol, r0; int32_t hmask, r1;
+                  unsigned long long hin; };
+    static_assert(sizeof(LRec) == 32, "per-layer record: two 16-byte loads");
     LRec* lrec = reinterpret_cast<LRec*>(reinterpret_cast<float4*>(sfir + 8 * 2 * 16) + 20);   // [L] behind wconst
     if (tid < L) {
         const int l = tid;
         LRec r;
-        r.nco = P.ncore[l]; r.dil = P.dil[l]; r.tcol = P.tap_base[l] * TCOLS;
+        r.nco = (int8_t)P.ncore[l]; r.dil = (int16_t)(P.dil[l] < 32767 ? P.dil[l] : 32767); r.tcol = (int16_t)(P.tap_base[l] * TCOLS);
         const bool hn_ = l + 1 < L && P.has_help[l + 1];
         r.hmask = hn_ ? P.hslots[l + 1] - 1 : -1;                  // -1: no helper behind this layer's output
         r.hin = hn_ ? (unsigned long long)(P.hin_ll + P.hin_off[l + 1]) : 0ull;
-        r.nco_next = P.ncore[(l + 1) % L]; r.tcol_next = P.tap_base[(l + 1) % L] * TCOLS;     // (the last layer: layer 0 of the next step)
+        r.nco_next = (int8_t)P.ncore[(l + 1) % L]; r.tcol_next = (int16_t)(P.tap_base[(l + 1) % L] * TCOLS);     // (the last layer: layer 0 of the next step)
         r.fat = SEG_FAT && P.ncore[l] == 1 && NPW * SEG <= 16;
         r.nxa_fat = SEG_FAT && P.ncore[(l + 1) % L] == 1 && NPW * SEG <= 16;
-        r.nxb_tcol = 0; r.nxb_nco = -1; r.nxb_wrap = 0; r.r0 = r.r1 = r.r2 = 0;
+        r.nxb_tcol = 0; r.nxb_nco = -1; r.nxb_wrap = 0; r.r0 = 0; r.r1 = 0;
         for (int k = 1; k <= L; ++k) {
             const int l2 = (l + k) % L;
-            if (!(SEG_FAT && P.ncore[l2] == 1 && NPW * SEG <= 16)) { r.nxb_tcol = P.tap_base[l2] * TCOLS; r.nxb_nco = P.ncore[l2]; r.nxb_wrap = l + k >= L; break; }
+            if (!(SEG_FAT && P.ncore[l2] == 1 && NPW * SEG <= 16)) { r.nxb_tcol = (int16_t)(P.tap_base[l2] * TCOLS); r.nxb_nco = (int8_t)P.ncore[l2]; r.nxb_wrap = l + k >= L; break; }
         }
         lrec[l] = r;
     }
@@ -469,11 +470,12 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
             }
             v = acc * rcp_approx(1.f + fabsf(acc));
         }
-        const uint32_t base = hx_peer + (uint32_t)((((itn & 1) * (L + 1)) * SEG * HP + in_row) * 4);
+        const uint32_t base = mapa(smem_u32(hx), (uint32_t)(lane & (CORE_CL - 1))) + (uint32_t)((((itn & 1) * (L + 1)) * SEG * HP + in_row) * 4);
+        const uint32_t mbp = mapa(smem_u32(mb), (uint32_t)(lane & (CORE_CL - 1)));
 #pragma unroll
         for (int cc = 0; cc < SEG; ++cc) {
             const float vc = __shfl_sync(0xffffffffu, v, cc);
-            if (lane < CORE_CL) st_async_f32(base + (uint32_t)(cc * HP * 4), vc, mb_peer);
+            if (lane < CORE_CL) st_async_f32(base + (uint32_t)(cc * HP * 4), vc, mbp);
         }
         if (lane >= 16 && lane < 16 + SEG && P.has_help[0])
             st_ll(P.hin_ll + P.hin_off[0] + ((size_t)(itn & (P.hslots[0] - 1)) * SEG + (lane - 16)) * H + in_row, v, (uint32_t)itn + 1u);
@@ -501,13 +503,14 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
         }
     };
     auto request_fat = [&](int tcol) { tmem_ld_at<TCOLS, 0>(taddr0 + tcol, wr); };
-    if (is_chain) {
+    auto request_first = [&]() {                                   // the taps of this warp's first own stage of a step
         const LRec l0 = lrec[0];
         if (l0.fat) {
             if (team == 0) request_fat(l0.tcol);
             else if (l0.nxb_nco > 0) request_w(l0.nxb_tcol, l0.nxb_nco);
         } else request_w(l0.tcol, l0.nco);
-    }
+    };
+    if (is_chain) request_first();
     for (int it = 0; it < P.n_it; ++it) {
         const bool active = it >= P.it0;
         const uint32_t par = (uint32_t)it & 1u;
@@ -575,7 +578,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                             st_ll(reinterpret_cast<unsigned long long*>(lr.hin) + ((size_t)(it & lr.hmask) * SEG + sc) * H + D.pair0 + prow, hn,
                                   (uint32_t)it + 1u);
                     }
-                    if (!lastl || it + 1 < P.n_it) {                          // the next layer's taps (team 0 takes part in every layer)
+                    if (!lastl || it + 1 < P.n_it) {        // the next layer's taps (team 0 takes part in every layer)
                         if (lr.nxa_fat) request_fat(lr.tcol_next);
                         else request_w(lr.tcol_next, lr.nco_next);
                     }
