@@ -138,6 +138,14 @@ __device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint
                  ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_mbar) : "memory");
 }
 
+// the same, executed only where `pred` is non-zero - as a predicated instruction, not a branch (a divergent `if` around the
+// asm statement made the compiler re-materialise the lane id and reload spilled addresses in every unrolled iteration)
+__device__ __forceinline__ void st_async_f32_if(uint32_t pred, uint32_t remote_addr, float v, uint32_t remote_mbar) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t"
+                 "@p st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];\n\t}"
+                 ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_mbar), "r"(pred) : "memory");
+}
+
 __device__ __forceinline__ void st_async_f32x2(uint32_t remote_addr, float lo, float hi, uint32_t remote_mbar) {
     const unsigned long long w = ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"

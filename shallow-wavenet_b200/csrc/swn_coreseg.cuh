@@ -472,10 +472,11 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
         }
         const uint32_t base = mapa(smem_u32(hx), (uint32_t)(lane & (CORE_CL - 1))) + (uint32_t)((((itn & 1) * (L + 1)) * SEG * HP + in_row) * 4);
         const uint32_t mbp = mapa(smem_u32(mb), (uint32_t)(lane & (CORE_CL - 1)));
+        const uint32_t lo16 = lane < CORE_CL ? 1u : 0u;
 #pragma unroll
         for (int cc = 0; cc < SEG; ++cc) {
             const float vc = __shfl_sync(0xffffffffu, v, cc);
-            if (lane < CORE_CL) st_async_f32(base + (uint32_t)(cc * HP * 4), vc, mbp);
+            st_async_f32_if(lo16, base + (uint32_t)(cc * HP * 4), vc, mbp);
         }
         if (lane >= 16 && lane < 16 + SEG && P.has_help[0])
             st_ll(P.hin_ll + P.hin_off[0] + ((size_t)(itn & (P.hslots[0] - 1)) * SEG + (lane - 16)) * H + in_row, v, (uint32_t)itn + 1u);
