@@ -1505,9 +1505,10 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
     }
     if (m->core_ok && seg > 1) {
         // seg > 1: the cluster kernel takes one utterance per launch; small batches run as launches one after the other.
-        // Measured for the recipe model (H=192, seg 5; profiles/r02z_crossover_cswnv.txt): 289 k samples/s at any B against
-        // 148 / 192 / 263 / 350 k for the layer-group kernel at B = 1 / 2 / 3 / 4 - up to three utterances it wins.
-        if (a->kernel_sel == 2 || (a->kernel_sel == 0 && a->batch_tile == 0 && B <= 3)) {
+        // Measured for the recipe model (H=192, seg 5; profiles/r02z_crossover_cswnv.txt): 354 k samples/s at any B against
+        // 148 / 193 / 262 / 349 k for the layer-group kernel at B = 1 / 2 / 3 / 4 and 341 k for the batch kernel at B = 4 (508 k
+        // at B = 6): up to four utterances it wins.
+        if (a->kernel_sel == 2 || (a->kernel_sel == 0 && a->batch_tile == 0 && B <= 4)) {
             int rc = 0;
             for (int b0 = 0; b0 < B && rc == 0; ++b0) rc = generate_coreseg(m, a, st, Tf, n_iter, b0, b0 == 0, b0 + 1 == B);
             if (rc == 0) return 0;

@@ -133,8 +133,8 @@ def test_free_running_matches_reference_fixture(name):
 def test_recipe_size_matches_reference_fixture(name):
     """tests/golden_large: outputs of the UNMODIFIED reference at the size the benchmark runs (H=192 seg 5 / H=256,
     k=7, L=6, R=690), written by oracle/build_ref.py.  Teacher-forced heads and samples, then free running on the
-    reference's own noise, through whichever kernel the plan selects for that batch size (cluster kernel at B<=2 and for seg 5 at B<=3,
-    layer groups for seg 5 at B=4, the batch kernel from 8 utterances)."""
+    reference's own noise, through whichever kernel the plan selects for that batch size (cluster kernel at B<=2 and for seg 5 at B<=4,
+    the batch kernel from 8 utterances)."""
     g = load_large(name)
     m = g["model"].cuda().eval()
     B, N = g["samples"].shape
