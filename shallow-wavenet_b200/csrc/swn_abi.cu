@@ -1357,7 +1357,7 @@ int swn_finalize(swn_handle m) {
         const bool fits1 = seg == 1 && !audio_in && H <= 256 && S <= 256 && n1 <= 256 && K <= swn::CORE_KMAX && L <= 16 &&
                            nct * tcols <= 128 && (is_c ? n2 <= 16 : n2 <= 256);
         // seg > 1: 4 NCH^2 tensor-memory columns per tap and thread, one (tap, column) per helper lane
-        const bool fits5 = is_c && (seg == 2 || seg == 5) && m->NCH <= 3 && H <= 192 && S <= 256 && n1 <= 256 && K <= swn::CORE_KMAX &&
+        const bool fits5 = is_c && seg >= 2 && seg <= 5 && m->NCH <= 3 && H <= 192 && S <= 256 && n1 <= 256 && K <= swn::CORE_KMAX &&
                            L <= 16 && nct * 4 * m->NCH * m->NCH <= 512 && n2 <= 16 && help_lanes_ok;
         const bool fits = fits1 || fits5;
         if (fits) {

@@ -57,6 +57,8 @@ core_fns SWN_CAT(find_coreseg_kernel_nch, SWN_NCH)(int seg) {
     core_fns f = {nullptr, nullptr};
     switch (seg) {
         case 2: f.prepare = &coreseg_prepare<SWN_NCH, 2>; f.launch = &coreseg_launch<SWN_NCH, 2>; break;
+        case 3: f.prepare = &coreseg_prepare<SWN_NCH, 3>; f.launch = &coreseg_launch<SWN_NCH, 3>; break;
+        case 4: f.prepare = &coreseg_prepare<SWN_NCH, 4>; f.launch = &coreseg_launch<SWN_NCH, 4>; break;
         case 5: f.prepare = &coreseg_prepare<SWN_NCH, 5>; f.launch = &coreseg_launch<SWN_NCH, 5>; break;
         default: break;
     }

@@ -22,7 +22,7 @@ core_fns find_core_kernel_nch1(int bs);
 core_fns find_core_kernel_nch2(int bs);
 core_fns find_core_kernel_nch3(int bs);
 core_fns find_core_kernel_nch4(int bs);
-// seg > 1 cluster kernel (swn_coreseg.cuh), one utterance per launch; instantiated for seg 2 and 5
+// seg > 1 cluster kernel (swn_coreseg.cuh), one utterance per launch; instantiated for seg 2 .. 5
 core_fns find_coreseg_kernel_nch1(int seg);
 core_fns find_coreseg_kernel_nch2(int seg);
 core_fns find_coreseg_kernel_nch3(int seg);

@@ -186,19 +186,20 @@ def _recipe_case(kind, fs, B, frames, seed, **over):
     return model.cuda(), cfg, sd, aux, kw
 
 
-@pytest.mark.parametrize("seg,lpc,B", [(5, 4, 1), (5, 4, 3), (1, 4, 2), (1, 4, 3), (1, 0, 4), (2, 0, 1), (10, 4, 1)])
+@pytest.mark.parametrize("seg,lpc,B", [(5, 4, 1), (5, 4, 3), (1, 4, 2), (1, 4, 3), (1, 0, 4), (2, 0, 1), (10, 4, 1), (3, 4, 2), (4, 2, 1), (5, 4, 5)])
 def test_recipe_size_cswnv_teacher_forced_vs_oracle(seg, lpc, B):
     model, cfg, sd, aux, kw = _recipe_case("cswnv", 22050, B, 2, 7, seg=seg, lpc=lpc)
     N = 2 * kw["upsampling_factor"]
     rng = np.random.default_rng(5)
     forced = np.clip(0.3 * rng.standard_normal((B, N)), -1, 1).astype(np.float32)
     noise = rng.uniform(-0.4999, 0.5, (B, N)).astype(np.float32)
+    n_gen = (N // seg) * seg                        # (seg 3: 219 of the 220 samples, as the reference's loop count)
+    forced, noise = forced[:, :n_gen], noise[:, :n_gen]
     outs, heads = model.batch_fast_generate(torch.zeros(B, seg), torch.from_numpy(aux), [N] * B, noise=noise,
                                             forced=forced, return_heads=True)
     ref_heads = O.teacher_forced(cfg, sd, aux, forced)
     _head_close(heads, ref_heads, "cswnv seg%d B=%d" % (seg, B), kind="cswnv", kw=kw, tol=_tol(model))
     # sampler given the oracle's view of the same heads / history / noise
-    n_gen = (N // seg) * seg
     lp = torch.zeros(B, lpc) if lpc else None
     ref = np.zeros((B, n_gen), np.float32)
     ft = torch.from_numpy(forced)
@@ -208,6 +209,15 @@ def test_recipe_size_cswnv_teacher_forced_vs_oracle(seg, lpc, B):
         if lpc:
             lp = torch.cat((lp, ft[:, i * seg:(i + 1) * seg]), 1)[:, -lpc:]
     assert float(np.abs(np.stack(outs) - ref).max()) <= SAMPLE_ATOL
+    if 2 <= seg <= 5 and B <= 4:
+        # the seg cluster kernel, one utterance per launch: the Philox draws of launch b use the global utterance index b
+        info = model.engine().info
+        assert info["kernel_variant"] == 2 and info["batch_tile"] == 1 and info["n_slots"] == B, info
+        from shallow_wavenet_b200.engine import philox_uniform
+        eps = np.stack([np.float32(-0.4999) + np.float32(0.9999) * philox_uniform(9, "cswnv", b, 0, n_gen) for b in range(B)])
+        a = np.stack(model.batch_fast_generate(torch.zeros(B, seg), torch.from_numpy(aux), [N] * B, seed=9))
+        b_ = np.stack(model.batch_fast_generate(torch.zeros(B, seg), torch.from_numpy(aux), [N] * B, noise=eps.astype(np.float32)))
+        assert float(np.abs(a - b_).max()) <= 1e-6
     if seg == 1 and B >= 3:
         # launches of two through the cluster kernel; the Philox draws of a later launch use the global utterance index
         info = model.engine().info
