@@ -192,6 +192,10 @@ __device__ __forceinline__ void b3_umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
                  ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
 }
+// the same with the accumulate flag fixed to 1 (no predicate set-up in front of every issue)
+__device__ __forceinline__ void b3_umma_tf32_acc(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, 1;" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc) : "memory");
+}
 __device__ __forceinline__ void b3_umma_commit(unsigned long long* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b3_smem(bar)) : "memory");
 }
@@ -549,16 +553,30 @@ __device__ void b3_stage_body(const BatchParams& P, const BCta& D, float* smem) 
             b3_tc_fence_after();
             const uint32_t xs = b3_smem(Xs + buf * xbuf_f);
             const uint32_t d_tmem = tbase + 2 * kp + db * NP;
-            // the two passes that only read the high half of the activations start as soon as it has landed
-            for (int ks = 0; ks < (kp >> 3); ++ks) {
-                const uint64_t dh = b3_udesc(xs + ks * kstep_bytes, NP);
-                b3_umma_tf32_ts(d_tmem, tbase + ks * 8, dh, idesc, ks > 0);
-                b3_umma_tf32_ts(d_tmem, tbase + kp + ks * 8, dh, idesc, 1);
+            // the two passes that only read the high half of the activations start as soon as it has landed.
+            // (One thread issues all 72 MMAs: the descriptor of a k-step is the previous one plus a constant in its address
+            // field, and the loops are unrolled - built from scratch per MMA, the integer work between two issues was as long
+            // as the instruction's own issue period of ~49 cycles, tools/microbench/umma_rate.cu.)
+            const uint64_t dstep = (uint64_t)(kstep_bytes >> 4);
+            uint64_t dh = b3_udesc(xs, NP);
+            uint32_t a_hi = tbase, a_lo = tbase + kp;
+            b3_umma_tf32_ts(d_tmem, a_hi, dh, idesc, 0);
+            b3_umma_tf32_ts(d_tmem, a_lo, dh, idesc, 1);
+#pragma unroll 4
+            for (int ks = 1; ks < (kp >> 3); ++ks) {
+                dh += dstep; a_hi += 8; a_lo += 8;
+                b3_umma_tf32_acc(d_tmem, a_hi, dh, idesc);
+                b3_umma_tf32_acc(d_tmem, a_lo, dh, idesc);
             }
             if (!b3_mbar_wait(&x_lo[buf], XU(q) & 1, P.status)) return;
             b3_tc_fence_after();
-            for (int ks = 0; ks < (kp >> 3); ++ks)
-                b3_umma_tf32_ts(d_tmem, tbase + ks * 8, b3_udesc(xs + utile * 4 + ks * kstep_bytes, NP), idesc, 1);
+            uint64_t dl = b3_udesc(xs + utile * 4, NP);
+            a_hi = tbase;
+#pragma unroll 4
+            for (int ks = 0; ks < (kp >> 3); ++ks) {
+                b3_umma_tf32_acc(d_tmem, a_hi, dl, idesc);
+                dl += dstep; a_hi += 8;
+            }
             b3_umma_commit(&d_full[db]);
             b3_umma_commit(&x_empty[buf]);
         }
