@@ -30,12 +30,8 @@
 #include "swn_core.cuh"
 #include "swn_core2.cuh"
 
-#define SEG_TMEM_EARLY 0        // (next layer's taps are requested behind the publish; before the reduction measured slower)
 #ifndef SEG_FAT
 #define SEG_FAT 1               // layers with a single core tap: ONE chain warp per tensor-memory quarter owns all its pairs
-#endif
-#ifndef SEG_NCO1
-#define SEG_NCO1 1              // fixed-address path for the layers whose only core tap is delay 0
 #endif
 #if SWN_STAMPS
 #define SWN_TSTAMP(ev, cond)                                                                        \
@@ -648,7 +644,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                             }
                         }
                     }
-                } else if (SEG_NCO1 && nco == 1 && !lastl) {
+                } else if (nco == 1 && !lastl) {
                     // dilation >= SEG (the usual case): delay 0 only, column c from column c - fixed addresses, all loads first
                     float2 h[SEG][NCH];
 #pragma unroll
@@ -707,7 +703,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                               (uint32_t)it + 1u);
                 }
                 SWN_TSTAMP(21, tid == 0 && l == 1);
-                if (!SEG_TMEM_EARLY) {
+                {
                     // behind the publish: the taps of this warp's next own stage
                     if (team == 0) {
                         if (more) {
