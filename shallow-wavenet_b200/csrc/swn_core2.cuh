@@ -42,6 +42,10 @@
 #define SWN_WSTAMP(ev) do {} while (0)
 #endif
 
+#ifndef SWN_JOINT2
+#define SWN_JOINT2 1            // two utterance columns: the chain warp evaluates both at once (one 8-slot reduction, one gate, one
+#endif                          // publish per stage) instead of one after the other behind their own barriers
+
 namespace swn {
 
 // The 8 per-lane partial sums are those of 4 gate pairs x {z, candidate} (v[2p], v[2p+1]).  Afterwards every lane of
@@ -64,6 +68,42 @@ __device__ __forceinline__ void reduce_pairs(const float (&v)[8], int lane, floa
     }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
+        z += __shfl_xor_sync(0xffffffffu, z, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    qz = z; qc = c;
+}
+
+// Totals of acc[c][z|c] (c < 8 column slots) over the 32 lanes: afterwards every lane of column group lane >> 2 holds
+// both totals of that column.  Three halving levels (16, 8, 4) and two butterflies: 18 shuffles for all columns.
+template <int SEG>
+__device__ __forceinline__ void reduce_columns(const float (&a)[SEG][2], int lane, float& qz, float& qc) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    float u[4][2], v[2][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int zc = 0; zc < 2; ++zc) {
+            const float lo = i < SEG ? a[i < SEG ? i : 0][zc] : 0.f, hi = i + 4 < SEG ? a[i + 4 < SEG ? i + 4 : 0][zc] : 0.f;
+            const float send = b4 ? lo : hi, keep = b4 ? hi : lo;
+            u[i][zc] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int zc = 0; zc < 2; ++zc) {
+            const float send = b3 ? u[i][zc] : u[i + 2][zc], keep = b3 ? u[i + 2][zc] : u[i][zc];
+            v[i][zc] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    float z, c;
+    {
+        const float sz = b2 ? v[0][0] : v[1][0], kz = b2 ? v[1][0] : v[0][0];
+        const float sc = b2 ? v[0][1] : v[1][1], kc = b2 ? v[1][1] : v[0][1];
+        z = kz + __shfl_xor_sync(0xffffffffu, sz, 4);
+        c = kc + __shfl_xor_sync(0xffffffffu, sc, 4);
+    }
+#pragma unroll
+    for (int o = 2; o > 0; o >>= 1) {
         z += __shfl_xor_sync(0xffffffffu, z, o);
         c += __shfl_xor_sync(0xffffffffu, c, o);
     }
@@ -407,6 +447,53 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
             uint32_t m0 = pmb0 + (uint32_t)(NC * 8), m1 = pmb1 + (uint32_t)(NC * 8);
             unsigned long long* bar = mb;
             for (int l = 0; l < L; ++l) {
+                if constexpr (NC == 2 && SWN_JOINT2 != 0) {
+                    // ---- two columns at once: 4 pairs x 2 columns = 8 (pair, column) slots, 4 lanes each after the reduction.
+                    // One reduction (18 shuffles for both columns instead of 2 x 13), one gate, one publish; the 16 independent
+                    // FMA chains fill the issue gaps a single column leaves.  12.1 -> 10.4 us per step for two utterances.
+                    // (The head stages stay one column after the other: evaluated jointly they were SLOWER, 11.2 us - there the
+                    // early publish of the first column is worth more than the interleaving.)
+                    const int slot = lane >> 2, sp = slot >> 1, scol = slot & 1, s4 = lane & 3;
+                    const int prow = 4 * quarter + sp;
+                    const bool sv = prow < np;
+                    const float4 g4 = gp[((sv ? prow : plocal) - plocal) * NC + scol];          // (gp points at this lane's own pair: rebase)
+                    ok = mbar_wait2(bar + 0, par, P, 500 + l) && ok;
+                    ok = mbar_wait2(bar + 1, par, P, 500 + l) && ok;
+#if SWN_STAMPS
+                    if (P.prof && tid == 0 && l < 6 && it >= P.prof_start && it < P.prof_start + P.prof_count)
+                        P.prof[((size_t)(it - P.prof_start) * gridDim.x + blockIdx.x) * 32 + 1 + l] = gtime();
+#endif
+                    float2 h0[NCH], h1[NCH];
+                    load_frag<NCH>(h0, hxl, lane);
+                    load_frag<NCH>(h1, hxl + HP, lane);
+                    const float carry = hxl[scol * HP + D.pair0 + (sv ? prow : 0)];
+                    tmem_wait_ld();
+                    float a8[8][2];
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+#pragma unroll
+                        for (int cc = 0; cc < NCH; ++cc) {
+                            a0 = fmaf(w[rr * FPT + 2 * cc], h0[cc].x, a0); b0 = fmaf(w[rr * FPT + 2 * cc + 1], h0[cc].y, b0);
+                            a1 = fmaf(w[rr * FPT + 2 * cc], h1[cc].x, a1); b1 = fmaf(w[rr * FPT + 2 * cc + 1], h1[cc].y, b1);
+                        }
+                        a8[(rr >> 1) * 2 + 0][rr & 1] = a0 + b0;                                  // slot = pair * 2 + column
+                        a8[(rr >> 1) * 2 + 1][rr & 1] = a1 + b1;
+                    }
+                    float qz, qc;
+                    reduce_columns<8>(a8, lane, qz, qc);
+                    const float hn = gate_out(fmaf(qz, g4.x, g4.y), fmaf(qc, g4.z, g4.w), carry);
+                    if (sv) {
+                        const uint32_t off = (uint32_t)((((l + 1) * NC + scol) * HP + D.pair0 + prow) * 4);
+                        const uint32_t mo = (uint32_t)(((l + 1) * NC + scol) * 8);
+                        const uint32_t hx0 = smem_u32(hx), mb0 = smem_u32(mb);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            st_async_f32(mapa(hx0 + off, (uint32_t)(s4 + 4 * k)), hn, mapa(mb0 + mo, (uint32_t)(s4 + 4 * k)));
+                        if (l + 1 < L && P.has_help[l + 1] && s4 == 0)
+                            st_ll(P.hin_ll + P.hin_off[l + 1] + ((it & (P.hslots[l + 1] - 1)) * NC + scol) * H + D.pair0 + prow, hn, (uint32_t)it + 1u);
+                    }
+                } else {
                 // the columns one after the other, each behind its own barrier: while the hop of column c is in flight
                 // the stage of column c + 1 is computed
 #pragma unroll
@@ -447,6 +534,7 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                     // ---- behind the publish (in the shadow of the hop): helper hand-off
                     if (l + 1 < L && P.has_help[l + 1] && pvalid && sub == 0)
                         st_ll(P.hin_ll + P.hin_off[l + 1] + ((it & (P.hslots[l + 1] - 1)) * NC + c) * H + my_i, hn, (uint32_t)it + 1u);
+                }
                 }
                 // next taps, running pointers
                 if (l + 1 < L) tmem_ldw<TCOLS>(taddr0 + P.tap_base[l + 1] * TCOLS, w);

@@ -141,42 +141,6 @@ __device__ void helper_cta_seg(const CoreParams& P, const HelpCta& D, float* sme
 }
 
 // ------------------------------------------------------------------ core CTA
-// Totals of acc[c][z|c] (c < 8 column slots) over the 32 lanes: afterwards every lane of column group lane >> 2 holds
-// both totals of that column.  Three halving levels (16, 8, 4) and two butterflies: 18 shuffles for all columns.
-template <int SEG>
-__device__ __forceinline__ void reduce_columns(const float (&a)[SEG][2], int lane, float& qz, float& qc) {
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-    float u[4][2], v[2][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int zc = 0; zc < 2; ++zc) {
-            const float lo = i < SEG ? a[i < SEG ? i : 0][zc] : 0.f, hi = i + 4 < SEG ? a[i + 4 < SEG ? i + 4 : 0][zc] : 0.f;
-            const float send = b4 ? lo : hi, keep = b4 ? hi : lo;
-            u[i][zc] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int zc = 0; zc < 2; ++zc) {
-            const float send = b3 ? u[i][zc] : u[i + 2][zc], keep = b3 ? u[i + 2][zc] : u[i][zc];
-            v[i][zc] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    float z, c;
-    {
-        const float sz = b2 ? v[0][0] : v[1][0], kz = b2 ? v[1][0] : v[0][0];
-        const float sc = b2 ? v[0][1] : v[1][1], kc = b2 ? v[1][1] : v[0][1];
-        z = kz + __shfl_xor_sync(0xffffffffu, sz, 4);
-        c = kc + __shfl_xor_sync(0xffffffffu, sc, 4);
-    }
-#pragma unroll
-    for (int o = 2; o > 0; o >>= 1) {
-        z += __shfl_xor_sync(0xffffffffu, z, o);
-        c += __shfl_xor_sync(0xffffffffu, c, o);
-    }
-    qz = z; qc = c;
-}
-
 // Totals of a[slot][z|c] (16 slots) over the 32 lanes: afterwards the two lanes of slot lane >> 1 hold both totals of that
 // slot.  Four halving levels (16, 8, 4, 2) and one butterfly: 32 shuffles for 16 (pair, column) slots.
 __device__ __forceinline__ void reduce_slots16(const float (&a)[16][2], int lane, float& qz, float& qc) {
