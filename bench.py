@@ -490,6 +490,7 @@ def main():
         l_total, l_e2e = reduce_max([rl["total_ms"], rl["e2e_ms"]])
         if rank == 0:
             lro = roofline_of(lk, lkw, rl, 3)
+            attach_traffic(lro, "cfg1", rl["info"].get("kernel_variant"))
             lval = world * rl["samples_per_step"] * 3 / (l_total * 1e-3)
             line["latency"] = {"cfg1": {
                 "workload": ldesc, "value": lval, "unit": "samples/s", "rtf": lval / lfs, "rtf_per_utterance": lval / lfs / (world * lB),
