@@ -85,7 +85,8 @@ typedef struct swn_gen_args {
     int32_t reserved;
     const int64_t* n_samples_list; /* optional HOST array [B]: samples wanted per utterance (the reference's
                                  n_samples_list, cswnv_shift1.py:291-295,426-428).  The batch kernel stops a pipeline
-                                 slot once all its utterances are complete; rows of out_dev are only defined up to each
+                                 slot once all its utterances are complete, the seg cluster kernel (one utterance per
+                                 launch) runs each for its own length; rows of out_dev are only defined up to each
                                  utterance's own length (rounded up to seg).  NULL = n_samples for everyone. */
 } swn_gen_args;
 

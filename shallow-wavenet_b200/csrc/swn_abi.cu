@@ -605,7 +605,11 @@ static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st
     const int rem = (m->R + 1) % seg;                      // the time-index contract of the layer-group kernel (swn_generate)
     P.t_first = rem == 0 ? 0 : rem - seg;
     P.it0 = (m->R + 1 - P.t_first) / seg - 1;
-    P.n_iter = (int)n_iter; P.n_it = P.it0 + (int)n_iter;
+    // one utterance per launch: it only runs for its own length (the reference generates every utterance to the longest,
+    // cswnv_shift1.py:291-295, and truncates afterwards; the rows beyond an utterance's length are not written here)
+    int64_t steps_b = n_iter;
+    if (a->n_samples_list) steps_b = std::max<int64_t>(1, std::min<int64_t>(n_iter, (a->n_samples_list[b0] + seg - 1) / seg));
+    P.n_iter = (int)n_iter; P.n_it = P.it0 + (int)steps_b;
     P.n_core_taps = m->n_core_taps; P.n_help = m->core_n_help;
     {   // (field reused as a flag) per-step cluster barrier also outside the warm-up: some chain warp owns no out_1 row
         int min_nb = 1 << 30;

@@ -498,6 +498,34 @@ def test_seg_cluster_kernel_matches_reference_fixture(name):
         assert float(np.abs(o - g["samples"][b, :len(o)]).max()) <= 5e-5
 
 
+@pytest.mark.parametrize("name,B", [("cswnv_seg5_lpc4_h64", 3), ("cswnv_seg2_lpc3", 4)])
+def test_seg_cluster_kernel_ragged_lengths_run_each_utterance_for_its_own_length(name, B):
+    """The seg cluster kernel launches one utterance at a time; with n_samples_list every launch runs only for its own
+    length (the reference runs all to the longest and truncates, cswnv_shift1.py:291-295,426-428): each utterance equals
+    the oracle's output truncated to its length, including lengths that are not multiples of seg and a 1-frame utterance."""
+    g = load_golden(name)
+    m = _model_from_golden(g)
+    kw, cfg = g["kw"], g["cfg"]
+    rng = np.random.default_rng(100 + B)
+    Tmax, U, seg = 5, kw["upsampling_factor"], cfg.eff_seg
+    frames = np.sort(rng.integers(1, Tmax + 1, B))
+    frames[0], frames[-1] = 1, Tmax
+    aux = np.zeros((B, kw["n_aux"], Tmax), np.float32)
+    for b, t in enumerate(frames):
+        aux[b, :, :t] = rng.standard_normal((kw["n_aux"], t))
+    lens = [int(t) * U - (3 if b % 2 == 1 and b < B - 1 and t * U > 3 else 0) for b, t in enumerate(frames)]
+    N = Tmax * U
+    n_gen = (N // seg) * seg
+    noise = rng.uniform(-0.4999, 0.5, (B, n_gen)).astype(np.float32)
+    outs = m.batch_fast_generate(_seed_audio(g["kind"], B, seg), torch.from_numpy(aux), lens, noise=noise, kernel_sel=2)
+    assert m.engine().info["kernel_variant"] == 2
+    ref_smp = O.generate(cfg, g["sd"], aux, N, noise)
+    for b, o in enumerate(outs):
+        want = min(lens[b], n_gen)
+        assert len(o) == want
+        assert float(np.abs(o - ref_smp[b, :want]).max()) <= 5e-5
+
+
 def test_seg_cluster_kernel_recipe_size_reference_fixture():
     """The recipe model (H=192, seg 5, lpc 4, k=7, L=6, R=690) on the seg cluster kernel against the unmodified reference's
     outputs (tests/golden_large, oracle/build_ref.py), and against the layer-group kernel on the same inputs."""
