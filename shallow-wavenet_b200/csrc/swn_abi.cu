@@ -485,8 +485,10 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
 
 
 // ---- seg > 1 cluster kernel (swn_coreseg.cuh), utterance b0 of the conditioned batch: 0 = launched, 2 = not applicable, 1 = error
+// ncl utterances (b0 .. b0+ncl-1) run side by side, one core cluster each, and share the helper CTAs; ncl_plan = the
+// largest ncl of this swn_generate call (it sizes the helper budget: max_cl - ncl_plan helper clusters).
 static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st, int Tf, int64_t n_iter, int b0, bool first,
-                            bool last) {
+                            bool last, int ncl, int ncl_plan) {
     const int H = m->H, Hp = m->Hp, K = m->K, L = m->L, S = m->S, seg = m->seg;
     swn::core_fns fn = {nullptr, nullptr};
     switch (m->NCH) {
@@ -495,7 +497,8 @@ static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st
         case 3: fn = swn::find_coreseg_kernel_nch3(seg); break;
     }
     if (!fn.launch) return 2;
-    const long long key = 1000 + seg;
+    if (ncl < 1 || ncl > ncl_plan || ncl_plan > swn::CORE_MAXCL) return 2;
+    const long long key = 1000 + seg + 100 * ncl_plan;
     if (key != m->core_plan_key) {
         CUDA_OK(cudaStreamSynchronize(st));
         const int smem_floats = SWN_MAX_SMEM / 4;
@@ -527,8 +530,8 @@ static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st
         CUDA_OK(fn.prepare(SWN_MAX_SMEM, &max_cl));
         int n_help_layers = 0, n_help_taps = 0;
         for (int l = 0; l < L; ++l) { n_help_layers += m->hl[l].ntaps > 0; n_help_taps += m->hl[l].ntaps; }
-        if (max_cl < 1 || (n_help_layers > 0 && max_cl < 2)) return 2;
-        const int n_help = n_help_layers ? (max_cl - 1) * swn::CORE_CL : 0;
+        if (max_cl < ncl_plan || (n_help_layers > 0 && max_cl < ncl_plan + 1)) return 2;
+        const int n_help = n_help_layers ? (max_cl - ncl_plan) * swn::CORE_CL : 0;
         if (n_help_layers && n_help < n_help_layers) return 2;
         // ---- helper CTAs: a share of the helper SMs per layer in proportion to its taps (at least one)
         std::vector<float>& V = m->wbuf2_h;
@@ -536,20 +539,46 @@ static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st
         auto alloc2 = [&](size_t n) { size_t off = (V.size() + 3) & ~size_t(3); V.resize(off + n, 0.f); return (int64_t)off; };
         std::vector<swn::HelpCta> hd;
         size_t help_used = 0;
-        int spare = n_help - n_help_layers;
+        // A helper CTA keeps, per gate pair it owns, the layer's helper taps (ntaps x 2 rows x Hp) and one ring of partial
+        // sums per core cluster (ring_len x 2): first the fewest CTAs per layer whose pairs fit the shared memory, then the
+        // spare CTAs one by one to the layer whose CTAs have the most work per step.
+        std::vector<int> GH(L, 0), rlen(L, 0);
+        {
+            int used_ctas = 0;
+            for (int l = 0; l < L; ++l) {
+                const auto& hl = m->hl[l];
+                if (!hl.ntaps) continue;
+                rlen[l] = hl.delay.back() + 2 * seg + 2;
+                const size_t per_pair = (size_t)hl.ntaps * 2 * Hp + (size_t)ncl_plan * rlen[l] * 2 + 8;
+                const size_t room = (size_t)smem_floats - (size_t)ncl_plan * seg * Hp - 16;
+                const int np_max = (int)std::min<size_t>(room / per_pair, (size_t)H);
+                if (np_max < 1) return 2;
+                GH[l] = (H + np_max - 1) / np_max;
+                used_ctas += GH[l];
+            }
+            if (used_ctas > n_help) return 2;
+            // (issue-bound mat-vecs, measured with the helper stamps of tools/gpu_prof_seghelp.py: a CTA's time per step goes
+            // with its pairs x (a fixed part - reductions, ring update - plus the taps' multiply-adds))
+            auto cost = [&](int l) { const int np = (H + GH[l] - 1) / GH[l]; return (long long)np * (250 + 130 * m->hl[l].ntaps); };
+            for (int spare = n_help - used_ctas; spare > 0; --spare) {
+                int best = -1;
+                for (int l = 0; l < L; ++l)
+                    if (GH[l] > 0 && GH[l] < H && (best < 0 || cost(l) > cost(best))) best = l;
+                if (best < 0) break;
+                GH[best]++;
+            }
+        }
         for (int l = 0; l < L; ++l) {
             const auto& hl = m->hl[l];
             if (!hl.ntaps) continue;
             const HostTensor* x = m->get("dil_h." + std::to_string(l) + ".conv.weight");
-            int GHe = 1 + (int)((long long)(n_help - n_help_layers) * hl.ntaps / n_help_taps);
-            GHe = std::min(GHe, 1 + spare); spare -= GHe - 1;
-            GHe = std::min(GHe, H);
+            const int GHe = GH[l];
             for (int g = 0; g < GHe; ++g) {
                 swn::HelpCta d;
                 memset(&d, 0, sizeof(d));
                 d.layer = l; d.dil = m->dil[l]; d.ntaps = hl.ntaps; d.dmin = hl.dmin;
                 split_range(H, GHe, g, &d.pair0, &d.npairs);
-                d.ring_len = 8; while (d.ring_len < hl.delay.back() + 2 * seg + 2) d.ring_len *= 2;      // power of two
+                d.ring_len = rlen[l];                              // (need not be a power of two: indexed modulo)
                 for (int j = 0; j < hl.ntaps; ++j) d.delay[j] = hl.delay[j];
                 const int np = d.npairs;
                 d.w_off = alloc2((size_t)hl.ntaps * np * 2 * Hp);
@@ -563,8 +592,8 @@ static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st
                 size_t u = 0;
                 auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
                 d.sm_w = take((size_t)hl.ntaps * np * 2 * Hp);
-                d.sm_h = take((size_t)seg * Hp);
-                d.sm_ring = take((size_t)d.ring_len * np * 2);
+                d.sm_h = take((size_t)ncl_plan * seg * Hp);
+                d.sm_ring = take((size_t)ncl_plan * d.ring_len * np * 2);        // one ring of partial sums per core cluster
                 d.ring_in_smem = 1;
                 if (u > (size_t)smem_floats) return 2;
                 help_used = std::max(help_used, u);
@@ -572,7 +601,7 @@ static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st
             }
         }
         const int n_help_used = (int)hd.size();
-        const int grid = swn::CORE_CL * (1 + (n_help_used + swn::CORE_CL - 1) / swn::CORE_CL);
+        const int grid = swn::CORE_CL * (ncl_plan + (n_help_used + swn::CORE_CL - 1) / swn::CORE_CL);
         if (grid / swn::CORE_CL > max_cl) return 2;
         m->core_smem = std::max(core_used, help_used) * 4;
         m->core_grid = grid; m->core_n_help = n_help_used; m->core_ring_total = 0;
@@ -595,7 +624,7 @@ static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st
             if (hl.ntaps) { n_hin += (size_t)P.hslots[l] * seg * H; n_hacc += (size_t)P.hacc_nt[l] * 2 * H; }
         }
         m->core_n_hin = n_hin; m->core_n_hacc = n_hacc;
-        if (m->ll2.ensure(n_hin + n_hacc + 8)) return 1;
+        if (m->ll2.ensure((size_t)ncl_plan * (n_hin + n_hacc) + 8)) return 1;
         m->core_plan_key = key;
     }
     swn::CoreParams P = m->core_tmpl;
@@ -607,8 +636,13 @@ static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st
     P.it0 = (m->R + 1 - P.t_first) / seg - 1;
     // one utterance per launch: it only runs for its own length (the reference generates every utterance to the longest,
     // cswnv_shift1.py:291-295, and truncates afterwards; the rows beyond an utterance's length are not written here)
+    // (utterances that share a launch run to the longer of their lengths)
     int64_t steps_b = n_iter;
-    if (a->n_samples_list) steps_b = std::max<int64_t>(1, std::min<int64_t>(n_iter, (a->n_samples_list[b0] + seg - 1) / seg));
+    if (a->n_samples_list) {
+        steps_b = 1;
+        for (int q = 0; q < ncl; ++q)
+            steps_b = std::max<int64_t>(steps_b, std::min<int64_t>(n_iter, (a->n_samples_list[b0 + q] + seg - 1) / seg));
+    }
     P.n_iter = (int)n_iter; P.n_it = P.it0 + (int)steps_b;
     P.n_core_taps = m->n_core_taps; P.n_help = m->core_n_help;
     {   // (field reused as a flag) per-step cluster barrier also outside the warm-up: some chain warp owns no out_1 row
@@ -618,28 +652,36 @@ static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st
     }
     P.n_out = n_iter * seg;
     P.cdesc = m->cdesc.p; P.hdesc = m->hdesc.p; P.wbuf = m->wbuf2.p;
-    P.P = m->ptab.p + (size_t)b0 * Tf * L * seg * 2 * H; P.pconst = m->pconst.p; P.gain = m->gain.p;
+    P.P = nullptr; P.pconst = m->pconst.p; P.gain = m->gain.p;
     P.in_tab = m->in_tab.p; P.in_bias = m->in_bias.p; P.xa_tab = nullptr;
-    P.hin_ll = m->ll2.p; P.hacc_ll = m->ll2.p + m->core_n_hin; P.ring_scratch = nullptr;
-    {
-        const size_t off = (size_t)b0 * (size_t)P.n_out;
-        P.b0 = b0;
-        P.noise = a->noise_dev ? a->noise_dev + off : nullptr;
-        P.forced = a->forced_dev ? (const char*)a->forced_dev + off * sizeof(float) : nullptr;
-        P.seedw = a->seed_dev ? (const char*)a->seed_dev + (size_t)b0 * seg * sizeof(float) : nullptr;
-        P.out = (char*)a->out_dev + off * sizeof(float);
-        P.head_out = a->head_dev ? a->head_dev + (size_t)b0 * (size_t)n_iter * m->n2 : nullptr;
+    P.hin_ll = nullptr; P.hacc_ll = nullptr; P.ring_scratch = nullptr;
+    P.n_cl = ncl; P.b0 = b0;
+    const size_t ll_per_cl = m->core_n_hin + m->core_n_hacc;
+    for (int q = 0; q < ncl; ++q) {
+        swn::CoreUtt& u = P.cl[q];
+        const int b = b0 + q;
+        const size_t off = (size_t)b * (size_t)P.n_out;
+        u.b0 = b;
+        u.P = m->ptab.p + (size_t)b * Tf * L * seg * 2 * H;
+        u.noise = a->noise_dev ? a->noise_dev + off : nullptr;
+        u.forced = a->forced_dev ? (const char*)a->forced_dev + off * sizeof(float) : nullptr;
+        u.seedw = a->seed_dev ? (const char*)a->seed_dev + (size_t)b * seg * sizeof(float) : nullptr;
+        u.out = (char*)a->out_dev + off * sizeof(float);
+        u.head_out = a->head_dev ? a->head_dev + (size_t)b * (size_t)n_iter * m->n2 : nullptr;
+        u.hin_ll = m->ll2.p + (size_t)q * ll_per_cl;
+        u.hacc_ll = u.hin_ll + m->core_n_hin;
     }
     P.seed = a->seed; P.status = m->status.p; P.timeout_cycles = 4000000000ULL;
     P.prof = (unsigned long long*)a->prof_dev; P.prof_start = a->prof_start; P.prof_count = a->prof_dev ? a->prof_count : 0;
-    CUDA_OK(cudaMemsetAsync(m->ll2.p, 0, (m->core_n_hin + m->core_n_hacc) * sizeof(unsigned long long), st));
+    CUDA_OK(cudaMemsetAsync(m->ll2.p, 0, (size_t)ncl * ll_per_cl * sizeof(unsigned long long), st));
     if (first) {
         CUDA_OK(cudaMemsetAsync(m->status.p, 0, 8 * sizeof(int32_t), st));
         CUDA_OK(cudaEventRecord(m->ev[2], st));
     }
     int max_cl_dummy_ = 0;
+    const int grid = m->core_grid - swn::CORE_CL * (ncl_plan - ncl);      // core clusters first, then the helpers
     cudaError_t e = fn.prepare(m->core_smem, &max_cl_dummy_);
-    if (e == cudaSuccess) e = fn.launch(P, m->core_grid, m->core_smem, st);
+    if (e == cudaSuccess) e = fn.launch(P, grid, m->core_smem, st);
     if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
         (void)cudaGetLastError();
         fail("cluster kernel not launched: %s (grid %d, %zu B smem)", cudaGetErrorString(e), m->core_grid, m->core_smem);
@@ -650,8 +692,8 @@ static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st
     m->gen_timed = true;
     m->info.kernel_launches++;
     m->info.smem_bytes = (int32_t)m->core_smem;
-    m->info.batch_tile = 1;
-    m->info.n_slots = first ? 1 : m->info.n_slots + 1;     // launches, one after the other
+    m->info.batch_tile = ncl_plan;                         // utterances side by side in one launch
+    m->info.n_slots = first ? ncl : m->info.n_slots + ncl; // utterances, over launches one after the other
     m->info.grid = m->core_grid;
     m->info.kernel_variant = 2;
     m->info.ctas_per_layer = swn::CORE_CL;
@@ -1508,13 +1550,29 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
         CUDA_OK(cudaStreamSynchronize(st));                 // not applicable after all: nothing was launched (rc == 2 comes first)
     }
     if (m->core_ok && seg > 1) {
-        // seg > 1: the cluster kernel takes one utterance per launch; small batches run as launches one after the other.
-        // Measured for the recipe model (H=192, seg 5; profiles/r02z_crossover_cswnv.txt): 354 k samples/s at any B against
-        // 148 / 193 / 262 / 349 k for the layer-group kernel at B = 1 / 2 / 3 / 4 and 341 k for the batch kernel at B = 4 (508 k
-        // at B = 6): up to four utterances it wins.
-        if (a->kernel_sel == 2 || (a->kernel_sel == 0 && a->batch_tile == 0 && B <= 4)) {
-            int rc = 0;
-            for (int b0 = 0; b0 < B && rc == 0; ++b0) rc = generate_coreseg(m, a, st, Tf, n_iter, b0, b0 == 0, b0 + 1 == B);
+        // seg > 1: one utterance per core cluster; up to three core clusters run side by side in one launch and share the helper
+        // CTAs (two: 80 helpers, three: 64 - the rings of partial sums of the long dilations are per utterance), larger batches
+        // as launches of balanced sizes one after the other.  Measured for the recipe model (H=192, seg 5, 0.33 s;
+        // profiles/r03_crossover_cswnv.txt): 8.0 / 8.0 / 9.1 ms for 1 / 2 / 3 utterances side by side (two on the three-cluster
+        // plan: 8.5 ms), against 33.4 ms for the batch kernel at any B <= 10: up to nine utterances the cluster kernel wins
+        // (B = 9: 27.3 ms), four run as 2 + 2 on the two-cluster plan.
+        static const int seg_ncl_env = getenv("SWN_SEG_NCL") ? atoi(getenv("SWN_SEG_NCL")) : 0;      // measurements: 1 = one utterance per launch
+        static const int seg_bmax_env = getenv("SWN_SEG_BMAX") ? atoi(getenv("SWN_SEG_BMAX")) : 0;
+        const int seg_bmax = seg_bmax_env > 0 ? seg_bmax_env : 9;
+        if (a->kernel_sel == 2 || (a->kernel_sel == 0 && a->batch_tile == 0 && B <= seg_bmax)) {
+            int ncl_plan = std::min(B, B == 4 ? 2 : (int)swn::CORE_MAXCL);
+            if (seg_ncl_env > 0) ncl_plan = std::min(B, std::min(seg_ncl_env, (int)swn::CORE_MAXCL));
+            int rc = 2;
+            for (; ncl_plan >= 1 && rc == 2; --ncl_plan) {
+                // the fewest launches, of balanced sizes (4 utterances: 2 + 2, not 3 + 1)
+                const int nl = (B + ncl_plan - 1) / ncl_plan, base = B / nl, extra = B % nl;
+                rc = 0;
+                for (int g = 0, b0 = 0; g < nl && rc == 0; ++g) {
+                    const int ncl = base + (g < extra ? 1 : 0);
+                    rc = generate_coreseg(m, a, st, Tf, n_iter, b0, g == 0, g + 1 == nl, ncl, ncl_plan);
+                    b0 += ncl;
+                }
+            }
             if (rc == 0) return 0;
             if (rc == 1) return 1;
             if (a->kernel_sel == 2) return fail("swn_generate: the cluster kernel is not applicable to this configuration");

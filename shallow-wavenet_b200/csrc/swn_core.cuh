@@ -52,6 +52,15 @@ struct HelpCta {                   // one per helper CTA
     int32_t delay[CORE_KMAX];
 };
 
+constexpr int CORE_MAXCL = 3;      // swn_coreseg.cuh: core clusters (utterances) of one launch that share the helper CTAs
+
+struct CoreUtt {                   // swn_coreseg.cuh: what differs between the core clusters of one launch
+    const float* P; const float* noise;
+    const void* forced; const void* seedw; void* out; float* head_out;
+    unsigned long long* hin_ll; unsigned long long* hacc_ll;
+    int32_t b0, pad;
+};
+
 struct CoreParams {
     int32_t kind, H, Hp, S, Sp, K, L, lpc, n1, n1p, n2, Q, U, R, B, Tf;
     int32_t it0, n_it, n_iter, n_core_taps, n_help, audio_in;
@@ -79,6 +88,8 @@ struct CoreParams {
     const void* forced; const void* seedw; void* out; float* head_out;
     int32_t* status; unsigned long long timeout_cycles;
     unsigned long long* prof; int32_t prof_start, prof_count;
+    int32_t n_cl, pad_cl;          // swn_coreseg.cuh: clusters 0 .. n_cl-1 are core clusters, one utterance each (cl[])
+    CoreUtt cl[CORE_MAXCL];
 };
 
 // ------------------------------------------------------------------ cluster / DSMEM / TMEM primitives

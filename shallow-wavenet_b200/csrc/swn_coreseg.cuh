@@ -58,6 +58,45 @@ __device__ __forceinline__ void tmem_ld_at(uint32_t a, float (&r)[M]) {
     for (int i = 0; i < N; i += 4) tmem_ld4(a + i, &r[O + i]);
 }
 
+// dot_frag with packed fp32 multiply-adds (fma.rn.f32x2: the same two accumulator chains as dot_frag, x and y parts, in half
+// the issue slots - the helper's mat-vecs are issue-bound).  Bit-identical to dot_frag.
+#ifndef SEG_HELP_FFMA2
+#define SEG_HELP_FFMA2 1
+#endif
+template <int NCH>
+__device__ __forceinline__ float dot_frag_packed(const float2 (&w)[NCH], const float2 (&h)[NCH]) {
+#if SEG_HELP_FFMA2
+    unsigned long long acc = 0ull;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        unsigned long long a, b;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(w[c].x), "f"(w[c].y));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(h[c].x), "f"(h[c].y));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+    }
+    float x, y;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(acc));
+    return x + y;
+#else
+    return dot_frag<NCH>(w, h);
+#endif
+}
+
+// Totals of v[slot] (32 slots) over the 32 lanes: afterwards lane i holds the total of slot i.  Five halving levels, 31 shuffles.
+__device__ __forceinline__ float reduce_slots32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const bool up = (lane & w) != 0;
+#pragma unroll
+        for (int k = 0; k < w; ++k) {
+            const float send = up ? v[k] : v[k + w];
+            const float keep = up ? v[k + w] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        }
+    }
+    return v[0];
+}
+
 // ------------------------------------------------------------------ helper CTA (time-granular targets)
 // Owns the taps of one layer with delay >= SEG.  The input column of relative time tau = it*SEG + c adds W_j . h into
 // the partial sum of time tau + delay_j; when the smallest delay has been applied the sum is complete and goes to the
@@ -73,58 +112,101 @@ __device__ void helper_cta_seg(const CoreParams& P, const HelpCta& D, float* sme
         float4* dst = reinterpret_cast<float4*>(sW);
         for (int i = tid; i < nt * np * 2 * HP / 4; i += SWN_NTHREADS) dst[i] = src[i];
     }
-    float* hb = smem + D.sm_h;                                 // [SEG][HP]
-    for (int i = tid; i < SEG * HP; i += SWN_NTHREADS) hb[i] = 0.f;
-    float* ring = smem + D.sm_ring;                            // [RL][np][2]
-    for (int i = tid; i < RL * np * 2; i += SWN_NTHREADS) ring[i] = 0.f;
+    float* hb_all = smem + D.sm_h;                             // [n_cl][SEG][HP]
+    for (int i = tid; i < P.n_cl * SEG * HP; i += SWN_NTHREADS) hb_all[i] = 0.f;
+    float* ring_all = smem + D.sm_ring;                        // [n_cl][RL][np][2]
+    for (int i = tid; i < P.n_cl * RL * np * 2; i += SWN_NTHREADS) ring_all[i] = 0.f;
     __syncthreads();
-    const unsigned long long* in_ll = P.hin_ll + P.hin_off[l];
-    unsigned long long* acc_ll = P.hacc_ll + P.hacc_off[l];
-    const int slot_mask = P.hslots[l] - 1, nt_mask = P.hacc_nt[l] - 1, rl_mask = RL - 1;   // all powers of two
+    const int slot_mask = P.hslots[l] - 1, nt_mask = P.hacc_nt[l] - 1;   // powers of two (RL need not be: the rings of the
+                                                                          // long dilations are what fills the helpers' shared memory)
     const int my_j = lane / SEG, my_c = lane - my_j * SEG;      // lane <-> (tap j, column c)
     const bool my_live = my_j < nt;
     const int my_delay = my_live ? D.delay[my_j] : 0;
+    constexpr int WPT = (SEG * HP + SWN_NTHREADS - 1) / SWN_NTHREADS;   // input words per thread and cluster
+    const int ncl = P.n_cl, n_words = SEG * H;
+    // The core clusters of the launch (one utterance each) share the weights and take turns; input rings, partial sums and
+    // hand-off rings are per cluster.  The input words of the NEXT turn are requested before this turn's mat-vecs (their L2
+    // round trip hides behind the arithmetic when the helper is the late one; a word that has not been written yet is polled
+    // as before).  Waiting for all clusters' inputs before computing any was measured slower (9.0 against 8.1 ms at two
+    // clusters): the clusters are not in lock step, and a cluster's sums must not wait for another cluster's inputs.
+    auto src_of = [&](int it_, int q_) { return P.cl[q_].hin_ll + P.hin_off[l] + (size_t)(it_ & slot_mask) * SEG * H; };
+    unsigned long long pre[WPT];
+    {
+        const unsigned long long* s0 = src_of(0, 0);
+#pragma unroll
+        for (int r = 0; r < WPT; ++r) {
+            const int i = tid + r * SWN_NTHREADS;
+            pre[r] = i < n_words ? ld_ll(s0 + i) : 0ull;
+        }
+    }
     for (int it = 0; it < P.n_it; ++it) {
         const uint32_t tag = (uint32_t)it + 1u;
+        for (int q = 0; q < ncl; ++q) {
+        const unsigned long long* src = src_of(it, q);
+        float* hbw = hb_all + (size_t)q * SEG * HP;
         bool ok = true;
-        {
-            const unsigned long long* src = in_ll + (size_t)(it & slot_mask) * SEG * H;
-            for (int i = tid; i < SEG * H; i += SWN_NTHREADS) {
-                unsigned long long v = ld_ll(src + i);
-                uint32_t bits = (uint32_t)v;
-                if ((uint32_t)(v >> 32) != tag) ok = wait_gword(src + i, tag, bits, P, 300 + l) && ok;
+#pragma unroll
+        for (int r = 0; r < WPT; ++r) {
+            const int i = tid + r * SWN_NTHREADS;
+            if (i < n_words) {
+                uint32_t bits = (uint32_t)pre[r];
+                if ((uint32_t)(pre[r] >> 32) != tag) ok = wait_gword(src + i, tag, bits, P, 300 + l) && ok;
                 const int c = i / H, k = i - c * H;
-                hb[c * HP + k] = __uint_as_float(bits);
+                hbw[c * HP + k] = __uint_as_float(bits);
             }
         }
         if (__syncthreads_or(!ok)) return;
+        SWN_TSTAMP(2 * q, tid == 0);                                // helper timeline: inputs of cluster q are in
+        {
+            int qn = q + 1, itn = it;
+            if (qn == ncl) { qn = 0; ++itn; }
+            if (itn < P.n_it) {
+                const unsigned long long* sn = src_of(itn, qn);
+#pragma unroll
+                for (int r = 0; r < WPT; ++r) {
+                    const int i = tid + r * SWN_NTHREADS;
+                    pre[r] = i < n_words ? ld_ll(sn + i) : 0ull;
+                }
+            }
+        }
+        unsigned long long* acc_ll = P.cl[q].hacc_ll + P.hacc_off[l];
+        float* ring = ring_all + (size_t)q * RL * np * 2;
+        const float* hb = hb_all + (size_t)q * SEG * HP;
         float2 h[SEG][NCH];
 #pragma unroll
         for (int c = 0; c < SEG; ++c) load_frag<NCH>(h[c], hb + c * HP, lane);
         for (int pi = warp; pi < np; pi += SWN_NWARPS) {
-            float mz = 0.f, mc = 0.f;
+            // the lane's partial dot products of every (tap j, column c), slot j*SEG + c, then ONE transposed reduction per
+            // row kind: 31 shuffles for up to 32 slots instead of five per slot (with three core clusters to serve, the
+            // shuffle unit was what bounded the helpers: 11.1 ms against 8.1 ms for one utterance)
+            float mzc[2];
 #pragma unroll
-            for (int j = 0; j < CORE_KMAX; ++j) {
-                if (j < nt) {
-                    const float* wr = sW + ((size_t)(j * np + pi) * 2) * HP;
-                    float2 wz[NCH], wc[NCH];
-                    load_frag<NCH>(wz, wr, lane);
-                    load_frag<NCH>(wc, wr + HP, lane);
+            for (int zc = 0; zc < 2; ++zc) {
+                float v[32];
 #pragma unroll
-                    for (int c = 0; c < SEG; ++c) {
-                        const float a = warp_sum(dot_frag<NCH>(wz, h[c])), b = warp_sum(dot_frag<NCH>(wc, h[c]));
-                        if (lane == j * SEG + c) { mz = a; mc = b; }
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+                for (int j = 0; j < CORE_KMAX; ++j) {
+                    if ((j + 1) * SEG <= 32 && j < nt) {
+                        float2 w[NCH];
+                        load_frag<NCH>(w, sW + ((size_t)(j * np + pi) * 2 + zc) * HP, lane);
+#pragma unroll
+                        for (int c = 0; c < SEG; ++c) v[(j * SEG + c) & 31] = dot_frag_packed<NCH>(w, h[c]);
                     }
                 }
+                mzc[zc] = reduce_slots32(v, lane);
             }
+            const float mz = mzc[0], mc = mzc[1];
             // ring update, one tap per round (within a round the SEG columns hit SEG different times); the smallest
             // delay comes last and finishes its target times
-            for (int j = nt - 1; j >= 0; --j) {
-                if (my_live && my_j == j) {
+            // (a dilation of at least SEG keeps all (tap, column) targets of a step distinct: one round)
+            const bool one_round = D.dil >= SEG;
+            for (int j = one_round ? 0 : nt - 1; j >= 0; --j) {
+                if (my_live && (one_round || my_j == j)) {
                     const int T = it * SEG + my_c + my_delay;
-                    float* r0 = ring + ((T & rl_mask) * np + pi) * 2;
+                    float* r0 = ring + ((T % RL) * np + pi) * 2;
                     const float a = r0[0] + mz, b = r0[1] + mc;
-                    if (j == 0) {
+                    if (my_j == 0) {
                         r0[0] = 0.f; r0[1] = 0.f;
                         unsigned long long* dst = acc_ll + (size_t)(T & nt_mask) * 2 * H;
                         st_ll(dst + D.pair0 + pi, a, (uint32_t)T + 1u);
@@ -135,6 +217,8 @@ __device__ void helper_cta_seg(const CoreParams& P, const HelpCta& D, float* sme
                 }
                 __syncwarp();
             }
+        }
+        SWN_TSTAMP(2 * q + 1, warp == SWN_NWARPS - 1 && lane == 0);  // ... the last warp has handed its sums over
         }
         __syncthreads();                                        // hb is rewritten by the next step's loads
     }
@@ -179,7 +263,8 @@ __device__ __forceinline__ void reduce_slots16(const float (&a)[16][2], int lane
 }
 
 template <int NCH, int SEG>
-__device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem) {
+__device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem, const int clid) {
+    const CoreUtt& U = P.cl[clid];                              // this cluster's utterance
     static_assert(NCH <= 3 && SEG <= 8, "chain warps 0 .. 4*NCH-1, service warps 12-15; 8 column slots in the reduction");
     constexpr int HP = NCH * 64, NPW = NCH, FPT = 2 * NCH, ROWS = 2 * NPW, TCOLS = ROWS * FPT;
     constexpr int WT = 2 * FPT;                                 // tensor-memory columns of one warp per tap: 2 rows x FPT weights
@@ -278,11 +363,11 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
         }
         tmem_wait_st();
     }
-    if (P.seedw) {
+    if (U.seedw) {
         // a_full = pad(R) ++ seed(SEG) ++ generated: the seed occupies generated-indices -SEG..-1; lp_x_buffer = last
         // lpc samples of the padded seed (cswnv_shift1.py:317-319)
         if (tid < SEG) {
-            const float v = ((const float*)P.seedw)[tid];
+            const float v = ((const float*)U.seedw)[tid];
             hist[(tid - SEG + HIST) & (HIST - 1)] = v;
             if (8 - SEG + tid >= 0) lpb[8 - SEG + tid] = v;            // newest last (slot 7); slots beyond lpc have zero coefficients
         }
@@ -319,7 +404,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
         r.nco = (int8_t)P.ncore[l]; r.dil = (int16_t)(P.dil[l] < 32767 ? P.dil[l] : 32767); r.tcol = (int16_t)(P.tap_base[l] * TCOLS);
         const bool hn_ = l + 1 < L && P.has_help[l + 1];
         r.hmask = hn_ ? P.hslots[l + 1] - 1 : -1;                  // -1: no helper behind this layer's output
-        r.hin = hn_ ? (unsigned long long)(P.hin_ll + P.hin_off[l + 1]) : 0ull;
+        r.hin = hn_ ? (unsigned long long)(U.hin_ll + P.hin_off[l + 1]) : 0ull;
         r.nco_next = (int8_t)P.ncore[(l + 1) % L]; r.tcol_next = (int16_t)(P.tap_base[(l + 1) % L] * TCOLS);     // (the last layer: layer 0 of the next step)
         r.fat = SEG_FAT && P.ncore[l] == 1 && NPW * SEG <= 16;
         r.nxa_fat = SEG_FAT && P.ncore[(l + 1) % L] == 1 && NPW * SEG <= 16;
@@ -366,11 +451,11 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
             float az = c4.x, ac = c4.y;
             int f = 0, j = 0;
             if (t >= P.R) { f = (t - P.R) / P.U; j = (t - P.R) - f * P.U; }
-            const float* pl = P.P + (size_t)l * SEG * twoH + row;
+            const float* pl = U.P + (size_t)l * SEG * twoH + row;
             float hz = 0.f, hc = 0.f;
             const int T = s_ * SEG + c;
             const bool hh = P.has_help[l] && T >= P.hdmin[l];
-            const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + (size_t)(T & (P.hacc_nt[l] - 1)) * twoH + row;
+            const unsigned long long* src = U.hacc_ll + P.hacc_off[l] + (size_t)(T & (P.hacc_nt[l] - 1)) * twoH + row;
             unsigned long long va = 0ull, vb = 0ull;
             if (hh) { va = ld_ll(src); vb = ld_ll(src + H); }
             int tau = t;
@@ -439,7 +524,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
             st_async_f32_if(lo16, base + (uint32_t)(cc * HP * 4), vc, mbp);
         }
         if (lane >= 16 && lane < 16 + SEG && P.has_help[0])
-            st_ll(P.hin_ll + P.hin_off[0] + ((size_t)(itn & (P.hslots[0] - 1)) * SEG + (lane - 16)) * H + in_row, v, (uint32_t)itn + 1u);
+            st_ll(U.hin_ll + P.hin_off[0] + ((size_t)(itn & (P.hslots[0] - 1)) * SEG + (lane - 16)) * H + in_row, v, (uint32_t)itn + 1u);
     };
 
     // ---- prologue: operands of the first two layers of step 0, inputs of block 0 (padding / seed)
@@ -681,7 +766,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
             // ======================= operand warps: noise, then gate operands - the late layers of this step, everything else of the next =======================
             if (active && warp == 15 && lane < SEG) {
                 const long long n = (long long)istep * SEG + lane;
-                const float e = P.noise ? __ldg(P.noise + n) : laplace_eps(P.seed, P.b0, n);
+                const float e = U.noise ? __ldg(U.noise + n) : laplace_eps(P.seed, U.b0, n);
                 const float sgn = (e > 0.f) ? 1.f : ((e < 0.f) ? -1.f : 0.f);
                 epsb[lane] = sgn * log1pf(-2.f * fabsf(e));
             }
@@ -826,7 +911,7 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                     // ass = a.flip(-1) times the buffer ordered oldest -> newest: a[0] multiplies the newest
                     aa[mm] = (7 - mm) < P.lpc ? o2[2 * SEG + (7 - mm)] : 0.f;
                 }
-                const float* forced = P.forced ? (const float*)P.forced + nbase : nullptr;
+                const float* forced = U.forced ? (const float*)U.forced + nbase : nullptr;
                 float smp[SEG];
 #pragma unroll
                 for (int j = 0; j < SEG; ++j) {
@@ -873,9 +958,9 @@ __device__ void core_cta_seg(const CoreParams& P, const CoreCta& D, float* smem)
                             float f = smp[0];
 #pragma unroll
                             for (int j = 1; j < SEG; ++j) f = lane == j ? smp[j] : f;
-                            ((float*)P.out)[nbase + lane] = f;
+                            ((float*)U.out)[nbase + lane] = f;
                         }
-                        if (P.head_out && lane < n2) P.head_out[(size_t)istep * n2 + lane] = o2[lane];
+                        if (U.head_out && lane < n2) U.head_out[(size_t)istep * n2 + lane] = o2[lane];
                     }
                 }
                 __syncwarp();
@@ -900,10 +985,11 @@ template <int NCH, int SEG>
 __global__ void __cluster_dims__(CORE_CL, 1, 1) __launch_bounds__(SWN_NTHREADS, 1)
 swn_coreseg_kernel(const __grid_constant__ CoreParams P) {
     extern __shared__ __align__(16) float smem[];
-    if (cluster_id_x() == 0) {
-        core_cta_seg<NCH, SEG>(P, P.cdesc[cluster_ctarank()], smem);
+    const int clid = (int)cluster_id_x();
+    if (clid < P.n_cl) {
+        core_cta_seg<NCH, SEG>(P, P.cdesc[cluster_ctarank()], smem, clid);
     } else {
-        const int hidx = (int)blockIdx.x - CORE_CL;
+        const int hidx = (int)blockIdx.x - CORE_CL * P.n_cl;
         if (hidx < P.n_help && P.hdesc[hidx].npairs > 0) helper_cta_seg<NCH, SEG>(P, P.hdesc[hidx], smem);
     }
 }

@@ -210,9 +210,9 @@ def test_recipe_size_cswnv_teacher_forced_vs_oracle(seg, lpc, B):
             lp = torch.cat((lp, ft[:, i * seg:(i + 1) * seg]), 1)[:, -lpc:]
     assert float(np.abs(np.stack(outs) - ref).max()) <= SAMPLE_ATOL
     if 2 <= seg <= 5 and B <= 4:
-        # the seg cluster kernel, one utterance per launch: the Philox draws of launch b use the global utterance index b
+        # the seg cluster kernel, one utterance per core cluster: the Philox draws of utterance b use its global index b
         info = model.engine().info
-        assert info["kernel_variant"] == 2 and info["batch_tile"] == 1 and info["n_slots"] == B, info
+        assert info["kernel_variant"] == 2 and 1 <= info["batch_tile"] <= B and info["n_slots"] == B, info
         from shallow_wavenet_b200.engine import philox_uniform
         eps = np.stack([np.float32(-0.4999) + np.float32(0.9999) * philox_uniform(9, "cswnv", b, 0, n_gen) for b in range(B)])
         a = np.stack(model.batch_fast_generate(torch.zeros(B, seg), torch.from_numpy(aux), [N] * B, seed=9))
