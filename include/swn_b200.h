@@ -79,14 +79,14 @@ typedef struct swn_gen_args {
     uint64_t* prof_dev;       /* optional instrumentation: [prof_count][grid][32] %globaltimer stamps */
     int32_t prof_start;       /* first loop iteration stamped */
     int32_t prof_count;
-    int32_t kernel_sel;       /* 0 = auto (B <= 4: cluster / layer-group kernel, B > 4: pipelined batch kernel),
+    int32_t kernel_sel;       /* 0 = auto (small batches: cluster / layer-group kernel, else the pipelined batch kernel; table in INTEGRATION.md),
                                  1 = force the layer-group kernel, 2 = force the cluster kernel,
                                  3 = force the batch kernel (tensor-core cells where they fit), 4 = batch kernel, FFMA cells */
     int32_t reserved;
     const int64_t* n_samples_list; /* optional HOST array [B]: samples wanted per utterance (the reference's
                                  n_samples_list, cswnv_shift1.py:291-295,426-428).  The batch kernel stops a pipeline
-                                 slot once all its utterances are complete, the seg cluster kernel (one utterance per
-                                 launch) runs each for its own length; rows of out_dev are only defined up to each
+                                 slot once all its utterances are complete, the seg cluster kernel runs the (up to three)
+                                 utterances that share a launch to the longest of them; rows of out_dev are only defined up to each
                                  utterance's own length (rounded up to seg).  NULL = n_samples for everyone. */
 } swn_gen_args;
 

@@ -498,11 +498,15 @@ def test_seg_cluster_kernel_matches_reference_fixture(name):
         assert float(np.abs(o - g["samples"][b, :len(o)]).max()) <= 5e-5
 
 
-@pytest.mark.parametrize("name,B", [("cswnv_seg5_lpc4_h64", 3), ("cswnv_seg2_lpc3", 4)])
-def test_seg_cluster_kernel_ragged_lengths_run_each_utterance_for_its_own_length(name, B):
-    """The seg cluster kernel launches one utterance at a time; with n_samples_list every launch runs only for its own
-    length (the reference runs all to the longest and truncates, cswnv_shift1.py:291-295,426-428): each utterance equals
-    the oracle's output truncated to its length, including lengths that are not multiples of seg and a 1-frame utterance."""
+@pytest.mark.parametrize("name,B,sel,side", [("cswnv_seg5_lpc4_h64", 3, 2, 3), ("cswnv_seg2_lpc3", 4, 2, 2),
+                                             ("cswnv_seg5_lpc4_h64", 7, 0, 3), ("cswnv_seg5_lpc4_wav", 9, 0, 3),
+                                             ("cswnv_seg5_lpc0_conv2d", 2, 0, 2), ("cswnv_seg2_lpc3", 5, 0, 3)])
+def test_seg_cluster_kernel_ragged_lengths_run_each_utterance_for_its_own_length(name, B, sel, side):
+    """The seg cluster kernel runs up to three utterances side by side (one core cluster each, shared helper CTAs), larger
+    batches - up to nine by default, e.g. the recipe's decode batch of 7 - as launches of balanced sizes; with n_samples_list
+    a launch runs for the longest of its utterances (the reference runs all to the longest of the batch and truncates,
+    cswnv_shift1.py:291-295,426-428): each utterance equals the oracle's output truncated to its length, including lengths
+    that are not multiples of seg and a 1-frame utterance."""
     g = load_golden(name)
     m = _model_from_golden(g)
     kw, cfg = g["kw"], g["cfg"]
@@ -517,8 +521,9 @@ def test_seg_cluster_kernel_ragged_lengths_run_each_utterance_for_its_own_length
     N = Tmax * U
     n_gen = (N // seg) * seg
     noise = rng.uniform(-0.4999, 0.5, (B, n_gen)).astype(np.float32)
-    outs = m.batch_fast_generate(_seed_audio(g["kind"], B, seg), torch.from_numpy(aux), lens, noise=noise, kernel_sel=2)
-    assert m.engine().info["kernel_variant"] == 2
+    outs = m.batch_fast_generate(_seed_audio(g["kind"], B, seg), torch.from_numpy(aux), lens, noise=noise, kernel_sel=sel)
+    info = m.engine().info
+    assert info["kernel_variant"] == 2 and info["batch_tile"] == side and info["n_slots"] == B, info
     ref_smp = O.generate(cfg, g["sd"], aux, N, noise)
     for b, o in enumerate(outs):
         want = min(lens[b], n_gen)
