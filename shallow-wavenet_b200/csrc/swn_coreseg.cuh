@@ -97,6 +97,25 @@ __device__ __forceinline__ float reduce_slots32(float (&v)[32], int lane) {
     return v[0];
 }
 
+#ifndef SEG_HELP_ZC_JOINT
+#define SEG_HELP_ZC_JOINT 1
+#endif
+// the same for two slot arrays at once (two independent chains per level)
+__device__ __forceinline__ void reduce_slots32x2(float (&a)[32], float (&b)[32], int lane, float& ra, float& rb) {
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const bool up = (lane & w) != 0;
+#pragma unroll
+        for (int k = 0; k < w; ++k) {
+            const float sa = up ? a[k] : a[k + w], ka = up ? a[k + w] : a[k];
+            const float sb = up ? b[k] : b[k + w], kb = up ? b[k + w] : b[k];
+            a[k] = ka + __shfl_xor_sync(0xffffffffu, sa, w);
+            b[k] = kb + __shfl_xor_sync(0xffffffffu, sb, w);
+        }
+    }
+    ra = a[0]; rb = b[0];
+}
+
 // ------------------------------------------------------------------ helper CTA (time-granular targets)
 // Owns the taps of one layer with delay >= SEG.  The input column of relative time tau = it*SEG + c adds W_j . h into
 // the partial sum of time tau + delay_j; when the smallest delay has been applied the sum is complete and goes to the
@@ -179,6 +198,27 @@ __device__ void helper_cta_seg(const CoreParams& P, const HelpCta& D, float* sme
             // the lane's partial dot products of every (tap j, column c), slot j*SEG + c, then ONE transposed reduction per
             // row kind: 31 shuffles for up to 32 slots instead of five per slot (with three core clusters to serve, the
             // shuffle unit was what bounded the helpers: 11.1 ms against 8.1 ms for one utterance)
+#if SEG_HELP_ZC_JOINT
+            // both row kinds at once: two independent reduction chains per level (a turn is latency-bound: 3-4 warps per scheduler)
+            float vz[32], vc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { vz[i] = 0.f; vc[i] = 0.f; }
+#pragma unroll
+            for (int j = 0; j < CORE_KMAX; ++j) {
+                if ((j + 1) * SEG <= 32 && j < nt) {
+                    float2 wz[NCH], wc[NCH];
+                    load_frag<NCH>(wz, sW + ((size_t)(j * np + pi) * 2) * HP, lane);
+                    load_frag<NCH>(wc, sW + ((size_t)(j * np + pi) * 2 + 1) * HP, lane);
+#pragma unroll
+                    for (int c = 0; c < SEG; ++c) {
+                        vz[(j * SEG + c) & 31] = dot_frag_packed<NCH>(wz, h[c]);
+                        vc[(j * SEG + c) & 31] = dot_frag_packed<NCH>(wc, h[c]);
+                    }
+                }
+            }
+            float mzc[2];
+            reduce_slots32x2(vz, vc, lane, mzc[0], mzc[1]);
+#else
             float mzc[2];
 #pragma unroll
             for (int zc = 0; zc < 2; ++zc) {
@@ -196,6 +236,7 @@ __device__ void helper_cta_seg(const CoreParams& P, const HelpCta& D, float* sme
                 }
                 mzc[zc] = reduce_slots32(v, lane);
             }
+#endif
             const float mz = mzc[0], mc = mzc[1];
             // ring update, one tap per round (within a round the SEG columns hit SEG different times); the smallest
             // delay comes last and finishes its target times
