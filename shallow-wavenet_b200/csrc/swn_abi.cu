@@ -1538,10 +1538,11 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
     // ---- small batches, one sample per step: the cluster kernel (v2); everything else: layer groups (v1)
     // 3-7 utterances of a one-sample-per-step model: two at a time through the cluster kernel, one launch after the
     // other (measured, DSWNV H=256: 145 k samples/s against 69-92 k for the layer-group kernel at B=3-4 and 111 k for
-    // the batch kernel at B=6; from 8 utterances on the batch kernel wins).  CSWNV seg=1 only where the alternative
-    // is the layer-group kernel (B <= 4): its batch kernel runs on the tensor cores.
+    // the batch kernel at B=6; from 8 utterances on the batch kernel wins).  CSWNV seg=1 (the recipe's default model,
+    // H=192; tools/gpu_seg1_probe.py, 0.2 s): 24.8 ms per launch of two against 161-165 ms for the batch kernel at any
+    // B <= 12 (its ring is latency-bound: 56 us per sample step) - up to 12 utterances the launches of two win.
     if (m->core_ok && seg == 1 && a->kernel_sel == 0 && a->batch_tile == 0 && !a->prof_dev && B >= 3 &&
-        B <= (m->cfg.kind == SWN_KIND_DSWNV ? 7 : 4)) {
+        B <= (m->cfg.kind == SWN_KIND_DSWNV ? 7 : 12)) {
         int rc = 0;
         for (int b0 = 0; b0 < B && rc == 0; b0 += 2)
             rc = generate_core(m, a, st, std::min(2, B - b0), Tf, n_iter, b0, b0 == 0, b0 + 2 >= B, 2);
