@@ -306,6 +306,9 @@ __device__ void helper_cta(const CoreParams& P, const HelpCta& D, float* smem) {
                 }
         }
         if (__syncthreads_or(!ok)) return;
+#if SWN_DBG_HELP_SLEEP_NS
+        __nanosleep(SWN_DBG_HELP_SLEEP_NS);                        // (robustness experiments: a late helper)
+#endif
         float2 h[NC][NCH];
 #pragma unroll
         for (int c = 0; c < NC; ++c) load_frag<NCH>(h[c], hbuf + c * HP, lane);
