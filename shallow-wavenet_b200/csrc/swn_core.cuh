@@ -306,8 +306,11 @@ __device__ void helper_cta(const CoreParams& P, const HelpCta& D, float* smem) {
                 }
         }
         if (__syncthreads_or(!ok)) return;
+#ifndef SWN_DBG_HELP_SLEEP_LAYER
+#define SWN_DBG_HELP_SLEEP_LAYER -1
+#endif
 #if SWN_DBG_HELP_SLEEP_NS
-        __nanosleep(SWN_DBG_HELP_SLEEP_NS);                        // (robustness experiments: a late helper)
+        if (SWN_DBG_HELP_SLEEP_LAYER < 0 || SWN_DBG_HELP_SLEEP_LAYER == l) __nanosleep(SWN_DBG_HELP_SLEEP_NS);                        // (robustness experiments: a late helper)
 #endif
         float2 h[NC][NCH];
 #pragma unroll

@@ -579,6 +579,11 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                     }
                 }
                 gop_commit(l, it + 1, gq_next, prz, prc, ha, hb, rz1, rc1);
+                // Reconverge before the next layer.  Only the operand lanes wait for a late helper in gop_commit; without this
+                // the other lanes of the warp ran on into the next dilation-1 layer's tcgen05.ld (.sync.aligned) and its
+                // full-mask shuffles with a partial warp, and the delay-1 sums of that layer came out wrong - silently, and
+                // only when a helper was late (profiles/r03_core2_late_helper_repro.txt).
+                __syncwarp();
             }
         } else {
             // ======================= skip warps: two rows of every out_skip; the head's first vector =======================

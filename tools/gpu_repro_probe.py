@@ -20,5 +20,13 @@ for rep in range(4):
 d = [float(np.abs(r - res[0]).max()) for r in res[1:]]
 first = [int(np.nonzero(np.abs(r - res[0]).reshape(B, n, -1).max(-1).max(0) > 0)[0][:1].sum()) for r in res[1:]]
 last = [int(np.nonzero(np.abs(r - res[0]).reshape(B, n, -1).max(-1).max(0) > 0)[0][-1:].sum()) for r in res[1:]]
+ref_path = os.environ.get("SWN_PROBE_REF")
+if ref_path and os.path.exists(ref_path):
+    ref = np.load(ref_path)
+    dd = np.abs(res[0] - ref).reshape(B, n, -1).max(-1).max(0)
+    nz = np.nonzero(dd > 0)[0]
+    print("   against %s: max %.3e, differing steps %d (first %s, last %s)" % (ref_path, dd.max(), len(nz), nz[:1], nz[-1:]))
+elif ref_path:
+    np.save(ref_path, res[0])
 print("%s: %.2f ms, max head diff vs run 0: %s, first/last differing step: %s %s" % (
     os.path.basename(os.environ.get("SWN_B200_LIB", "default")), eng.info["last_gen_ms"], d, first, last))
