@@ -82,7 +82,9 @@ typedef struct swn_gen_args {
     int32_t kernel_sel;       /* 0 = auto (small batches: cluster / layer-group kernel, else the pipelined batch kernel; table in INTEGRATION.md),
                                  1 = force the layer-group kernel, 2 = force the cluster kernel,
                                  3 = force the batch kernel (tensor-core cells where they fit), 4 = batch kernel, FFMA cells */
-    int32_t reserved;
+    int32_t debug_helper_delay_ns; /* test hook, 0 in production: every helper CTA of the cluster kernels sleeps this long per
+                                 turn, so that the core has to wait for the helper sums (tests/test_gpu_parity.py holds the
+                                 kernel to bit-identical output under such delays) */
     const int64_t* n_samples_list; /* optional HOST array [B]: samples wanted per utterance (the reference's
                                  n_samples_list, cswnv_shift1.py:291-295,426-428).  The batch kernel stops a pipeline
                                  slot once all its utterances are complete, the seg cluster kernel runs the (up to three)

@@ -34,7 +34,7 @@ class SwnGenArgs(ctypes.Structure):
                 ("forced_dev", ctypes.c_void_p), ("out_dev", ctypes.c_void_p), ("head_dev", ctypes.c_void_p),
                 ("seed_dev", ctypes.c_void_p), ("batch_tile", ctypes.c_int32), ("poll_mode", ctypes.c_int32),
                 ("prof_dev", ctypes.c_void_p), ("prof_start", ctypes.c_int32), ("prof_count", ctypes.c_int32),
-                ("kernel_sel", ctypes.c_int32), ("reserved", ctypes.c_int32), ("n_samples_list", ctypes.c_void_p)]
+                ("kernel_sel", ctypes.c_int32), ("debug_helper_delay_ns", ctypes.c_int32), ("n_samples_list", ctypes.c_void_p)]
 
 
 class SwnFwdArgs(ctypes.Structure):

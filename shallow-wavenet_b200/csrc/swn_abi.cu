@@ -454,6 +454,7 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
         P.head_out = a->head_dev ? a->head_dev + off * m->n2 : nullptr;
     }
     P.seed = a->seed; P.status = m->status.p; P.timeout_cycles = 4000000000ULL;
+    P.help_delay_ns = a->debug_helper_delay_ns > 0 ? a->debug_helper_delay_ns : 0;
     P.prof = (unsigned long long*)a->prof_dev; P.prof_start = a->prof_start; P.prof_count = a->prof_dev ? a->prof_count : 0;
     CUDA_OK(cudaMemsetAsync(m->ll2.p, 0, (m->core_n_hin + m->core_n_hacc) * sizeof(unsigned long long), st));
     if (m->core_ring_total) CUDA_OK(cudaMemsetAsync(m->ring2.p, 0, m->core_ring_total * sizeof(float), st));
@@ -672,6 +673,7 @@ static int generate_coreseg(swn_model* m, const swn_gen_args* a, cudaStream_t st
         u.hacc_ll = u.hin_ll + m->core_n_hin;
     }
     P.seed = a->seed; P.status = m->status.p; P.timeout_cycles = 4000000000ULL;
+    P.help_delay_ns = a->debug_helper_delay_ns > 0 ? a->debug_helper_delay_ns : 0;
     P.prof = (unsigned long long*)a->prof_dev; P.prof_start = a->prof_start; P.prof_count = a->prof_dev ? a->prof_count : 0;
     CUDA_OK(cudaMemsetAsync(m->ll2.p, 0, (size_t)ncl * ll_per_cl * sizeof(unsigned long long), st));
     if (first) {

@@ -64,7 +64,8 @@ struct CoreUtt {                   // swn_coreseg.cuh: what differs between the 
 struct CoreParams {
     int32_t kind, H, Hp, S, Sp, K, L, lpc, n1, n1p, n2, Q, U, R, B, Tf;
     int32_t it0, n_it, n_iter, n_core_taps, n_help, audio_in;
-    int32_t b0, pad_b0;            // index of this launch's first utterance in the caller's batch (Philox counter)
+    int32_t b0, help_delay_ns;     // index of this launch's first utterance in the caller's batch (Philox counter); test hook:
+                                   // nanoseconds every helper CTA sleeps per turn (swn_gen_args::debug_helper_delay_ns)
     int64_t n_out;
     int32_t dil[16];
     int32_t tap_base[16];          // first core tap index of layer l (tap 0 = delay 0, tap 1 = delay 1)
@@ -306,12 +307,7 @@ __device__ void helper_cta(const CoreParams& P, const HelpCta& D, float* smem) {
                 }
         }
         if (__syncthreads_or(!ok)) return;
-#ifndef SWN_DBG_HELP_SLEEP_LAYER
-#define SWN_DBG_HELP_SLEEP_LAYER -1
-#endif
-#if SWN_DBG_HELP_SLEEP_NS
-        if (SWN_DBG_HELP_SLEEP_LAYER < 0 || SWN_DBG_HELP_SLEEP_LAYER == l) __nanosleep(SWN_DBG_HELP_SLEEP_NS);                        // (robustness experiments: a late helper)
-#endif
+        if (P.help_delay_ns > 0) __nanosleep((unsigned)P.help_delay_ns);   // test hook: a late helper (the core must wait for its sums)
         float2 h[NC][NCH];
 #pragma unroll
         for (int c = 0; c < NC; ++c) load_frag<NCH>(h[c], hbuf + c * HP, lane);

@@ -176,6 +176,7 @@ __device__ void helper_cta_seg(const CoreParams& P, const HelpCta& D, float* sme
         }
         if (__syncthreads_or(!ok)) return;
         SWN_TSTAMP(2 * q, tid == 0);                                // helper timeline: inputs of cluster q are in
+        if (P.help_delay_ns > 0) __nanosleep((unsigned)P.help_delay_ns);   // test hook: a late helper
         {
             int qn = q + 1, itn = it;
             if (qn == ncl) { qn = 0; ++itn; }

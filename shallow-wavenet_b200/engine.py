@@ -52,7 +52,8 @@ class Engine(object):
         self._B = B
 
     def generate(self, n_samples, seed=0, noise=None, forced=None, seed_audio=None, return_heads=False,
-                 batch_tile=0, sync=True, poll_mode=0, prof=None, prof_start=0, kernel_sel=0, n_samples_list=None):
+                 batch_tile=0, sync=True, poll_mode=0, prof=None, prof_start=0, kernel_sel=0, n_samples_list=None,
+                 helper_delay_ns=0):
         info = self.info
         seg, hd = info["eff_seg"], info["head_dim"]
         B = self._B
@@ -78,6 +79,7 @@ class Engine(object):
         a.out_dev = out.data_ptr()
         a.head_dev = heads.data_ptr() if heads is not None else None
         a.batch_tile = int(batch_tile)
+        a.debug_helper_delay_ns = int(helper_delay_ns)      # test hook (cluster kernels): late helper CTAs
         a.poll_mode = int(poll_mode)
         a.kernel_sel = int(kernel_sel) or int(os.environ.get("SWN_KERNEL_SEL", "0"))   # debugging aid
         if n_samples_list is not None:

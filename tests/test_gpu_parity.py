@@ -552,6 +552,35 @@ def test_seg_cluster_kernel_recipe_size_reference_fixture():
         assert float(np.abs(o - g["samples"][b, :len(o)]).max()) <= 5e-5
 
 
+@pytest.mark.parametrize("kind,over,B", [("cswnv", dict(seg=1, lpc=4), 1), ("cswnv", dict(seg=1, lpc=4), 2), ("dswnv", dict(), 1),
+                                         ("cswnv", dict(seg=5, lpc=4), 3)])
+def test_cluster_kernels_with_late_helper_ctas_are_bit_identical(kind, over, B):
+    """The helper CTAs of the cluster kernels normally finish a turn long before the core needs their sums, so the core's
+    wait-for-a-late-helper path is almost never taken.  With every helper turn delayed (swn_gen_args::debug_helper_delay_ns)
+    it is taken at every step: the per-step heads must not change by a bit.  (Before the reconvergence after the operand
+    commit of swn_core2.cuh they were wrong by up to 0.7 at 20 us and irreproducible at 8 us.)"""
+    from shallow_wavenet_b200 import synth
+    kw = synth.cswnv_kwargs(22050) if kind == "cswnv" else synth.dswnv_kwargs(16000)
+    kw.update(over)
+    model = synth.make_model(kind, **kw).cuda()
+    eng = model.engine()
+    frames = 3
+    n = frames * kw["upsampling_factor"]
+    aux = torch.from_numpy(synth.synth_aux(kw["n_aux"], frames, B)).cuda()
+    rng = np.random.default_rng(B)
+    forced = (0.3 * rng.standard_normal((B, n))).astype(np.float32) if kind == "cswnv" else rng.integers(0, 256, (B, n))
+    ref = None
+    for delay in (0, 8000, 20000):
+        eng.condition(aux)
+        out, heads = eng.generate(n, seed=7, kernel_sel=2, forced=forced, return_heads=True, helper_delay_ns=delay)
+        assert eng.info["kernel_variant"] == 2
+        h = heads.cpu().numpy()
+        if ref is None:
+            ref = h
+        else:
+            assert np.array_equal(h, ref), "helper delay %d ns: max |diff| %.3e" % (delay, float(np.abs(h - ref).max()))
+
+
 def test_cluster_kernel_is_used_for_the_headline_workload():
     model, cfg, sd, aux, kw = _recipe_case("dswnv", 16000, 1, 2, 3)
     N = 2 * kw["upsampling_factor"]
