@@ -117,6 +117,7 @@ struct swn_model {
     DevBuf<swn::HelpCta> hdesc;
     DevBuf<unsigned long long> ll2;
     long long core_plan_key = -1;
+    int core_multi_ok = -1;            // side-by-side core clusters of the one-sample-per-step kernel: -1 untried, 0 do not fit, 1 ok
     int core_grid = 0, core_n_help = 0;
     size_t core_smem = 0, core_ring_total = 0;
     swn::CoreParams core_tmpl;
@@ -281,26 +282,33 @@ static int pack_v1(swn_model* m, int geff) {
     return 0;
 }
 
-static cudaError_t m_core_launch_dispatch(swn_model* m, int BS, const swn::CoreParams& P, cudaStream_t st) {
-    swn::core_fns fn = {nullptr, nullptr};
-    switch (m->NCH) {
-        case 1: fn = swn::find_core_kernel_nch1(BS); break;
-        case 2: fn = swn::find_core_kernel_nch2(BS); break;
-        case 3: fn = swn::find_core_kernel_nch3(BS); break;
-        case 4: fn = swn::find_core_kernel_nch4(BS); break;
+static swn::core_fns find_core_fns(int nch, int BS, bool multi) {
+    switch (nch) {
+        case 1: return swn::find_core_kernel_nch1(BS, multi);
+        case 2: return swn::find_core_kernel_nch2(BS, multi);
+        case 3: return swn::find_core_kernel_nch3(BS, multi);
+        case 4: return swn::find_core_kernel_nch4(BS, multi);
     }
+    return swn::core_fns{nullptr, nullptr};
+}
+
+static cudaError_t m_core_launch_dispatch(swn_model* m, int BS, bool multi, int grid, const swn::CoreParams& P, cudaStream_t st) {
+    swn::core_fns fn = find_core_fns(m->NCH, BS, multi);
     if (!fn.launch) return cudaErrorInvalidValue;
     int dummy = 0;
     cudaError_t e = fn.prepare(m->core_smem, &dummy);
     if (e != cudaSuccess) return e;
-    return fn.launch(P, m->core_grid, m->core_smem, st);
+    return fn.launch(P, grid, m->core_smem, st);
 }
 
 // ---- v2 launch: returns 0 = launched, 2 = not applicable (caller falls back to v1), 1 = error
 // b0 / first / last: this launch handles utterances b0 .. b0+B-1 of the conditioned batch (swn_generate cuts batches of
 // 3-7 utterances into launches of two, see there); pointers are offset here, the Philox counter in the kernel.
+// ncl_plan > 1 (swn_core_kernel2<.., MULTI>): up to ncl_plan core clusters side by side, each with up to BS utterances of its
+// own, sharing the helper CTAs (max_cl - ncl_plan helper clusters; per-cluster hand-off rings and partial sums); this launch
+// uses ceil(B / BS) of them.
 static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, int B, int Tf, int64_t n_iter,
-                         int b0 = 0, bool first = true, bool last = true, int force_bs = 0) {
+                         int b0 = 0, bool first = true, bool last = true, int force_bs = 0, int ncl_plan = 1) {
     const int H = m->H, Hp = m->Hp, K = m->K, L = m->L, S = m->S, Q = m->Q;
     const bool is_c = m->cfg.kind == SWN_KIND_CSWNV;
     if (m->seg != 1) return 2;                           // (seg > 1: generate_coreseg)
@@ -309,18 +317,15 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
     if (a->batch_tile > 0) BS = a->batch_tile;
     if (force_bs > 0) BS = force_bs;                     // (an odd last launch keeps the plan of the others)
     if (BS != 1 && BS != 2 && BS != 4) return 2;
-    if (B > BS) return 2;
+    const bool multi = ncl_plan > 1;
+    const int ncl = multi ? (B + BS - 1) / BS : 1;         // core clusters of this launch
+    if (ncl_plan < 1 || ncl_plan > swn::CORE_MAXCL || ncl > ncl_plan) return 2;
+    if (B > BS * ncl) return 2;
     if ((K - 1) * BS > 32) return 2;
     const int NC = BS;
-    swn::core_fns fn = {nullptr, nullptr};
-    switch (m->NCH) {
-        case 1: fn = swn::find_core_kernel_nch1(BS); break;
-        case 2: fn = swn::find_core_kernel_nch2(BS); break;
-        case 3: fn = swn::find_core_kernel_nch3(BS); break;
-        case 4: fn = swn::find_core_kernel_nch4(BS); break;
-    }
+    swn::core_fns fn = find_core_fns(m->NCH, BS, multi);
     if (!fn.launch) return 2;
-    const long long key = BS;
+    const long long key = BS + 10 * (ncl_plan - 1);
     if (key != m->core_plan_key) {
         CUDA_OK(cudaStreamSynchronize(st));
         const int smem_floats = SWN_MAX_SMEM / 4;
@@ -361,10 +366,42 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
         CUDA_OK(fn.prepare(SWN_MAX_SMEM, &max_cl));
         int n_help_layers = 0;
         for (int l = 0; l < L; ++l) n_help_layers += m->hl[l].ntaps > 0;
-        if (max_cl < 1 || (n_help_layers > 0 && max_cl < 2)) return 2;
-        const int n_help = n_help_layers ? (max_cl - 1) * swn::CORE_CL : 0;
+        if (max_cl < ncl_plan || (n_help_layers > 0 && max_cl < ncl_plan + 1)) return 2;
+        const int n_help = n_help_layers ? (max_cl - ncl_plan) * swn::CORE_CL : 0;
         const int GH = n_help_layers ? n_help / n_help_layers : 0;
         if (n_help_layers && GH < 1) return 2;
+        // MULTI: CTAs per layer by shared-memory need first (weights + ncl_plan rings of exact length per pair), then the spare
+        // ones to the layer with the most pairs x taps per CTA (as generate_coreseg)
+        std::vector<int> GHl(L, GH), rlen(L, 0);
+        for (int l = 0; l < L; ++l) {
+            const auto& hl = m->hl[l];
+            if (!hl.ntaps) { GHl[l] = 0; continue; }
+            rlen[l] = 4; while (rlen[l] < hl.delay.back() + 2) rlen[l] *= 2;       // power of two
+            GHl[l] = std::min(GH, H);
+        }
+        if (multi) {
+            int used_ctas = 0;
+            for (int l = 0; l < L; ++l) {
+                const auto& hl = m->hl[l];
+                if (!hl.ntaps) continue;
+                rlen[l] = hl.delay.back() + 2;
+                const size_t per_pair = (size_t)hl.ntaps * 2 * Hp + (size_t)ncl_plan * rlen[l] * 2 * BS + 8;
+                const size_t room = (size_t)smem_floats - (size_t)ncl_plan * 2 * NC * Hp - 16;
+                const int np_max = (int)std::min<size_t>(room / per_pair, (size_t)H);
+                if (np_max < 1) return 2;
+                GHl[l] = (H + np_max - 1) / np_max;
+                used_ctas += GHl[l];
+            }
+            if (used_ctas > n_help) return 2;
+            auto cost = [&](int l) { const int np = (H + GHl[l] - 1) / GHl[l]; return (long long)np * (2 + m->hl[l].ntaps); };
+            for (int spare = n_help - used_ctas; spare > 0; --spare) {
+                int best = -1;
+                for (int l = 0; l < L; ++l)
+                    if (GHl[l] > 0 && GHl[l] < H && (best < 0 || cost(l) > cost(best))) best = l;
+                if (best < 0) break;
+                GHl[best]++;
+            }
+        }
         // ---- helper CTAs: pack their taps, place their rings
         std::vector<float>& V = m->wbuf2_h;
         V.resize(m->wbuf2_core_floats);
@@ -376,13 +413,13 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
             const auto& hl = m->hl[l];
             if (!hl.ntaps) continue;
             const HostTensor* x = m->get("dil_h." + std::to_string(l) + ".conv.weight");
-            const int GHe = std::min(GH, H);
+            const int GHe = GHl[l];
             for (int g = 0; g < GHe; ++g) {
                 swn::HelpCta d;
                 memset(&d, 0, sizeof(d));
                 d.layer = l; d.dil = m->dil[l]; d.ntaps = hl.ntaps; d.dmin = hl.dmin;
                 split_range(H, GHe, g, &d.pair0, &d.npairs);
-                d.ring_len = 4; while (d.ring_len < hl.delay.back() + 2) d.ring_len *= 2;      // power of two
+                d.ring_len = rlen[l];                              // power of two (indexed by mask) unless MULTI (modulo)
                 for (int j = 0; j < hl.ntaps; ++j) d.delay[j] = hl.delay[j];
                 const int np = d.npairs;
                 d.w_off = alloc2((size_t)hl.ntaps * np * 2 * Hp);
@@ -396,8 +433,8 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
                 size_t u = 0;
                 auto take = [&](size_t n) { size_t o = u; u += (n + 3) & ~size_t(3); return (int32_t)o; };
                 d.sm_w = take((size_t)hl.ntaps * np * 2 * Hp);
-                d.sm_h = take((size_t)2 * NC * Hp);
-                const size_t ring_f = (size_t)d.ring_len * np * 2 * BS;
+                d.sm_h = take((size_t)ncl_plan * 2 * NC * Hp);
+                const size_t ring_f = (size_t)ncl_plan * d.ring_len * np * 2 * BS;      // one ring per core cluster
                 d.sm_ring = (int32_t)u;
                 d.ring_in_smem = (u + ring_f <= (size_t)smem_floats);
                 if (d.ring_in_smem) u += (ring_f + 3) & ~size_t(3);
@@ -409,7 +446,7 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
         }
         (void)twoH;
         const int n_help_used = (int)hd.size();
-        const int grid = swn::CORE_CL * (1 + (n_help_used + swn::CORE_CL - 1) / swn::CORE_CL);
+        const int grid = swn::CORE_CL * (ncl_plan + (n_help_used + swn::CORE_CL - 1) / swn::CORE_CL);
         if (grid / swn::CORE_CL > max_cl) return 2;
         m->core_smem = std::max(core_used, help_used) * 4;
         m->core_grid = grid; m->core_n_help = n_help_used; m->core_ring_total = ring_total;
@@ -431,7 +468,7 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
             if (hl.ntaps) { n_hin += (size_t)P.hslots[l] * NC * H; n_hacc += (size_t)P.hacc_nt[l] * 2 * H * NC; }
         }
         m->core_n_hin = n_hin; m->core_n_hacc = n_hacc;
-        if (m->ll2.ensure(n_hin + n_hacc + 8) || m->ring2.ensure(std::max<size_t>(ring_total, 4))) return 1;
+        if (m->ll2.ensure((size_t)ncl_plan * (n_hin + n_hacc) + 8) || m->ring2.ensure(std::max<size_t>(ring_total, 4))) return 1;
         m->core_plan_key = key;
     }
     swn::CoreParams P = m->core_tmpl;
@@ -444,25 +481,35 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
     P.P = m->ptab.p + (size_t)b0 * Tf * L * 2 * H; P.pconst = m->pconst.p; P.gain = m->gain.p;
     P.in_tab = m->in_tab.p; P.in_bias = m->in_bias.p; P.xa_tab = nullptr;
     P.hin_ll = m->ll2.p; P.hacc_ll = m->ll2.p + m->core_n_hin; P.ring_scratch = m->ring2.p;
-    {
-        const size_t esz = is_c ? sizeof(float) : sizeof(long long), off = (size_t)b0 * (size_t)n_iter;
-        P.b0 = b0;
-        P.noise = a->noise_dev ? a->noise_dev + off * (is_c ? 1 : Q) : nullptr;
-        P.forced = a->forced_dev ? (const char*)a->forced_dev + off * esz : nullptr;
-        P.seedw = a->seed_dev ? (const char*)a->seed_dev + (size_t)b0 * esz : nullptr;
-        P.out = (char*)a->out_dev + off * esz;
-        P.head_out = a->head_dev ? a->head_dev + off * m->n2 : nullptr;
+    const size_t ll_per_cl = m->core_n_hin + m->core_n_hacc;
+    P.n_cl = ncl;
+    for (int q = 0; q < ncl; ++q) {
+        // cluster q: utterances b0 + q*BS .. (at most BS of them); q = 0 is also what the single-cluster kernel reads
+        const int bq = b0 + q * BS;
+        const size_t esz = is_c ? sizeof(float) : sizeof(long long), off = (size_t)bq * (size_t)n_iter;
+        swn::CoreUtt& u = P.cl[q];
+        u.b0 = bq; u.nb = std::min(BS, b0 + B - bq);
+        u.P = m->ptab.p + (size_t)bq * Tf * L * 2 * H;
+        u.noise = a->noise_dev ? a->noise_dev + off * (is_c ? 1 : Q) : nullptr;
+        u.forced = a->forced_dev ? (const char*)a->forced_dev + off * esz : nullptr;
+        u.seedw = a->seed_dev ? (const char*)a->seed_dev + (size_t)bq * esz : nullptr;
+        u.out = (char*)a->out_dev + off * esz;
+        u.head_out = a->head_dev ? a->head_dev + off * m->n2 : nullptr;
+        u.hin_ll = m->ll2.p + (size_t)q * ll_per_cl;
+        u.hacc_ll = u.hin_ll + m->core_n_hin;
     }
+    P.b0 = P.cl[0].b0; P.B = multi ? BS : B;
+    P.noise = P.cl[0].noise; P.forced = P.cl[0].forced; P.seedw = P.cl[0].seedw; P.out = P.cl[0].out; P.head_out = P.cl[0].head_out;
     P.seed = a->seed; P.status = m->status.p; P.timeout_cycles = 4000000000ULL;
     P.help_delay_ns = a->debug_helper_delay_ns > 0 ? a->debug_helper_delay_ns : 0;
     P.prof = (unsigned long long*)a->prof_dev; P.prof_start = a->prof_start; P.prof_count = a->prof_dev ? a->prof_count : 0;
-    CUDA_OK(cudaMemsetAsync(m->ll2.p, 0, (m->core_n_hin + m->core_n_hacc) * sizeof(unsigned long long), st));
+    CUDA_OK(cudaMemsetAsync(m->ll2.p, 0, (size_t)ncl * ll_per_cl * sizeof(unsigned long long), st));
     if (m->core_ring_total) CUDA_OK(cudaMemsetAsync(m->ring2.p, 0, m->core_ring_total * sizeof(float), st));
     if (first) {        // a failed launch leaves its status for swn_sync; the launches after it see it and stop at once
         CUDA_OK(cudaMemsetAsync(m->status.p, 0, 8 * sizeof(int32_t), st));
         CUDA_OK(cudaEventRecord(m->ev[2], st));
     }
-    cudaError_t e = m_core_launch_dispatch(m, BS, P, st);
+    cudaError_t e = m_core_launch_dispatch(m, BS, multi, m->core_grid - swn::CORE_CL * (ncl_plan - ncl), P, st);
     if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
         // the clusters cannot all be co-resident right now (SMs held by other work): not applicable, the caller goes on
         // to the cooperatively launched layer-group kernel
@@ -476,7 +523,7 @@ static int generate_core(swn_model* m, const swn_gen_args* a, cudaStream_t st, i
     m->info.kernel_launches++;
     m->info.smem_bytes = (int32_t)m->core_smem;
     m->info.batch_tile = BS;
-    m->info.n_slots = first ? 1 : m->info.n_slots + 1;     // launches, one after the other
+    m->info.n_slots = first ? ncl : m->info.n_slots + ncl; // core clusters (of up to BS utterances), side by side and over launches
     m->info.grid = m->core_grid;
     m->info.kernel_variant = 2;
     m->info.ctas_per_layer = swn::CORE_CL;          // the core cluster; the other CTAs are helpers
@@ -1544,10 +1591,27 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
     // H=192; tools/gpu_seg1_probe.py, 0.2 s): 24.8 ms per launch of two against 161-165 ms for the batch kernel at any
     // B <= 12 (its ring is latency-bound: 56 us per sample step) - up to 12 utterances the launches of two win.
     if (m->core_ok && seg == 1 && a->kernel_sel == 0 && a->batch_tile == 0 && !a->prof_dev && B >= 3 &&
-        B <= (m->cfg.kind == SWN_KIND_DSWNV ? 7 : 12)) {
-        int rc = 0;
-        for (int b0 = 0; b0 < B && rc == 0; b0 += 2)
-            rc = generate_core(m, a, st, std::min(2, B - b0), Tf, n_iter, b0, b0 == 0, b0 + 2 >= B, 2);
+        B <= (m->cfg.kind == SWN_KIND_DSWNV ? 7 : 16)) {
+        // Two core clusters of two utterances side by side where the helpers' shared memory holds the rings of four utterances
+        // (hid_chn <= 192: the CSWNV recipe model; the DSWNV recipe model's helper taps alone need 84 CTAs): launches of
+        // up to four, of balanced sizes.
+        static const int core_ncl_env = getenv("SWN_CORE_NCL") ? atoi(getenv("SWN_CORE_NCL")) : 0;   // measurements: 1 = launches of two
+        int rc = 2;
+        if (m->core_multi_ok != 0 && core_ncl_env != 1) {
+            const int per = 4, nl = (B + per - 1) / per, base = B / nl, extra = B % nl;
+            rc = 0;
+            for (int g = 0, b0 = 0; g < nl && rc == 0; ++g) {
+                const int Bg = base + (g < extra ? 1 : 0);
+                rc = generate_core(m, a, st, Bg, Tf, n_iter, b0, g == 0, g + 1 == nl, 2, 2);
+                b0 += Bg;
+            }
+            m->core_multi_ok = rc == 2 ? 0 : 1;
+        }
+        if (rc == 2) {
+            rc = 0;
+            for (int b0 = 0; b0 < B && rc == 0; b0 += 2)
+                rc = generate_core(m, a, st, std::min(2, B - b0), Tf, n_iter, b0, b0 == 0, b0 + 2 >= B, 2);
+        }
         if (rc == 0) return 0;
         if (rc == 1) return 1;
         CUDA_OK(cudaStreamSynchronize(st));                 // not applicable after all: nothing was launched (rc == 2 comes first)

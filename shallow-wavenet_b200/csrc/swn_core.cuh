@@ -58,7 +58,7 @@ struct CoreUtt {                   // swn_coreseg.cuh: what differs between the 
     const float* P; const float* noise;
     const void* forced; const void* seedw; void* out; float* head_out;
     unsigned long long* hin_ll; unsigned long long* hacc_ll;
-    int32_t b0, pad;
+    int32_t b0, nb;                // first utterance (Philox counter) and number of utterances of the cluster
 };
 
 struct CoreParams {
@@ -261,30 +261,32 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long* b, uint32_t parity
 // Owns the taps of one layer whose contribution is needed >= 2 steps in the future.  Scatter form:
 // the input vector of time `it` adds W_j . h into the partial sum of time it + delay_j; when the
 // smallest delay has been applied the sum of that target time is complete and is handed to the core.
-template <int NCH, int BS>
+template <int NCH, int BS, bool MULTI>
 __device__ void helper_cta(const CoreParams& P, const HelpCta& D, float* smem) {
     constexpr int NC = BS, HP = NCH * 64;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int l = D.layer, np = D.npairs, H = P.H, RL = D.ring_len, nt = D.ntaps;
+    // MULTI: several core clusters (their own utterances) share this helper's weights; inputs, partial sums and hand-off
+    // rings are per cluster, the clusters take turns (swn_coreseg.cuh has the same scheme)
+    const int ncl = MULTI ? P.n_cl : 1;
     float* sW = smem + D.sm_w;
     {
         const float4* src = reinterpret_cast<const float4*>(P.wbuf + D.w_off);
         float4* dst = reinterpret_cast<float4*>(sW);
         for (int i = tid; i < nt * np * 2 * HP / 4; i += SWN_NTHREADS) dst[i] = src[i];
     }
-    float* hb = smem + D.sm_h;                                 // [2][NC][HP]
-    for (int i = tid; i < 2 * NC * HP; i += SWN_NTHREADS) hb[i] = 0.f;
-    float* ring;                                               // [RL][np][2][BS]
+    float* hb = smem + D.sm_h;                                 // [ncl][2][NC][HP]
+    for (int i = tid; i < ncl * 2 * NC * HP; i += SWN_NTHREADS) hb[i] = 0.f;
+    const size_t ring_f = (size_t)RL * np * 2 * BS;            // [ncl][RL][np][2][BS]
+    float* ring0;
     if (D.ring_in_smem) {
-        ring = smem + D.sm_ring;
-        for (int i = tid; i < RL * np * 2 * BS; i += SWN_NTHREADS) ring[i] = 0.f;
+        ring0 = smem + D.sm_ring;
+        for (int i = tid; i < (int)(ncl * ring_f); i += SWN_NTHREADS) ring0[i] = 0.f;
     } else {
-        ring = P.ring_scratch + D.ring_off;                    // zeroed by the host
+        ring0 = P.ring_scratch + D.ring_off;                   // zeroed by the host
     }
     __syncthreads();
-    const unsigned long long* in_ll = P.hin_ll + P.hin_off[l];
-    unsigned long long* acc_ll = P.hacc_ll + P.hacc_off[l];
-    const int slot_mask = P.hslots[l] - 1, nt_mask = P.hacc_nt[l] - 1, rl_mask = RL - 1;   // all powers of two
+    const int slot_mask = P.hslots[l] - 1, nt_mask = P.hacc_nt[l] - 1, rl_mask = RL - 1;   // powers of two (MULTI: RL need not be)
     // lane <-> (tap j, column c) for the ring update
     const int my_j = lane / NC, my_c = lane - my_j * NC;
     const bool my_live = my_j < nt;
@@ -292,8 +294,11 @@ __device__ void helper_cta(const CoreParams& P, const HelpCta& D, float* smem) {
     int hsel = 0;
     for (int it = 0; it < P.n_it; ++it) {
         const uint32_t tag = (uint32_t)it + 1u;
-        float* hbuf = hb + hsel * NC * HP;
-        hsel ^= 1;
+        for (int q = 0; q < ncl; ++q) {
+        const unsigned long long* in_ll = (MULTI ? P.cl[q].hin_ll : P.hin_ll) + P.hin_off[l];
+        unsigned long long* acc_ll = (MULTI ? P.cl[q].hacc_ll : P.hacc_ll) + P.hacc_off[l];
+        float* ring = ring0 + (size_t)q * ring_f;
+        float* hbuf = hb + (size_t)(q * 2 + hsel) * NC * HP;
         bool ok = true;
         {
             const unsigned long long* src = in_ll + (size_t)(it & slot_mask) * NC * H;
@@ -330,7 +335,7 @@ __device__ void helper_cta(const CoreParams& P, const HelpCta& D, float* smem) {
             }
             if (my_live) {
                 const int T = it + my_delay;
-                float* r0 = ring + (((T & rl_mask) * np + pi) * 2) * BS + my_c;
+                float* r0 = ring + (((MULTI ? T % RL : T & rl_mask) * np + pi) * 2) * BS + my_c;
                 const float a = r0[0] + mz, b = r0[BS] + mc;
                 if (my_j == 0) {
                     // smallest delay: the sum for target time T is complete -> hand it to the core, clear the slot
@@ -344,6 +349,8 @@ __device__ void helper_cta(const CoreParams& P, const HelpCta& D, float* smem) {
             }
             __syncwarp();
         }
+        }
+        hsel ^= 1;
     }
 }
 

@@ -137,8 +137,13 @@ __device__ __forceinline__ bool mbar_wait2(unsigned long long* b, uint32_t parit
     return mbar_wait_slow2(b, parity, P, where);
 }
 
-template <int NCH, int BS>
-__device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
+// Several core clusters side by side in one launch (MULTI, swn_abi.cu generate_core): cluster clid works on its own
+// utterances (CoreParams::cl[clid]: conditioning table, noise, outputs, Philox utterance index, input / hand-off rings); the
+// single-cluster instantiation reads the same fields of CoreParams itself, as before (identical code).
+#define SWN_CU(field, legacy) (MULTI ? P.cl[clid].field : P.legacy)
+
+template <int NCH, int BS, bool MULTI>
+__device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem, const int clid) {
     // TMEM columns per tap per thread: a quarter-warp-group thread keeps 8 rows (4 gate pairs) x FPT weights
     constexpr int NC = BS, HP = NCH * 64, FPT = 2 * NCH, TCOLS = 8 * FPT;
     constexpr int HIST = 16;
@@ -241,11 +246,11 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
         }
         tmem_wait_st();
     }
-    if (P.seedw) {
+    if (SWN_CU(seedw, seedw)) {
         for (int e = tid; e < NC; e += SWN_NTHREADS) {
-            const int bglob = min(e, P.B - 1);
-            const float v = is_c ? ((const float*)P.seedw)[bglob]
-                                 : __int_as_float(pos_mod(((const long long*)P.seedw)[bglob], Q));
+            const int bglob = min(e, SWN_CU(nb, B) - 1);
+            const float v = is_c ? ((const float*)SWN_CU(seedw, seedw))[bglob]
+                                 : __int_as_float(pos_mod(((const long long*)SWN_CU(seedw, seedw))[bglob], Q));
             hist[e * HIST + (HIST - 1)] = v;                       // generated-index -1
             if (is_c && P.lpc > 0) lpb[e * 8 + P.lpc - 1] = v;
         }
@@ -305,15 +310,15 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
     //   { pz, (bz + rz + hz) * pz, pc, (bc + rc + hc) * pc }
     // in gop[tt & 1][l][pair][col]; the chain warp's stage then needs one LDS.128 and two FMAs before the gate.
     const bool pf_lane = warp >= 4 && warp < 8 && pvalid && sub < NC;
-    const int bg_col = min(sub, P.B - 1);
-    const float* ptab_b = P.P + (size_t)bg_col * P.Tf * L * twoH + my_i;
+    const int bg_col = min(sub, SWN_CU(nb, B) - 1);
+    const float* ptab_b = SWN_CU(P, P) + (size_t)bg_col * P.Tf * L * twoH + my_i;
     bool gok = true;
     auto gop_issue = [&](int l, int tt, const float* prow, float& prz, float& prc, unsigned long long& ha, unsigned long long& hb) {
         prz = 0.f; prc = 0.f; ha = 0ull; hb = 0ull;
         if (pf_lane && tt < P.n_it) {
             prz = __ldg(prow + l * twoH); prc = __ldg(prow + l * twoH + H);
             if (P.has_help[l] && tt >= P.hdmin[l]) {
-                const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + ((tt & (P.hacc_nt[l] - 1)) * twoH + my_i) * NC + sub;
+                const unsigned long long* src = SWN_CU(hacc_ll, hacc_ll) + P.hacc_off[l] + ((tt & (P.hacc_nt[l] - 1)) * twoH + my_i) * NC + sub;
                 ha = ld_ll(src); hb = ld_ll(src + H * NC);
             }
         }
@@ -326,7 +331,7 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                 const uint32_t tg = (uint32_t)tt + 1u;
                 uint32_t a = (uint32_t)ha, b = (uint32_t)hb;
                 if ((uint32_t)(ha >> 32) != tg || (uint32_t)(hb >> 32) != tg) {      // the helper is late: wait for it here
-                    const unsigned long long* src = P.hacc_ll + P.hacc_off[l] + ((tt & (P.hacc_nt[l] - 1)) * twoH + my_i) * NC + sub;
+                    const unsigned long long* src = SWN_CU(hacc_ll, hacc_ll) + P.hacc_off[l] + ((tt & (P.hacc_nt[l] - 1)) * twoH + my_i) * NC + sub;
                     gok = wait_gword(src, tg, a, P, 400 + l) && gok;
                     gok = wait_gword(src + H * NC, tg, b, P, 400 + l) && gok;
                 }
@@ -344,10 +349,10 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
     auto draw_gumbel = [&](int isn) {
         const int idx = (warp - 8) * 32 + lane;
         if (gn_team && warp >= 8 && idx < 16 * NC) {
-            const int row = idx & 15, c = idx >> 4, bglob = min(c, P.B - 1);
+            const int row = idx & 15, c = idx >> 4, bglob = min(c, SWN_CU(nb, B) - 1);
             if (row < D.nc) {
-                const float q = P.noise ? __ldg(P.noise + ((size_t)bglob * P.n_out + isn) * Q + D.c0 + row)
-                                        : softmax_q(P.seed, P.b0 + bglob, isn, D.c0 + row);
+                const float q = SWN_CU(noise, noise) ? __ldg(SWN_CU(noise, noise) + ((size_t)bglob * P.n_out + isn) * Q + D.c0 + row)
+                                        : softmax_q(P.seed, SWN_CU(b0, b0) + bglob, isn, D.c0 + row);
                 gnz[((isn & 1) * 16 + row) * NC + c] = -logf(q);
             }
         }
@@ -396,7 +401,7 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
         const float v = acc * rcp_approx(1.f + fabsf(acc));
         if (lane < CORE_CL) st_async_f32(hx_peer + (uint32_t)((c * HP + in_row) * 4), v, mb_peer + (uint32_t)(c * 8));
         if (lane == 16 && P.has_help[0])
-            st_ll(P.hin_ll + P.hin_off[0] + ((itn & (P.hslots[0] - 1)) * NC + c) * H + in_row, v, (uint32_t)itn + 1u);
+            st_ll(SWN_CU(hin_ll, hin_ll) + P.hin_off[0] + ((itn & (P.hslots[0] - 1)) * NC + c) * H + in_row, v, (uint32_t)itn + 1u);
     };
     auto input_publish = [&](int itn, const float (&fed)[NC]) {
 #pragma unroll
@@ -491,7 +496,7 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                         for (int k = 0; k < 4; ++k)
                             st_async_f32(mapa(hx0 + off, (uint32_t)(s4 + 4 * k)), hn, mapa(mb0 + mo, (uint32_t)(s4 + 4 * k)));
                         if (l + 1 < L && P.has_help[l + 1] && s4 == 0)
-                            st_ll(P.hin_ll + P.hin_off[l + 1] + ((it & (P.hslots[l + 1] - 1)) * NC + scol) * H + D.pair0 + prow, hn, (uint32_t)it + 1u);
+                            st_ll(SWN_CU(hin_ll, hin_ll) + P.hin_off[l + 1] + ((it & (P.hslots[l + 1] - 1)) * NC + scol) * H + D.pair0 + prow, hn, (uint32_t)it + 1u);
                     }
                 } else {
                 // the columns one after the other, each behind its own barrier: while the hop of column c is in flight
@@ -533,7 +538,7 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                     }
                     // ---- behind the publish (in the shadow of the hop): helper hand-off
                     if (l + 1 < L && P.has_help[l + 1] && pvalid && sub == 0)
-                        st_ll(P.hin_ll + P.hin_off[l + 1] + ((it & (P.hslots[l + 1] - 1)) * NC + c) * H + my_i, hn, (uint32_t)it + 1u);
+                        st_ll(SWN_CU(hin_ll, hin_ll) + P.hin_off[l + 1] + ((it & (P.hslots[l + 1] - 1)) * NC + c) * H + my_i, hn, (uint32_t)it + 1u);
                 }
                 }
                 // next taps, running pointers
@@ -712,9 +717,9 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                     } else {
 #pragma unroll
                         for (int c = 0; c < NC; ++c) {
-                            const int bglob = min(c, P.B - 1);
-                            const float q = P.noise ? __ldg(P.noise + ((size_t)bglob * P.n_out + istep) * Q + c0row)
-                                                    : softmax_q(P.seed, P.b0 + bglob, istep, c0row);
+                            const int bglob = min(c, SWN_CU(nb, B) - 1);
+                            const float q = SWN_CU(noise, noise) ? __ldg(SWN_CU(noise, noise) + ((size_t)bglob * P.n_out + istep) * Q + c0row)
+                                                    : softmax_q(P.seed, SWN_CU(b0, b0) + bglob, istep, c0row);
                             gn[c] = -logf(q);
                         }
                     }
@@ -742,7 +747,7 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                         if (lane == 0) o2[c * 16 + r] = o;
                     } else {
                         if (lane < CORE_CL) st_async_f32(dst + (uint32_t)(c * 256 * 4), o + gn[c], mbh + (uint32_t)((2 * NC + c) * 8));
-                        if (lane == 16 && P.head_out && c < P.B) P.head_out[((size_t)c * P.n_iter + istep) * n2 + c0row] = o;
+                        if (lane == 16 && SWN_CU(head_out, head_out) && c < SWN_CU(nb, B)) SWN_CU(head_out, head_out)[((size_t)c * P.n_iter + istep) * n2 + c0row] = o;
                     }
                 }
             } else if (tid == 0) {
@@ -755,16 +760,16 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
             if (is_c) {
                 __syncthreads();
                 if (tid < NC) {
-                    const int c = tid, bglob = min(c, P.B - 1);
+                    const int c = tid, bglob = min(c, SWN_CU(nb, B) - 1);
                     float eps[1], smp[1];
-                    eps[0] = P.noise ? P.noise[(size_t)bglob * P.n_out + istep] : laplace_eps(P.seed, P.b0 + bglob, istep);
-                    const float* forced = P.forced ? (const float*)P.forced + (size_t)bglob * P.n_out + istep : nullptr;
+                    eps[0] = SWN_CU(noise, noise) ? SWN_CU(noise, noise)[(size_t)bglob * P.n_out + istep] : laplace_eps(P.seed, SWN_CU(b0, b0) + bglob, istep);
+                    const float* forced = SWN_CU(forced, forced) ? (const float*)SWN_CU(forced, forced) + (size_t)bglob * P.n_out + istep : nullptr;
                     laplace_step<1>(P.lpc, o2 + c * 16, lpb + c * 8, eps, forced, smp);
                     hist[c * HIST + (istep % HIST)] = forced ? forced[0] : smp[0];
-                    if (rank == 0 && c < P.B) {
-                        ((float*)P.out)[(size_t)c * P.n_out + istep] = smp[0];
-                        if (P.head_out)
-                            for (int r = 0; r < n2; ++r) P.head_out[((size_t)c * P.n_iter + istep) * n2 + r] = o2[c * 16 + r];
+                    if (rank == 0 && c < SWN_CU(nb, B)) {
+                        ((float*)SWN_CU(out, out))[(size_t)c * P.n_out + istep] = smp[0];
+                        if (SWN_CU(head_out, head_out))
+                            for (int r = 0; r < n2; ++r) SWN_CU(head_out, head_out)[((size_t)c * P.n_iter + istep) * n2 + r] = o2[c * 16 + r];
                     }
                 }
                 __syncthreads();
@@ -798,9 +803,9 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
                     const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
                     bi = (int)__reduce_min_sync(0xffffffffu, key == kmax ? (uint32_t)bi : 0xffffffffu);
                     int f = bi;
-                    if (c < P.B) {
-                        if (rank == 0 && tid == 0) ((long long*)P.out)[(size_t)c * P.n_out + istep] = bi;
-                        if (P.forced) f = clamp_idx(__ldg((const long long*)P.forced + (size_t)c * P.n_out + istep), Q);
+                    if (c < SWN_CU(nb, B)) {
+                        if (rank == 0 && tid == 0) ((long long*)SWN_CU(out, out))[(size_t)c * P.n_out + istep] = bi;
+                        if (SWN_CU(forced, forced)) f = clamp_idx(__ldg((const long long*)SWN_CU(forced, forced) + (size_t)c * P.n_out + istep), Q);
                     }
                     fed[c] = __int_as_float(f);
                     if (it + 1 < P.n_it) input_publish_col(it + 1, c, fed[c]);   // straight on to this column's next input row
@@ -827,15 +832,18 @@ __device__ void core_cta2(const CoreParams& P, const CoreCta& D, float* smem) {
     if (warp == 0) tmem_free_all(tbase);
 }
 
-template <int NCH, int BS>
+#undef SWN_CU
+
+template <int NCH, int BS, bool MULTI>
 __global__ void __cluster_dims__(CORE_CL, 1, 1) __launch_bounds__(SWN_NTHREADS, 1)
 swn_core_kernel2(const __grid_constant__ CoreParams P) {
     extern __shared__ __align__(16) float smem[];
-    if (cluster_id_x() == 0) {
-        core_cta2<NCH, BS>(P, P.cdesc[cluster_ctarank()], smem);
+    const int clid = (int)cluster_id_x(), ncl = MULTI ? P.n_cl : 1;     // clusters 0 .. ncl-1 are core clusters
+    if (clid < ncl) {
+        core_cta2<NCH, BS, MULTI>(P, P.cdesc[cluster_ctarank()], smem, clid);
     } else {
-        const int hidx = (int)blockIdx.x - CORE_CL;
-        if (hidx < P.n_help && P.hdesc[hidx].npairs > 0) helper_cta<NCH, BS>(P, P.hdesc[hidx], smem);
+        const int hidx = (int)blockIdx.x - CORE_CL * ncl;
+        if (hidx < P.n_help && P.hdesc[hidx].npairs > 0) helper_cta<NCH, BS, MULTI>(P, P.hdesc[hidx], smem);
     }
 }
 

@@ -11,9 +11,9 @@
 
 namespace swn {
 
-template <int NCH, int BS>
+template <int NCH, int BS, bool MULTI>
 static cudaError_t core_prepare(size_t smem, int* max_clusters) {
-    auto k = swn_core_kernel2<NCH, BS>;
+    auto k = swn_core_kernel2<NCH, BS, MULTI>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -29,9 +29,9 @@ static cudaError_t core_prepare(size_t smem, int* max_clusters) {
     return cudaOccupancyMaxActiveClusters(max_clusters, (const void*)k, &cfg);
 }
 
-template <int NCH, int BS>
+template <int NCH, int BS, bool MULTI>
 static cudaError_t core_launch(const CoreParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto k = swn_core_kernel2<NCH, BS>;
+    auto k = swn_core_kernel2<NCH, BS, MULTI>;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(SWN_NTHREADS);
@@ -60,12 +60,24 @@ static cudaError_t core_launch(const CoreParams& p, int grid, size_t smem, cudaS
 #define SWN_CAT2(a, b) a##b
 #define SWN_CAT(a, b) SWN_CAT2(a, b)
 
-core_fns SWN_CAT(find_core_kernel_nch, SWN_NCH)(int bs) {
+// multi = several core clusters side by side (one or two utterances each) sharing the helper CTAs: instantiated where the
+// helpers' shared memory can hold more than one utterance group's rings (hid_chn <= 192)
+core_fns SWN_CAT(find_core_kernel_nch, SWN_NCH)(int bs, bool multi) {
     core_fns f = {nullptr, nullptr};
+    if (multi) {
+#if SWN_NCH <= 3
+        switch (bs) {
+            case 1: f.prepare = &core_prepare<SWN_NCH, 1, true>; f.launch = &core_launch<SWN_NCH, 1, true>; break;
+            case 2: f.prepare = &core_prepare<SWN_NCH, 2, true>; f.launch = &core_launch<SWN_NCH, 2, true>; break;
+            default: break;
+        }
+#endif
+        return f;
+    }
     switch (bs) {
-        case 1: f.prepare = &core_prepare<SWN_NCH, 1>; f.launch = &core_launch<SWN_NCH, 1>; break;
-        case 2: f.prepare = &core_prepare<SWN_NCH, 2>; f.launch = &core_launch<SWN_NCH, 2>; break;
-        case 4: f.prepare = &core_prepare<SWN_NCH, 4>; f.launch = &core_launch<SWN_NCH, 4>; break;
+        case 1: f.prepare = &core_prepare<SWN_NCH, 1, false>; f.launch = &core_launch<SWN_NCH, 1, false>; break;
+        case 2: f.prepare = &core_prepare<SWN_NCH, 2, false>; f.launch = &core_launch<SWN_NCH, 2, false>; break;
+        case 4: f.prepare = &core_prepare<SWN_NCH, 4, false>; f.launch = &core_launch<SWN_NCH, 4, false>; break;
         default: break;
     }
     return f;

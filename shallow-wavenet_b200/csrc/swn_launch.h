@@ -18,10 +18,10 @@ struct core_fns {
     cudaError_t (*prepare)(size_t smem, int* max_clusters);
     cudaError_t (*launch)(const CoreParams& p, int grid, size_t smem, cudaStream_t st);
 };
-core_fns find_core_kernel_nch1(int bs);
-core_fns find_core_kernel_nch2(int bs);
-core_fns find_core_kernel_nch3(int bs);
-core_fns find_core_kernel_nch4(int bs);
+core_fns find_core_kernel_nch1(int bs, bool multi = false);
+core_fns find_core_kernel_nch2(int bs, bool multi = false);
+core_fns find_core_kernel_nch3(int bs, bool multi = false);
+core_fns find_core_kernel_nch4(int bs, bool multi = false);
 // seg > 1 cluster kernel (swn_coreseg.cuh), one utterance per launch; instantiated for seg 2 .. 5
 core_fns find_coreseg_kernel_nch1(int seg);
 core_fns find_coreseg_kernel_nch2(int seg);
