@@ -117,6 +117,7 @@ struct swn_model {
     DevBuf<swn::HelpCta> hdesc;
     DevBuf<unsigned long long> ll2;
     long long core_plan_key = -1;
+    int core_multi1_ok[2] = {-1, -1};  // the same with one utterance per cluster, for 2 / 3 utterances
     int core_multi_ok = -1;            // side-by-side core clusters of the one-sample-per-step kernel: -1 untried, 0 do not fit, 1 ok
     int core_grid = 0, core_n_help = 0;
     size_t core_smem = 0, core_ring_total = 0;
@@ -1590,6 +1591,17 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
     // the batch kernel at B=6; from 8 utterances on the batch kernel wins).  CSWNV seg=1 (the recipe's default model,
     // H=192; tools/gpu_seg1_probe.py, 0.2 s): 24.8 ms per launch of two against 161-165 ms for the batch kernel at any
     // B <= 12 (its ring is latency-bound: 56 us per sample step) - up to 12 utterances the launches of two win.
+    // Two utterances: one core cluster EACH where the helpers hold two rings (a cluster steps one column in 6.7 us and two columns
+    // in 8.6 us; CSWNV seg 1, H=192: 24.9 -> 19.6 ms).  Three clusters of one utterance are helper-bound on the 64 helper CTAs they
+    // leave (28.0 ms against 25.9 ms for two clusters of two), so three utterances take the path below.
+    if (m->core_ok && seg == 1 && a->kernel_sel == 0 && a->batch_tile == 0 && !a->prof_dev && B == 2 &&
+        m->core_multi1_ok[B - 2] != 0 && !(getenv("SWN_CORE_NCL") && atoi(getenv("SWN_CORE_NCL")) == 1)) {
+        const int rc = generate_core(m, a, st, B, Tf, n_iter, 0, true, true, 1, B);
+        m->core_multi1_ok[B - 2] = rc == 2 ? 0 : 1;
+        if (rc == 0) return 0;
+        if (rc == 1) return 1;
+        CUDA_OK(cudaStreamSynchronize(st));
+    }
     if (m->core_ok && seg == 1 && a->kernel_sel == 0 && a->batch_tile == 0 && !a->prof_dev && B >= 3 &&
         B <= (m->cfg.kind == SWN_KIND_DSWNV ? 7 : 16)) {
         // Two core clusters of two utterances side by side where the helpers' shared memory holds the rings of four utterances

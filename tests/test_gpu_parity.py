@@ -553,8 +553,8 @@ def test_seg_cluster_kernel_recipe_size_reference_fixture():
 
 
 @pytest.mark.parametrize("kind,over,B", [("cswnv", dict(seg=1, lpc=4), 1), ("cswnv", dict(seg=1, lpc=4), 2), ("dswnv", dict(), 1),
-                                         ("cswnv", dict(seg=5, lpc=4), 3), ("cswnv", dict(seg=1, lpc=4), 4),
-                                         ("cswnv", dict(seg=1, lpc=4), 7)])
+                                         ("cswnv", dict(seg=5, lpc=4), 3), ("cswnv", dict(seg=1, lpc=4), 3),
+                                         ("cswnv", dict(seg=1, lpc=4), 4), ("cswnv", dict(seg=1, lpc=4), 7), ("dswnv", dict(), 2)])
 def test_cluster_kernels_with_late_helper_ctas_are_bit_identical(kind, over, B):
     """The helper CTAs of the cluster kernels normally finish a turn long before the core needs their sums, so the core's
     wait-for-a-late-helper path is almost never taken.  With every helper turn delayed (swn_gen_args::debug_helper_delay_ns)
@@ -574,10 +574,12 @@ def test_cluster_kernels_with_late_helper_ctas_are_bit_identical(kind, over, B):
     for delay in (0, 8000, 20000):
         eng.condition(aux)
         # (B >= 3 with one sample per step: automatic choice = two core clusters of two utterances side by side per launch)
-        out, heads = eng.generate(n, seed=7, kernel_sel=2 if B <= 3 else 0, forced=forced, return_heads=True, helper_delay_ns=delay)
+        out, heads = eng.generate(n, seed=7, kernel_sel=2 if B == 1 else 0, forced=forced, return_heads=True, helper_delay_ns=delay)
         assert eng.info["kernel_variant"] == 2
         if B > 3:
             assert eng.info["batch_tile"] == 2 and eng.info["n_slots"] == -(-B // 2), eng.info
+        elif B == 2 and kind == "cswnv" and over.get("seg") == 1:       # one core cluster per utterance
+            assert eng.info["batch_tile"] == 1 and eng.info["n_slots"] == 2, eng.info
         h = heads.cpu().numpy()
         if ref is None:
             ref = h
