@@ -41,6 +41,9 @@ WORKLOADS = {
                "cfg1 x 3: the cfg1 model, 3 utterances of 1 s side by side (one core cluster each, shared helper CTAs)"),
     "cfg1x7": ("cswnv", 22050, dict(seg=5, lpc=4), 7, 200,
                "cfg1 x 7: the cfg1 model at the recipe's decode batch (decode_batch_size=7, egs/shallow-wavenet/run.sh:280), 7 x 1 s"),
+    "seg1x7": ("cswnv", 22050, dict(seg=1, lpc=4), 7, 200,
+               "recipe default x 7: CSWNV Laplace seg=1 lpc=4 H=192 (model=laplace, seg=1: egs/shallow-wavenet/run.sh:159-219) at the "
+               "recipe's decode batch of 7, 7 x 1 s"),
     "cfg2": ("dswnv", 16000, dict(), 1, 1000,
              "cfg2: DSWNV mu-law softmax H=256 S=256 Q=256 k=7 L=6, 16 kHz, batch 1, 5 s (80000 samples)"),
     "cfg3": ("cswnv", 22050, dict(seg=5, lpc=4), 64, 1000,
@@ -507,8 +510,8 @@ def main():
 
     # ---- decode-batch sub-record: the cfg1 model at the recipe's default decode batch of 7 utterances (run.sh:280): seg cluster
     # kernel, three utterances side by side per launch (3 + 2 + 2)
-    if not args.no_extras and args.workload == "cfg2":
-        dk, dfs, dover, dB, dframes, ddesc = WORKLOADS["cfg1x7"]
+    for dname in (("cfg1x7", "seg1x7") if (not args.no_extras and args.workload == "cfg2") else ()):
+        dk, dfs, dover, dB, dframes, ddesc = WORKLOADS[dname]
         dkw = model_kwargs(dk, dfs, dover)
         dn = dframes * dkw["upsampling_factor"]
         rd = measure(dk, dkw, synth.synth_aux(dkw["n_aux"], dframes, dB, seed=3456 + rank), [dn] * dB, 3, 2, 3)
@@ -516,14 +519,14 @@ def main():
         if rank == 0:
             dro = roofline_of(dk, dkw, rd, 3)
             dval = world * rd["samples_per_step"] * 3 / (d_total * 1e-3)
-            line["decode_batch"] = {"cfg1x7": {
+            line.setdefault("decode_batch", {})[dname] = {
                 "workload": ddesc, "value": dval, "unit": "samples/s", "rtf": dval / dfs, "rtf_per_utterance": dval / dfs / (world * dB),
                 "steps": 3, "warmup": 2, "scaling": "weak", "ms_per_step": d_total / 3, "kernel_ms": rd["kern_ms"],
                 "conditioning_ms": rd["cond_ms"],
                 "e2e": {"value": world * rd["samples_per_step"] / (d_e2e * 1e-3), "unit": "samples/s",
                         "h2d_bytes_per_step": rd["h2d"], "d2h_bytes_per_step": rd["d2h"]},
                 "roofline": dro, "clocks": rd["clocks"], "gpu_launches": rd["launches"],
-                "plan": {k: rd["info"][k] for k in ("kernel_variant", "grid", "batch_tile", "n_slots", "ctas_per_layer", "head_ctas")}}}
+                "plan": {k: rd["info"][k] for k in ("kernel_variant", "grid", "batch_tile", "n_slots", "ctas_per_layer", "head_ctas")}}
 
     # ---- sharded sub-record: BASELINE.json configs[3], 512 utterances of unequal length split over the ranks the way
     # the decode scripts split their list (contiguous np.array_split, decode_cswnv_laplace-shift1.py:200-201), each
