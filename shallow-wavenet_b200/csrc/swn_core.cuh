@@ -292,6 +292,16 @@ __device__ void helper_cta(const CoreParams& P, const HelpCta& D, float* smem) {
     const bool my_live = my_j < nt;
     const int my_delay = my_live ? D.delay[my_j] : 0;
     int hsel = 0;
+    constexpr int WPT = (NC * HP + SWN_NTHREADS - 1) / SWN_NTHREADS;          // input words per thread and turn
+    unsigned long long pre[WPT];
+    if (MULTI) {
+        const unsigned long long* s0 = P.cl[0].hin_ll + P.hin_off[l];
+#pragma unroll
+        for (int r = 0; r < WPT; ++r) {
+            const int i = tid + r * SWN_NTHREADS;
+            pre[r] = i < NC * H ? ld_ll(s0 + i) : 0ull;
+        }
+    }
     for (int it = 0; it < P.n_it; ++it) {
         const uint32_t tag = (uint32_t)it + 1u;
         for (int q = 0; q < ncl; ++q) {
@@ -300,7 +310,21 @@ __device__ void helper_cta(const CoreParams& P, const HelpCta& D, float* smem) {
         float* ring = ring0 + (size_t)q * ring_f;
         float* hbuf = hb + (size_t)(q * 2 + hsel) * NC * HP;
         bool ok = true;
-        {
+        if (MULTI) {
+            // the words of this turn were requested before the previous turn's arithmetic (below): with several clusters to serve
+            // the two L2 round trips per turn are what made three clusters helper-bound (as in swn_coreseg.cuh)
+            const unsigned long long* src = in_ll + (size_t)(it & slot_mask) * NC * H;
+#pragma unroll
+            for (int r = 0; r < WPT; ++r) {
+                const int i = tid + r * SWN_NTHREADS;
+                if (i < NC * H) {
+                    uint32_t bits = (uint32_t)pre[r];
+                    if ((uint32_t)(pre[r] >> 32) != tag) ok = wait_gword(src + i, tag, bits, P, 300 + l) && ok;
+                    const int c = i / H, k = i - c * H;
+                    hbuf[c * HP + k] = __uint_as_float(bits);
+                }
+            }
+        } else {
             const unsigned long long* src = in_ll + (size_t)(it & slot_mask) * NC * H;
 #pragma unroll
             for (int c = 0; c < NC; ++c)
@@ -312,6 +336,18 @@ __device__ void helper_cta(const CoreParams& P, const HelpCta& D, float* smem) {
                 }
         }
         if (__syncthreads_or(!ok)) return;
+        if (MULTI) {
+            int qn = q + 1, itn = it;
+            if (qn == ncl) { qn = 0; ++itn; }
+            if (itn < P.n_it) {
+                const unsigned long long* sn = P.cl[qn].hin_ll + P.hin_off[l] + (size_t)(itn & slot_mask) * NC * H;
+#pragma unroll
+                for (int r = 0; r < WPT; ++r) {
+                    const int i = tid + r * SWN_NTHREADS;
+                    pre[r] = i < NC * H ? ld_ll(sn + i) : 0ull;
+                }
+            }
+        }
         if (P.help_delay_ns > 0) __nanosleep((unsigned)P.help_delay_ns);   // test hook: a late helper (the core must wait for its sums)
         float2 h[NC][NCH];
 #pragma unroll
