@@ -308,6 +308,37 @@ def test_non_default_seed_waveform():
     assert np.abs(heads - O.teacher_forced(g["cfg"], g["sd"], aux, np.stack(outs))).max() > 1e-4   # the seed matters
 
 
+def test_side_by_side_core_clusters_with_seed_waveform():
+    """Five utterances of a one-sample-per-step CSWNV through the automatic choice: launches of 3 + 2, two core clusters
+    side by side (two utterances + one, one + one), each cluster with its own seed sample, noise, conditioning table and
+    outputs (CoreParams::cl[]): per-step heads against the oracle run with the same seed waveform."""
+    g = load_golden("cswnv_seg1_lpc0")
+    m = _model_from_golden(g)
+    kw = g["kw"]
+    rng = np.random.default_rng(5)
+    B, T = 5, g["aux"].shape[2]
+    N = T * kw["upsampling_factor"]
+    aux = rng.standard_normal((B, kw["n_aux"], T)).astype(np.float32)
+    seed_wav = (0.2 * rng.standard_normal((B, 1))).astype(np.float32)
+    eps = rng.uniform(-0.4999, 0.5, (B, N)).astype(np.float32)
+    outs, heads = m.batch_fast_generate(torch.from_numpy(seed_wav), torch.from_numpy(aux), [N] * B, noise=eps,
+                                        return_heads=True)
+    info = m.engine().info
+    assert info["kernel_variant"] == 2 and info["batch_tile"] == 2 and info["n_slots"] == 3, info
+    orig = O._audio_full
+
+    def seeded(cfg, gen, Bn, n):
+        a = orig(cfg, gen, Bn, n)
+        a[:, cfg.receptive_field: cfg.receptive_field + cfg.seg] = torch.from_numpy(seed_wav)
+        return a
+    O._audio_full = seeded
+    try:
+        ref_heads = O.teacher_forced(g["cfg"], g["sd"], aux, np.stack(outs))
+    finally:
+        O._audio_full = orig
+    _head_close(heads, ref_heads, "side-by-side clusters, seeded", g, tol=_tol(m))
+
+
 def test_philox_stream_is_reproducible_and_matches_host_replica():
     from shallow_wavenet_b200 import engine as E
     g = load_golden("dswnv_base")
