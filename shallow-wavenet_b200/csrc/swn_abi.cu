@@ -1594,8 +1594,7 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
     // Two utterances: one core cluster EACH where the helpers hold two rings (a cluster steps one column in 6.7 us and two columns
     // in 8.6 us; CSWNV seg 1, H=192: 24.9 -> 19.6 ms).  Three clusters of one utterance are helper-bound on the 64 helper CTAs they
     // leave (28.0 ms against 25.9 ms for two clusters of two), so three utterances take the path below.
-    static const int core1_max_env = getenv("SWN_CORE1_MAX") ? atoi(getenv("SWN_CORE1_MAX")) : 2;     // (measurements: 3 = also three clusters of one)
-    if (m->core_ok && seg == 1 && a->kernel_sel == 0 && a->batch_tile == 0 && !a->prof_dev && B >= 2 && B <= std::min(3, core1_max_env) &&
+    if (m->core_ok && seg == 1 && a->kernel_sel == 0 && a->batch_tile == 0 && !a->prof_dev && B == 2 &&
         m->core_multi1_ok[B - 2] != 0 && !(getenv("SWN_CORE_NCL") && atoi(getenv("SWN_CORE_NCL")) == 1)) {
         const int rc = generate_core(m, a, st, B, Tf, n_iter, 0, true, true, 1, B);
         m->core_multi1_ok[B - 2] = rc == 2 ? 0 : 1;
@@ -1637,8 +1636,7 @@ int swn_generate(swn_handle m, const swn_gen_args* a, void* stream) {
         // plan: 8.5 ms), against 33.4 ms for the batch kernel at any B <= 10: up to nine utterances the cluster kernel wins
         // (B = 9: 27.3 ms), four run as 2 + 2 on the two-cluster plan.
         static const int seg_ncl_env = getenv("SWN_SEG_NCL") ? atoi(getenv("SWN_SEG_NCL")) : 0;      // measurements: 1 = one utterance per launch
-        static const int seg_bmax_env = getenv("SWN_SEG_BMAX") ? atoi(getenv("SWN_SEG_BMAX")) : 0;
-        const int seg_bmax = seg_bmax_env > 0 ? seg_bmax_env : 9;
+        const int seg_bmax = 9;
         if (a->kernel_sel == 2 || (a->kernel_sel == 0 && a->batch_tile == 0 && B <= seg_bmax)) {
             int ncl_plan = std::min(B, B == 4 ? 2 : (int)swn::CORE_MAXCL);
             if (seg_ncl_env > 0) ncl_plan = std::min(B, std::min(seg_ncl_env, (int)swn::CORE_MAXCL));
